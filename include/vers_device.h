@@ -1,0 +1,180 @@
+/*
+ * vers_device.h — C ABI of the B200-native device layer behind vers' `Index<N>` trait.
+ *
+ * The reference (ashrielbrian/vers) has no process or device boundary; this header IS the boundary the
+ * north-star introduces: Rust host (rust/vers-cuda-sys) -> extern "C" -> CUDA (sm_100a).
+ * Every entry point names the reference code it replaces (paths relative to /root/reference/vers/src).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `usize` == uint64_t; rows arrive as `const float*` with a stride in floats
+ *     (size_of::<Vector<N>>()/4: 320 for N=300, 768, 128 — indexes/base.rs:15 `#[repr(align(256))]`).
+ *   - every function returns int32_t: 0 = VERS_OK, negative = error class; the message is in vers_last_error()
+ *     (thread-local).  VERS_ERR_PANIC marks inputs on which the reference itself panics (unwrap / index OOB);
+ *     the Rust shim turns any non-zero status into panic!, matching the reference's error behaviour.
+ *   - results are structure-of-arrays (ids[], dists[], counts[]) because Vec<(usize, f32)> has no stable layout.
+ *     Unused result slots are filled with id = UINT64_MAX, dist = +inf.
+ *   - returned distances are SQUARED L2 (indexes/base.rs:119-126) unless metric = VERS_METRIC_COSINE
+ *     (1 - dot, indexes/base.rs:155).
+ *   - `_dev` variants take DEVICE pointers and enqueue on the context's stream without synchronising: they are
+ *     what bench.py times with inputs resident in HBM, and what the multi-GPU driver calls between collectives.
+ *     The un-suffixed variants take HOST pointers, copy, run, copy back and synchronise (the `e2e` path).
+ *   - there is no CPU fallback: without a CUDA device every call fails with VERS_ERR_CUDA.
+ */
+#ifndef VERS_DEVICE_H
+#define VERS_DEVICE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VERS_OK 0
+#define VERS_ERR_ARG (-1)
+#define VERS_ERR_CUDA (-2)
+#define VERS_ERR_NOMEM (-3)
+#define VERS_ERR_PANIC (-4)       /* the reference would panic on these inputs */
+#define VERS_ERR_UNSUPPORTED (-5) /* valid in the reference, outside this build's limits (e.g. top_k > 128) */
+
+#define VERS_METRIC_L2SQ 0u
+#define VERS_METRIC_COSINE 1u
+
+#define VERS_MAX_TOPK 128u
+
+typedef struct vers_ctx vers_ctx;         /* one per GPU: device id, stream, scratch arena                     */
+typedef struct vers_dataset vers_dataset; /* Vec<Vector<N>> resident in HBM, row-major, ld = round_up(dim, 4)  */
+typedef struct vers_kmeans vers_kmeans;   /* k-means state (centroids, assignments) on one GPU's row shard     */
+typedef struct vers_ivf vers_ivf;         /* IVFFlatIndex<N> (indexes/ivfflat.rs:9-15), list-major in HBM      */
+typedef struct vers_lsh vers_lsh;         /* ANNIndex<N>     (indexes/lsh.rs:47-55), forest + rows in HBM      */
+
+const char* vers_last_error(void);
+int32_t vers_abi_version(void);
+
+/* ---- context -------------------------------------------------------------------------------------------- */
+int32_t vers_ctx_create(int32_t device, vers_ctx** out);
+int32_t vers_ctx_destroy(vers_ctx* ctx);
+/* borrow a cudaStream_t (e.g. torch's current stream) so that the caller's CUDA events bracket our kernels */
+int32_t vers_ctx_set_stream(vers_ctx* ctx, void* cuda_stream);
+int32_t vers_ctx_sync(vers_ctx* ctx);
+/* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches) */
+int32_t vers_ctx_launch_count(vers_ctx* ctx, uint64_t* out);
+/* name + device time (ms, CUDA events on ctx's stream) of the most recent launch of each kernel family, for
+ * bench.py's roofline line.  which: 0 = list scan, 1 = flat scan, 2 = k-means assign, 3 = k-means sums,
+ * 4 = lsh hash, 5 = probe.  Timing is only recorded while enabled. */
+int32_t vers_ctx_enable_timing(vers_ctx* ctx, int32_t on);
+int32_t vers_ctx_last_kernel_ms(vers_ctx* ctx, int32_t which, float* ms, uint64_t* launches);
+
+/* ---- datasets: Vec<Vector<N>> (indexes/base.rs:15-17) ----------------------------------------------------- */
+/* id_base: global id of local row 0 (row shards of a multi-GPU index are contiguous blocks of the global rows) */
+int32_t vers_dataset_upload(vers_ctx* ctx, const float* rows, uint64_t n, uint32_t dim, uint32_t stride_floats,
+                            uint64_t id_base, vers_dataset** out);
+/* counter-based synthetic rows generated on the device, see vers_synth.h; rows [row0, row0+n), id_base = row0 */
+int32_t vers_dataset_synth(vers_ctx* ctx, uint64_t seed, uint64_t center_seed, uint32_t kind, uint32_t n_centers,
+                           uint64_t row0, uint64_t n, uint32_t dim, int32_t normalize, vers_dataset** out);
+int32_t vers_dataset_info(const vers_dataset* ds, uint64_t* n, uint32_t* dim, uint32_t* ld, uint64_t* id_base);
+/* Vector::normalize on every row in place (indexes/base.rs:95-105; the loader applies it, utils.rs:7-66) */
+int32_t vers_dataset_normalize(vers_dataset* ds);
+int32_t vers_dataset_download(const vers_dataset* ds, uint64_t row0, uint64_t n, float* out, uint32_t stride_floats);
+int32_t vers_dataset_device_ptr(const vers_dataset* ds, void** ptr);
+int32_t vers_dataset_free(vers_dataset* ds);
+
+/* ---- exhaustive search: utils::search_exhaustive (utils.rs:68-82) ----------------------------------------- */
+/* top_k nearest rows per query by (distance, id); ids are id_base + row. counts[q] = min(top_k, n). */
+int32_t vers_flat_search(vers_dataset* ds, const float* queries, uint32_t nq, uint32_t q_stride_floats,
+                         uint32_t top_k, uint32_t metric, uint64_t* ids, float* dists, uint32_t* counts);
+/* d_queries: device, nq rows of ld floats (ld = dataset ld, zero padded); outputs device [nq][top_k] */
+int32_t vers_flat_search_dev(vers_dataset* ds, const float* d_queries, uint32_t nq, uint32_t top_k, uint32_t metric,
+                             uint64_t* d_ids, float* d_dists, uint32_t* d_counts);
+
+/* ---- k-means: IVFFlatIndex::{assign_to_clusters, update_centroids, build_kmeans, calculate_kmeans_cost}
+ *      (indexes/ivfflat.rs:29-46, :47-71, :73-100, :138-149) ------------------------------------------------ */
+int32_t vers_kmeans_create(vers_dataset* ds, uint32_t num_clusters, vers_kmeans** out);
+int32_t vers_kmeans_free(vers_kmeans* km);
+/* initialize_centroids (ivfflat.rs:18-27) with the random draws injected: centroid j = copy of LOCAL row
+ * init_rows[j] (single GPU), or set explicitly from host memory (multi-GPU: rank owning the row broadcasts it) */
+int32_t vers_kmeans_init_from_rows(vers_kmeans* km, const uint64_t* init_rows);
+int32_t vers_kmeans_set_centroids(vers_kmeans* km, const float* centroids, uint32_t stride_floats);
+int32_t vers_kmeans_get_centroids(vers_kmeans* km, float* centroids, uint32_t stride_floats);
+int32_t vers_kmeans_get_assignments(vers_kmeans* km, uint64_t* assignments);
+int32_t vers_kmeans_centroids_device_ptr(vers_kmeans* km, void** ptr, uint32_t* ld);
+/* assign_to_clusters over the local rows with the current centroids (first minimum wins) */
+int32_t vers_kmeans_assign_step(vers_kmeans* km);
+/* the Σ of update_centroids over the LOCAL rows in row order, continuing from the running sums in
+ * d_sums_io [C][ld] f32 / d_counts_io [C] u64 (device; pass zeros on the first shard).  Chaining shards in row
+ * order reproduces the reference's global left-to-right association exactly. */
+int32_t vers_kmeans_sums_step_dev(vers_kmeans* km, float* d_sums_io, uint64_t* d_counts_io);
+/* new = sums / count (zero vector when count == 0, ivfflat.rs:63-67); *changed = bit patterns differ from the
+ * current centroids (ivfflat.rs:84-93); the new centroids are adopted only when they differ. */
+int32_t vers_kmeans_finalize_step_dev(vers_kmeans* km, const float* d_sums, const uint64_t* d_counts,
+                                      uint32_t* changed);
+/* calculate_kmeans_cost over the local rows: acc = *cost_io; acc += l2sq(row, centroid[assign]) in row order */
+int32_t vers_kmeans_cost_step(vers_kmeans* km, float* cost_io);
+/* build_kmeans on one GPU: <= max_iterations of (assign, update, bitwise compare) + the final assign */
+int32_t vers_kmeans_fit(vers_kmeans* km, uint32_t max_iterations, uint32_t* iterations_run);
+/* host-pointer conveniences used by the parity tests (one step each, reference argument meaning) */
+int32_t vers_kmeans_assign(vers_dataset* ds, const float* centroids, uint32_t num_clusters, uint32_t stride_floats,
+                           uint64_t* assignments);
+int32_t vers_kmeans_update(vers_dataset* ds, const uint64_t* assignments, uint32_t num_clusters,
+                           float* centroids /* [C][dim] */, uint64_t* counts);
+
+/* ---- IVFFlatIndex (indexes/ivfflat.rs) --------------------------------------------------------------------- */
+/* build_index (ivfflat.rs:102-136): best of num_attempts k-means runs by strict `<` on cost; init_rows is
+ * [num_attempts][num_clusters] local row numbers. */
+int32_t vers_ivf_build_index(vers_dataset* ds, uint32_t num_clusters, uint32_t num_attempts,
+                             uint32_t max_iterations, const uint64_t* init_rows, vers_ivf** out);
+/* take centroids + assignments from a fitted k-means state (multi-GPU build) */
+int32_t vers_ivf_from_kmeans(vers_kmeans* km, vers_ivf** out);
+/* rebuild the device mirror from deserialised parts (after Index::load_index, base.rs:45-58);
+ * assignments == NULL recomputes them on the device */
+int32_t vers_ivf_from_parts(vers_dataset* ds, const float* centroids, uint32_t num_clusters, uint32_t stride_floats,
+                            const uint64_t* assignments, vers_ivf** out);
+int32_t vers_ivf_free(vers_ivf* ivf);
+int32_t vers_ivf_info(const vers_ivf* ivf, uint64_t* n, uint32_t* dim, uint32_t* num_clusters, float* best_cost,
+                      uint32_t* best_attempt);
+int32_t vers_ivf_get_centroids(const vers_ivf* ivf, float* centroids, uint32_t stride_floats);
+int32_t vers_ivf_get_assignments(const vers_ivf* ivf, uint64_t* assignments);
+int32_t vers_ivf_get_list_sizes(const vers_ivf* ivf, uint64_t* sizes);
+/* Index::search_approximate (ivfflat.rs:153-198) for a batch.  nprobe == 0: the reference's semantics (nearest
+ * list, spill to the next list while fewer than top_k found, output = concatenated per-list prefixes).
+ * nprobe >= 1 (extension, BASELINE config 4): global top_k by (distance, id) over the nprobe nearest lists. */
+int32_t vers_ivf_search(vers_ivf* ivf, const float* queries, uint32_t nq, uint32_t q_stride_floats, uint32_t top_k,
+                        uint32_t nprobe, uint64_t* ids, float* dists, uint32_t* counts);
+int32_t vers_ivf_search_dev(vers_ivf* ivf, const float* d_queries, uint32_t nq, uint32_t top_k, uint32_t nprobe,
+                            uint64_t* d_ids, float* d_dists, uint32_t* d_counts);
+/* Index::add (ivfflat.rs:200-213): nearest centroid by first minimum; vec_id is IGNORED like the reference
+ * (the id is assignments.len()); *assigned_id / *cluster report what was stored. */
+int32_t vers_ivf_add(vers_ivf* ivf, const float* embedding, uint64_t vec_id, uint64_t* assigned_id,
+                     uint32_t* cluster);
+
+/* merge `parts` per-shard result lists per query into the global top_k by (distance, id): the step after the
+ * NCCL all-gather of per-GPU top-k.  d_ids_all/d_dists_all are [parts][nq][top_k] (device). */
+int32_t vers_topk_merge_dev(vers_ctx* ctx, const uint64_t* d_ids_all, const float* d_dists_all, uint32_t parts,
+                            uint32_t nq, uint32_t top_k, uint64_t* d_ids, float* d_dists, uint32_t* d_counts);
+
+/* ---- "LSH" random-hyperplane forest (indexes/lsh.rs) -------------------------------------------------------- */
+/* Hyperplane::point_is_above (lsh.rs:27-29) for every row x every plane: bits[r*P + p] = dot(plane_p, row_r) +
+ * consts[p] >= 0.0 */
+int32_t vers_lsh_hash(vers_dataset* ds, const float* planes, uint32_t num_planes, uint32_t plane_stride_floats,
+                      const float* consts, uint8_t* bits);
+int32_t vers_lsh_hash_dev(vers_dataset* ds, const float* d_planes /* [P][ld] */, uint32_t num_planes,
+                          const float* d_consts, uint8_t* d_bits);
+/* ANNIndex::build_index (lsh.rs:132-161): dedup by bit pattern, num_trees trees, leaves of < max_size rows.
+ * The two sample rows per node (choose_multiple(thread_rng, 2), lsh.rs:63-65) come from vers_lsh_pick_pair(seed…) */
+int32_t vers_lsh_build_index(vers_ctx* ctx, const float* rows, uint64_t n, uint32_t dim, uint32_t stride_floats,
+                             const uint64_t* vector_ids, uint32_t num_trees, uint32_t max_size, uint64_t seed,
+                             vers_lsh** out);
+int32_t vers_lsh_free(vers_lsh* lsh);
+int32_t vers_lsh_info(const vers_lsh* lsh, uint64_t* num_values, uint32_t* num_trees, uint64_t* num_nodes);
+/* preorder dump of one tree (node, above-subtree, below-subtree) for structural parity checks; pass NULLs to size */
+int32_t vers_lsh_flatten(const vers_lsh* lsh, uint32_t tree, uint8_t* kind, uint32_t* leaf_len, float* planes,
+                         float* consts, uint32_t* items, uint32_t* n_nodes, uint32_t* n_inner, uint64_t* n_items);
+/* Index::search_approximate (lsh.rs:264-282) for a batch; ties by deduplicated row index */
+int32_t vers_lsh_search(vers_lsh* lsh, const float* queries, uint32_t nq, uint32_t q_stride_floats, uint32_t top_k,
+                        uint64_t* ids, float* dists, uint32_t* counts);
+/* Index::add (lsh.rs:255-263) */
+int32_t vers_lsh_add(vers_lsh* lsh, const float* embedding, uint64_t vec_id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VERS_DEVICE_H */

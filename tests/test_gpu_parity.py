@@ -1,0 +1,340 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+Bar: bit-exact ids / assignments / hash bits AND bit-exact distances / centroids (the device computes in the
+reference's own summation order, so the 1e-5 tolerance of the north star is met with zero slack)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def data(vo, n, dim, seed=1, kind=1, n_centers=16, normalize=True):
+    return vo.synth(seed, n, dim, kind=kind, n_centers=n_centers, center_seed=7, normalize=normalize)
+
+
+# ---------------------------------------------------------------------------------------------- datasets
+@pytest.mark.parametrize("dim", [300, 128, 7, 33])
+@pytest.mark.parametrize("kind", [0, 1])
+def test_synth_and_normalize_bits(vb, vo, ctx, dim, kind):
+    n = 1000
+    ds = vb.Dataset.synth(ctx, 11, n, dim, kind=kind, n_centers=5, center_seed=9, row0=123, normalize=True)
+    want = vo.synth(11, n, dim, kind=kind, n_centers=5, center_seed=9, row0=123, normalize=True)
+    got = ds.download()
+    assert np.array_equal(bits(got), bits(want))
+    assert ds.id_base == 123
+
+
+def test_upload_strided_like_reference_vector(vb, vo, ctx):
+    # size_of::<Vector<300>>() = 1280 B => stride 320 floats (base.rs:15)
+    rows = data(vo, 257, 300)
+    buf = np.zeros((257, 320), np.float32)
+    buf[:, :300] = rows
+    buf[:, 300:] = 777.0  # padding garbage must be ignored
+    ds = vb.Dataset.upload_strided(ctx, buf, 257, 300, 320)
+    assert np.array_equal(bits(ds.download()), bits(rows))
+
+
+def test_normalize_tiny_rows_unchanged(vb, vo, ctx):
+    rows = data(vo, 64, 20, normalize=False)
+    rows[3] = 0.0
+    rows[5] = 1e-9
+    ds = vb.Dataset.upload(ctx, rows)
+    ds.normalize()
+    assert np.array_equal(bits(ds.download()), bits(vo.normalize_rows(rows)))
+
+
+# ---------------------------------------------------------------------------------------------- exhaustive
+@pytest.mark.parametrize("n,dim,nq,k", [(10000, 300, 100, 10), (5000, 128, 3, 1), (777, 33, 40, 128), (50, 7, 9, 10),
+                                        (20000, 768, 33, 10)])
+@pytest.mark.parametrize("metric", [0, 1])
+def test_flat_search_matches_search_exhaustive(vb, vo, ctx, n, dim, nq, k, metric):
+    rows = data(vo, n, dim)
+    q = data(vo, nq, dim, seed=2)
+    ds = vb.Dataset.upload(ctx, rows, id_base=1000)
+    ids, d, cnt = vb.search_exhaustive_batch(ds, q, k, metric)
+    oi, od, oc = vo.exhaustive(rows, q, k, metric, id_base=1000)
+    assert np.array_equal(cnt, oc)
+    assert np.array_equal(ids, oi)
+    assert np.array_equal(bits(d), bits(od))
+
+
+def test_flat_search_ties_broken_by_id(vb, vo, ctx):
+    rows = data(vo, 300, 64)
+    rows[100:200] = rows[7]  # 101 identical rows -> identical distances
+    q = data(vo, 5, 64, seed=2)
+    q[0] = rows[7]
+    ds = vb.Dataset.upload(ctx, rows)
+    ids, d, cnt = vb.search_exhaustive_batch(ds, q, 20)
+    oi, od, oc = vo.exhaustive(rows, q, 20)
+    assert np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od))
+    assert list(ids[0][:3]) == [7, 100, 101]
+
+
+def test_flat_search_fewer_rows_than_k_and_single(vb, vo, ctx):
+    rows = data(vo, 6, 300)
+    q = data(vo, 2, 300, seed=2)
+    ds = vb.Dataset.upload(ctx, rows)
+    ids, d, cnt = vb.search_exhaustive_batch(ds, q, 10)
+    oi, od, oc = vo.exhaustive(rows, q, 10)
+    assert list(cnt) == [6, 6]
+    assert np.array_equal(ids, oi)
+    got = vb.search_exhaustive(ds, q[0], 3)
+    assert [g[0] for g in got] == list(oi[0][:3])
+
+
+# ---------------------------------------------------------------------------------------------- k-means
+@pytest.mark.parametrize("n,dim,C", [(10000, 300, 16), (4000, 128, 100), (3000, 768, 5), (999, 33, 64)])
+def test_assign_to_clusters_bit_exact(vb, vo, ctx, n, dim, C):
+    rows = data(vo, n, dim)
+    cents = rows[vo.init_rows(3, 1, C, n)[0].astype(np.int64)].copy()
+    ds = vb.Dataset.upload(ctx, rows)
+    got = vb.assign_to_clusters(ds, cents)
+    assert np.array_equal(got, vo.assign(rows, cents))
+
+
+def test_assign_first_minimum_on_duplicate_centroids(vb, vo, ctx):
+    rows = data(vo, 2000, 64)
+    cents = rows[[5, 9, 5, 9, 11, 5]].copy()  # duplicates: the FIRST minimum must win (min_by, ivfflat.rs:36-42)
+    ds = vb.Dataset.upload(ctx, rows)
+    got = vb.assign_to_clusters(ds, cents)
+    want = vo.assign(rows, cents)
+    assert np.array_equal(got, want)
+    assert not np.any(np.isin(got, [2, 3, 5]))
+
+
+@pytest.mark.parametrize("n,dim,C", [(10000, 300, 16), (5000, 128, 64), (1000, 20, 7)])
+def test_update_centroids_bit_exact(vb, vo, ctx, n, dim, C):
+    rows = data(vo, n, dim, normalize=False)
+    rng = np.random.default_rng(5)
+    assign = rng.integers(0, C, n).astype(np.uint64)
+    assign[assign == 3] = 2  # cluster 3 empty -> zero vector (ivfflat.rs:63-67)
+    ds = vb.Dataset.upload(ctx, rows)
+    cents, counts = vb.update_centroids(ds, assign, C)
+    oc, on = vo.update(rows, assign, C)
+    assert np.array_equal(counts, on)
+    assert np.array_equal(bits(cents), bits(oc))
+    assert counts[3] == 0 and not cents[3].any()
+
+
+def test_kmeans_fit_and_cost_bit_exact(vb, vo, ctx):
+    n, dim, C = 10000, 300, 16
+    rows = data(vo, n, dim)
+    init = vo.init_rows(3, 1, C, n)[0]
+    ds = vb.Dataset.upload(ctx, rows)
+    km = vb.KMeans(ds, C)
+    km.init_from_rows(init)
+    iters = km.fit(20)
+    cents, assign, oit = vo.kmeans_fit(rows, init, 20)
+    assert iters == oit
+    assert np.array_equal(km.assignments(), assign)
+    assert np.array_equal(bits(km.centroids()), bits(cents))
+    cost = km.cost_step(0.0)
+    assert bits(np.float32(cost)) == bits(vo.kmeans_cost(rows, cents, assign))
+
+
+def test_kmeans_chained_shards_reproduce_global_order(vb, vo, ctx):
+    """two row shards whose sums are chained in row order == the single-GPU / reference association"""
+    import torch
+
+    n, dim, C = 6000, 128, 32
+    rows = data(vo, n, dim, normalize=False)
+    cents0 = rows[vo.init_rows(3, 1, C, n)[0].astype(np.int64)].copy()
+    assign = vo.assign(rows, cents0)
+    want, wcnt = vo.update(rows, assign, C)
+    h = n // 2 + 17
+    shards = [vb.Dataset.upload(ctx, rows[:h]), vb.Dataset.upload(ctx, rows[h:], id_base=h)]
+    kms = []
+    for ds in shards:
+        km = vb.KMeans(ds, C)
+        km.set_centroids(cents0)
+        km.assign_step()
+        kms.append(km)
+    ld = shards[0].ld
+    sums = torch.zeros(C * ld, dtype=torch.float32, device="cuda")
+    counts = torch.zeros(C, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    for km in kms:  # rank order == row order
+        km.sums_step_dev(sums.data_ptr(), counts.data_ptr())
+    ctx.sync()
+    changed = kms[0].finalize_step_dev(sums.data_ptr(), counts.data_ptr())
+    assert changed
+    assert np.array_equal(counts.cpu().numpy().astype(np.uint64), wcnt)
+    assert np.array_equal(bits(kms[0].centroids()), bits(want))
+
+
+# ---------------------------------------------------------------------------------------------- IVFFlat
+@pytest.fixture(scope="module")
+def ivf_c1(vb, vo, ctx):
+    """BASELINE config 1: 10k x 300 normalized, 16 clusters"""
+    n, dim, C = 10000, 300, 16
+    rows = data(vo, n, dim)
+    init = vo.init_rows(3, 2, C, n)
+    idx = vb.IVFFlatIndex.build_index(C, 2, 20, rows, init_rows=init, ctx=ctx)
+    cents, assign, cost, best = vo.ivf_build_index(rows, C, 2, 20, init)
+    return dict(rows=rows, idx=idx, cents=cents, assign=assign, cost=cost, best=best, C=C)
+
+
+def test_ivf_build_index_bit_exact(ivf_c1):
+    s = ivf_c1
+    assert s["idx"].best_attempt == s["best"]
+    assert bits(np.float32(s["idx"].best_cost)) == bits(np.float32(s["cost"]))
+    assert np.array_equal(s["idx"].assignments, s["assign"])
+    assert np.array_equal(bits(s["idx"].centroids), bits(s["cents"]))
+    assert np.array_equal(s["idx"].list_sizes, np.bincount(s["assign"].astype(np.int64), minlength=s["C"]))
+
+
+@pytest.mark.parametrize("k", [1, 10, 37])
+@pytest.mark.parametrize("nprobe", [0, 1, 4, 16])
+def test_ivf_search_bit_exact(vo, ivf_c1, k, nprobe):
+    s = ivf_c1
+    q = data(vo, 100, 300, seed=2)
+    off, lr = vo.ivf_lists(s["assign"], s["C"])
+    ids, d, cnt = s["idx"].search_batch(q, k, nprobe=nprobe)
+    oi, od, oc = vo.ivf_search(s["rows"], s["cents"], off, lr, q, k, nprobe=nprobe)
+    assert np.array_equal(cnt, oc)
+    assert np.array_equal(ids, oi)
+    assert np.array_equal(bits(d), bits(od))
+
+
+def test_ivf_search_approximate_single_query_trait_call(vo, ivf_c1):
+    s = ivf_c1
+    q = data(vo, 3, 300, seed=2)
+    off, lr = vo.ivf_lists(s["assign"], s["C"])
+    oi, od, oc = vo.ivf_search(s["rows"], s["cents"], off, lr, q, 10, nprobe=0)
+    for i in range(3):
+        got = s["idx"].search_approximate(q[i], 10)
+        assert [g[0] for g in got] == list(oi[i][: oc[i]])
+        assert np.array_equal(bits(np.array([g[1] for g in got], np.float32)), bits(od[i][: oc[i]]))
+
+
+def test_ivf_spill_semantics_small_lists(vb, vo, ctx):
+    """lists shorter than top_k force the reference's spill path (ivfflat.rs:181-185): concatenated, not re-sorted"""
+    n, dim, C, k = 300, 32, 64, 20
+    rows = data(vo, n, dim, n_centers=40)
+    init = vo.init_rows(3, 1, C, n)
+    idx = vb.IVFFlatIndex.build_index(C, 1, 5, rows, init_rows=init, ctx=ctx)
+    cents, assign, _, _ = vo.ivf_build_index(rows, C, 1, 5, init)
+    assert np.array_equal(idx.assignments, assign)
+    off, lr = vo.ivf_lists(assign, C)
+    q = data(vo, 64, dim, seed=2, n_centers=40)
+    ids, d, cnt = idx.search_batch(q, k, nprobe=0)
+    oi, od, oc = vo.ivf_search(rows, cents, off, lr, q, k, nprobe=0)
+    assert np.array_equal(cnt, oc) and np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od))
+    # at least one query must actually have spilled, else the test is vacuous
+    first = vo.assign(q, cents)
+    sizes = np.bincount(assign.astype(np.int64), minlength=C)
+    assert np.any(sizes[first.astype(np.int64)] < k)
+
+
+def test_ivf_search_panics_like_reference_when_index_too_small(vb, vo, ctx):
+    rows = data(vo, 8, 16)
+    init = vo.init_rows(3, 1, 4, 8)
+    idx = vb.IVFFlatIndex.build_index(4, 1, 3, rows, init_rows=init, ctx=ctx)
+    with pytest.raises(vb.VersPanic):
+        idx.search_approximate(rows[0], 9)  # index out of bounds at ivfflat.rs:169
+    assert len(idx.search_approximate(rows[0], 8)) == 8
+
+
+def test_ivf_add_then_search(vb, vo, ctx):
+    n, dim, C = 2000, 64, 8
+    rows = data(vo, n, dim)
+    extra = data(vo, 300, dim, seed=5)
+    init = vo.init_rows(3, 1, C, n)
+    idx = vb.IVFFlatIndex.build_index(C, 1, 10, rows, init_rows=init, ctx=ctx)
+    cents, assign, _, _ = vo.ivf_build_index(rows, C, 1, 10, init)
+    all_rows = np.vstack([rows, extra])
+    all_assign = list(assign)
+    for i in range(extra.shape[0]):
+        new_id, cl = idx.add(extra[i], vec_id=999999)  # the caller's id is ignored (ivfflat.rs:209)
+        assert new_id == n + i
+        assert cl == vo.nearest_centroid(cents, extra[i])
+        all_assign.append(cl)
+    all_assign = np.array(all_assign, np.uint64)
+    assert len(idx) == n + 300
+    assert np.array_equal(idx.assignments, all_assign)
+    off, lr = vo.ivf_lists(all_assign, C)
+    q = data(vo, 50, dim, seed=2)
+    for nprobe in (0, 3):
+        ids, d, cnt = idx.search_batch(q, 10, nprobe=nprobe)
+        oi, od, oc = vo.ivf_search(all_rows, cents, off, lr, q, 10, nprobe=nprobe)
+        assert np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od)) and np.array_equal(cnt, oc)
+
+
+def test_ivf_from_parts_and_save_load_roundtrip(vb, vo, ctx, tmp_path, ivf_c1):
+    s = ivf_c1
+    p = str(tmp_path / "ivf.bin")
+    s["idx"].save_index(p)
+    idx2 = vb.IVFFlatIndex.load_index(p, ctx=ctx)
+    q = data(vo, 20, 300, seed=2)
+    a = s["idx"].search_batch(q, 10, nprobe=0)
+    b = idx2.search_batch(q, 10, nprobe=0)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(bits(a[1]), bits(b[1]))
+    assert np.array_equal(idx2.assignments, s["assign"])
+
+
+def test_ivf_recall_identical_to_oracle(vo, ivf_c1):
+    s = ivf_c1
+    q = data(vo, 100, 300, seed=2)
+    off, lr = vo.ivf_lists(s["assign"], s["C"])
+    gt, _, _ = vo.exhaustive(s["rows"], q, 10)
+    ids, _, _ = s["idx"].search_batch(q, 10, nprobe=4)
+    oi, _, _ = vo.ivf_search(s["rows"], s["cents"], off, lr, q, 10, nprobe=4)
+    rec = lambda a: np.mean([len(set(a[i]) & set(gt[i])) / 10 for i in range(len(gt))])
+    assert rec(ids) == rec(oi)
+
+
+# ---------------------------------------------------------------------------------------------- merge
+def test_topk_merge_by_distance_then_id(vb, ctx):
+    import ctypes as C
+
+    import torch
+
+    parts, nq, k = 3, 50, 10
+    rng = np.random.default_rng(0)
+    d = rng.integers(0, 20, (parts, nq, k)).astype(np.float32)  # many ties
+    d.sort(axis=2)
+    ids = rng.permutation(parts * nq * k).reshape(parts, nq, k).astype(np.uint64)
+    ids[2, :, 7:] = np.iinfo(np.uint64).max  # short lists
+    d[2, :, 7:] = np.inf
+    t_ids = torch.from_numpy(ids.view(np.int64)).cuda()
+    t_d = torch.from_numpy(d).cuda()
+    o_ids = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    o_d = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    o_c = torch.empty((nq,), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    vb._abi.check(vb.lib().vers_topk_merge_dev(ctx.h, C.c_void_p(t_ids.data_ptr()), C.c_void_p(t_d.data_ptr()), parts,
+                                               nq, k, C.c_void_p(o_ids.data_ptr()), C.c_void_p(o_d.data_ptr()),
+                                               C.c_void_p(o_c.data_ptr())))
+    ctx.sync()
+    got = o_ids.cpu().numpy().view(np.uint64)
+    for q in range(nq):
+        cand = [(d[p, q, e], ids[p, q, e]) for p in range(parts) for e in range(k) if ids[p, q, e] != np.iinfo(np.uint64).max]
+        cand.sort()
+        assert [c[1] for c in cand[:k]] == list(got[q])
+
+
+# ---------------------------------------------------------------------------------------------- LSH hashing
+@pytest.mark.parametrize("n,dim,P", [(10000, 300, 16), (3000, 128, 100), (500, 33, 1)])
+def test_lsh_hash_bits_exact(vb, vo, ctx, n, dim, P):
+    rows = data(vo, n, dim)
+    rng = np.random.default_rng(1)
+    planes = np.empty((P, dim), np.float32)
+    consts = np.empty(P, np.float32)
+    for p in range(P):
+        a, b = rng.choice(n, 2, replace=False)
+        planes[p], consts[p] = vo.lsh_make_plane(rows[a], rows[b])
+    ds = vb.Dataset.upload(ctx, rows)
+    got = vb.lsh_hash(ds, planes, consts)
+    assert np.array_equal(got, vo.lsh_hash(rows, planes, consts))
+    assert 0.2 < got.mean() < 0.8
+
+
+def test_no_cpu_fallback_symbols(vb):
+    # the product library must not depend on the oracle
+    import subprocess
+
+    out = subprocess.run(["ldd", vb.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out

@@ -1,0 +1,146 @@
+// common.cuh — shared host/device plumbing of libvers_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/vers_device.h"
+#include "../../include/vers_synth.h"
+
+namespace vers {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+int32_t fail(int32_t code, const char* fmt, ...);
+
+#define VERS_CUDA(expr)                                                                              \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return ::vers::fail(_e == cudaErrorMemoryAllocation ? VERS_ERR_NOMEM : VERS_ERR_CUDA,    \
+                                "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define VERS_TRY(expr)               \
+    do {                             \
+        int32_t _rc = (expr);        \
+        if (_rc != VERS_OK) return _rc; \
+    } while (0)
+
+// kernel families for vers_ctx_last_kernel_ms
+enum KernelFamily { KF_LIST_SCAN = 0, KF_FLAT_SCAN = 1, KF_ASSIGN = 2, KF_SUMS = 3, KF_LSH_HASH = 4, KF_PROBE = 5, KF_COUNT = 6 };
+
+}  // namespace vers
+
+// ---------------------------------------------------------------- handles
+struct vers_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    bool timing = false;
+    cudaEvent_t ev0[vers::KF_COUNT] = {};
+    cudaEvent_t ev1[vers::KF_COUNT] = {};
+    bool ev_valid[vers::KF_COUNT] = {};
+    uint64_t fam_launches[vers::KF_COUNT] = {};
+    // scratch arena (grow-only), owned by ctx, used by search calls; guarded by mu
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    std::mutex mu;
+};
+
+struct vers_dataset {
+    vers_ctx* ctx = nullptr;
+    float* d_rows = nullptr;  // [n][ld]
+    uint64_t n = 0;
+    uint32_t dim = 0;
+    uint32_t ld = 0;  // round_up(dim, 4), pad columns are zero
+    uint64_t id_base = 0;
+    bool owned = true;
+};
+
+namespace vers {
+
+inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
+inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// grow-only scratch; caller holds ctx->mu
+int32_t scratch_reserve(vers_ctx* ctx, size_t bytes);
+
+struct ScratchCarver {
+    char* base;
+    size_t off = 0;
+    explicit ScratchCarver(void* b) : base((char*)b) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = (off + 255) & ~size_t(255);
+        T* p = (T*)(base + off);
+        off += count * sizeof(T);
+        return p;
+    }
+    template <typename T>
+    void plan(size_t count) {
+        off = (off + 255) & ~size_t(255);
+        off += count * sizeof(T);
+    }
+};
+
+// records family timing events around a launch when enabled
+struct FamilyTimer {
+    vers_ctx* ctx;
+    int fam;
+    FamilyTimer(vers_ctx* c, int f) : ctx(c), fam(f) {
+        if (ctx->timing) cudaEventRecord(ctx->ev0[fam], ctx->stream);
+    }
+    ~FamilyTimer() {
+        if (ctx->timing) {
+            cudaEventRecord(ctx->ev1[fam], ctx->stream);
+            ctx->ev_valid[fam] = true;
+        }
+        ctx->fam_launches[fam] += 1;
+    }
+};
+
+#define VERS_LAUNCH_CHECK(ctx)                                                                          \
+    do {                                                                                                \
+        (ctx)->launches += 1;                                                                           \
+        cudaError_t _e = cudaGetLastError();                                                            \
+        if (_e != cudaSuccess)                                                                          \
+            return ::vers::fail(VERS_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                                __FILE__, __LINE__);                                                    \
+    } while (0)
+
+// ---------------------------------------------------------------- device helpers
+#if defined(__CUDACC__)
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+// total order used everywhere a stable sort by distance is restated: (distance, position/id)
+__device__ __forceinline__ bool pair_less(float d0, uint32_t p0, float d1, uint32_t p1) {
+    return (d0 < d1) || (d0 == d1 && p0 < p1);
+}
+__device__ __forceinline__ bool pair_less64(float d0, uint64_t p0, float d1, uint64_t p1) {
+    return (d0 < d1) || (d0 == d1 && p0 < p1);
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 16 : 0;  // src-size 0 => 16 zero bytes written
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+#endif  // __CUDACC__
+
+}  // namespace vers

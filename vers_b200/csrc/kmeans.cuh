@@ -1,0 +1,30 @@
+// kmeans.cuh — device k-means state shared by kmeans.cu and ivf.cu
+#pragma once
+#include "engine.cuh"
+
+struct vers_kmeans {
+    vers_dataset* ds = nullptr;
+    uint32_t C = 0;
+    float* d_cents = nullptr;        // [C][ld] current centroids (pad columns zero)
+    float* d_next = nullptr;         // [C][ld] candidate centroids
+    uint32_t* d_assign = nullptr;    // [n] cluster of each local row
+    uint32_t* d_sorted_rows = nullptr;  // [n] rows grouped by cluster, ascending row inside a cluster
+    uint32_t* d_sorted_keys = nullptr;  // [n]
+    uint32_t* d_iota = nullptr;         // [n] 0..n-1
+    uint32_t* d_hist = nullptr;         // [C]
+    uint64_t* d_off = nullptr;          // [C+1]
+    float* d_sums = nullptr;            // [C][ld] used by fit()/update on one GPU
+    uint64_t* d_counts = nullptr;       // [C]
+    float* d_rowdist = nullptr;         // [n] cost scratch (allocated lazily)
+    uint32_t* d_flag = nullptr;         // [1]
+    void* d_cub = nullptr;
+    size_t cub_bytes = 0;
+    bool csr_valid = false;  // d_sorted_rows/d_off describe the current d_assign
+};
+
+namespace vers {
+// groups the local rows by cluster in ascending row order (stable): fills d_sorted_rows and d_off
+int32_t kmeans_build_csr(vers_kmeans* km);
+int32_t kmeans_assign_rows(vers_ctx* ctx, const RowSrc& rows, const float* d_cents, uint32_t C, uint32_t ld,
+                           uint32_t* d_assign);
+}  // namespace vers

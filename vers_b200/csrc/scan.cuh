@@ -1,0 +1,60 @@
+// scan.cuh — range scan + partial top-k + merge, declared for flat.cu / ivf.cu / lsh.cu.
+#pragma once
+#include "engine.cuh"
+
+namespace vers {
+
+// partial results: for query q, part t (t < nparts): k entries at ((q * nparts) + t) * k
+struct FlatScanParams {
+    RowSrc A;  // database rows
+    RowSrc B;  // queries
+    uint32_t ld;
+    uint32_t k, kpad;
+    uint64_t rows_per_chunk;
+    uint32_t nparts;  // gridDim.x * NSPLIT
+    float* part_d;
+    uint32_t* part_p;
+};
+
+// Generic merge: one warp per query folds the entries [begin, end) of (d, p) into the final top-k by (d, id).
+//   id = map ? map[p] : id_base + p;  entries with p == 0xffffffff are empty.
+struct MergeParams {
+    const float* part_d;
+    const uint32_t* part_p;
+    const uint64_t* seg;    // optional entry offsets: query q owns [seg[q*seg_stride], seg[(q+1)*seg_stride]) * seg_scale
+    uint64_t seg_scale;     // multiplier applied to seg[] values
+    uint32_t seg_stride;    // stride between consecutive queries' boundaries in seg[]
+    uint64_t per_query;     // entries per query when seg == null
+    const uint64_t* map;    // optional position -> id
+    uint64_t id_base;
+    uint32_t nq, k;
+    uint64_t* out_ids;      // [nq][k]
+    float* out_d;           // [nq][k]
+    uint32_t* out_cnt;      // [nq] optional
+};
+
+// scan rows [0, A.n) of A against nq queries (B), exact order; writes the global top-k per query.
+// metric: VERS_METRIC_*; family: KernelFamily for timing.  Uses ctx scratch (caller holds ctx->mu).
+int32_t scan_topk_dev(vers_ctx* ctx, const RowSrc& A, const RowSrc& B, uint32_t nq, uint32_t ld, uint32_t k,
+                      uint32_t metric, const uint64_t* id_map, uint64_t id_base, uint64_t* d_ids, float* d_d,
+                      uint32_t* d_cnt, int family);
+
+struct ScanPlan {
+    bool narrow;
+    uint64_t nchunks, rows_per_chunk;
+    uint32_t nparts;
+    size_t entries;
+    size_t bytes;  // scratch needed by scan_topk_run
+};
+ScanPlan scan_topk_plan(const vers_ctx* ctx, uint64_t nA, uint32_t nq, uint32_t k);
+// same as scan_topk_dev but carves its partial buffers from `scratch` (>= pl.bytes, 256-byte aligned)
+int32_t scan_topk_run(vers_ctx* ctx, const ScanPlan& pl, void* scratch, const RowSrc& A, const RowSrc& B, uint32_t nq,
+                      uint32_t ld, uint32_t k, uint32_t metric, const uint64_t* id_map, uint64_t id_base,
+                      uint64_t* d_ids, float* d_d, uint32_t* d_cnt, int family);
+
+int32_t launch_merge(vers_ctx* ctx, const MergeParams& mp);
+
+// exclusive scan of n uint32 -> uint64 out[n+1] (single block; n up to a few million is fine)
+int32_t launch_exclusive_scan(vers_ctx* ctx, const uint32_t* d_in, uint64_t n, uint64_t* d_out);
+
+}  // namespace vers

@@ -1,0 +1,93 @@
+"""CPU tier: the C-ABI library loads, exports every symbol include/vers_device.h declares, and fails loudly
+(no CPU fallback) when there is no CUDA device.  No compute calls here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "vers_device.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(vers_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(vb):
+    syms = header_symbols()
+    assert len(syms) >= 50
+    out = subprocess.run(["nm", "-D", "--defined-only", vb.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (vers_[a-z0-9_]+)", out))
+    missing = [s for s in syms if s not in exported]
+    assert not missing, f"declared but not exported: {missing}"
+    # and the ctypes table covers the header exactly
+    assert sorted(vb._abi.SIGNATURES) == syms
+
+
+def test_library_is_sm100a_and_independent_of_the_oracle(vb):
+    out = subprocess.run(["cuobjdump", "--list-elf", vb.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert "sm_90" not in out and "sm_80" not in out
+    ldd = subprocess.run(["ldd", vb.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd and "torch" not in ldd
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "vers_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "vers_oracle" not in src, f
+
+
+def test_abi_version_and_error_string(vb):
+    assert vb.lib().vers_abi_version() == 1
+    assert isinstance(vb.lib().vers_last_error(), (bytes, type(None)))
+
+
+def test_fails_loudly_without_a_gpu(vb):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(vb.VersError) as e:
+        vb.Context(0)
+    assert e.value.code == vb.ERR_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_null_arguments_are_rejected_not_crashed(vb):
+    L = vb.lib()
+    assert L.vers_ctx_create(0, None) == vb.ERR_ARG
+    assert L.vers_dataset_normalize(None) == vb.ERR_ARG
+    assert L.vers_ivf_search(None, None, 1, 1, 1, 0, None, None, None) == vb.ERR_ARG
+    assert L.vers_kmeans_fit(None, 1, None) == vb.ERR_ARG
+    assert L.vers_lsh_hash(None, None, 1, 1, None, None) == vb.ERR_ARG
+    assert b"null" in L.vers_last_error()
+
+
+def test_bincode_layout_roundtrip(tmp_path):
+    """Index::save_index layout (base.rs:31-43; struct at ivfflat.rs:9-15) without touching the GPU"""
+    from vers_b200.bincode import read_ivfflat, write_ivfflat
+
+    rng = np.random.default_rng(0)
+    values = rng.standard_normal((50, 7)).astype(np.float32)
+    cents = rng.standard_normal((4, 7)).astype(np.float32)
+    assign = rng.integers(0, 4, 50).astype(np.uint64)
+    assign[assign == 2] = 1  # an empty list
+    p = str(tmp_path / "x.bin")
+    write_ivfflat(p, 4, values, cents, assign)
+    raw = open(p, "rb").read()
+    # hand-check the head of the layout: u64 num_centroids, u64 len(values), first row as 7 raw f32
+    assert int.from_bytes(raw[0:8], "little") == 4 and int.from_bytes(raw[8:16], "little") == 50
+    assert np.array_equal(np.frombuffer(raw, "<f4", 7, 16), values[0])
+    expected = 8 + (8 + 50 * 28) + (8 + 4 * 28) + (8 + 50 * 8) + 8 + 4 * 8 + 50 * 8
+    assert len(raw) == expected
+    nc, v2, c2, a2, ids = read_ivfflat(p)
+    assert nc == 4 and np.array_equal(v2, values) and np.array_equal(c2, cents) and np.array_equal(a2, assign)
+    assert len(ids[2]) == 0
+    for c in range(4):
+        assert np.array_equal(ids[c], np.nonzero(assign == c)[0].astype(np.uint64))

@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — IVFFlat QPS @ recall@10 on 10M x 768 synthetic vectors (BASELINE.json configs[3]), batch 1k,
+nlist 4096, nprobe 32, k 10, rows sharded over N B200s with an NCCL all-gather + merge of the per-GPU top-k.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                      the CPU arm: the oracle port of vers' own search path
+
+One "step" = one search_approximate batch (1000 queries) over the whole index.
+  value  : QPS with the query batch already resident in HBM (device-timed, CUDA events, max over ranks)
+  e2e    : QPS through the reference-facing C-ABI call with HOST (pinned) buffers: H2D of the queries and D2H of
+           ids+distances inside the timed region
+  roofline: the list-scan kernel's algorithmic bytes (rows of the DISTINCT probed lists x dim x 4 B, per launch)
+           over its CUDA-event duration, against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline / --impl reference: the oracle (kind "port": the Rust reference cannot be compiled in this image),
+           all host cores over queries, on a bounded sample (see `sample`)
+Synthetic data (include/vers_synth.h), random-init k-means (a few Lloyd iterations, reported as build_s).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SEED_DATA, SEED_QUERY, SEED_INIT, SEED_CENTERS = 1, 2, 3, 7
+CPU_SCALE = 32  # the CPU arms run on rows/32 with nlist/32: same rows per list, same nprobe => same scan work per query
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--nlist", type=int, default=4096)
+    ap.add_argument("--nprobe", type=int, default=32)
+    ap.add_argument("--nq", type=int, default=1000)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--n-centers", type=int, default=1024, help="natural clusters of the synthetic data")
+    ap.add_argument("--kmeans-iters", type=int, default=2, help="max Lloyd iterations of the index build")
+    ap.add_argument("--reduce", default="chained", choices=["chained", "allreduce"])
+    ap.add_argument("--recall-queries", type=int, default=100)
+    ap.add_argument("--cpu-queries", type=int, default=256, help="queries in the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_arm(args, steps, warmup, nq_sample):
+    """the reference's CPU search path (oracle port) on the bounded sample; returns (qps, ms_per_step, info)"""
+    import oracle as vo
+
+    rows_n = max(args.rows // CPU_SCALE, 1000)
+    nlist = max(args.nlist // CPU_SCALE, 1)
+    nprobe = min(args.nprobe, nlist)
+    cores = vo.num_threads()
+    rows = vo.synth(SEED_DATA, rows_n, args.dim, kind=1, n_centers=args.n_centers, center_seed=SEED_CENTERS)
+    q = vo.synth(SEED_QUERY, nq_sample, args.dim, kind=1, n_centers=args.n_centers, center_seed=SEED_CENTERS)
+    init = vo.init_rows(SEED_INIT, 1, nlist, rows_n)
+    t0 = time.perf_counter()
+    cents, assign, _ = vo.kmeans_fit(rows, init[0], args.kmeans_iters)
+    build_s = time.perf_counter() - t0
+    off, lr = vo.ivf_lists(assign, nlist)
+    for _ in range(warmup):
+        vo.ivf_search(rows, cents, off, lr, q[: max(8, nq_sample // 8)], args.k, nprobe=nprobe)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        vo.ivf_search(rows, cents, off, lr, q, args.k, nprobe=nprobe)
+    dt = time.perf_counter() - t0
+    qps = nq_sample * steps / dt
+    sample = (f"{nq_sample} queries/step on rows/{CPU_SCALE} ({rows_n}x{args.dim}) with nlist/{CPU_SCALE} ({nlist}) and "
+              f"nprobe {nprobe}: the same ~{nprobe * rows_n // nlist} rows scanned per query as the full config "
+              f"(nprobe*rows/nlist), centroid probe {CPU_SCALE}x smaller (<5% of a query's work); OpenMP over queries")
+    return qps, dt / steps * 1e3, dict(cores=cores, kind="port", sample=sample, cpu_build_s=round(build_s, 2))
+
+
+def config_dict(args, n_gpus):
+    return {"workload": f"IVFFlat search_approximate batch: {args.rows}x{args.dim} fp32 synthetic clustered+normalized, "
+                        f"nlist {args.nlist}, nprobe {args.nprobe}, top_k {args.k}, {args.nq}-query batch "
+                        f"(BASELINE.json configs[3])",
+            "rows": args.rows, "dim": args.dim, "nlist": args.nlist, "nprobe": args.nprobe, "top_k": args.k,
+            "batch": args.nq, "sharding": f"rows/{n_gpus} per GPU, all-gather+merge of per-GPU top-k",
+            "kmeans_iters": args.kmeans_iters,
+            "l2": "per-step scan (>= 3.8 GB per GPU) is far larger than the 126 MB L2; no flush needed"}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    qps, ms, info = cpu_arm(args, args.steps, args.warmup, args.cpu_queries)
+    line = {"impl": "reference", "metric": "IVFFlat QPS@recall10 (10Mx768, batch 1k)", "value": qps, "unit": "queries/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, args.gpus),
+            "cpu_baseline": {"value": qps, "unit": "queries/s", **info},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import vers_b200 as vb
+    from vers_b200 import _abi
+    from vers_b200.sharded import ShardedIVFFlat, shard_bounds
+
+    rank = int(os.environ.get("RANK", "0"))
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if ws > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if ws == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = vb.Context(local_rank)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    # ---- data + index build (not in the QPS timed region; build seconds reported separately)
+    row0, n_local = shard_bounds(args.rows, rank, ws)
+    ds = vb.Dataset.synth(ctx, SEED_DATA, n_local, args.dim, kind=1, n_centers=args.n_centers,
+                          center_seed=SEED_CENTERS, row0=row0, normalize=True)
+    init = vb.synth_init_rows(SEED_INIT, 1, args.nlist, args.rows)[0]
+    barrier()
+    t0 = time.perf_counter()
+    index = ShardedIVFFlat.build(ds, args.nlist, args.kmeans_iters, init, reduce=args.reduce)
+    barrier()
+    build_s = max_over_ranks(time.perf_counter() - t0)
+
+    qds = vb.Dataset.synth(ctx, SEED_QUERY, args.nq, args.dim, kind=1, n_centers=args.n_centers,
+                           center_seed=SEED_CENTERS, row0=0, normalize=True)
+    from vers_b200.sharded import device_view
+
+    d_q = device_view(qds.device_ptr, (args.nq, qds.ld))
+    h_q = torch.empty((args.nq, qds.ld), dtype=torch.float32).pin_memory()
+    h_q.copy_(d_q)
+    h_ids = torch.empty((args.nq, args.k), dtype=torch.int64).pin_memory()
+    h_d = torch.empty((args.nq, args.k), dtype=torch.float32).pin_memory()
+    h_c = torch.empty((args.nq,), dtype=torch.int32).pin_memory()
+    d_q_stage = torch.empty_like(d_q)
+
+    # ---- recall@10 against the exhaustive ground truth (flat scan of every shard + the same merge)
+    nrec = min(args.recall_queries, args.nq)
+    recall = None
+    if nrec > 0:
+        import ctypes as C
+
+        g_ids = torch.empty((nrec, args.k), dtype=torch.int64, device=dev)
+        g_d = torch.empty((nrec, args.k), dtype=torch.float32, device=dev)
+        g_c = torch.empty((nrec,), dtype=torch.int32, device=dev)
+        _abi.check(vb.lib().vers_flat_search_dev(ds.h, C.c_void_p(d_q.data_ptr()), nrec, args.k, 0,
+                                                 C.c_void_p(g_ids.data_ptr()), C.c_void_p(g_d.data_ptr()),
+                                                 C.c_void_p(g_c.data_ptr())))
+        if ws > 1:
+            a_ids = torch.empty((ws, nrec, args.k), dtype=torch.int64, device=dev)
+            a_d = torch.empty((ws, nrec, args.k), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(a_ids, g_ids)
+            dist.all_gather_into_tensor(a_d, g_d)
+            _abi.check(vb.lib().vers_topk_merge_dev(ctx.h, C.c_void_p(a_ids.data_ptr()), C.c_void_p(a_d.data_ptr()),
+                                                    ws, 0, 0, nrec, args.k, C.c_void_p(g_ids.data_ptr()),
+                                                    C.c_void_p(g_d.data_ptr()), C.c_void_p(g_c.data_ptr())))
+        ids, _, _ = index.search_dev(d_q[:nrec].contiguous(), args.k, args.nprobe)
+        torch.cuda.synchronize()
+        gt = g_ids.cpu().numpy()
+        got = ids.cpu().numpy()
+        recall = float(np.mean([len(set(got[i]) & set(gt[i])) / args.k for i in range(nrec)]))
+
+    # ---- device-timed QPS (queries resident in HBM)
+    for _ in range(args.warmup):
+        index.search_dev(d_q, args.k, args.nprobe)
+    barrier()
+    ctx.enable_timing(True)
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        index.search_dev(d_q, args.k, args.nprobe)
+    ev1.record()
+    barrier()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launch_count - launches0
+    scan_ms, scan_n = ctx.kernel_ms(_abi.KF_LIST_SCAN)
+    probe_ms, probe_n = ctx.kernel_ms(_abi.KF_PROBE)
+    ctx.enable_timing(False)
+    stats = index.ivf.last_search_stats()
+    qps = args.nq * args.steps / (dev_ms * 1e-3)
+
+    # ---- e2e: host (pinned) queries in, host ids+distances out, every step
+    def e2e_step():
+        if ws == 1:
+            # the reference-facing C-ABI call with host buffers
+            _abi.check(vb.lib().vers_ivf_search(index.ivf.h, h_q.data_ptr(), args.nq, qds.ld, args.k, args.nprobe,
+                                                h_ids.data_ptr(), h_d.data_ptr(), h_c.data_ptr()))
+        else:
+            d_q_stage.copy_(h_q, non_blocking=True)
+            ids, d, c = index.search_dev(d_q_stage, args.k, args.nprobe)
+            h_ids.copy_(ids, non_blocking=True)
+            h_d.copy_(d, non_blocking=True)
+            h_c.copy_(c, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_qps = args.nq * args.steps / e2e_s
+    # the e2e result must equal the device-resident result
+    ids_dev, _, _ = index.search_dev(d_q, args.k, args.nprobe)
+    torch.cuda.synchronize()
+    e2e_matches = bool(torch.equal(ids_dev.cpu(), h_ids))
+
+    # ---- roofline of the dominant kernel (list scan)
+    peak, peak_src = measured_peaks()
+    alg_bytes = stats["distinct_list_rows"] * args.dim * 4
+    roof = None
+    if scan_n:
+        avg_ms = scan_ms / scan_n
+        achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "list_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
+                "kernel_share_of_step": scan_ms / dev_ms if ws == 1 else None,
+                "probe_avg_launch_ms": probe_ms / probe_n if probe_n else None,
+                "pair_rows_per_launch": stats["pair_rows"], "lists_touched": stats["lists_touched"],
+                "note": "exact-order fp32 SIMT scan: 3 fp32 instr per (row,query,dim); compute-bound below the HBM "
+                        "roof, see DESIGN.md"}
+
+    cpu = None
+    if rank == 0 and ws == 1 and not args.no_cpu_baseline:
+        cqps, _, info = cpu_arm(args, 1, 1, args.cpu_queries)
+        cpu = {"value": cqps, "unit": "queries/s", **info}
+
+    if rank == 0:
+        line = {"metric": "IVFFlat QPS@recall10 (10Mx768, batch 1k)", "value": qps, "unit": "queries/s", "n_gpus": ws,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config_dict(args, ws), "recall_at_10": recall,
+                "build_s": build_s, "kmeans_reduce": args.reduce,
+                "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": args.nq * qds.ld * 4,
+                        "d2h_bytes_per_step": args.nq * args.k * 12 + args.nq * 4, "ids_match_device_path": e2e_matches},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if ws > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

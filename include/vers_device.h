@@ -58,11 +58,12 @@ int32_t vers_ctx_set_stream(vers_ctx* ctx, void* cuda_stream);
 int32_t vers_ctx_sync(vers_ctx* ctx);
 /* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches) */
 int32_t vers_ctx_launch_count(vers_ctx* ctx, uint64_t* out);
-/* name + device time (ms, CUDA events on ctx's stream) of the most recent launch of each kernel family, for
- * bench.py's roofline line.  which: 0 = list scan, 1 = flat scan, 2 = k-means assign, 3 = k-means sums,
- * 4 = lsh hash, 5 = probe.  Timing is only recorded while enabled. */
+/* device time of each kernel family, measured with CUDA event pairs recorded on ctx's stream around every launch
+ * while timing is on (up to 512 launches per family per window) — bench.py's live roofline numbers.
+ * which: 0 = list scan, 1 = flat scan, 2 = k-means assign, 3 = k-means sums, 4 = lsh hash, 5 = probe.
+ * enable_timing(on) starts a new window; kernel_ms sums the window (synchronises on the recorded events). */
 int32_t vers_ctx_enable_timing(vers_ctx* ctx, int32_t on);
-int32_t vers_ctx_last_kernel_ms(vers_ctx* ctx, int32_t which, float* ms, uint64_t* launches);
+int32_t vers_ctx_kernel_ms(vers_ctx* ctx, int32_t which, float* total_ms, uint64_t* timed_launches);
 
 /* ---- datasets: Vec<Vector<N>> (indexes/base.rs:15-17) ----------------------------------------------------- */
 /* id_base: global id of local row 0 (row shards of a multi-GPU index are contiguous blocks of the global rows) */
@@ -134,6 +135,12 @@ int32_t vers_ivf_info(const vers_ivf* ivf, uint64_t* n, uint32_t* dim, uint32_t*
 int32_t vers_ivf_get_centroids(const vers_ivf* ivf, float* centroids, uint32_t stride_floats);
 int32_t vers_ivf_get_assignments(const vers_ivf* ivf, uint64_t* assignments);
 int32_t vers_ivf_get_list_sizes(const vers_ivf* ivf, uint64_t* sizes);
+/* ids[list] (ivfflat.rs:14) and, optionally, the rows of that list in the same order (rows may be NULL) */
+int32_t vers_ivf_get_list(const vers_ivf* ivf, uint32_t list, uint64_t* ids, float* rows, uint32_t stride_floats);
+/* work done by the most recent search on this index (device counters, synchronises):
+ * out[0] = rows in the DISTINCT lists touched (the algorithmic HBM stream), out[1] = Σ over (query, list) pairs of
+ * the list length (un-deduplicated rows x queries), out[2] = work items, out[3] = distinct lists touched */
+int32_t vers_ivf_last_search_stats(const vers_ivf* ivf, uint64_t out[4]);
 /* Index::search_approximate (ivfflat.rs:153-198) for a batch.  nprobe == 0: the reference's semantics (nearest
  * list, spill to the next list while fewer than top_k found, output = concatenated per-list prefixes).
  * nprobe >= 1 (extension, BASELINE config 4): global top_k by (distance, id) over the nprobe nearest lists. */
@@ -147,9 +154,11 @@ int32_t vers_ivf_add(vers_ivf* ivf, const float* embedding, uint64_t vec_id, uin
                      uint32_t* cluster);
 
 /* merge `parts` per-shard result lists per query into the global top_k by (distance, id): the step after the
- * NCCL all-gather of per-GPU top-k.  d_ids_all/d_dists_all are [parts][nq][top_k] (device). */
+ * NCCL all-gather of per-GPU top-k.  Part p's [nq][top_k] block starts at d_ids_all + p*part_stride_ids (u64
+ * elements) and d_dists_all + p*part_stride_dists (floats); a stride of 0 means the dense nq*top_k. */
 int32_t vers_topk_merge_dev(vers_ctx* ctx, const uint64_t* d_ids_all, const float* d_dists_all, uint32_t parts,
-                            uint32_t nq, uint32_t top_k, uint64_t* d_ids, float* d_dists, uint32_t* d_counts);
+                            uint64_t part_stride_ids, uint64_t part_stride_dists, uint32_t nq, uint32_t top_k,
+                            uint64_t* d_ids, float* d_dists, uint32_t* d_counts);
 
 /* ---- "LSH" random-hyperplane forest (indexes/lsh.rs) -------------------------------------------------------- */
 /* Hyperplane::point_is_above (lsh.rs:27-29) for every row x every plane: bits[r*P + p] = dot(plane_p, row_r) +

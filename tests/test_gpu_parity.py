@@ -306,7 +306,7 @@ def test_topk_merge_by_distance_then_id(vb, ctx):
     o_c = torch.empty((nq,), dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()
     vb._abi.check(vb.lib().vers_topk_merge_dev(ctx.h, C.c_void_p(t_ids.data_ptr()), C.c_void_p(t_d.data_ptr()), parts,
-                                               nq, k, C.c_void_p(o_ids.data_ptr()), C.c_void_p(o_d.data_ptr()),
+                                               0, 0, nq, k, C.c_void_p(o_ids.data_ptr()), C.c_void_p(o_d.data_ptr()),
                                                C.c_void_p(o_c.data_ptr())))
     ctx.sync()
     got = o_ids.cpu().numpy().view(np.uint64)

@@ -41,7 +41,7 @@ SIGNATURES = {
     "vers_ctx_sync": [vp],
     "vers_ctx_launch_count": [vp, C.POINTER(u64)],
     "vers_ctx_enable_timing": [vp, i32],
-    "vers_ctx_last_kernel_ms": [vp, i32, C.POINTER(f32), C.POINTER(u64)],
+    "vers_ctx_kernel_ms": [vp, i32, C.POINTER(f32), C.POINTER(u64)],
     "vers_dataset_upload": [vp, vp, u64, u32, u32, u64, pvp],
     "vers_dataset_synth": [vp, u64, u64, u32, u32, u64, u64, u32, i32, pvp],
     "vers_dataset_info": [vp, C.POINTER(u64), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)],
@@ -73,10 +73,12 @@ SIGNATURES = {
     "vers_ivf_get_centroids": [vp, vp, u32],
     "vers_ivf_get_assignments": [vp, vp],
     "vers_ivf_get_list_sizes": [vp, vp],
+    "vers_ivf_get_list": [vp, u32, vp, vp, u32],
+    "vers_ivf_last_search_stats": [vp, vp],
     "vers_ivf_search": [vp, vp, u32, u32, u32, u32, vp, vp, vp],
     "vers_ivf_search_dev": [vp, vp, u32, u32, u32, vp, vp, vp],
     "vers_ivf_add": [vp, vp, u64, C.POINTER(u64), C.POINTER(u32)],
-    "vers_topk_merge_dev": [vp, vp, vp, u32, u32, u32, vp, vp, vp],
+    "vers_topk_merge_dev": [vp, vp, vp, u32, u64, u64, u32, u32, vp, vp, vp],
     "vers_lsh_hash": [vp, vp, u32, u32, vp, vp],
     "vers_lsh_hash_dev": [vp, vp, u32, vp, vp],
     "vers_lsh_build_index": [vp, vp, u64, u32, u32, vp, u32, u32, u64, pvp],

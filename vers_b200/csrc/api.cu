@@ -37,6 +37,18 @@ int32_t scratch_reserve(vers_ctx* ctx, size_t bytes) {
     return VERS_OK;
 }
 
+int32_t io_reserve(vers_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->io_bytes) return VERS_OK;
+    VERS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->io) cudaFree(ctx->io);
+    ctx->io = nullptr;
+    ctx->io_bytes = 0;
+    size_t want = bytes + bytes / 4 + (1u << 16);
+    VERS_CUDA(cudaMalloc(&ctx->io, want));
+    ctx->io_bytes = want;
+    return VERS_OK;
+}
+
 int32_t upload_queries(vers_ctx* ctx, const float* q, uint32_t nq, uint32_t stride, uint32_t dim, uint32_t ld,
                        float** d_q) {
     *d_q = nullptr;
@@ -123,10 +135,6 @@ extern "C" int32_t vers_ctx_create(int32_t device, vers_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     VERS_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->own_stream = true;
-    for (int i = 0; i < KF_COUNT; ++i) {
-        VERS_CUDA(cudaEventCreate(&ctx->ev0[i]));
-        VERS_CUDA(cudaEventCreate(&ctx->ev1[i]));
-    }
     *out = ctx;
     return VERS_OK;
 }
@@ -136,9 +144,10 @@ extern "C" int32_t vers_ctx_destroy(vers_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->io) cudaFree(ctx->io);
     for (int i = 0; i < KF_COUNT; ++i) {
-        cudaEventDestroy(ctx->ev0[i]);
-        cudaEventDestroy(ctx->ev1[i]);
+        for (cudaEvent_t e : ctx->ev0[i]) cudaEventDestroy(e);
+        for (cudaEvent_t e : ctx->ev1[i]) cudaEventDestroy(e);
     }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -169,20 +178,35 @@ extern "C" int32_t vers_ctx_launch_count(vers_ctx* ctx, uint64_t* out) {
 
 extern "C" int32_t vers_ctx_enable_timing(vers_ctx* ctx, int32_t on) {
     if (!ctx) return fail(VERS_ERR_ARG, "ctx_enable_timing: null");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    VERS_CUDA(cudaSetDevice(ctx->device));
+    if (on && ctx->ev0[0].empty()) {
+        for (int i = 0; i < KF_COUNT; ++i) {
+            ctx->ev0[i].resize(vers_ctx::EV_RING);
+            ctx->ev1[i].resize(vers_ctx::EV_RING);
+            for (int j = 0; j < vers_ctx::EV_RING; ++j) {
+                VERS_CUDA(cudaEventCreate(&ctx->ev0[i][j]));
+                VERS_CUDA(cudaEventCreate(&ctx->ev1[i][j]));
+            }
+        }
+    }
+    for (int i = 0; i < KF_COUNT; ++i) ctx->ev_used[i] = 0;  // (re)start the measurement window
     ctx->timing = on != 0;
     return VERS_OK;
 }
 
-extern "C" int32_t vers_ctx_last_kernel_ms(vers_ctx* ctx, int32_t which, float* ms, uint64_t* launches) {
-    if (!ctx || which < 0 || which >= KF_COUNT) return fail(VERS_ERR_ARG, "ctx_last_kernel_ms: bad argument");
-    if (launches) *launches = ctx->fam_launches[which];
-    if (ms) {
-        *ms = -1.0f;
-        if (ctx->ev_valid[which]) {
-            VERS_CUDA(cudaEventSynchronize(ctx->ev1[which]));
-            VERS_CUDA(cudaEventElapsedTime(ms, ctx->ev0[which], ctx->ev1[which]));
-        }
+extern "C" int32_t vers_ctx_kernel_ms(vers_ctx* ctx, int32_t which, float* total_ms, uint64_t* timed_launches) {
+    if (!ctx || which < 0 || which >= KF_COUNT) return fail(VERS_ERR_ARG, "ctx_kernel_ms: bad argument");
+    VERS_CUDA(cudaSetDevice(ctx->device));
+    float total = 0.f;
+    for (uint64_t j = 0; j < ctx->ev_used[which]; ++j) {
+        float ms = 0.f;
+        VERS_CUDA(cudaEventSynchronize(ctx->ev1[which][j]));
+        VERS_CUDA(cudaEventElapsedTime(&ms, ctx->ev0[which][j], ctx->ev1[which][j]));
+        total += ms;
     }
+    if (total_ms) *total_ms = total;
+    if (timed_launches) *timed_launches = ctx->ev_used[which];
     return VERS_OK;
 }
 

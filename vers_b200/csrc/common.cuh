@@ -46,10 +46,15 @@ struct vers_ctx {
     bool own_stream = false;
     uint64_t launches = 0;
     bool timing = false;
-    cudaEvent_t ev0[vers::KF_COUNT] = {};
-    cudaEvent_t ev1[vers::KF_COUNT] = {};
-    bool ev_valid[vers::KF_COUNT] = {};
+    // per kernel family: ring of CUDA event pairs recorded on `stream` around each launch while timing is on
+    static constexpr int EV_RING = 512;
+    std::vector<cudaEvent_t> ev0[vers::KF_COUNT];
+    std::vector<cudaEvent_t> ev1[vers::KF_COUNT];
+    uint64_t ev_used[vers::KF_COUNT] = {};
     uint64_t fam_launches[vers::KF_COUNT] = {};
+    // grow-only device staging for the host-pointer entry points (queries in, results out)
+    void* io = nullptr;
+    size_t io_bytes = 0;
     // scratch arena (grow-only), owned by ctx, used by search calls; guarded by mu
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -73,6 +78,8 @@ inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 
 // grow-only scratch; caller holds ctx->mu
 int32_t scratch_reserve(vers_ctx* ctx, size_t bytes);
+// grow-only device staging for host-pointer calls; caller holds ctx->mu
+int32_t io_reserve(vers_ctx* ctx, size_t bytes);
 
 struct ScratchCarver {
     char* base;
@@ -96,13 +103,15 @@ struct ScratchCarver {
 struct FamilyTimer {
     vers_ctx* ctx;
     int fam;
+    bool on;
     FamilyTimer(vers_ctx* c, int f) : ctx(c), fam(f) {
-        if (ctx->timing) cudaEventRecord(ctx->ev0[fam], ctx->stream);
+        on = ctx->timing && ctx->ev_used[fam] < (uint64_t)vers_ctx::EV_RING;
+        if (on) cudaEventRecord(ctx->ev0[fam][ctx->ev_used[fam]], ctx->stream);
     }
     ~FamilyTimer() {
-        if (ctx->timing) {
-            cudaEventRecord(ctx->ev1[fam], ctx->stream);
-            ctx->ev_valid[fam] = true;
+        if (on) {
+            cudaEventRecord(ctx->ev1[fam][ctx->ev_used[fam]], ctx->stream);
+            ctx->ev_used[fam] += 1;
         }
         ctx->fam_launches[fam] += 1;
     }

@@ -243,7 +243,8 @@ int32_t scan_topk_dev(vers_ctx* ctx, const RowSrc& A, const RowSrc& B, uint32_t 
 // merge of already-global (id, dist) lists: [parts][nq][k] -> [nq][k]; the step after the all-gather of per-GPU top-k
 __global__ void __launch_bounds__(MERGE_WARPS * 32)
     merge_ids_kernel(const uint64_t* __restrict__ ids_all, const float* __restrict__ d_all, uint32_t parts,
-                     uint32_t nq, uint32_t k, uint64_t* out_ids, float* out_d, uint32_t* out_cnt) {
+                     uint64_t stride_ids, uint64_t stride_d, uint32_t nq, uint32_t k, uint64_t* out_ids, float* out_d,
+                     uint32_t* out_cnt) {
     extern __shared__ __align__(16) unsigned char msm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * MERGE_WARPS + warp;
@@ -261,9 +262,9 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32)
         float v = 0.f;
         uint64_t id = 0xffffffffffffffffull;
         if (e < total) {
-            uint64_t at = ((uint64_t)(e / k) * nq + q) * k + (e % k);
-            id = ids_all[at];
-            v = d_all[at];
+            uint64_t part = e / k, at = (uint64_t)q * k + (e % k);
+            id = ids_all[part * stride_ids + at];
+            v = d_all[part * stride_d + at];
         }
         bool live = id != 0xffffffffffffffffull;
         while (true) {
@@ -353,7 +354,8 @@ extern "C" int32_t vers_flat_search(vers_dataset* ds, const float* queries, uint
 }
 
 extern "C" int32_t vers_topk_merge_dev(vers_ctx* ctx, const uint64_t* d_ids_all, const float* d_dists_all,
-                                       uint32_t parts, uint32_t nq, uint32_t top_k, uint64_t* d_ids, float* d_dists,
+                                       uint32_t parts, uint64_t part_stride_ids, uint64_t part_stride_dists,
+                                       uint32_t nq, uint32_t top_k, uint64_t* d_ids, float* d_dists,
                                        uint32_t* d_counts) {
     if (!ctx || !d_ids_all || !d_dists_all || !d_ids || !d_dists) return fail(VERS_ERR_ARG, "topk_merge_dev: null");
     if (top_k > VERS_MAX_TOPK) return fail(VERS_ERR_UNSUPPORTED, "top_k %u > %u", top_k, VERS_MAX_TOPK);
@@ -361,7 +363,9 @@ extern "C" int32_t vers_topk_merge_dev(vers_ctx* ctx, const uint64_t* d_ids_all,
     std::lock_guard<std::mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     merge_ids_kernel<<<(unsigned)ceil_div(nq, MERGE_WARPS), MERGE_WARPS * 32, (size_t)MERGE_WARPS * top_k * 12,
-                       ctx->stream>>>(d_ids_all, d_dists_all, parts, nq, top_k, d_ids, d_dists, d_counts);
+                       ctx->stream>>>(d_ids_all, d_dists_all, parts, part_stride_ids ? part_stride_ids : (uint64_t)nq * top_k,
+                                      part_stride_dists ? part_stride_dists : (uint64_t)nq * top_k, nq, top_k, d_ids,
+                                      d_dists, d_counts);
     VERS_LAUNCH_CHECK(ctx);
     return VERS_OK;
 }

@@ -38,6 +38,7 @@ struct vers_ivf {
     std::vector<uint32_t> assign_tail;  // assignments of rows added later
     float best_cost = 0.f;
     uint32_t best_attempt = 0;
+    unsigned long long* d_stats = nullptr;  // [4] counters of the most recent search (vers_ivf_last_search_stats)
 };
 
 namespace vers {
@@ -72,6 +73,7 @@ struct GroupParams {
     uint32_t* item_cnt;   // [C]   work items per list
     const uint64_t* lq_off;  // [C+1]
     uint32_t* cursor;     // [C]
+    unsigned long long* stats;  // [4]
     uint32_t* lq_query;   // [npairs] query of each grouped pair
     uint32_t* lq_pair;    // [npairs] pair index q*np+s of each grouped pair
 };
@@ -95,7 +97,14 @@ __global__ void group_items_kernel(GroupParams g) {
     if (l >= g.C) return;
     uint32_t m = g.lq_cnt[l];
     uint32_t nch = (g.seg_len[l] + LIST_CHUNK_ROWS - 1) / LIST_CHUNK_ROWS;
-    g.item_cnt[l] = ((m + ScanCfg::TB - 1) / ScanCfg::TB) * nch;
+    uint32_t items = ((m + ScanCfg::TB - 1) / ScanCfg::TB) * nch;
+    g.item_cnt[l] = items;
+    if (m) {
+        atomicAdd(&g.stats[0], (unsigned long long)g.seg_len[l]);
+        atomicAdd(&g.stats[1], (unsigned long long)g.seg_len[l] * m);
+        atomicAdd(&g.stats[2], (unsigned long long)items);
+        atomicAdd(&g.stats[3], 1ull);
+    }
 }
 
 __global__ void group_fill_kernel(GroupParams g) {
@@ -310,6 +319,7 @@ static int32_t ivf_from_state(vers_kmeans* km, float cost, uint32_t attempt, ver
     VERS_CUDA(cudaMalloc(&ivf->d_seg_off, (size_t)km->C * 8));
     VERS_CUDA(cudaMalloc(&ivf->d_seg_len, (size_t)km->C * 4));
     VERS_CUDA(cudaMalloc(&ivf->d_assign, n1 * 4));
+    VERS_CUDA(cudaMalloc(&ivf->d_stats, 32));
     ivf->cap_total = ds->n;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
@@ -455,6 +465,7 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
     VERS_CUDA(cudaMemsetAsync(lq_cnt, 0, (size_t)ivf->C * 4, ctx->stream));
     VERS_CUDA(cudaMemsetAsync(cursor, 0, (size_t)ivf->C * 4, ctx->stream));
     VERS_CUDA(cudaMemsetAsync(counter, 0, 16, ctx->stream));
+    VERS_CUDA(cudaMemsetAsync(ivf->d_stats, 0, 32, ctx->stream));
     uint32_t* short_flag = reinterpret_cast<uint32_t*>(counter + 1);
     if (ref_mode) {
         ref_plan_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, ctx->stream>>>(probe_ids, ivf->d_seg_len, nq, np, k, used,
@@ -473,6 +484,7 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
     g.item_cnt = item_cnt;
     g.lq_off = lq_off;
     g.cursor = cursor;
+    g.stats = ivf->d_stats;
     g.lq_query = lq_query;
     g.lq_pair = lq_pair;
     group_count_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, ctx->stream>>>(g);
@@ -559,6 +571,7 @@ extern "C" int32_t vers_ivf_free(vers_ivf* ivf) {
     cudaFree(ivf->d_seg_off);
     cudaFree(ivf->d_seg_len);
     cudaFree(ivf->d_assign);
+    cudaFree(ivf->d_stats);
     delete ivf;
     return VERS_OK;
 }
@@ -721,30 +734,56 @@ extern "C" int32_t vers_ivf_search(vers_ivf* ivf, const float* queries, uint32_t
         return VERS_OK;
     }
     vers_ctx* ctx = ivf->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
-    float* d_q = nullptr;
-    uint64_t* d_ids = nullptr;
-    float* d_d = nullptr;
-    uint32_t* d_c = nullptr;
-    size_t nk = (size_t)nq * top_k;
-    int32_t rc = upload_queries(ctx, queries, nq, q_stride_floats, ivf->dim, ivf->ld, &d_q);
-    if (rc == VERS_OK && cudaMalloc(&d_ids, nk * 8) != cudaSuccess) rc = fail(VERS_ERR_NOMEM, "cudaMalloc ids");
-    if (rc == VERS_OK && cudaMalloc(&d_d, nk * 4) != cudaSuccess) rc = fail(VERS_ERR_NOMEM, "cudaMalloc dists");
-    if (rc == VERS_OK && cudaMalloc(&d_c, (size_t)nq * 4) != cudaSuccess) rc = fail(VERS_ERR_NOMEM, "cudaMalloc cnt");
-    if (rc == VERS_OK) rc = vers_ivf_search_dev(ivf, d_q, nq, top_k, nprobe, d_ids, d_d, d_c);
-    if (rc == VERS_OK) {
-        cudaError_t e = cudaMemcpyAsync(ids, d_ids, nk * 8, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(dists, d_d, nk * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess && counts)
-            e = cudaMemcpyAsync(counts, d_c, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) rc = fail(VERS_ERR_CUDA, "ivf_search copy back: %s", cudaGetErrorString(e));
-    }
-    cudaFree(d_q);
-    cudaFree(d_ids);
-    cudaFree(d_d);
-    cudaFree(d_c);
-    return rc;
+    const size_t nk = (size_t)nq * top_k;
+    ScratchCarver plan(nullptr);
+    plan.plan<float>((size_t)nq * ivf->ld);
+    plan.plan<uint64_t>(nk);
+    plan.plan<float>(nk);
+    plan.plan<uint32_t>(nq);
+    VERS_TRY(io_reserve(ctx, plan.off + 256));
+    ScratchCarver io(ctx->io);
+    float* d_q = io.take<float>((size_t)nq * ivf->ld);
+    uint64_t* d_ids = io.take<uint64_t>(nk);
+    float* d_d = io.take<float>(nk);
+    uint32_t* d_c = io.take<uint32_t>(nq);
+    if (ivf->ld != ivf->dim) VERS_CUDA(cudaMemsetAsync(d_q, 0, (size_t)nq * ivf->ld * 4, ctx->stream));
+    VERS_CUDA(cudaMemcpy2DAsync(d_q, (size_t)ivf->ld * 4, queries, (size_t)q_stride_floats * 4, (size_t)ivf->dim * 4,
+                                nq, cudaMemcpyHostToDevice, ctx->stream));
+    VERS_TRY(ivf_search_dev_locked(ivf, d_q, nq, top_k, nprobe, d_ids, d_d, d_c));
+    VERS_CUDA(cudaMemcpyAsync(ids, d_ids, nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VERS_CUDA(cudaMemcpyAsync(dists, d_d, nk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (counts) VERS_CUDA(cudaMemcpyAsync(counts, d_c, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    VERS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VERS_OK;
+}
+
+extern "C" int32_t vers_ivf_get_list(const vers_ivf* ivf, uint32_t list, uint64_t* ids, float* rows,
+                                     uint32_t stride_floats) {
+    if (!ivf) return fail(VERS_ERR_ARG, "ivf_get_list: null");
+    if (list >= ivf->C) return fail(VERS_ERR_ARG, "ivf_get_list: list %u >= %u", list, ivf->C);
+    if (rows && stride_floats < ivf->dim) return fail(VERS_ERR_ARG, "ivf_get_list: stride < dim");
+    const uint32_t len = ivf->seg_len[list];
+    if (len == 0) return VERS_OK;
+    vers_ctx* ctx = ivf->ctx;
+    VERS_CUDA(cudaSetDevice(ctx->device));
+    if (ids) VERS_CUDA(cudaMemcpyAsync(ids, ivf->d_lm_ids + ivf->seg_off[list], (size_t)len * 8, cudaMemcpyDeviceToHost,
+                                       ctx->stream));
+    if (rows)
+        VERS_CUDA(cudaMemcpy2DAsync(rows, (size_t)stride_floats * 4, ivf->d_lm + ivf->seg_off[list] * ivf->ld,
+                                    (size_t)ivf->ld * 4, (size_t)ivf->dim * 4, len, cudaMemcpyDeviceToHost,
+                                    ctx->stream));
+    VERS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VERS_OK;
+}
+
+extern "C" int32_t vers_ivf_last_search_stats(const vers_ivf* ivf, uint64_t out[4]) {
+    if (!ivf || !out) return fail(VERS_ERR_ARG, "ivf_last_search_stats: null");
+    VERS_CUDA(cudaSetDevice(ivf->ctx->device));
+    VERS_CUDA(cudaMemcpyAsync(out, ivf->d_stats, 32, cudaMemcpyDeviceToHost, ivf->ctx->stream));
+    VERS_CUDA(cudaStreamSynchronize(ivf->ctx->stream));
+    return VERS_OK;
 }
 
 extern "C" int32_t vers_ivf_add(vers_ivf* ivf, const float* embedding, uint64_t vec_id, uint64_t* assigned_id,

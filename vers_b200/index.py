@@ -63,9 +63,10 @@ class Context:
     def enable_timing(self, on: bool = True):
         check(lib().vers_ctx_enable_timing(self.h, int(on)))
 
-    def last_kernel_ms(self, family: int) -> Tuple[float, int]:
+    def kernel_ms(self, family: int) -> Tuple[float, int]:
+        """(total device ms, launches) of one kernel family since enable_timing(True)"""
         ms, n = C.c_float(0), C.c_uint64(0)
-        check(lib().vers_ctx_last_kernel_ms(self.h, family, C.byref(ms), C.byref(n)))
+        check(lib().vers_ctx_kernel_ms(self.h, family, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
 
@@ -324,6 +325,20 @@ class IVFFlatIndex:
         out = np.empty(self.num_centroids, np.uint64)
         check(lib().vers_ivf_get_list_sizes(self.h, ptr(out)))
         return out
+
+    def get_list(self, c: int, with_rows: bool = False):
+        """ids[c] (and optionally the rows of list c, in list order) straight from the device layout"""
+        n = int(self.list_sizes[c])
+        ids = np.empty(n, np.uint64)
+        rows = np.empty((n, self.dim), np.float32) if with_rows else None
+        check(lib().vers_ivf_get_list(self.h, c, ptr(ids), None if rows is None else ptr(rows), self.dim))
+        return (ids, rows) if with_rows else ids
+
+    def last_search_stats(self) -> dict:
+        out = np.zeros(4, np.uint64)
+        check(lib().vers_ivf_last_search_stats(self.h, ptr(out)))
+        return dict(distinct_list_rows=int(out[0]), pair_rows=int(out[1]), work_items=int(out[2]),
+                    lists_touched=int(out[3]))
 
     @property
     def ids(self) -> List[np.ndarray]:

@@ -1,0 +1,177 @@
+"""Multi-GPU driver: one process per GPU (torch.distributed, NCCL over NVLink), rows sharded in contiguous blocks so
+every GPU holds 1/G of every inverted list.
+
+  k-means : assign is embarrassingly parallel.  update needs Σ over ALL rows in row order (ivfflat.rs:52-55):
+            reduce="chained" passes the running (sums, counts) from rank r-1 to rank r, which continues the
+            left-to-right sum over its own rows, then the last rank broadcasts: the association is exactly the
+            reference's, so centroids and assignments stay BIT-IDENTICAL to the CPU reference at any GPU count.
+            reduce="allreduce" is the plain NCCL all-reduce of per-shard sums (fastest, association != reference's).
+  search  : every GPU searches its shard for the whole query batch; the per-GPU top-k (ids+dists packed in one
+            buffer) are all-gathered and merged by (distance, id) on every rank.
+torch is used for what it is here for: device buffers, streams and the process group.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ._abi import check, lib
+from .index import Context, Dataset, IVFFlatIndex, KMeans
+
+
+class _DevArray:
+    """zero-copy torch view of library-owned device memory"""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(ptr, False), version=2)
+
+
+def device_view(ptr: int, shape, dtype=torch.float32) -> torch.Tensor:
+    typestr = {torch.float32: "<f4", torch.int32: "<i4", torch.int64: "<i8", torch.uint8: "|u1"}[dtype]
+    return torch.as_tensor(_DevArray(ptr, shape, typestr), device="cuda")
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n_total: int, rank: int, world_size: int):
+    per = (n_total + world_size - 1) // world_size
+    r0 = min(n_total, rank * per)
+    return r0, min(n_total, r0 + per) - r0
+
+
+def kmeans_fit_sharded(km: KMeans, init_rows_global: np.ndarray, max_iterations: int, reduce: str = "chained",
+                       group=None) -> int:
+    """IVFFlatIndex::build_kmeans (ivfflat.rs:73-100) over row shards.  init_rows_global are GLOBAL row numbers."""
+    rank, ws = world()
+    ds = km.ds
+    Cn, ld = km.C, ds.ld
+    dev = torch.device("cuda", torch.cuda.current_device())
+    # initialize_centroids: the rank owning row init[j] contributes it; integer all-reduce of the bit patterns of
+    # (row or zeros) is exact (it also preserves -0.0, which a float add would not)
+    rows = device_view(ds.device_ptr, (max(ds.n, 1), ld))
+    init = torch.as_tensor(np.ascontiguousarray(init_rows_global, np.int64), device=dev)
+    local = init - ds.id_base
+    mine = (local >= 0) & (local < ds.n)
+    cents = torch.zeros((Cn, ld), dtype=torch.float32, device=dev)
+    if ds.n:
+        cents[mine] = rows[local[mine]]
+    if ws > 1:
+        ci = cents.view(torch.int32)
+        dist.all_reduce(ci, op=dist.ReduceOp.SUM, group=group)
+
+    def cur_centroids() -> torch.Tensor:
+        p, l = C.c_void_p(), C.c_uint32()
+        check(lib().vers_kmeans_centroids_device_ptr(km.h, C.byref(p), C.byref(l)))
+        return device_view(p.value, (Cn, ld))
+
+    cur_centroids().copy_(cents)
+    sums = torch.zeros((Cn, ld), dtype=torch.float32, device=dev)
+    counts = torch.zeros((Cn,), dtype=torch.int64, device=dev)
+    it = 0
+    while it < max_iterations:
+        km.assign_step()
+        if ws == 1:
+            sums.zero_(), counts.zero_()
+            km.sums_step_dev(sums.data_ptr(), counts.data_ptr())
+        elif reduce == "chained":
+            if rank == 0:
+                sums.zero_(), counts.zero_()
+            else:
+                dist.recv(sums, src=rank - 1, group=group)
+                dist.recv(counts, src=rank - 1, group=group)
+            km.sums_step_dev(sums.data_ptr(), counts.data_ptr())
+            if rank < ws - 1:
+                dist.send(sums, dst=rank + 1, group=group)
+                dist.send(counts, dst=rank + 1, group=group)
+            dist.broadcast(sums, src=ws - 1, group=group)
+            dist.broadcast(counts, src=ws - 1, group=group)
+        elif reduce == "allreduce":
+            sums.zero_(), counts.zero_()
+            km.sums_step_dev(sums.data_ptr(), counts.data_ptr())
+            dist.all_reduce(sums, group=group)
+            dist.all_reduce(counts, group=group)
+        else:
+            raise ValueError(reduce)
+        changed = km.finalize_step_dev(sums.data_ptr(), counts.data_ptr())
+        it += 1
+        if not changed:
+            break
+    km.assign_step()
+    return it
+
+
+def kmeans_cost_sharded(km: KMeans, group=None) -> np.float32:
+    """calculate_kmeans_cost (ivfflat.rs:138-149) folded in global row order: rank r continues rank r-1's value"""
+    rank, ws = world()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    acc = torch.zeros(1, dtype=torch.float32, device=dev)
+    if ws > 1 and rank > 0:
+        dist.recv(acc, src=rank - 1, group=group)
+    cost = km.cost_step(float(acc.item()))
+    acc.fill_(float(cost))
+    if ws > 1:
+        if rank < ws - 1:
+            dist.send(acc, dst=rank + 1, group=group)
+        dist.broadcast(acc, src=ws - 1, group=group)
+    return np.float32(acc.item())
+
+
+class ShardedIVFFlat:
+    """IVFFlatIndex whose rows are sharded over the ranks of the default process group."""
+
+    def __init__(self, ivf: IVFFlatIndex, ctx: Context):
+        self.ivf = ivf
+        self.ctx = ctx
+        self.rank, self.world = world()
+        self._bufs = {}
+
+    @classmethod
+    def build(cls, ds: Dataset, num_clusters: int, max_iterations: int, init_rows_global: np.ndarray,
+              reduce: str = "chained") -> "ShardedIVFFlat":
+        km = KMeans(ds, num_clusters)
+        kmeans_fit_sharded(km, init_rows_global, max_iterations, reduce)
+        ivf = IVFFlatIndex.from_kmeans(km)
+        km.close()
+        return cls(ivf, ds.ctx)
+
+    def _buffers(self, nq: int, k: int):
+        key = (nq, k)
+        if key not in self._bufs:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            nk = nq * k
+            L = nk + (nk + 1) // 2  # int64 words: nk ids, then nk floats packed two per word
+            local = torch.empty(L, dtype=torch.int64, device=dev)
+            allb = torch.empty((self.world, L), dtype=torch.int64, device=dev)
+            out_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            out_c = torch.empty((nq,), dtype=torch.int32, device=dev)
+            self._bufs[key] = (local, allb, out_ids, out_d, out_c, L)
+        return self._bufs[key]
+
+    def search_dev(self, d_queries: torch.Tensor, top_k: int, nprobe: int):
+        """d_queries: [nq, ld] float32 on this rank's GPU (the same batch on every rank).  Returns device tensors
+        (ids int64 [nq,k] holding u64 bit patterns, dists [nq,k], counts [nq]) — the global result on every rank."""
+        nq = d_queries.shape[0]
+        local, allb, out_ids, out_d, out_c, L = self._buffers(nq, top_k)
+        nk = nq * top_k
+        ids_ptr = local.data_ptr()
+        d_ptr = ids_ptr + nk * 8
+        if self.world == 1:
+            self.ivf.search_batch_dev(d_queries.data_ptr(), nq, top_k, nprobe, out_ids.data_ptr(), out_d.data_ptr(),
+                                      out_c.data_ptr())
+            return out_ids, out_d, out_c
+        self.ivf.search_batch_dev(d_queries.data_ptr(), nq, top_k, nprobe, ids_ptr, d_ptr, out_c.data_ptr())
+        dist.all_gather_into_tensor(allb, local)
+        base = allb.data_ptr()
+        check(lib().vers_topk_merge_dev(self.ctx.h, C.c_void_p(base), C.c_void_p(base + nk * 8), self.world, L, 2 * L,
+                                        nq, top_k, C.c_void_p(out_ids.data_ptr()), C.c_void_p(out_d.data_ptr()),
+                                        C.c_void_p(out_c.data_ptr())))
+        return out_ids, out_d, out_c

@@ -53,6 +53,8 @@ def lib():
         "vo_normalize_rows": (None, [_f32p, u64, u32, u32]),
         "vo_synth": (None, [u64, u64, u32, u32, u64, u64, u32, u32, i32, _f32p]),
         "vo_assign": (i32, [_f32p, u64, u32, u32, _f32p, u32, u32, _u64p]),
+        "vo_partial_sums": (None, [_f32p, u64, u32, u32, _u64p, u32, _f32p, _u64p]),
+        "vo_finalize_centroids": (None, [_f32p, _u64p, u32, u32, _f32p]),
         "vo_update": (i32, [_f32p, u64, u32, u32, _u64p, u32, _f32p, _u64p]),
         "vo_update_sharded": (i32, [_f32p, u64, u32, u32, _u64p, u32, u32, _f32p, _u64p]),
         "vo_kmeans_cost": (f32, [_f32p, u64, u32, u32, _f32p, u32, _u64p]),
@@ -177,6 +179,21 @@ def update(rows, assignments, C_, shards=0):
     else:
         _chk(lib().vo_update(rows, rows.shape[0], rows.shape[1], rows.shape[1], a, C_, cents, counts), "update")
     return cents, counts
+
+
+def partial_sums(rows, assignments, C_, sums, counts):
+    """continue the running per-cluster sums/counts IN PLACE over these rows in row order (ivfflat.rs:52-55)"""
+    rows = _rows(rows)
+    a = np.ascontiguousarray(assignments, np.uint64)
+    assert sums.dtype == np.float32 and sums.shape == (C_, rows.shape[1]) and sums.flags.c_contiguous
+    assert counts.dtype == np.uint64 and counts.flags.c_contiguous
+    lib().vo_partial_sums(rows, rows.shape[0], rows.shape[1], rows.shape[1], a, C_, sums, counts)
+
+
+def finalize_centroids(sums, counts):
+    out = np.empty_like(sums)
+    lib().vo_finalize_centroids(sums, counts, sums.shape[0], sums.shape[1], out)
+    return out
 
 
 def kmeans_cost(rows, cents, assignments) -> np.float32:

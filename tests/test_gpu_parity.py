@@ -338,3 +338,20 @@ def test_no_cpu_fallback_symbols(vb):
 
     out = subprocess.run(["ldd", vb.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_multi_gpu_sharded_parity_when_two_gpus_present():
+    """runs tests/mgpu_check.py under torchrun on 2 GPUs (skipped on a 1-GPU box)"""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "mgpu_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "mgpu_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

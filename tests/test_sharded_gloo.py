@@ -1,0 +1,82 @@
+"""N>1 host logic on CPU: world_size-2 gloo process group (no GPU).  Covers the rank-chained ordered accumulation
+that keeps multi-GPU k-means bit-identical to the single-process reference order, the exact initial-centroid
+exchange, and the shard arithmetic.  The per-shard arithmetic itself is the oracle's here (tests may use it); on
+the GPU box the same driver code calls the CUDA kernels (tests/test_gpu_parity.py::test_kmeans_chained_shards...)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, ws, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        import oracle as vo
+        from vers_b200.sharded import chained_accumulate, gather_init_centroids, shard_bounds
+
+        n, dim, C = 5003, 24, 13
+        rows = vo.synth(1, n, dim, normalize=False)
+        rows[17, 3] = -0.0  # must survive the centroid exchange bit for bit
+        init = np.array([17, 4999, 17, 2500, 2501, 0, 5002, 1234, 1, 2, 3, 4, 4000], np.uint64)
+        r0, nl = shard_bounds(n, rank, ws)
+        local = torch.from_numpy(rows[r0:r0 + nl].copy())
+        cents = gather_init_centroids(local, r0, nl, init, dim).numpy()
+        assert np.array_equal(cents.view(np.uint32), rows[init.astype(np.int64)].view(np.uint32))
+        assign = vo.assign(rows, cents)
+        sums = torch.zeros((C, dim), dtype=torch.float32)
+        counts = torch.zeros((C,), dtype=torch.int64)
+
+        def step():
+            s, c = sums.numpy(), counts.numpy().view(np.uint64)
+            vo.partial_sums(rows[r0:r0 + nl], assign[r0:r0 + nl], C, s, c)
+
+        chained_accumulate([sums, counts], step)
+        new = vo.finalize_centroids(sums.numpy(), counts.numpy().view(np.uint64))
+        want, wcnt = vo.update(rows, assign, C)  # the single-process reference order
+        assert np.array_equal(counts.numpy().view(np.uint64), wcnt)
+        assert np.array_equal(new.view(np.uint32), want.view(np.uint32)), "chained sums differ from global row order"
+        # a plain all-reduce would NOT reproduce the reference association on this input
+        part = np.zeros((C, dim), np.float32)
+        pc = np.zeros(C, np.uint64)
+        vo.partial_sums(rows[r0:r0 + nl], assign[r0:r0 + nl], C, part, pc)
+        t = torch.from_numpy(part.copy())
+        dist.all_reduce(t)
+        ar = vo.finalize_centroids(t.numpy(), wcnt)
+        sharded, _ = vo.update(rows, assign, C, shards=ws)
+        assert np.array_equal(ar.view(np.uint32), sharded.view(np.uint32))  # == the oracle's sharded-order mode
+        assert not np.array_equal(ar.view(np.uint32), want.view(np.uint32))
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_chained_accumulate_world2_gloo(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def test_shard_bounds_cover_all_rows():
+    from vers_b200.sharded import shard_bounds
+
+    for n in (0, 1, 7, 8, 10_000_000, 10_000_001):
+        for ws in (1, 2, 3, 4, 8):
+            got = [shard_bounds(n, r, ws) for r in range(ws)]
+            assert sum(c for _, c in got) == n
+            pos = 0
+            for r0, c in got:
+                assert r0 == pos or c == 0
+                pos += c

@@ -47,6 +47,43 @@ def shard_bounds(n_total: int, rank: int, world_size: int):
     return r0, min(n_total, r0 + per) - r0
 
 
+def chained_accumulate(tensors, local_step, group=None):
+    """Ordered cross-rank accumulation: rank 0 zeroes `tensors`, every rank r > 0 first receives them from r-1, then
+    `local_step()` continues the running values IN PLACE over its own rows, forwards them to r+1, and the last rank
+    broadcasts the final values.  The association is that of one process walking all rows in order."""
+    rank, ws = world()
+    if rank == 0:
+        for t in tensors:
+            t.zero_()
+    else:
+        for t in tensors:
+            dist.recv(t, src=rank - 1, group=group)
+    local_step()
+    if ws > 1:
+        if rank < ws - 1:
+            for t in tensors:
+                dist.send(t, dst=rank + 1, group=group)
+        for t in tensors:
+            dist.broadcast(t, src=ws - 1, group=group)
+
+
+def gather_init_centroids(rows: torch.Tensor, id_base: int, n_local: int, init_rows_global, ld: int, group=None):
+    """initialize_centroids (ivfflat.rs:18-27) over row shards: the rank owning global row init[j] contributes it,
+    everyone else zeros; an INTEGER all-reduce of the bit patterns is exact (and keeps -0.0, which a float add
+    would turn into +0.0)."""
+    _, ws = world()
+    init = torch.as_tensor(np.ascontiguousarray(init_rows_global, np.int64), device=rows.device)
+    local = init - id_base
+    mine = (local >= 0) & (local < n_local)
+    cents = torch.zeros((init.shape[0], ld), dtype=torch.float32, device=rows.device)
+    if n_local:
+        cents[mine] = rows[local[mine]]
+    if ws > 1:
+        ci = cents.view(torch.int32)
+        dist.all_reduce(ci, op=dist.ReduceOp.SUM, group=group)
+    return cents
+
+
 def kmeans_fit_sharded(km: KMeans, init_rows_global: np.ndarray, max_iterations: int, reduce: str = "chained",
                        group=None) -> int:
     """IVFFlatIndex::build_kmeans (ivfflat.rs:73-100) over row shards.  init_rows_global are GLOBAL row numbers."""
@@ -54,18 +91,8 @@ def kmeans_fit_sharded(km: KMeans, init_rows_global: np.ndarray, max_iterations:
     ds = km.ds
     Cn, ld = km.C, ds.ld
     dev = torch.device("cuda", torch.cuda.current_device())
-    # initialize_centroids: the rank owning row init[j] contributes it; integer all-reduce of the bit patterns of
-    # (row or zeros) is exact (it also preserves -0.0, which a float add would not)
     rows = device_view(ds.device_ptr, (max(ds.n, 1), ld))
-    init = torch.as_tensor(np.ascontiguousarray(init_rows_global, np.int64), device=dev)
-    local = init - ds.id_base
-    mine = (local >= 0) & (local < ds.n)
-    cents = torch.zeros((Cn, ld), dtype=torch.float32, device=dev)
-    if ds.n:
-        cents[mine] = rows[local[mine]]
-    if ws > 1:
-        ci = cents.view(torch.int32)
-        dist.all_reduce(ci, op=dist.ReduceOp.SUM, group=group)
+    cents = gather_init_centroids(rows, ds.id_base, ds.n, init_rows_global, ld, group)
 
     def cur_centroids() -> torch.Tensor:
         p, l = C.c_void_p(), C.c_uint32()
@@ -78,21 +105,8 @@ def kmeans_fit_sharded(km: KMeans, init_rows_global: np.ndarray, max_iterations:
     it = 0
     while it < max_iterations:
         km.assign_step()
-        if ws == 1:
-            sums.zero_(), counts.zero_()
-            km.sums_step_dev(sums.data_ptr(), counts.data_ptr())
-        elif reduce == "chained":
-            if rank == 0:
-                sums.zero_(), counts.zero_()
-            else:
-                dist.recv(sums, src=rank - 1, group=group)
-                dist.recv(counts, src=rank - 1, group=group)
-            km.sums_step_dev(sums.data_ptr(), counts.data_ptr())
-            if rank < ws - 1:
-                dist.send(sums, dst=rank + 1, group=group)
-                dist.send(counts, dst=rank + 1, group=group)
-            dist.broadcast(sums, src=ws - 1, group=group)
-            dist.broadcast(counts, src=ws - 1, group=group)
+        if ws == 1 or reduce == "chained":
+            chained_accumulate([sums, counts], lambda: km.sums_step_dev(sums.data_ptr(), counts.data_ptr()), group)
         elif reduce == "allreduce":
             sums.zero_(), counts.zero_()
             km.sums_step_dev(sums.data_ptr(), counts.data_ptr())

@@ -139,8 +139,14 @@ int32_t vers_ivf_get_list_sizes(const vers_ivf* ivf, uint64_t* sizes);
 int32_t vers_ivf_get_list(const vers_ivf* ivf, uint32_t list, uint64_t* ids, float* rows, uint32_t stride_floats);
 /* work done by the most recent search on this index (device counters, synchronises):
  * out[0] = rows in the DISTINCT lists touched (the algorithmic HBM stream), out[1] = Σ over (query, list) pairs of
- * the list length (un-deduplicated rows x queries), out[2] = work items, out[3] = distinct lists touched */
-int32_t vers_ivf_last_search_stats(const vers_ivf* ivf, uint64_t out[4]);
+ * the list length (un-deduplicated rows x queries), out[2] = work items, out[3] = distinct lists touched,
+ * out[4] = queries whose certificate failed and were redone by the exact-order scan, out[5] = candidates
+ * re-ranked in exact order, out[6..7] reserved */
+int32_t vers_ivf_last_search_stats(const vers_ivf* ivf, uint64_t out[8]);
+/* nprobe >= 1 searches: 0 (default) = candidate pass (FMA, any summation order) + exact-order rerank of the
+ * candidates + a rounding-error certificate, uncertified queries redone in exact order; 1 = exact order everywhere.
+ * Both modes return the reference's ids and distance bits; the knob exists for tests and for timing. */
+int32_t vers_ivf_set_mode(vers_ivf* ivf, int32_t mode);
 /* Index::search_approximate (ivfflat.rs:153-198) for a batch.  nprobe == 0: the reference's semantics (nearest
  * list, spill to the next list while fewer than top_k found, output = concatenated per-list prefixes).
  * nprobe >= 1 (extension, BASELINE config 4): global top_k by (distance, id) over the nprobe nearest lists. */

@@ -186,17 +186,51 @@ def test_ivf_build_index_bit_exact(ivf_c1):
     assert np.array_equal(s["idx"].list_sizes, np.bincount(s["assign"].astype(np.int64), minlength=s["C"]))
 
 
-@pytest.mark.parametrize("k", [1, 10, 37])
+@pytest.mark.parametrize("exact_mode", [False, True])
+@pytest.mark.parametrize("k", [1, 10, 37, 100])
 @pytest.mark.parametrize("nprobe", [0, 1, 4, 16])
-def test_ivf_search_bit_exact(vo, ivf_c1, k, nprobe):
+def test_ivf_search_bit_exact(vo, ivf_c1, k, nprobe, exact_mode):
+    """exact_mode=False: candidate pass (FMA) + exact-order rerank + certificate (+ exact redo when uncertified);
+    exact_mode=True: exact order everywhere.  Both must return the oracle's ids AND distance bits."""
     s = ivf_c1
     q = data(vo, 100, 300, seed=2)
     off, lr = vo.ivf_lists(s["assign"], s["C"])
-    ids, d, cnt = s["idx"].search_batch(q, k, nprobe=nprobe)
+    s["idx"].set_mode(exact_mode)
+    try:
+        ids, d, cnt = s["idx"].search_batch(q, k, nprobe=nprobe)
+        st = s["idx"].last_search_stats()
+    finally:
+        s["idx"].set_mode(False)
     oi, od, oc = vo.ivf_search(s["rows"], s["cents"], off, lr, q, k, nprobe=nprobe)
     assert np.array_equal(cnt, oc)
     assert np.array_equal(ids, oi)
     assert np.array_equal(bits(d), bits(od))
+    if not exact_mode and nprobe > 0 and k <= 48:
+        assert st["reranked"] > 0  # the candidate path really ran
+        assert st["uncertified_queries"] <= 10
+
+
+def test_ivf_candidate_path_falls_back_on_ties(vb, vo, ctx):
+    """more exact duplicates than the candidate list holds: the rounding-error certificate cannot separate them,
+    the queries must be redone in exact order and still return the reference's (distance, id) order"""
+    n, dim, C, k = 6000, 96, 8, 10
+    rows = data(vo, n, dim)
+    rows[1000:1100] = rows[17]           # 101 copies of row 17
+    rows[2000:2040] = rows[23]           # 41 copies of row 23
+    init = vo.init_rows(3, 1, C, n)
+    idx = vb.IVFFlatIndex.build_index(C, 1, 6, rows, init_rows=init, ctx=ctx)
+    cents, assign, _, _ = vo.ivf_build_index(rows, C, 1, 6, init)
+    off, lr = vo.ivf_lists(assign, C)
+    q = data(vo, 40, dim, seed=2)
+    q[0] = rows[17]
+    q[1] = rows[23]
+    q[2] = (rows[17] + np.float32(1e-4)).astype(np.float32)
+    ids, d, cnt = idx.search_batch(q, k, nprobe=4)
+    st = idx.last_search_stats()
+    oi, od, oc = vo.ivf_search(rows, cents, off, lr, q, k, nprobe=4)
+    assert np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od)) and np.array_equal(cnt, oc)
+    assert list(ids[0]) == [17] + list(range(1000, 1009))
+    assert st["uncertified_queries"] >= 2  # the duplicate-heavy queries took the exact redo
 
 
 def test_ivf_search_approximate_single_query_trait_call(vo, ivf_c1):

@@ -75,6 +75,7 @@ SIGNATURES = {
     "vers_ivf_get_list_sizes": [vp, vp],
     "vers_ivf_get_list": [vp, u32, vp, vp, u32],
     "vers_ivf_last_search_stats": [vp, vp],
+    "vers_ivf_set_mode": [vp, i32],
     "vers_ivf_search": [vp, vp, u32, u32, u32, u32, vp, vp, vp],
     "vers_ivf_search_dev": [vp, vp, u32, u32, u32, vp, vp, vp],
     "vers_ivf_add": [vp, vp, u64, C.POINTER(u64), C.POINTER(u32)],

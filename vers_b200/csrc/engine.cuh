@@ -18,7 +18,7 @@
 
 namespace vers {
 
-enum { OP_L2SQ = 0, OP_DOT = 1 };
+enum { OP_L2SQ = 0, OP_DOT = 1, OP_DOT_FMA = 2 };  // OP_DOT_FMA: candidate pass only, any rounding
 
 // source of tile rows: row r lives at base + (idx ? idx[r] : r) * ld
 struct RowSrc {
@@ -48,14 +48,19 @@ struct TileCfg {
 using WideCfg = TileCfg<128, 64, 8, 4>;
 // few columns (<= 8): inverted-list scan (about nq*nprobe/nlist queries per list), small-batch GEMV-style scans
 using NarrowCfg = TileCfg<256, 8, 4, 2>;
+// candidate pass of the inverted-list scan: every thread owns 2 rows x all 8 queries of the group, so each row
+// element is read from shared memory exactly once and the 8 query values are warp-wide broadcasts
+using StreamCfg = TileCfg<512, 8, 2, 8>;
 
 template <int OP>
 __device__ __forceinline__ void pair_step(float& acc, float a, float b) {
     if (OP == OP_L2SQ) {
         float t = __fsub_rn(a, b);
         acc = __fadd_rn(acc, __fmul_rn(t, t));
-    } else {
+    } else if (OP == OP_DOT) {
         acc = __fadd_rn(acc, __fmul_rn(a, b));
+    } else {
+        acc = __fmaf_rn(a, b, acc);  // 1 instruction per pair-dimension; NOT the reference's rounding
     }
 }
 
@@ -207,12 +212,15 @@ __device__ __forceinline__ void warp_topk_insert(float* sd, P* sp, int k, float 
 }
 
 // Fold the register micro-tile of one computed tile into the per-(warp, column) private top-k lists.
-// XF: 0 = value as is, 1 = cosine distance 1 - dot (indexes/base.rs:155).
+// XF: 0 = value as is, 1 = cosine distance 1 - dot (indexes/base.rs:155),
+//     2 = candidate key ||x||^2 - 2 x.q (rownorm[p] holds ||x||^2 of the row at position p; ||q||^2 is a per-query
+//         constant and is added back by the certifier).
 // position stored = (u32)(row + pos_add): monotone in id order inside one scan range.
 template <class Cfg, int XF>
 __device__ __forceinline__ void tile_select_topk(const float (&acc)[Cfg::MA][Cfg::MB], uint64_t a0, uint64_t r_end,
                                                  uint64_t b0, uint64_t nB, uint32_t k, uint32_t kpad, float* list_d,
-                                                 uint32_t* list_p, uint64_t pos_add) {
+                                                 uint32_t* list_p, uint64_t pos_add,
+                                                 const float* __restrict__ rownorm = nullptr) {
     constexpr int MA = Cfg::MA, MB = Cfg::MB, NTA = Cfg::NTA, NTB = Cfg::NTB;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ta = tid % NTA, tb = tid / NTA;
@@ -230,6 +238,7 @@ __device__ __forceinline__ void tile_select_topk(const float (&acc)[Cfg::MA][Cfg
             if (XF == 1) v = __fsub_rn(1.0f, v);
             const uint32_t p = (uint32_t)(row + pos_add);
             bool live = colvalid && row < r_end;
+            if (XF == 2) v = live ? __fmaf_rn(-2.0f, v, __ldg(rownorm + p)) : v;
             while (true) {
                 float tv = sd[k - 1];
                 uint32_t tp = sp[k - 1];

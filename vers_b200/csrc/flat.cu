@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) merge_topk_kernel(MergeParam
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * MERGE_WARPS + warp;
     if (q >= p.nq) return;
+    if (p.qmask && p.qmask[q] == 0) return;
     uint64_t* sp = reinterpret_cast<uint64_t*>(msm) + (size_t)warp * p.k;
     float* sd = reinterpret_cast<float*>(msm + (size_t)MERGE_WARPS * p.k * 8) + (size_t)warp * p.k;
     for (uint32_t e = lane; e < p.k; e += 32) {
@@ -228,6 +229,7 @@ int32_t scan_topk_run(vers_ctx* ctx, const ScanPlan& pl, void* scratch, const Ro
     mp.out_ids = d_ids;
     mp.out_d = d_d;
     mp.out_cnt = d_cnt;
+    mp.qmask = nullptr;
     return launch_merge(ctx, mp);
 }
 

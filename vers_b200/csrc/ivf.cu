@@ -38,7 +38,10 @@ struct vers_ivf {
     std::vector<uint32_t> assign_tail;  // assignments of rows added later
     float best_cost = 0.f;
     uint32_t best_attempt = 0;
-    unsigned long long* d_stats = nullptr;  // [4] counters of the most recent search (vers_ivf_last_search_stats)
+    unsigned long long* d_stats = nullptr;  // [8] counters of the most recent search (vers_ivf_last_search_stats)
+    float* d_lm_norm = nullptr;             // [cap_total] ||row||^2 (any summation order; candidate pass only)
+    uint32_t* d_nxmax = nullptr;            // [1] bit pattern of max ||row||^2 over the index (non-negative floats order as uints)
+    int mode = 0;                           // 0 = candidate pass + exact rerank + certificate, 1 = exact-order everywhere
 };
 
 namespace vers {
@@ -62,11 +65,36 @@ __global__ void gather_list_major_kernel(const float* __restrict__ rows, uint32_
     }
 }
 
+// ||row||^2 for the candidate pass (one warp per row, lane-parallel FMA + shuffle tree: any order is fine here, the
+// certificate's error bound covers every summation order) and the running maximum over the index
+__global__ void rownorm_kernel(const float* __restrict__ lm, uint32_t ld, uint64_t pos0, uint64_t count,
+                               float* __restrict__ norm, uint32_t* nxmax) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    float mx = 0.0f;
+    for (uint64_t j = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); j < count; j += warps) {
+        const float4* r = reinterpret_cast<const float4*>(lm + (pos0 + j) * ld);
+        float s = 0.0f;
+        for (uint32_t c = lane; c < (ld >> 2); c += 32) {
+            float4 v = r[c];
+            s = __fmaf_rn(v.x, v.x, s);
+            s = __fmaf_rn(v.y, v.y, s);
+            s = __fmaf_rn(v.z, v.z, s);
+            s = __fmaf_rn(v.w, v.w, s);
+        }
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL_MASK, s, o);
+        if (lane == 0) norm[pos0 + j] = s;
+        mx = fmaxf(mx, s);
+    }
+    if (lane == 0 && mx > 0.0f) atomicMax(nxmax, __float_as_uint(mx));
+}
+
 // ---------------------------------------------------------------- grouping of (query, probe) pairs by list
 struct GroupParams {
     const uint64_t* probe_ids;  // [nq][np]
     const uint32_t* seg_len;    // [C]
     const uint32_t* used;       // optional [nq]: only slots s < used[q] are active (reference spill mode)
+    const uint32_t* qmask;      // optional [nq]: only queries with a non-zero mask are active (exact fallback pass)
     uint32_t nq, np, C;
     uint32_t* lq_cnt;     // [C]   queries per list
     uint32_t* pair_nch;   // [nq*np] chunks of the pair's list (0 for inactive pairs / empty lists)
@@ -83,7 +111,7 @@ __global__ void group_count_kernel(GroupParams g) {
     if (pi >= g.nq * g.np) return;
     uint32_t q = pi / g.np, s = pi % g.np;
     uint32_t nch = 0;
-    if (!g.used || s < g.used[q]) {
+    if ((!g.used || s < g.used[q]) && (!g.qmask || g.qmask[q] != 0)) {
         uint32_t l = (uint32_t)g.probe_ids[pi];
         uint32_t len = g.seg_len[l];
         nch = (len + LIST_CHUNK_ROWS - 1) / LIST_CHUNK_ROWS;
@@ -99,7 +127,7 @@ __global__ void group_items_kernel(GroupParams g) {
     uint32_t nch = (g.seg_len[l] + LIST_CHUNK_ROWS - 1) / LIST_CHUNK_ROWS;
     uint32_t items = ((m + ScanCfg::TB - 1) / ScanCfg::TB) * nch;
     g.item_cnt[l] = items;
-    if (m) {
+    if (m && g.stats) {
         atomicAdd(&g.stats[0], (unsigned long long)g.seg_len[l]);
         atomicAdd(&g.stats[1], (unsigned long long)g.seg_len[l] * m);
         atomicAdd(&g.stats[2], (unsigned long long)items);
@@ -134,10 +162,13 @@ struct ListScanParams {
     float* part_d;
     uint32_t* part_p;
     unsigned long long* counter;
+    const float* lm_norm;  // MODE 1 only
 };
 
-__global__ void __launch_bounds__(ScanCfg::NT, 2) list_scan_kernel(ListScanParams p) {
-    using Cfg = ScanCfg;
+// MODE 0: exact order (OP_L2SQ), private top-k by (distance, position)
+// MODE 1: candidate pass (FMA dot, key = ||x||^2 - 2 x.q), private top-M by (key, position); p.k == p.kpad == M
+template <class Cfg, int MODE>
+__global__ void __launch_bounds__(Cfg::NT, MODE == 0 ? 2 : 1) list_scan_kernel(ListScanParams p) {
     extern __shared__ __align__(16) float smem[];
     float* list_d = smem + Cfg::TILE_FLOATS;
     uint32_t* list_p = reinterpret_cast<uint32_t*>(list_d + Cfg::NLISTS * p.kpad);
@@ -179,8 +210,13 @@ __global__ void __launch_bounds__(ScanCfg::NT, 2) list_scan_kernel(ListScanParam
         lists_init<Cfg>(list_d, list_p, p.kpad);
         for (uint64_t a0 = r0; a0 < r1; a0 += Cfg::TA) {
             float acc[Cfg::MA][Cfg::MB];
-            tile_compute<Cfg, OP_L2SQ>(acc, A, a0, B, 0, p.ld, smem);
-            tile_select_topk<Cfg, 0>(acc, a0, r1, 0, nB, p.k, p.kpad, list_d, list_p, base_pos);
+            if (MODE == 0) {
+                tile_compute<Cfg, OP_L2SQ>(acc, A, a0, B, 0, p.ld, smem);
+                tile_select_topk<Cfg, 0>(acc, a0, r1, 0, nB, p.k, p.kpad, list_d, list_p, base_pos);
+            } else {
+                tile_compute<Cfg, OP_DOT_FMA>(acc, A, a0, B, 0, p.ld, smem);
+                tile_select_topk<Cfg, 2>(acc, a0, r1, 0, nB, p.k, p.kpad, list_d, list_p, base_pos, p.lm_norm);
+            }
         }
         __syncwarp();
         constexpr int SLOTS_PER_WARP = Cfg::TBS_PER_WARP * Cfg::MB;
@@ -319,7 +355,10 @@ static int32_t ivf_from_state(vers_kmeans* km, float cost, uint32_t attempt, ver
     VERS_CUDA(cudaMalloc(&ivf->d_seg_off, (size_t)km->C * 8));
     VERS_CUDA(cudaMalloc(&ivf->d_seg_len, (size_t)km->C * 4));
     VERS_CUDA(cudaMalloc(&ivf->d_assign, n1 * 4));
-    VERS_CUDA(cudaMalloc(&ivf->d_stats, 32));
+    VERS_CUDA(cudaMalloc(&ivf->d_stats, 64));
+    VERS_CUDA(cudaMalloc(&ivf->d_lm_norm, n1 * 4));
+    VERS_CUDA(cudaMalloc(&ivf->d_nxmax, 4));
+    VERS_CUDA(cudaMemsetAsync(ivf->d_nxmax, 0, 4, ctx->stream));
     ivf->cap_total = ds->n;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
@@ -330,6 +369,9 @@ static int32_t ivf_from_state(vers_kmeans* km, float cost, uint32_t attempt, ver
             VERS_CUDA(cudaMemcpyAsync(ivf->d_assign, km->d_assign, ds->n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
             gather_list_major_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
                 ds->d_rows, ds->ld, km->d_sorted_rows, ds->n, ds->id_base, ivf->d_lm, ivf->d_lm_ids);
+            VERS_LAUNCH_CHECK(ctx);
+            rownorm_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ivf->d_lm, ds->ld, 0, ds->n, ivf->d_lm_norm,
+                                                                      ivf->d_nxmax);
             VERS_LAUNCH_CHECK(ctx);
         }
         std::vector<uint64_t> off((size_t)km->C + 1);
@@ -363,10 +405,13 @@ static int32_t ivf_relayout(vers_ivf* ivf) {
     if (total >= 0xffffffffull) return fail(VERS_ERR_UNSUPPORTED, "ivf: more than 2^32-2 list slots per GPU shard");
     float* nlm = nullptr;
     uint64_t* nids = nullptr;
+    float* nnorm = nullptr;
     VERS_CUDA(cudaMalloc(&nlm, (size_t)total * ivf->ld * 4));
     cudaError_t e = cudaMalloc(&nids, (size_t)total * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&nnorm, (size_t)total * 4);
     if (e != cudaSuccess) {
         cudaFree(nlm);
+        cudaFree(nids);
         return fail(VERS_ERR_NOMEM, "ivf relayout: %s", cudaGetErrorString(e));
     }
     for (uint32_t c = 0; c < ivf->C && e == cudaSuccess; ++c) {
@@ -377,17 +422,23 @@ static int32_t ivf_relayout(vers_ivf* ivf) {
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(nids + noff[c], ivf->d_lm_ids + ivf->seg_off[c], (size_t)len * 8,
                                 cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(nnorm + noff[c], ivf->d_lm_norm + ivf->seg_off[c], (size_t)len * 4,
+                                cudaMemcpyDeviceToDevice, ctx->stream);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         cudaFree(nlm);
         cudaFree(nids);
+        cudaFree(nnorm);
         return fail(VERS_ERR_CUDA, "ivf relayout: %s", cudaGetErrorString(e));
     }
     cudaFree(ivf->d_lm);
     cudaFree(ivf->d_lm_ids);
+    cudaFree(ivf->d_lm_norm);
     ivf->d_lm = nlm;
     ivf->d_lm_ids = nids;
+    ivf->d_lm_norm = nnorm;
     ivf->cap_total = total;
     ivf->seg_off = noff;
     ivf->seg_cap = ncap;
@@ -405,156 +456,347 @@ static uint64_t ivf_max_chunks_per_query(const vers_ivf* ivf, uint32_t np) {
     return s;
 }
 
+// ---------------------------------------------------------------- candidate pass: merge, exact rerank, certificate
+// Error model.  u = 2^-24, n = ld.
+//   candidate value  d~ = ||x||^2 + ||q||^2 - 2 x.q with FMA / tree sums:  |d~ - d_true| <= E(x,q),
+//                    E = 1.01 * (2n + 8) * u * (||x||^2 + ||q||^2)
+//   reference value  d_ref (left-to-right fp32, base.rs:119-126):          d_ref >= d_true * (1 - (n + 3) u)
+// A row that is NOT exactly re-ranked has d~ >= bound, hence d_ref >= (bound - Emax) * (1 - (n+3)u) =: lower.
+// If lower > (exact distance of the k-th re-ranked row) no such row can enter or tie the top-k: certified.
+// Otherwise the query is flagged and redone by the exact-order scan.
+
+// one warp per query: top-M by (key, position) over the query's partial lists; bound = the smallest key any
+// non-selected row can have = min(last key of every FULL partial list, M-th merged key if the merged list is full)
+__global__ void __launch_bounds__(128)
+    cand_merge_kernel(const float* __restrict__ part_d, const uint32_t* __restrict__ part_p,
+                      const uint64_t* __restrict__ pair_chunk_off, uint32_t nq, uint32_t np, uint32_t M,
+                      uint32_t nsplit, uint32_t* __restrict__ cand_pos, float* __restrict__ cand_bound) {
+    extern __shared__ __align__(16) unsigned char csm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * 4 + warp;
+    if (q >= nq) return;
+    uint32_t* sp = reinterpret_cast<uint32_t*>(csm) + (size_t)warp * M;
+    float* sd = reinterpret_cast<float*>(csm + (size_t)4 * M * 4) + (size_t)warp * M;
+    for (uint32_t e = lane; e < M; e += 32) {
+        sd[e] = __int_as_float(0x7f800000);
+        sp[e] = 0xffffffffu;
+    }
+    __syncwarp();
+    const uint64_t beg = pair_chunk_off[(uint64_t)q * np] * nsplit * M;
+    const uint64_t end = pair_chunk_off[(uint64_t)(q + 1) * np] * nsplit * M;
+    float tfull = __int_as_float(0x7f800000);
+    for (uint64_t e0 = beg; e0 < end; e0 += 32) {
+        uint64_t e = e0 + lane;  // (end - beg) is a multiple of M, M a multiple of 32
+        uint32_t pp = part_p[e];
+        float v = part_d[e];
+        bool live = pp != 0xffffffffu;
+        if (live && ((e - beg) % M) == M - 1) tfull = fminf(tfull, v);  // last slot of a full partial list
+        while (true) {
+            bool pass = live && entry_less<uint32_t>(v, pp, sd[M - 1], sp[M - 1]);
+            unsigned m = __ballot_sync(FULL_MASK, pass);
+            if (!m) break;
+            int src = __ffs(m) - 1;
+            float bv = __shfl_sync(FULL_MASK, v, src);
+            uint32_t bp = __shfl_sync(FULL_MASK, pp, src);
+            warp_topk_insert<uint32_t>(sd, sp, (int)M, bv, bp, lane);
+            if (lane == src) live = false;
+        }
+    }
+    for (int o = 16; o; o >>= 1) tfull = fminf(tfull, __shfl_xor_sync(FULL_MASK, tfull, o));
+    for (uint32_t e = lane; e < M; e += 32) cand_pos[(uint64_t)q * M + e] = sp[e];
+    if (lane == 0) {
+        float b = tfull;
+        if (sp[M - 1] != 0xffffffffu) b = fminf(b, sd[M - 1]);
+        cand_bound[q] = b;
+    }
+}
+
+// one warp per query: exact-order l2sq of the M candidates (lane = candidate, strictly sequential over the
+// dimensions like base.rs:119-126), top-k by (distance, id), certificate.
+constexpr int RERANK_QCHUNK = 256;  // query floats staged per step
+__global__ void __launch_bounds__(128)
+    rerank_certify_kernel(const float* __restrict__ lm, const uint64_t* __restrict__ lm_ids, uint32_t ld,
+                          const float* __restrict__ queries, uint32_t nq, uint32_t k, uint32_t M,
+                          const uint32_t* __restrict__ cand_pos, const float* __restrict__ cand_bound,
+                          const uint32_t* __restrict__ nxmax_bits, uint64_t* out_ids, float* out_d, uint32_t* out_cnt,
+                          uint32_t* fail_flag, unsigned long long* stats) {
+    extern __shared__ __align__(16) unsigned char rsm2[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * 4 + warp;
+    if (q >= nq) return;
+    float* qs = reinterpret_cast<float*>(rsm2) + (size_t)warp * RERANK_QCHUNK;
+    uint64_t* sp = reinterpret_cast<uint64_t*>(rsm2 + (size_t)4 * RERANK_QCHUNK * 4) + (size_t)warp * k;
+    float* sd = reinterpret_cast<float*>(rsm2 + (size_t)4 * RERANK_QCHUNK * 4 + (size_t)4 * k * 8) + (size_t)warp * k;
+    for (uint32_t e = lane; e < k; e += 32) {
+        sd[e] = __int_as_float(0x7f800000);
+        sp[e] = 0xffffffffffffffffull;
+    }
+    const float* qrow = queries + (uint64_t)q * ld;
+    float nq2 = 0.0f;  // ||q||^2, lane-partial
+    uint32_t reranked = 0;
+    for (uint32_t c0 = 0; c0 < M; c0 += 32) {
+        const uint32_t pos = cand_pos[(uint64_t)q * M + c0 + lane];
+        const bool live = pos != 0xffffffffu;
+        const float4* row = reinterpret_cast<const float4*>(lm + (uint64_t)(live ? pos : 0) * ld);
+        float s = 0.0f;
+        for (uint32_t k0 = 0; k0 < ld; k0 += RERANK_QCHUNK) {
+            const uint32_t kn = min((uint32_t)RERANK_QCHUNK, ld - k0);  // multiple of 4
+            __syncwarp();
+            for (uint32_t i = lane; i < kn; i += 32) {
+                float v = qrow[k0 + i];
+                qs[i] = v;
+                if (c0 == 0) nq2 = __fmaf_rn(v, v, nq2);
+            }
+            __syncwarp();
+            if (live) {
+                for (uint32_t i = 0; i < kn; i += 4) {
+                    float4 a = row[(k0 + i) >> 2];
+                    float4 b = *reinterpret_cast<const float4*>(qs + i);
+                    float t;
+                    t = __fsub_rn(a.x, b.x); s = __fadd_rn(s, __fmul_rn(t, t));
+                    t = __fsub_rn(a.y, b.y); s = __fadd_rn(s, __fmul_rn(t, t));
+                    t = __fsub_rn(a.z, b.z); s = __fadd_rn(s, __fmul_rn(t, t));
+                    t = __fsub_rn(a.w, b.w); s = __fadd_rn(s, __fmul_rn(t, t));
+                }
+            }
+        }
+        reranked += __popc(__ballot_sync(FULL_MASK, live));
+        uint64_t id = live ? lm_ids[pos] : 0xffffffffffffffffull;
+        bool pend = live;
+        while (true) {
+            bool pass = pend && entry_less<uint64_t>(s, id, sd[k - 1], sp[k - 1]);
+            unsigned m = __ballot_sync(FULL_MASK, pass);
+            if (!m) break;
+            int src = __ffs(m) - 1;
+            float bv = __shfl_sync(FULL_MASK, s, src);
+            uint64_t bid = __shfl_sync(FULL_MASK, id, src);
+            warp_topk_insert<uint64_t>(sd, sp, (int)k, bv, bid, lane);
+            if (lane == src) pend = false;
+        }
+    }
+    for (int o = 16; o; o >>= 1) nq2 += __shfl_xor_sync(FULL_MASK, nq2, o);
+    uint32_t cnt = 0;
+    for (uint32_t e0 = 0; e0 < k; e0 += 32) {
+        uint32_t e = e0 + lane;
+        bool have = false;
+        if (e < k) {
+            out_ids[(uint64_t)q * k + e] = sp[e];
+            out_d[(uint64_t)q * k + e] = sd[e];
+            have = sp[e] != 0xffffffffffffffffull;
+        }
+        cnt += __popc(__ballot_sync(FULL_MASK, have));
+    }
+    if (lane == 0) {
+        if (out_cnt) out_cnt[q] = cnt;
+        const float bound = cand_bound[q];  // key bound: d~ = key + ||q||^2
+        bool certified;
+        if (bound == __int_as_float(0x7f800000)) {
+            certified = true;  // every row of the probed lists was re-ranked exactly
+        } else if (cnt < k) {
+            certified = false;
+        } else {
+            const double u = 5.9604644775390625e-08;  // 2^-24
+            const double nxmax = (double)__uint_as_float(*nxmax_bits);
+            const double E = 1.01 * (2.0 * ld + 8.0) * u * (nxmax + (double)nq2);
+            const double lower = ((double)bound + (double)nq2 - E) * (1.0 - (ld + 3.0) * u);
+            certified = lower > (double)sd[k - 1];
+        }
+        fail_flag[q] = certified ? 0u : 1u;
+        if (!certified) atomicAdd(&stats[4], 1ull);
+        atomicAdd(&stats[5], (unsigned long long)reranked);
+    }
+}
+
+// ---------------------------------------------------------------- host: one batched search
+struct SearchBufs {
+    uint64_t* probe_ids;
+    float* probe_d;
+    uint32_t *lq_cnt, *cursor, *item_cnt, *pair_nch, *lq_query, *lq_pair, *used, *fail_flag, *cand_pos;
+    uint64_t *lq_off, *item_off, *pair_chunk_off;
+    unsigned long long* counter;  // [0] work counter, [1] short flag
+    float* cand_bound;
+    float* part_d;
+    uint32_t* part_p;
+};
+
+static int32_t run_group(vers_ivf* ivf, const SearchBufs& b, uint32_t nq, uint32_t np, const uint32_t* used,
+                         const uint32_t* qmask, bool record_stats) {
+    vers_ctx* ctx = ivf->ctx;
+    const uint64_t npairs = (uint64_t)nq * np;
+    VERS_CUDA(cudaMemsetAsync(b.lq_cnt, 0, (size_t)ivf->C * 4, ctx->stream));
+    VERS_CUDA(cudaMemsetAsync(b.cursor, 0, (size_t)ivf->C * 4, ctx->stream));
+    VERS_CUDA(cudaMemsetAsync(b.counter, 0, 8, ctx->stream));
+    GroupParams g;
+    g.probe_ids = b.probe_ids;
+    g.seg_len = ivf->d_seg_len;
+    g.used = used;
+    g.qmask = qmask;
+    g.nq = nq;
+    g.np = np;
+    g.C = ivf->C;
+    g.lq_cnt = b.lq_cnt;
+    g.pair_nch = b.pair_nch;
+    g.item_cnt = b.item_cnt;
+    g.lq_off = b.lq_off;
+    g.cursor = b.cursor;
+    g.stats = record_stats ? ivf->d_stats : nullptr;
+    g.lq_query = b.lq_query;
+    g.lq_pair = b.lq_pair;
+    group_count_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, ctx->stream>>>(g);
+    VERS_LAUNCH_CHECK(ctx);
+    group_items_kernel<<<(unsigned)ceil_div(ivf->C, 256), 256, 0, ctx->stream>>>(g);
+    VERS_LAUNCH_CHECK(ctx);
+    VERS_TRY(launch_exclusive_scan(ctx, b.lq_cnt, ivf->C, b.lq_off));
+    VERS_TRY(launch_exclusive_scan(ctx, b.item_cnt, ivf->C, b.item_off));
+    VERS_TRY(launch_exclusive_scan(ctx, b.pair_nch, npairs, b.pair_chunk_off));
+    group_fill_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, ctx->stream>>>(g);
+    VERS_LAUNCH_CHECK(ctx);
+    return VERS_OK;
+}
+
+template <class Cfg, int MODE>
+static int32_t run_list_scan(vers_ivf* ivf, const SearchBufs& b, const float* d_queries, uint32_t nq, uint32_t klist) {
+    vers_ctx* ctx = ivf->ctx;
+    ListScanParams lp;
+    lp.lm = ivf->d_lm;
+    lp.queries = d_queries;
+    lp.ld = ivf->ld;
+    lp.C = ivf->C;
+    lp.k = klist;
+    lp.kpad = round_up(klist, 32);
+    lp.seg_off = ivf->d_seg_off;
+    lp.seg_len = ivf->d_seg_len;
+    lp.lq_query = b.lq_query;
+    lp.lq_pair = b.lq_pair;
+    lp.lq_off = b.lq_off;
+    lp.item_off = b.item_off;
+    lp.pair_chunk_off = b.pair_chunk_off;
+    lp.nq = nq;
+    lp.part_d = b.part_d;
+    lp.part_p = b.part_p;
+    lp.counter = b.counter;
+    lp.lm_norm = ivf->d_lm_norm;
+    auto kern = list_scan_kernel<Cfg, MODE>;
+    size_t smem = scan_smem_bytes(Cfg::TILE_FLOATS, Cfg::NLISTS, lp.kpad);
+    VERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FamilyTimer ft(ctx, KF_LIST_SCAN);
+    kern<<<ctx->sm_count * (MODE == 0 ? 2 : 1), Cfg::NT, smem, ctx->stream>>>(lp);
+    VERS_LAUNCH_CHECK(ctx);
+    return VERS_OK;
+}
+
 static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint32_t nq, uint32_t k, uint32_t nprobe,
                                      uint64_t* d_ids, float* d_d, uint32_t* d_cnt) {
     vers_ctx* ctx = ivf->ctx;
     const bool ref_mode = nprobe == 0;
     const uint32_t np = ref_mode ? std::min<uint32_t>(ivf->C, VERS_MAX_TOPK) : std::min<uint32_t>(nprobe, ivf->C);
     if (np > VERS_MAX_TOPK) return fail(VERS_ERR_UNSUPPORTED, "nprobe %u > %u", np, VERS_MAX_TOPK);
+    // candidate list length of the approximate pass; beyond 64 the private lists no longer fit next to the tiles
+    const uint32_t M = round_up(k + 16, 32);
+    const bool approx = !ref_mode && ivf->mode == 0 && M <= 64;
     const uint64_t npairs = (uint64_t)nq * np;
-    const uint64_t max_chunks = (uint64_t)nq * ivf_max_chunks_per_query(ivf, np);
-    const size_t entries = (size_t)std::max<uint64_t>(max_chunks, 1) * ScanCfg::NSPLIT * k;
+    const uint64_t max_chunks = std::max<uint64_t>((uint64_t)nq * ivf_max_chunks_per_query(ivf, np), 1);
+    size_t entries = (size_t)max_chunks * ScanCfg::NSPLIT * k;
+    if (approx) entries = std::max(entries, (size_t)max_chunks * StreamCfg::NSPLIT * M);
 
     // the probe carves its partial buffers from the front of the arena, ours come after it
     const ScanPlan probe_plan = scan_topk_plan(ctx, ivf->C, nq, np);
-    ScratchCarver plan(nullptr);
     const size_t probe_reserve = (probe_plan.bytes + 255) & ~size_t(255);
-    plan.off = probe_reserve;
-    plan.plan<uint64_t>(npairs);                   // probe ids
-    plan.plan<float>(npairs);                      // probe dists
-    plan.plan<uint32_t>(ivf->C);                   // lq_cnt
-    plan.plan<uint32_t>(ivf->C);                   // cursor
-    plan.plan<uint32_t>(ivf->C);                   // item_cnt
-    plan.plan<uint32_t>(npairs);                   // pair_nch
-    plan.plan<uint64_t>((size_t)ivf->C + 1);       // lq_off
-    plan.plan<uint64_t>((size_t)ivf->C + 1);       // item_off
-    plan.plan<uint64_t>(npairs + 1);               // pair_chunk_off
-    plan.plan<uint32_t>(npairs);                   // lq_query
-    plan.plan<uint32_t>(npairs);                   // lq_pair
-    plan.plan<uint32_t>(nq);                       // used
-    plan.plan<unsigned long long>(2);              // counter, flag
-    plan.plan<float>(entries);
-    plan.plan<uint32_t>(entries);
-    VERS_TRY(scratch_reserve(ctx, plan.off + 4096));
-
-    // 1. probe
+    SearchBufs b;
+    auto carve = [&](ScratchCarver& sc) {
+        sc.off = probe_reserve;
+        b.probe_ids = sc.take<uint64_t>(npairs);
+        b.probe_d = sc.take<float>(npairs);
+        b.lq_cnt = sc.take<uint32_t>(ivf->C);
+        b.cursor = sc.take<uint32_t>(ivf->C);
+        b.item_cnt = sc.take<uint32_t>(ivf->C);
+        b.pair_nch = sc.take<uint32_t>(npairs);
+        b.lq_off = sc.take<uint64_t>((size_t)ivf->C + 1);
+        b.item_off = sc.take<uint64_t>((size_t)ivf->C + 1);
+        b.pair_chunk_off = sc.take<uint64_t>(npairs + 1);
+        b.lq_query = sc.take<uint32_t>(npairs);
+        b.lq_pair = sc.take<uint32_t>(npairs);
+        b.used = sc.take<uint32_t>(nq);
+        b.fail_flag = sc.take<uint32_t>(nq);
+        b.cand_pos = sc.take<uint32_t>((size_t)nq * M);
+        b.cand_bound = sc.take<float>(nq);
+        b.counter = sc.take<unsigned long long>(2);
+        b.part_d = sc.take<float>(entries);
+        b.part_p = sc.take<uint32_t>(entries);
+    };
+    {
+        ScratchCarver plan(nullptr);
+        carve(plan);
+        VERS_TRY(scratch_reserve(ctx, plan.off + 4096));
+    }
     ScratchCarver sc(ctx->scratch);
-    sc.off = probe_reserve;
-    uint64_t* probe_ids = sc.take<uint64_t>(npairs);
-    float* probe_d = sc.take<float>(npairs);
-    uint32_t* lq_cnt = sc.take<uint32_t>(ivf->C);
-    uint32_t* cursor = sc.take<uint32_t>(ivf->C);
-    uint32_t* item_cnt = sc.take<uint32_t>(ivf->C);
-    uint32_t* pair_nch = sc.take<uint32_t>(npairs);
-    uint64_t* lq_off = sc.take<uint64_t>((size_t)ivf->C + 1);
-    uint64_t* item_off = sc.take<uint64_t>((size_t)ivf->C + 1);
-    uint64_t* pair_chunk_off = sc.take<uint64_t>(npairs + 1);
-    uint32_t* lq_query = sc.take<uint32_t>(npairs);
-    uint32_t* lq_pair = sc.take<uint32_t>(npairs);
-    uint32_t* used = sc.take<uint32_t>(nq);
-    unsigned long long* counter = sc.take<unsigned long long>(2);
-    float* part_d = sc.take<float>(entries);
-    uint32_t* part_p = sc.take<uint32_t>(entries);
+    carve(sc);
 
+    // 1. probe: exact-order distances to every centroid, top-np by (distance, centroid index)
     RowSrc CA{ivf->d_cents, nullptr, ivf->ld, ivf->C};
     RowSrc QB{d_queries, nullptr, ivf->ld, nq};
     VERS_TRY(scan_topk_run(ctx, probe_plan, ctx->scratch, CA, QB, nq, ivf->ld, np, VERS_METRIC_L2SQ, nullptr, 0,
-                           probe_ids, probe_d, nullptr, KF_PROBE));
+                           b.probe_ids, b.probe_d, nullptr, KF_PROBE));
+    VERS_CUDA(cudaMemsetAsync(ivf->d_stats, 0, 64, ctx->stream));
+    VERS_CUDA(cudaMemsetAsync(b.counter, 0, 16, ctx->stream));
+    uint32_t* short_flag = reinterpret_cast<uint32_t*>(b.counter + 1);
 
-    // 2. group pairs by list
-    VERS_CUDA(cudaMemsetAsync(lq_cnt, 0, (size_t)ivf->C * 4, ctx->stream));
-    VERS_CUDA(cudaMemsetAsync(cursor, 0, (size_t)ivf->C * 4, ctx->stream));
-    VERS_CUDA(cudaMemsetAsync(counter, 0, 16, ctx->stream));
-    VERS_CUDA(cudaMemsetAsync(ivf->d_stats, 0, 32, ctx->stream));
-    uint32_t* short_flag = reinterpret_cast<uint32_t*>(counter + 1);
     if (ref_mode) {
-        ref_plan_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, ctx->stream>>>(probe_ids, ivf->d_seg_len, nq, np, k, used,
-                                                                             short_flag);
+        // the reference's nearest-list-plus-spill semantics, exact order everywhere
+        ref_plan_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, ctx->stream>>>(b.probe_ids, ivf->d_seg_len, nq, np, k,
+                                                                             b.used, short_flag);
         VERS_LAUNCH_CHECK(ctx);
-    }
-    GroupParams g;
-    g.probe_ids = probe_ids;
-    g.seg_len = ivf->d_seg_len;
-    g.used = ref_mode ? used : nullptr;
-    g.nq = nq;
-    g.np = np;
-    g.C = ivf->C;
-    g.lq_cnt = lq_cnt;
-    g.pair_nch = pair_nch;
-    g.item_cnt = item_cnt;
-    g.lq_off = lq_off;
-    g.cursor = cursor;
-    g.stats = ivf->d_stats;
-    g.lq_query = lq_query;
-    g.lq_pair = lq_pair;
-    group_count_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, ctx->stream>>>(g);
-    VERS_LAUNCH_CHECK(ctx);
-    group_items_kernel<<<(unsigned)ceil_div(ivf->C, 256), 256, 0, ctx->stream>>>(g);
-    VERS_LAUNCH_CHECK(ctx);
-    VERS_TRY(launch_exclusive_scan(ctx, lq_cnt, ivf->C, lq_off));
-    VERS_TRY(launch_exclusive_scan(ctx, item_cnt, ivf->C, item_off));
-    VERS_TRY(launch_exclusive_scan(ctx, pair_nch, npairs, pair_chunk_off));
-    group_fill_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, ctx->stream>>>(g);
-    VERS_LAUNCH_CHECK(ctx);
-
-    // 3. list scan
-    ListScanParams lp;
-    lp.lm = ivf->d_lm;
-    lp.queries = d_queries;
-    lp.ld = ivf->ld;
-    lp.C = ivf->C;
-    lp.k = k;
-    lp.kpad = round_up(k, 32);
-    lp.seg_off = ivf->d_seg_off;
-    lp.seg_len = ivf->d_seg_len;
-    lp.lq_query = lq_query;
-    lp.lq_pair = lq_pair;
-    lp.lq_off = lq_off;
-    lp.item_off = item_off;
-    lp.pair_chunk_off = pair_chunk_off;
-    lp.nq = nq;
-    lp.part_d = part_d;
-    lp.part_p = part_p;
-    lp.counter = counter;
-    {
-        size_t smem = scan_smem_bytes(ScanCfg::TILE_FLOATS, ScanCfg::NLISTS, lp.kpad);
-        VERS_CUDA(cudaFuncSetAttribute(list_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        FamilyTimer ft(ctx, KF_LIST_SCAN);
-        list_scan_kernel<<<ctx->sm_count * 2, ScanCfg::NT, smem, ctx->stream>>>(lp);
+        VERS_TRY(run_group(ivf, b, nq, np, b.used, nullptr, true));
+        VERS_TRY((run_list_scan<ScanCfg, 0>(ivf, b, d_queries, nq, k)));
+        ref_assemble_kernel<<<(unsigned)ceil_div(nq, 4), 128, (size_t)4 * k * 8, ctx->stream>>>(
+            b.part_d, b.part_p, b.pair_chunk_off, b.used, ivf->d_lm_ids, nq, np, k, ScanCfg::NSPLIT, d_ids, d_d, d_cnt);
         VERS_LAUNCH_CHECK(ctx);
+        uint32_t flag = 0;
+        VERS_CUDA(cudaMemcpyAsync(&flag, short_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        VERS_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (flag) {
+            if (np == ivf->C)
+                return fail(VERS_ERR_PANIC,
+                            "ivf_search: fewer than top_k rows reachable (index out of bounds at ivfflat.rs:169)");
+            return fail(VERS_ERR_UNSUPPORTED, "ivf_search: the %u nearest lists hold fewer than top_k rows", np);
+        }
+        return VERS_OK;
     }
 
-    // 4. merge
-    if (!ref_mode) {
-        MergeParams mp;
-        mp.part_d = part_d;
-        mp.part_p = part_p;
-        mp.seg = pair_chunk_off;
-        mp.seg_scale = (uint64_t)ScanCfg::NSPLIT * k;
-        mp.seg_stride = np;
-        mp.per_query = 0;
-        mp.map = ivf->d_lm_ids;
-        mp.id_base = 0;
-        mp.nq = nq;
-        mp.k = k;
-        mp.out_ids = d_ids;
-        mp.out_d = d_d;
-        mp.out_cnt = d_cnt;
-        return launch_merge(ctx, mp);
+    const uint32_t* qmask = nullptr;
+    if (approx) {
+        // 2a. candidate pass (FMA, HBM-streaming) -> top-M per query -> exact-order rerank -> certificate
+        VERS_TRY(run_group(ivf, b, nq, np, nullptr, nullptr, true));
+        VERS_TRY((run_list_scan<StreamCfg, 1>(ivf, b, d_queries, nq, M)));
+        cand_merge_kernel<<<(unsigned)ceil_div(nq, 4), 128, (size_t)4 * M * 8, ctx->stream>>>(
+            b.part_d, b.part_p, b.pair_chunk_off, nq, np, M, StreamCfg::NSPLIT, b.cand_pos, b.cand_bound);
+        VERS_LAUNCH_CHECK(ctx);
+        size_t rsm = (size_t)4 * RERANK_QCHUNK * 4 + (size_t)4 * k * 12;
+        rerank_certify_kernel<<<(unsigned)ceil_div(nq, 4), 128, rsm, ctx->stream>>>(
+            ivf->d_lm, ivf->d_lm_ids, ivf->ld, d_queries, nq, k, M, b.cand_pos, b.cand_bound, ivf->d_nxmax, d_ids, d_d,
+            d_cnt, b.fail_flag, ivf->d_stats);
+        VERS_LAUNCH_CHECK(ctx);
+        qmask = b.fail_flag;  // 2b. exact-order redo of the (rare) uncertified queries, no host round trip
     }
-    ref_assemble_kernel<<<(unsigned)ceil_div(nq, 4), 128, (size_t)4 * k * 8, ctx->stream>>>(
-        part_d, part_p, pair_chunk_off, used, ivf->d_lm_ids, nq, np, k, ScanCfg::NSPLIT, d_ids, d_d, d_cnt);
-    VERS_LAUNCH_CHECK(ctx);
-    uint32_t flag = 0;
-    VERS_CUDA(cudaMemcpyAsync(&flag, short_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    VERS_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (flag) {
-        if (np == ivf->C)
-            return fail(VERS_ERR_PANIC,
-                        "ivf_search: fewer than top_k rows reachable (index out of bounds at ivfflat.rs:169)");
-        return fail(VERS_ERR_UNSUPPORTED, "ivf_search: the %u nearest lists hold fewer than top_k rows", np);
-    }
-    return VERS_OK;
+    // 2b / exact mode: exact-order scan of the probed lists, merge by (distance, id)
+    VERS_TRY(run_group(ivf, b, nq, np, nullptr, qmask, !approx));
+    VERS_TRY((run_list_scan<ScanCfg, 0>(ivf, b, d_queries, nq, k)));
+    MergeParams mp;
+    mp.part_d = b.part_d;
+    mp.part_p = b.part_p;
+    mp.seg = b.pair_chunk_off;
+    mp.seg_scale = (uint64_t)ScanCfg::NSPLIT * k;
+    mp.seg_stride = np;
+    mp.per_query = 0;
+    mp.map = ivf->d_lm_ids;
+    mp.id_base = 0;
+    mp.nq = nq;
+    mp.k = k;
+    mp.out_ids = d_ids;
+    mp.out_d = d_d;
+    mp.out_cnt = d_cnt;
+    mp.qmask = qmask;
+    return launch_merge(ctx, mp);
 }
 
 }  // namespace vers
@@ -572,6 +814,8 @@ extern "C" int32_t vers_ivf_free(vers_ivf* ivf) {
     cudaFree(ivf->d_seg_len);
     cudaFree(ivf->d_assign);
     cudaFree(ivf->d_stats);
+    cudaFree(ivf->d_lm_norm);
+    cudaFree(ivf->d_nxmax);
     delete ivf;
     return VERS_OK;
 }
@@ -778,10 +1022,16 @@ extern "C" int32_t vers_ivf_get_list(const vers_ivf* ivf, uint32_t list, uint64_
     return VERS_OK;
 }
 
-extern "C" int32_t vers_ivf_last_search_stats(const vers_ivf* ivf, uint64_t out[4]) {
+extern "C" int32_t vers_ivf_set_mode(vers_ivf* ivf, int32_t mode) {
+    if (!ivf || mode < 0 || mode > 1) return fail(VERS_ERR_ARG, "ivf_set_mode: bad argument");
+    ivf->mode = mode;
+    return VERS_OK;
+}
+
+extern "C" int32_t vers_ivf_last_search_stats(const vers_ivf* ivf, uint64_t out[8]) {
     if (!ivf || !out) return fail(VERS_ERR_ARG, "ivf_last_search_stats: null");
     VERS_CUDA(cudaSetDevice(ivf->ctx->device));
-    VERS_CUDA(cudaMemcpyAsync(out, ivf->d_stats, 32, cudaMemcpyDeviceToHost, ivf->ctx->stream));
+    VERS_CUDA(cudaMemcpyAsync(out, ivf->d_stats, 64, cudaMemcpyDeviceToHost, ivf->ctx->stream));
     VERS_CUDA(cudaStreamSynchronize(ivf->ctx->stream));
     return VERS_OK;
 }
@@ -822,6 +1072,11 @@ extern "C" int32_t vers_ivf_add(vers_ivf* ivf, const float* embedding, uint64_t 
                                             cudaMemcpyDeviceToDevice, ctx->stream);
             if (e == cudaSuccess)
                 e = cudaMemcpyAsync(ivf->d_lm_ids + pos, &new_id, 8, cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) {
+                rownorm_kernel<<<1, 32, 0, ctx->stream>>>(ivf->d_lm, ivf->ld, pos, 1, ivf->d_lm_norm, ivf->d_nxmax);
+                ctx->launches += 1;
+                e = cudaGetLastError();
+            }
             ivf->seg_len[c] += 1;
             if (e == cudaSuccess)
                 e = cudaMemcpyAsync(ivf->d_seg_len + c, &ivf->seg_len[c], 4, cudaMemcpyHostToDevice, ctx->stream);

@@ -31,6 +31,7 @@ struct MergeParams {
     uint64_t* out_ids;      // [nq][k]
     float* out_d;           // [nq][k]
     uint32_t* out_cnt;      // [nq] optional
+    const uint32_t* qmask;  // optional [nq]: only queries with a non-zero mask are merged/written
 };
 
 // scan rows [0, A.n) of A against nq queries (B), exact order; writes the global top-k per query.

@@ -335,10 +335,14 @@ class IVFFlatIndex:
         return (ids, rows) if with_rows else ids
 
     def last_search_stats(self) -> dict:
-        out = np.zeros(4, np.uint64)
+        out = np.zeros(8, np.uint64)
         check(lib().vers_ivf_last_search_stats(self.h, ptr(out)))
         return dict(distinct_list_rows=int(out[0]), pair_rows=int(out[1]), work_items=int(out[2]),
-                    lists_touched=int(out[3]))
+                    lists_touched=int(out[3]), uncertified_queries=int(out[4]), reranked=int(out[5]))
+
+    def set_mode(self, exact: bool):
+        """False (default): candidate pass + exact-order rerank + certificate; True: exact order everywhere"""
+        check(lib().vers_ivf_set_mode(self.h, int(bool(exact))))
 
     @property
     def ids(self) -> List[np.ndarray]:

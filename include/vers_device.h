@@ -60,7 +60,8 @@ int32_t vers_ctx_sync(vers_ctx* ctx);
 int32_t vers_ctx_launch_count(vers_ctx* ctx, uint64_t* out);
 /* device time of each kernel family, measured with CUDA event pairs recorded on ctx's stream around every launch
  * while timing is on (up to 512 launches per family per window) — bench.py's live roofline numbers.
- * which: 0 = list scan, 1 = flat scan, 2 = k-means assign, 3 = k-means sums, 4 = lsh hash, 5 = probe.
+ * which: 0 = list scan (exact order), 1 = flat scan, 2 = k-means assign, 3 = k-means sums, 4 = lsh hash, 5 = probe,
+ * 6 = list scan candidate pass, 7 = exact rerank + certificate.
  * enable_timing(on) starts a new window; kernel_ms sums the window (synchronises on the recorded events). */
 int32_t vers_ctx_enable_timing(vers_ctx* ctx, int32_t on);
 int32_t vers_ctx_kernel_ms(vers_ctx* ctx, int32_t which, float* total_ms, uint64_t* timed_launches);

@@ -14,7 +14,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_PANIC, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 METRIC_L2SQ, METRIC_COSINE = 0, 1
 MAX_TOPK = 128
 SYNTH_UNIFORM, SYNTH_CLUSTERED = 0, 1
-KF_LIST_SCAN, KF_FLAT_SCAN, KF_ASSIGN, KF_SUMS, KF_LSH_HASH, KF_PROBE = range(6)
+KF_LIST_SCAN, KF_FLAT_SCAN, KF_ASSIGN, KF_SUMS, KF_LSH_HASH, KF_PROBE, KF_CAND_SCAN, KF_RERANK = range(8)
 
 
 class VersError(RuntimeError):

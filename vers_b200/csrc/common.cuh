@@ -34,7 +34,7 @@ int32_t fail(int32_t code, const char* fmt, ...);
     } while (0)
 
 // kernel families for vers_ctx_last_kernel_ms
-enum KernelFamily { KF_LIST_SCAN = 0, KF_FLAT_SCAN = 1, KF_ASSIGN = 2, KF_SUMS = 3, KF_LSH_HASH = 4, KF_PROBE = 5, KF_COUNT = 6 };
+enum KernelFamily { KF_LIST_SCAN = 0, KF_FLAT_SCAN = 1, KF_ASSIGN = 2, KF_SUMS = 3, KF_LSH_HASH = 4, KF_PROBE = 5, KF_CAND_SCAN = 6, KF_RERANK = 7, KF_COUNT = 8 };
 
 }  // namespace vers
 

@@ -28,11 +28,11 @@ struct RowSrc {
     uint64_t n;           // number of rows addressable through this source
 };
 
-template <int TA_, int TB_, int MA_, int MB_>
+template <int TA_, int TB_, int MA_, int MB_, int STAGES_ = 2>
 struct TileCfg {
     static constexpr int TA = TA_, TB = TB_, MA = MA_, MB = MB_;
     static constexpr int NTA = TA / MA, NTB = TB / MB, NT = NTA * NTB;
-    static constexpr int KC = 32, LDS = KC + 4, STAGES = 2;
+    static constexpr int KC = 32, LDS = KC + 4, STAGES = STAGES_;
     static constexpr int TILE_FLOATS = STAGES * (TA + TB) * LDS;
     static constexpr int NWARPS = NT / 32;
     static constexpr int LANES_PER_TB = NTA < 32 ? NTA : 32;    // lanes of a warp that share one tb
@@ -50,7 +50,7 @@ using WideCfg = TileCfg<128, 64, 8, 4>;
 using NarrowCfg = TileCfg<256, 8, 4, 2>;
 // candidate pass of the inverted-list scan: every thread owns 2 rows x all 8 queries of the group, so each row
 // element is read from shared memory exactly once and the 8 query values are warp-wide broadcasts
-using StreamCfg = TileCfg<512, 8, 2, 8>;
+using StreamCfg = TileCfg<256, 8, 1, 8, 2>;  // 2 CTAs/SM (16 warps): measured best of {512x2, 256x1} x {2,4 stages}
 
 template <int OP>
 __device__ __forceinline__ void pair_step(float& acc, float a, float b) {
@@ -128,47 +128,53 @@ __device__ __forceinline__ void tile_compute(float (&acc)[Cfg::MA][Cfg::MB], con
         cp_async_commit();
     };
 
+    // STAGES-deep cp.async ring: chunks c+1 .. c+STAGES-1 are in flight while chunk c is consumed, one
+    // __syncthreads per chunk (the refill of a buffer is issued after the barrier that retires its last reader)
+    constexpr int S = Cfg::STAGES;
     const uint32_t nchunks = (ld + KC - 1) / KC;
-    load_chunk(0, 0);
-    for (uint32_t c = 0; c < nchunks; ++c) {
-        if (c + 1 < nchunks) {
-            load_chunk((c + 1) & 1, (c + 1) * KC);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
-        const float* As = smem + (c & 1) * (TA + TB) * LDS + ta * LDS;
-        const float* Bs = smem + (c & 1) * (TA + TB) * LDS + TA * LDS + tb * LDS;
-        const int kmax = (int)min((uint32_t)KC, ld - c * KC);  // multiple of 4
-#pragma unroll 2
-        for (int kk = 0; kk < KC; kk += 4) {
-            if (kk < kmax) {
-                float4 a[MA], b[MB];
 #pragma unroll
-                for (int i = 0; i < MA; ++i) a[i] = *reinterpret_cast<const float4*>(As + i * NTA * LDS + kk);
-#pragma unroll
-                for (int j = 0; j < MB; ++j) b[j] = *reinterpret_cast<const float4*>(Bs + j * NTB * LDS + kk);
-#pragma unroll
-                for (int i = 0; i < MA; ++i)
-#pragma unroll
-                    for (int j = 0; j < MB; ++j) pair_step<OP>(acc[i][j], a[i].x, b[j].x);
-#pragma unroll
-                for (int i = 0; i < MA; ++i)
-#pragma unroll
-                    for (int j = 0; j < MB; ++j) pair_step<OP>(acc[i][j], a[i].y, b[j].y);
-#pragma unroll
-                for (int i = 0; i < MA; ++i)
-#pragma unroll
-                    for (int j = 0; j < MB; ++j) pair_step<OP>(acc[i][j], a[i].z, b[j].z);
-#pragma unroll
-                for (int i = 0; i < MA; ++i)
-#pragma unroll
-                    for (int j = 0; j < MB; ++j) pair_step<OP>(acc[i][j], a[i].w, b[j].w);
-            }
-        }
-        __syncthreads();
+    for (int st = 0; st < S - 1; ++st) {
+        if ((uint32_t)st < nchunks) load_chunk(st, (uint32_t)st * KC); else cp_async_commit();
     }
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        cp_async_wait<S - 2>();
+        __syncthreads();
+        if (c + S - 1 < nchunks) load_chunk((int)((c + S - 1) % S), (c + S - 1) * KC); else cp_async_commit();
+        const float* As = smem + (int)(c % S) * (TA + TB) * LDS + ta * LDS;
+        const float* Bs = smem + (int)(c % S) * (TA + TB) * LDS + TA * LDS + tb * LDS;
+        const int kmax = (int)min((uint32_t)KC, ld - c * KC);  // multiple of 4
+        auto kstep = [&](int kk) {
+            float4 a[MA], b[MB];
+#pragma unroll
+            for (int i = 0; i < MA; ++i) a[i] = *reinterpret_cast<const float4*>(As + i * NTA * LDS + kk);
+#pragma unroll
+            for (int j = 0; j < MB; ++j) b[j] = *reinterpret_cast<const float4*>(Bs + j * NTB * LDS + kk);
+#pragma unroll
+            for (int i = 0; i < MA; ++i)
+#pragma unroll
+                for (int j = 0; j < MB; ++j) pair_step<OP>(acc[i][j], a[i].x, b[j].x);
+#pragma unroll
+            for (int i = 0; i < MA; ++i)
+#pragma unroll
+                for (int j = 0; j < MB; ++j) pair_step<OP>(acc[i][j], a[i].y, b[j].y);
+#pragma unroll
+            for (int i = 0; i < MA; ++i)
+#pragma unroll
+                for (int j = 0; j < MB; ++j) pair_step<OP>(acc[i][j], a[i].z, b[j].z);
+#pragma unroll
+            for (int i = 0; i < MA; ++i)
+#pragma unroll
+                for (int j = 0; j < MB; ++j) pair_step<OP>(acc[i][j], a[i].w, b[j].w);
+        };
+        if (kmax == KC) {  // full chunk: branch-free so the loads of step k+1 can be hoisted over the math of step k
+#pragma unroll(Cfg::MA * Cfg::MB <= 16 ? 8 : 2)
+            for (int kk = 0; kk < KC; kk += 4) kstep(kk);
+        } else {
+            for (int kk = 0; kk < kmax; kk += 4) kstep(kk);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();  // shared memory is free on return
 }
 
 // ---------------------------------------------------------------- warp top-k over (distance, position)

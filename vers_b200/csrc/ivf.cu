@@ -168,7 +168,7 @@ struct ListScanParams {
 // MODE 0: exact order (OP_L2SQ), private top-k by (distance, position)
 // MODE 1: candidate pass (FMA dot, key = ||x||^2 - 2 x.q), private top-M by (key, position); p.k == p.kpad == M
 template <class Cfg, int MODE>
-__global__ void __launch_bounds__(Cfg::NT, MODE == 0 ? 2 : 1) list_scan_kernel(ListScanParams p) {
+__global__ void __launch_bounds__(Cfg::NT, (Cfg::TILE_FLOATS * 4 > 110 * 1024) ? 1 : 2) list_scan_kernel(ListScanParams p) {
     extern __shared__ __align__(16) float smem[];
     float* list_d = smem + Cfg::TILE_FLOATS;
     uint32_t* list_p = reinterpret_cast<uint32_t*>(list_d + Cfg::NLISTS * p.kpad);
@@ -207,28 +207,86 @@ __global__ void __launch_bounds__(Cfg::NT, MODE == 0 ? 2 : 1) list_scan_kernel(L
         RowSrc B{p.queries, p.lq_query + q0, p.ld, nB};
         const uint64_t r0 = (uint64_t)chunk * LIST_CHUNK_ROWS;
         const uint64_t r1 = min((uint64_t)len, r0 + LIST_CHUNK_ROWS);
-        lists_init<Cfg>(list_d, list_p, p.kpad);
-        for (uint64_t a0 = r0; a0 < r1; a0 += Cfg::TA) {
-            float acc[Cfg::MA][Cfg::MB];
-            if (MODE == 0) {
+        if (MODE == 0) {
+            lists_init<Cfg>(list_d, list_p, p.kpad);
+            for (uint64_t a0 = r0; a0 < r1; a0 += Cfg::TA) {
+                float acc[Cfg::MA][Cfg::MB];
                 tile_compute<Cfg, OP_L2SQ>(acc, A, a0, B, 0, p.ld, smem);
                 tile_select_topk<Cfg, 0>(acc, a0, r1, 0, nB, p.k, p.kpad, list_d, list_p, base_pos);
-            } else {
-                tile_compute<Cfg, OP_DOT_FMA>(acc, A, a0, B, 0, p.ld, smem);
-                tile_select_topk<Cfg, 2>(acc, a0, r1, 0, nB, p.k, p.kpad, list_d, list_p, base_pos, p.lm_norm);
             }
-        }
-        __syncwarp();
-        constexpr int SLOTS_PER_WARP = Cfg::TBS_PER_WARP * Cfg::MB;
-        for (int s = 0; s < SLOTS_PER_WARP; ++s) {
-            int slot = warp * SLOTS_PER_WARP + s, col, split;
-            slot_to_col<Cfg>(slot, col, split);
-            if ((uint64_t)col >= nB) continue;
-            uint32_t pair = p.lq_pair[q0 + col];
-            uint64_t base = ((p.pair_chunk_off[pair] + chunk) * Cfg::NSPLIT + split) * p.k;
-            for (uint32_t e = lane; e < p.k; e += 32) {
-                p.part_d[base + e] = list_d[slot * p.kpad + e];
-                p.part_p[base + e] = list_p[slot * p.kpad + e];
+            __syncwarp();
+            constexpr int SLOTS_PER_WARP = Cfg::TBS_PER_WARP * Cfg::MB;
+            for (int s = 0; s < SLOTS_PER_WARP; ++s) {
+                int slot = warp * SLOTS_PER_WARP + s, col, split;
+                slot_to_col<Cfg>(slot, col, split);
+                if ((uint64_t)col >= nB) continue;
+                uint32_t pair = p.lq_pair[q0 + col];
+                uint64_t base = ((p.pair_chunk_off[pair] + chunk) * Cfg::NSPLIT + split) * p.k;
+                for (uint32_t e = lane; e < p.k; e += 32) {
+                    p.part_d[base + e] = list_d[slot * p.kpad + e];
+                    p.part_p[base + e] = list_p[slot * p.kpad + e];
+                }
+            }
+        } else {
+            // candidate pass: every warp keeps, per query column, a private top-32 by (key, position) IN REGISTERS
+            // (lane l holds the l-th smallest); an insert is one ballot + one shuffle-up.  Requires the layout of
+            // StreamCfg: all lanes of a warp share tb (= 0) and own all MB columns.
+            static_assert(MODE == 0 || (Cfg::TBS_PER_WARP == 1 && Cfg::NTB == 1), "register lists need StreamCfg");
+            float rl_d[Cfg::MB];
+            uint32_t rl_p[Cfg::MB];
+            float tau_d[Cfg::MB];
+            uint32_t tau_p[Cfg::MB];
+#pragma unroll
+            for (int j = 0; j < Cfg::MB; ++j) {
+                rl_d[j] = tau_d[j] = __int_as_float(0x7f800000);
+                rl_p[j] = tau_p[j] = 0xffffffffu;
+            }
+            const int ta = threadIdx.x % Cfg::NTA;
+            for (uint64_t a0 = r0; a0 < r1; a0 += Cfg::TA) {
+                float acc[Cfg::MA][Cfg::MB];
+                tile_compute<Cfg, OP_DOT_FMA>(acc, A, a0, B, 0, p.ld, smem);
+#pragma unroll
+                for (int i = 0; i < Cfg::MA; ++i) {
+                    const uint64_t row = a0 + (uint64_t)(ta + i * Cfg::NTA);
+                    const bool rowlive = row < r1;
+                    const uint32_t pos = (uint32_t)(row + base_pos);
+                    const float nx = rowlive ? __ldg(p.lm_norm + pos) : 0.0f;
+#pragma unroll
+                    for (int j = 0; j < Cfg::MB; ++j) {
+                        const float v = __fmaf_rn(-2.0f, acc[i][j], nx);  // ||x||^2 - 2 x.q
+                        bool live = rowlive && (uint64_t)j < nB;
+                        while (true) {
+                            bool pass = live && entry_less<uint32_t>(v, pos, tau_d[j], tau_p[j]);
+                            unsigned m = __ballot_sync(FULL_MASK, pass);
+                            if (!m) break;
+                            int src = __ffs(m) - 1;
+                            float cv = __shfl_sync(FULL_MASK, v, src);
+                            uint32_t cp = __shfl_sync(FULL_MASK, pos, src);
+                            int ins = __popc(__ballot_sync(FULL_MASK, entry_less<uint32_t>(rl_d[j], rl_p[j], cv, cp)));
+                            float ud = __shfl_up_sync(FULL_MASK, rl_d[j], 1);
+                            uint32_t up = __shfl_up_sync(FULL_MASK, rl_p[j], 1);
+                            if (lane > ins) {
+                                rl_d[j] = ud;
+                                rl_p[j] = up;
+                            } else if (lane == ins) {
+                                rl_d[j] = cv;
+                                rl_p[j] = cp;
+                            }
+                            tau_d[j] = __shfl_sync(FULL_MASK, rl_d[j], 31);
+                            tau_p[j] = __shfl_sync(FULL_MASK, rl_p[j], 31);
+                            if (lane == src) live = false;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < Cfg::MB; ++j) {
+                if ((uint64_t)j < nB) {
+                    uint32_t pair = p.lq_pair[q0 + j];
+                    uint64_t base = ((p.pair_chunk_off[pair] + chunk) * Cfg::NSPLIT + warp) * 32;
+                    p.part_d[base + lane] = rl_d[j];
+                    p.part_p[base + lane] = rl_p[j];
+                }
             }
         }
         __syncthreads();  // s_item / lists are rewritten by the next iteration
@@ -679,8 +737,8 @@ static int32_t run_list_scan(vers_ivf* ivf, const SearchBufs& b, const float* d_
     auto kern = list_scan_kernel<Cfg, MODE>;
     size_t smem = scan_smem_bytes(Cfg::TILE_FLOATS, Cfg::NLISTS, lp.kpad);
     VERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FamilyTimer ft(ctx, KF_LIST_SCAN);
-    kern<<<ctx->sm_count * (MODE == 0 ? 2 : 1), Cfg::NT, smem, ctx->stream>>>(lp);
+    FamilyTimer ft(ctx, MODE == 0 ? KF_LIST_SCAN : KF_CAND_SCAN);
+    kern<<<ctx->sm_count * ((Cfg::TILE_FLOATS * 4 > 110 * 1024) ? 1 : 2), Cfg::NT, smem, ctx->stream>>>(lp);
     VERS_LAUNCH_CHECK(ctx);
     return VERS_OK;
 }
@@ -691,9 +749,9 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
     const bool ref_mode = nprobe == 0;
     const uint32_t np = ref_mode ? std::min<uint32_t>(ivf->C, VERS_MAX_TOPK) : std::min<uint32_t>(nprobe, ivf->C);
     if (np > VERS_MAX_TOPK) return fail(VERS_ERR_UNSUPPORTED, "nprobe %u > %u", np, VERS_MAX_TOPK);
-    // candidate list length of the approximate pass; beyond 64 the private lists no longer fit next to the tiles
-    const uint32_t M = round_up(k + 16, 32);
-    const bool approx = !ref_mode && ivf->mode == 0 && M <= 64;
+    // candidate list length of the approximate pass: the private lists are one register per lane
+    const uint32_t M = 32;
+    const bool approx = !ref_mode && ivf->mode == 0 && k <= 16;
     const uint64_t npairs = (uint64_t)nq * np;
     const uint64_t max_chunks = std::max<uint64_t>((uint64_t)nq * ivf_max_chunks_per_query(ivf, np), 1);
     size_t entries = (size_t)max_chunks * ScanCfg::NSPLIT * k;
@@ -772,6 +830,7 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
             b.part_d, b.part_p, b.pair_chunk_off, nq, np, M, StreamCfg::NSPLIT, b.cand_pos, b.cand_bound);
         VERS_LAUNCH_CHECK(ctx);
         size_t rsm = (size_t)4 * RERANK_QCHUNK * 4 + (size_t)4 * k * 12;
+        FamilyTimer ftr(ctx, KF_RERANK);
         rerank_certify_kernel<<<(unsigned)ceil_div(nq, 4), 128, rsm, ctx->stream>>>(
             ivf->d_lm, ivf->d_lm_ids, ivf->ld, d_queries, nq, k, M, b.cand_pos, b.cand_bound, ivf->d_nxmax, d_ids, d_d,
             d_cnt, b.fail_flag, ivf->d_stats);

@@ -108,25 +108,4 @@ extern "C" int32_t vers_lsh_hash(vers_dataset* ds, const float* planes, uint32_t
     return rc;
 }
 
-// ---- forest entry points: implemented in lsh_forest.cu
-// TEMPORARY until lsh_forest.cu lands: fail loudly rather than pretend.
-struct vers_lsh { int unused; };
-extern "C" int32_t vers_lsh_build_index(vers_ctx*, const float*, uint64_t, uint32_t, uint32_t, const uint64_t*, uint32_t,
-                                        uint32_t, uint64_t, vers_lsh** out) {
-    if (out) *out = nullptr;
-    return fail(VERS_ERR_UNSUPPORTED, "lsh forest: not implemented in this build");
-}
-extern "C" int32_t vers_lsh_free(vers_lsh*) { return VERS_OK; }
-extern "C" int32_t vers_lsh_info(const vers_lsh*, uint64_t*, uint32_t*, uint64_t*) {
-    return fail(VERS_ERR_UNSUPPORTED, "lsh forest: not implemented in this build");
-}
-extern "C" int32_t vers_lsh_flatten(const vers_lsh*, uint32_t, uint8_t*, uint32_t*, float*, float*, uint32_t*, uint32_t*,
-                                    uint32_t*, uint64_t*) {
-    return fail(VERS_ERR_UNSUPPORTED, "lsh forest: not implemented in this build");
-}
-extern "C" int32_t vers_lsh_search(vers_lsh*, const float*, uint32_t, uint32_t, uint32_t, uint64_t*, float*, uint32_t*) {
-    return fail(VERS_ERR_UNSUPPORTED, "lsh forest: not implemented in this build");
-}
-extern "C" int32_t vers_lsh_add(vers_lsh*, const float*, uint64_t) {
-    return fail(VERS_ERR_UNSUPPORTED, "lsh forest: not implemented in this build");
-}
+// ---- forest entry points (build / search / add / flatten): lsh_forest.cu

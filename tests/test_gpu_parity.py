@@ -389,3 +389,88 @@ def test_multi_gpu_sharded_parity_when_two_gpus_present():
                         "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "mgpu_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "mgpu_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+# ---------------------------------------------------------------------------------------------- LSH forest
+def _same_forest(vb_idx, vo_idx, T):
+    for t in range(T):
+        a, b = vb_idx.flatten(t), vo_idx.flatten(t)
+        assert np.array_equal(a["kind"], b["kind"]), f"tree {t}: shape differs"
+        assert np.array_equal(a["leaf_len"], b["leaf_len"])
+        assert np.array_equal(bits(a["planes"]), bits(b["planes"])), f"tree {t}: plane coefficient bits differ"
+        assert np.array_equal(bits(a["consts"]), bits(b["consts"]))
+        assert np.array_equal(a["items"], b["items"]), f"tree {t}: leaf members / order differ"
+
+
+@pytest.mark.parametrize("n,dim,T,max_size", [(6000, 300, 4, 100), (3000, 24, 6, 12), (500, 33, 3, 2)])
+def test_lsh_forest_build_identical_to_oracle(vb, vo, ctx, n, dim, T, max_size):
+    rows = data(vo, n, dim, n_centers=20)
+    rows[100] = rows[7]  # a duplicate: dropped by deduplicate (lsh.rs:113-130)
+    ids = np.arange(n, dtype=np.uint64) + 1000
+    g = vb.ANNIndex.build_index(T, max_size, rows, ids, seed=4, ctx=ctx)
+    o = vo.LSH(rows, ids, T, max_size, 4)
+    assert g.info()["num_values"] == o.num_values == n - 1
+    _same_forest(g, o, T)
+
+
+@pytest.mark.parametrize("k", [1, 10, 50])
+def test_lsh_search_identical_to_oracle(vb, vo, ctx, k):
+    n, dim, T, max_size = 8000, 300, 8, 100
+    rows = data(vo, n, dim, n_centers=30)
+    g = vb.ANNIndex.build_index(T, max_size, rows, None, seed=4, ctx=ctx)
+    o = vo.LSH(rows, None, T, max_size, 4)
+    q = data(vo, 120, dim, seed=2, n_centers=30)
+    ids, d, cnt = g.search_batch(q, k)
+    oi, od, oc = o.search(q, k)
+    assert np.array_equal(cnt, oc)
+    assert np.array_equal(ids, oi)
+    assert np.array_equal(bits(d), bits(od))
+    got = g.search_approximate(q[0], k)
+    assert [x[0] for x in got] == list(oi[0][: oc[0]])
+
+
+def test_lsh_search_backtracks_through_small_leaves(vb, vo, ctx):
+    """max_size smaller than top_k: every leaf is short, tree_result backtracks all the way up (lsh.rs:203-213)"""
+    n, dim, T, max_size, k = 1500, 16, 5, 6, 20
+    rows = data(vo, n, dim, n_centers=10)
+    g = vb.ANNIndex.build_index(T, max_size, rows, None, seed=9, ctx=ctx)
+    o = vo.LSH(rows, None, T, max_size, 9)
+    _same_forest(g, o, T)
+    q = data(vo, 64, dim, seed=2, n_centers=10)
+    ids, d, cnt = g.search_batch(q, k)
+    oi, od, oc = o.search(q, k)
+    assert np.array_equal(cnt, oc) and np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od))
+
+
+def test_lsh_add_splits_and_search(vb, vo, ctx):
+    n, dim, T, max_size = 600, 32, 3, 10
+    rows = data(vo, n, dim, n_centers=8)
+    extra = data(vo, 250, dim, seed=5, n_centers=8)
+    g = vb.ANNIndex.build_index(T, max_size, rows, None, seed=4, ctx=ctx)
+    o = vo.LSH(rows, None, T, max_size, 4)
+    for i in range(extra.shape[0]):
+        g.add(extra[i], n + i)
+        o.add(extra[i], n + i)
+    assert g.info()["num_values"] == o.num_values == n + 250
+    _same_forest(g, o, T)
+    q = np.vstack([extra[:20], data(vo, 20, dim, seed=2, n_centers=8)])
+    ids, d, cnt = g.search_batch(q, 5)
+    oi, od, oc = o.search(q, 5)
+    assert np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od)) and np.array_equal(cnt, oc)
+    assert [int(ids[i][0]) for i in range(20)] == [n + i for i in range(20)]
+    with pytest.raises(vb.VersPanic):
+        g.add(extra[0], 10**6)  # vec_id is stored as a row index (lsh.rs:247): out of range
+
+
+def test_lsh_1m_shape_hash_parity_sample(vb, vo, ctx):
+    """BASELINE config 3 shape (scaled rows): 16 planes over many rows, every bit equal"""
+    n, dim, P = 200000, 300, 16
+    rows = data(vo, n, dim, n_centers=64)
+    rng = np.random.default_rng(2)
+    planes = np.empty((P, dim), np.float32)
+    consts = np.empty(P, np.float32)
+    for p in range(P):
+        a, b = rng.choice(n, 2, replace=False)
+        planes[p], consts[p] = vo.lsh_make_plane(rows[a], rows[b])
+    ds = vb.Dataset.upload(ctx, rows)
+    assert np.array_equal(vb.lsh_hash(ds, planes, consts), vo.lsh_hash(rows, planes, consts))

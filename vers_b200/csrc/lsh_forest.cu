@@ -858,56 +858,65 @@ extern "C" int32_t vers_lsh_search(vers_lsh* L, const float* queries, uint32_t n
     std::lock_guard<std::mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     VERS_TRY(sync_device_mirror(L));
-    const uint32_t cand_cap = 24 * top_k + 2 * L->slot_cap + 64;
+    // every leaf is visited at most once per traversal, so L->n candidates per tree always suffice; start small and
+    // retry larger in the rare case the reference's cascading backtracking (lsh.rs:210-213) visits many leaves
+    uint64_t cand_cap = 24ull * top_k + 2ull * L->slot_cap + 64;
     const size_t nk = (size_t)nq * top_k, npt = (size_t)nq * L->num_trees;
-    ScratchCarver plan(nullptr);
-    plan.plan<float>((size_t)nq * L->ld);
-    plan.plan<uint64_t>(nk);
-    plan.plan<float>(nk);
-    plan.plan<uint32_t>(nq);
-    plan.plan<uint32_t>(npt * cand_cap);
-    plan.plan<uint32_t>(npt);
-    plan.plan<uint32_t>(4);
-    VERS_TRY(scratch_reserve(ctx, plan.off + 256));
-    ScratchCarver sc(ctx->scratch);
-    float* d_q = sc.take<float>((size_t)nq * L->ld);
-    uint64_t* d_ids = sc.take<uint64_t>(nk);
-    float* d_d = sc.take<float>(nk);
-    uint32_t* d_c = sc.take<uint32_t>(nq);
-    uint32_t* d_cand = sc.take<uint32_t>(npt * cand_cap);
-    uint32_t* d_cnt = sc.take<uint32_t>(npt);
-    uint32_t* d_over = sc.take<uint32_t>(4);
-    if (L->ld != L->dim) VERS_CUDA(cudaMemsetAsync(d_q, 0, (size_t)nq * L->ld * 4, ctx->stream));
-    VERS_CUDA(cudaMemcpy2DAsync(d_q, (size_t)L->ld * 4, queries, (size_t)q_stride_floats * 4, (size_t)L->dim * 4, nq,
-                                cudaMemcpyHostToDevice, ctx->stream));
-    VERS_CUDA(cudaMemsetAsync(d_over, 0, 16, ctx->stream));
     ForestDev f = forest_dev(L);
-    {
-        size_t per_warp = ((size_t)L->ld * 4 + LSH_STACK * 12 + (size_t)top_k * 8 + 15) & ~size_t(15);
-        size_t smem = per_warp * 4;
-        VERS_CUDA(cudaFuncSetAttribute(forest_traverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        forest_traverse_kernel<<<(unsigned)ceil_div(npt, 4), 128, smem, ctx->stream>>>(f, d_q, nq, top_k, cand_cap, d_cand,
-                                                                                      d_cnt, d_over);
-        VERS_LAUNCH_CHECK(ctx);
+    for (;;) {
+        if (cand_cap > L->n) cand_cap = std::max<uint64_t>(L->n, 1);
+        ScratchCarver plan(nullptr);
+        plan.plan<float>((size_t)nq * L->ld);
+        plan.plan<uint64_t>(nk);
+        plan.plan<float>(nk);
+        plan.plan<uint32_t>(nq);
+        plan.plan<uint32_t>(npt * cand_cap);
+        plan.plan<uint32_t>(npt);
+        plan.plan<uint32_t>(4);
+        VERS_TRY(scratch_reserve(ctx, plan.off + 256));
+        ScratchCarver sc(ctx->scratch);
+        float* d_q = sc.take<float>((size_t)nq * L->ld);
+        uint64_t* d_ids = sc.take<uint64_t>(nk);
+        float* d_d = sc.take<float>(nk);
+        uint32_t* d_c = sc.take<uint32_t>(nq);
+        uint32_t* d_cand = sc.take<uint32_t>(npt * cand_cap);
+        uint32_t* d_cnt = sc.take<uint32_t>(npt);
+        uint32_t* d_over = sc.take<uint32_t>(4);
+        if (L->ld != L->dim) VERS_CUDA(cudaMemsetAsync(d_q, 0, (size_t)nq * L->ld * 4, ctx->stream));
+        VERS_CUDA(cudaMemcpy2DAsync(d_q, (size_t)L->ld * 4, queries, (size_t)q_stride_floats * 4, (size_t)L->dim * 4, nq,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+        VERS_CUDA(cudaMemsetAsync(d_over, 0, 16, ctx->stream));
+        {
+            size_t per_warp = ((size_t)L->ld * 4 + LSH_STACK * 12 + (size_t)top_k * 8 + 15) & ~size_t(15);
+            size_t smem = per_warp * 4;
+            VERS_CUDA(cudaFuncSetAttribute(forest_traverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            forest_traverse_kernel<<<(unsigned)ceil_div(npt, 4), 128, smem, ctx->stream>>>(
+                f, d_q, nq, top_k, (uint32_t)cand_cap, d_cand, d_cnt, d_over);
+            VERS_LAUNCH_CHECK(ctx);
+        }
+        uint32_t over = 0;
+        VERS_CUDA(cudaMemcpyAsync(&over, d_over, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        VERS_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (over) {
+            if (cand_cap >= L->n)
+                return fail(VERS_ERR_UNSUPPORTED, "lsh_search: a traversal needs more than %d stack frames", LSH_STACK);
+            cand_cap *= 8;
+            continue;
+        }
+        {
+            size_t per_warp = ((size_t)L->ld * 4 + (size_t)top_k * 8 + 15) & ~size_t(15);
+            size_t smem = per_warp * 4;
+            VERS_CUDA(cudaFuncSetAttribute(forest_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            forest_rerank_kernel<<<(unsigned)ceil_div(nq, 4), 128, smem, ctx->stream>>>(
+                f, d_q, nq, top_k, (uint32_t)cand_cap, d_cand, d_cnt, L->d_ids, d_ids, d_d, d_c);
+            VERS_LAUNCH_CHECK(ctx);
+        }
+        VERS_CUDA(cudaMemcpyAsync(ids, d_ids, nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        VERS_CUDA(cudaMemcpyAsync(dists, d_d, nk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (counts) VERS_CUDA(cudaMemcpyAsync(counts, d_c, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        VERS_CUDA(cudaStreamSynchronize(ctx->stream));
+        return VERS_OK;
     }
-    {
-        size_t per_warp = ((size_t)L->ld * 4 + (size_t)top_k * 8 + 15) & ~size_t(15);
-        size_t smem = per_warp * 4;
-        VERS_CUDA(cudaFuncSetAttribute(forest_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        forest_rerank_kernel<<<(unsigned)ceil_div(nq, 4), 128, smem, ctx->stream>>>(f, d_q, nq, top_k, cand_cap, d_cand,
-                                                                                   d_cnt, L->d_ids, d_ids, d_d, d_c);
-        VERS_LAUNCH_CHECK(ctx);
-    }
-    uint32_t over = 0;
-    VERS_CUDA(cudaMemcpyAsync(&over, d_over, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    VERS_CUDA(cudaMemcpyAsync(ids, d_ids, nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    VERS_CUDA(cudaMemcpyAsync(dists, d_d, nk * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (counts) VERS_CUDA(cudaMemcpyAsync(counts, d_c, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    VERS_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (over)
-        return fail(VERS_ERR_UNSUPPORTED, "lsh_search: a traversal exceeded %u candidates per tree or %d stack frames",
-                    cand_cap, LSH_STACK);
-    return VERS_OK;
 }
 
 extern "C" int32_t vers_lsh_add(vers_lsh* L, const float* embedding, uint64_t vec_id) {

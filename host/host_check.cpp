@@ -1,0 +1,62 @@
+// host_check.cpp — exercises host/vers_index.hpp on a GPU: build, search, add, save/load round trip.
+// Built and run by tests/test_gpu_parity.py::test_cpp_host_mirror (prints "host_check ok").
+#include <cstdio>
+#include <cstdlib>
+
+#include "vers_index.hpp"
+#include "../include/vers_synth.h"
+
+using namespace vers;
+constexpr size_t N = 300;
+
+int main(int argc, char** argv) {
+    const char* path = argc > 1 ? argv[1] : "/tmp/host_check_ivf.bin";
+    const size_t n = 5000, C = 16, k = 10;
+    static_assert(sizeof(Vector<N>) == 1280, "size_of::<Vector<300>>() in the reference (repr(align(256)))");
+    std::vector<Vector<N>> rows(n);
+    for (size_t r = 0; r < n; ++r)
+        for (size_t c = 0; c < N; ++c) rows[r][c] = vers_synth_elem(1, 7, VERS_SYNTH_CLUSTERED, 16, r, (uint32_t)c, N);
+    std::vector<uint64_t> init(C);
+    for (size_t j = 0; j < C; ++j) init[j] = vers_synth_init_row(3, 0, (uint32_t)j, n);
+    Context ctx(0);
+    auto ix = IVFFlatIndex<N>::build_index(ctx, C, 1, 10, rows, init);
+    auto exact = search_exhaustive(ctx, rows, rows[42], k);
+    auto approx = ix->search_approximate(rows[42], k);
+    if (exact.size() != k || approx.size() != k || exact[0].first != 42 || approx[0].first != 42 || approx[0].second != 0.0f) {
+        std::printf("unexpected neighbours\n");
+        return 1;
+    }
+    Vector<N> extra = rows[7];
+    extra[0] += 0.125f;
+    ix->add(extra, 999999);
+    auto near = ix->search_approximate(extra, 2);
+    if (near[0].first != n) {  // the reference ignores vec_id and stores assignments.len()
+        std::printf("add: stored id %zu, expected %zu\n", near[0].first, n);
+        return 1;
+    }
+    ix->save_index(path);
+    auto ix2 = IVFFlatIndex<N>::load_index(ctx, path);
+    auto again = ix2->search_approximate(rows[42], k);
+    for (size_t i = 0; i < k; ++i)
+        if (again[i] != approx[i]) {
+            std::printf("save/load changed result %zu\n", i);
+            return 1;
+        }
+    std::vector<uint64_t> ids(n);
+    for (size_t i = 0; i < n; ++i) ids[i] = i;
+    auto ann = ANNIndex<N>::build_index(ctx, 4, 100, rows, ids, 4);
+    auto l = ann->search_approximate(rows[42], k);
+    if (l.empty() || l[0].first != 42) {
+        std::printf("lsh: nearest of a member is not itself\n");
+        return 1;
+    }
+    bool threw = false;
+    try {
+        ix->search_approximate(rows[0], 200);  // > VERS_MAX_TOPK
+    } catch (const Panic&) {
+        threw = true;
+    }
+    if (!threw) return 1;
+    std::printf("host_check ok\n");
+    return 0;
+}

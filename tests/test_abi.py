@@ -91,3 +91,12 @@ def test_bincode_layout_roundtrip(tmp_path):
     assert len(ids[2]) == 0
     for c in range(4):
         assert np.array_equal(ids[c], np.nonzero(assign == c)[0].astype(np.uint64))
+
+
+def test_cpp_host_mirror_compiles_and_links(vb, tmp_path):
+    """the C++ host mirror builds against the header and links against the library (no GPU needed)"""
+    libdir = os.path.dirname(vb.LIB_PATH)
+    exe = str(tmp_path / "host_check")
+    subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "host", "host_check.cpp"), "-o", exe, "-L" + libdir,
+                    "-lvers_b200", "-Wl,-rpath," + libdir], check=True)
+    assert os.path.exists(exe)

@@ -474,3 +474,17 @@ def test_lsh_1m_shape_hash_parity_sample(vb, vo, ctx):
         planes[p], consts[p] = vo.lsh_make_plane(rows[a], rows[b])
     ds = vb.Dataset.upload(ctx, rows)
     assert np.array_equal(vb.lsh_hash(ds, planes, consts), vo.lsh_hash(rows, planes, consts))
+
+
+def test_cpp_host_mirror(vb, tmp_path):
+    """host/vers_index.hpp (C++ mirror of Index<N> / IVFFlatIndex / ANNIndex over the C ABI) end to end"""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_check")
+    libdir = os.path.dirname(vb.LIB_PATH)
+    subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(root, "host", "host_check.cpp"), "-o", exe, "-L" + libdir,
+                    "-lvers_b200", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe, str(tmp_path / "ivf.bin")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "host_check ok" in r.stdout, r.stdout + r.stderr

@@ -186,12 +186,13 @@ def test_ivf_build_index_bit_exact(ivf_c1):
     assert np.array_equal(s["idx"].list_sizes, np.bincount(s["assign"].astype(np.int64), minlength=s["C"]))
 
 
-@pytest.mark.parametrize("exact_mode", [False, True])
+@pytest.mark.parametrize("exact_mode", [0, 1, 2])
 @pytest.mark.parametrize("k", [1, 10, 37, 100])
 @pytest.mark.parametrize("nprobe", [0, 1, 4, 16])
 def test_ivf_search_bit_exact(vo, ivf_c1, k, nprobe, exact_mode):
-    """exact_mode=False: candidate pass (FMA) + exact-order rerank + certificate (+ exact redo when uncertified);
-    exact_mode=True: exact order everywhere.  Both must return the oracle's ids AND distance bits."""
+    """mode 0: tensor-core (TMA + tcgen05 TF32) candidate pass + exact-order rerank + certificate (+ exact redo when
+    uncertified); mode 2: the same with an fp32 FMA candidate pass; mode 1: exact order everywhere.
+    Every mode must return the oracle's ids AND distance bits."""
     s = ivf_c1
     q = data(vo, 100, 300, seed=2)
     off, lr = vo.ivf_lists(s["assign"], s["C"])
@@ -200,14 +201,14 @@ def test_ivf_search_bit_exact(vo, ivf_c1, k, nprobe, exact_mode):
         ids, d, cnt = s["idx"].search_batch(q, k, nprobe=nprobe)
         st = s["idx"].last_search_stats()
     finally:
-        s["idx"].set_mode(False)
+        s["idx"].set_mode(0)
     oi, od, oc = vo.ivf_search(s["rows"], s["cents"], off, lr, q, k, nprobe=nprobe)
     assert np.array_equal(cnt, oc)
     assert np.array_equal(ids, oi)
     assert np.array_equal(bits(d), bits(od))
-    if not exact_mode and nprobe > 0 and k <= 16:
+    if exact_mode != 1 and nprobe > 0 and k <= 16:
         assert st["reranked"] > 0  # the candidate path really ran
-        assert st["uncertified_queries"] <= 10
+        assert st["uncertified_queries"] <= (10 if exact_mode == 2 else 100)
 
 
 def test_ivf_candidate_path_falls_back_on_ties(vb, vo, ctx):

@@ -1,4 +1,7 @@
 // api.cu — context, errors, scratch arena and datasets (Vec<Vector<N>> resident in HBM).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "common.cuh"
 
 namespace vers {
@@ -57,6 +60,29 @@ int32_t upload_queries(vers_ctx* ctx, const float* q, uint32_t nq, uint32_t stri
     if (ld != dim) VERS_CUDA(cudaMemsetAsync(*d_q, 0, (size_t)nq * ld * sizeof(float), ctx->stream));
     VERS_CUDA(cudaMemcpy2DAsync(*d_q, (size_t)ld * 4, q, (size_t)stride * 4, (size_t)dim * 4, nq,
                                 cudaMemcpyHostToDevice, ctx->stream));
+    return VERS_OK;
+}
+
+// cuTensorMapEncodeTiled is a driver-API entry point; resolve it through the runtime so the library only links cudart
+int32_t make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t row_stride_floats,
+                         uint32_t box_rows, uint32_t box_cols) {
+    static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+            return fail(VERS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {row_stride_floats * sizeof(float)};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(VERS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return VERS_OK;
 }
 

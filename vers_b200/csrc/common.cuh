@@ -1,5 +1,6 @@
 // common.cuh — shared host/device plumbing of libvers_b200 (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -75,6 +76,10 @@ namespace vers {
 
 inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
 inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// host: 2D fp32 TMA tensor map {inner = cols, outer = rows}, box {box_cols, box_rows}, 128-byte swizzle, zero fill
+int32_t make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t row_stride_floats,
+                         uint32_t box_rows, uint32_t box_cols);
 
 // grow-only scratch; caller holds ctx->mu
 int32_t scratch_reserve(vers_ctx* ctx, size_t bytes);

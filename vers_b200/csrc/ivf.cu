@@ -96,6 +96,7 @@ struct GroupParams {
     const uint32_t* used;       // optional [nq]: only slots s < used[q] are active (reference spill mode)
     const uint32_t* qmask;      // optional [nq]: only queries with a non-zero mask are active (exact fallback pass)
     uint32_t nq, np, C;
+    uint32_t tb;          // queries per work-item group (8 for the SIMT scans, 16 for the tensor-core scan)
     uint32_t* lq_cnt;     // [C]   queries per list
     uint32_t* pair_nch;   // [nq*np] chunks of the pair's list (0 for inactive pairs / empty lists)
     uint32_t* item_cnt;   // [C]   work items per list
@@ -125,7 +126,7 @@ __global__ void group_items_kernel(GroupParams g) {
     if (l >= g.C) return;
     uint32_t m = g.lq_cnt[l];
     uint32_t nch = (g.seg_len[l] + LIST_CHUNK_ROWS - 1) / LIST_CHUNK_ROWS;
-    uint32_t items = ((m + ScanCfg::TB - 1) / ScanCfg::TB) * nch;
+    uint32_t items = ((m + g.tb - 1) / g.tb) * nch;
     g.item_cnt[l] = items;
     if (m && g.stats) {
         atomicAdd(&g.stats[0], (unsigned long long)g.seg_len[l]);
@@ -292,6 +293,10 @@ __global__ void __launch_bounds__(Cfg::NT, (Cfg::TILE_FLOATS * 4 > 110 * 1024) ?
         __syncthreads();  // s_item / lists are rewritten by the next iteration
     }
 }
+
+}  // namespace vers
+#include "ivf_tc.cuh"
+namespace vers {
 
 // ---------------------------------------------------------------- reference spill semantics (nprobe == 0)
 // how many lists the reference opens for each query: lists are taken in probe order while the rows found so far
@@ -576,8 +581,8 @@ __global__ void __launch_bounds__(128)
     rerank_certify_kernel(const float* __restrict__ lm, const uint64_t* __restrict__ lm_ids, uint32_t ld,
                           const float* __restrict__ queries, uint32_t nq, uint32_t k, uint32_t M,
                           const uint32_t* __restrict__ cand_pos, const float* __restrict__ cand_bound,
-                          const uint32_t* __restrict__ nxmax_bits, uint64_t* out_ids, float* out_d, uint32_t* out_cnt,
-                          uint32_t* fail_flag, unsigned long long* stats) {
+                          const uint32_t* __restrict__ nxmax_bits, int tf32_pass, uint64_t* out_ids, float* out_d,
+                          uint32_t* out_cnt, uint32_t* fail_flag, unsigned long long* stats) {
     extern __shared__ __align__(16) unsigned char rsm2[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * 4 + warp;
@@ -655,7 +660,12 @@ __global__ void __launch_bounds__(128)
         } else {
             const double u = 5.9604644775390625e-08;  // 2^-24
             const double nxmax = (double)__uint_as_float(*nxmax_bits);
-            const double E = 1.01 * (2.0 * ld + 8.0) * u * (nxmax + (double)nq2);
+            // fp32 terms (norms, key arithmetic, and the FMA dot of the SIMT pass) + for the tensor-core pass the TF32
+            // operand truncation (|x - tf32(x)| <= 2^-10 |x| per operand => 2^-9 (1 + 2^-11) per product, times
+            // x.q <= (||x||^2 + ||q||^2)/2, times the factor 2 of the key) and an accumulation allowance of
+            // (n + 8) 2^-21 per unit of sum |x_i q_i| (4x the bound of a correctly rounded fp32 chain)
+            double E = 1.01 * (2.0 * ld + 8.0) * u * (nxmax + (double)nq2);
+            if (tf32_pass) E += (1.001 / 512.0 + (ld + 8.0) * 4.76837158203125e-07) * (nxmax + (double)nq2);
             const double lower = ((double)bound + (double)nq2 - E) * (1.0 - (ld + 3.0) * u);
             certified = lower > (double)sd[k - 1];
         }
@@ -675,10 +685,11 @@ struct SearchBufs {
     float* cand_bound;
     float* part_d;
     uint32_t* part_p;
+    float* gq;  // [npairs + 16][ld] queries regrouped by list (tensor-core scan only)
 };
 
 static int32_t run_group(vers_ivf* ivf, const SearchBufs& b, uint32_t nq, uint32_t np, const uint32_t* used,
-                         const uint32_t* qmask, bool record_stats) {
+                         const uint32_t* qmask, bool record_stats, uint32_t tb = ScanCfg::TB) {
     vers_ctx* ctx = ivf->ctx;
     const uint64_t npairs = (uint64_t)nq * np;
     VERS_CUDA(cudaMemsetAsync(b.lq_cnt, 0, (size_t)ivf->C * 4, ctx->stream));
@@ -692,6 +703,7 @@ static int32_t run_group(vers_ivf* ivf, const SearchBufs& b, uint32_t nq, uint32
     g.nq = nq;
     g.np = np;
     g.C = ivf->C;
+    g.tb = tb;
     g.lq_cnt = b.lq_cnt;
     g.pair_nch = b.pair_nch;
     g.item_cnt = b.item_cnt;
@@ -743,6 +755,34 @@ static int32_t run_list_scan(vers_ivf* ivf, const SearchBufs& b, const float* d_
     return VERS_OK;
 }
 
+static int32_t run_list_scan_tc(vers_ivf* ivf, const SearchBufs& b, const float* d_queries, uint32_t nq, uint32_t np) {
+    vers_ctx* ctx = ivf->ctx;
+    const uint64_t npairs = (uint64_t)nq * np;
+    gather_queries_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_queries, b.lq_query, b.lq_off, ivf->C, ivf->ld,
+                                                                     b.gq);
+    VERS_LAUNCH_CHECK(ctx);
+    CUtensorMap tm_rows, tm_q;
+    VERS_TRY(make_tmap_2d_f32(&tm_rows, ivf->d_lm, ivf->cap_total ? ivf->cap_total : 1, ivf->ld, ivf->ld, TC_M, TC_KC));
+    VERS_TRY(make_tmap_2d_f32(&tm_q, b.gq, npairs + 16, ivf->ld, ivf->ld, TC_N, TC_KC));
+    TcScanParams tp;
+    tp.ld = ivf->ld;
+    tp.C = ivf->C;
+    tp.seg_off = ivf->d_seg_off;
+    tp.seg_len = ivf->d_seg_len;
+    tp.lq_pair = b.lq_pair;
+    tp.lq_off = b.lq_off;
+    tp.item_off = b.item_off;
+    tp.pair_chunk_off = b.pair_chunk_off;
+    tp.lm_norm = ivf->d_lm_norm;
+    tp.part_d = b.part_d;
+    tp.part_p = b.part_p;
+    VERS_CUDA(cudaFuncSetAttribute(tc_list_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    FamilyTimer ft(ctx, KF_CAND_SCAN);
+    tc_list_scan_kernel<<<ctx->sm_count, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(tm_rows, tm_q, tp);
+    VERS_LAUNCH_CHECK(ctx);
+    return VERS_OK;
+}
+
 static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint32_t nq, uint32_t k, uint32_t nprobe,
                                      uint64_t* d_ids, float* d_d, uint32_t* d_cnt) {
     vers_ctx* ctx = ivf->ctx;
@@ -751,11 +791,12 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
     if (np > VERS_MAX_TOPK) return fail(VERS_ERR_UNSUPPORTED, "nprobe %u > %u", np, VERS_MAX_TOPK);
     // candidate list length of the approximate pass: the private lists are one register per lane
     const uint32_t M = 32;
-    const bool approx = !ref_mode && ivf->mode == 0 && k <= 16;
+    const bool approx = !ref_mode && ivf->mode != 1 && k <= 16;
+    const bool use_tc = approx && ivf->mode == 0 && ivf->ld >= TC_KC && ivf->cap_total < 0x7fffffffull;
     const uint64_t npairs = (uint64_t)nq * np;
     const uint64_t max_chunks = std::max<uint64_t>((uint64_t)nq * ivf_max_chunks_per_query(ivf, np), 1);
     size_t entries = (size_t)max_chunks * ScanCfg::NSPLIT * k;
-    if (approx) entries = std::max(entries, (size_t)max_chunks * StreamCfg::NSPLIT * M);
+    if (approx) entries = std::max(entries, (size_t)max_chunks * std::max<size_t>(StreamCfg::NSPLIT, TC_EPI_WARPS) * M);
 
     // the probe carves its partial buffers from the front of the arena, ours come after it
     const ScanPlan probe_plan = scan_topk_plan(ctx, ivf->C, nq, np);
@@ -781,6 +822,7 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
         b.counter = sc.take<unsigned long long>(2);
         b.part_d = sc.take<float>(entries);
         b.part_p = sc.take<uint32_t>(entries);
+        b.gq = sc.take<float>(use_tc ? (size_t)(npairs + 16) * ivf->ld : 4);
     };
     {
         ScratchCarver plan(nullptr);
@@ -824,16 +866,24 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
     const uint32_t* qmask = nullptr;
     if (approx) {
         // 2a. candidate pass (FMA, HBM-streaming) -> top-M per query -> exact-order rerank -> certificate
-        VERS_TRY(run_group(ivf, b, nq, np, nullptr, nullptr, true));
-        VERS_TRY((run_list_scan<StreamCfg, 1>(ivf, b, d_queries, nq, M)));
+        uint32_t nsplit;
+        if (use_tc) {
+            VERS_TRY(run_group(ivf, b, nq, np, nullptr, nullptr, true, TC_N));
+            VERS_TRY(run_list_scan_tc(ivf, b, d_queries, nq, np));
+            nsplit = TC_EPI_WARPS;
+        } else {
+            VERS_TRY(run_group(ivf, b, nq, np, nullptr, nullptr, true));
+            VERS_TRY((run_list_scan<StreamCfg, 1>(ivf, b, d_queries, nq, M)));
+            nsplit = StreamCfg::NSPLIT;
+        }
         cand_merge_kernel<<<(unsigned)ceil_div(nq, 4), 128, (size_t)4 * M * 8, ctx->stream>>>(
-            b.part_d, b.part_p, b.pair_chunk_off, nq, np, M, StreamCfg::NSPLIT, b.cand_pos, b.cand_bound);
+            b.part_d, b.part_p, b.pair_chunk_off, nq, np, M, nsplit, b.cand_pos, b.cand_bound);
         VERS_LAUNCH_CHECK(ctx);
         size_t rsm = (size_t)4 * RERANK_QCHUNK * 4 + (size_t)4 * k * 12;
         FamilyTimer ftr(ctx, KF_RERANK);
         rerank_certify_kernel<<<(unsigned)ceil_div(nq, 4), 128, rsm, ctx->stream>>>(
-            ivf->d_lm, ivf->d_lm_ids, ivf->ld, d_queries, nq, k, M, b.cand_pos, b.cand_bound, ivf->d_nxmax, d_ids, d_d,
-            d_cnt, b.fail_flag, ivf->d_stats);
+            ivf->d_lm, ivf->d_lm_ids, ivf->ld, d_queries, nq, k, M, b.cand_pos, b.cand_bound, ivf->d_nxmax, use_tc ? 1 : 0,
+            d_ids, d_d, d_cnt, b.fail_flag, ivf->d_stats);
         VERS_LAUNCH_CHECK(ctx);
         qmask = b.fail_flag;  // 2b. exact-order redo of the (rare) uncertified queries, no host round trip
     }
@@ -1082,7 +1132,7 @@ extern "C" int32_t vers_ivf_get_list(const vers_ivf* ivf, uint32_t list, uint64_
 }
 
 extern "C" int32_t vers_ivf_set_mode(vers_ivf* ivf, int32_t mode) {
-    if (!ivf || mode < 0 || mode > 1) return fail(VERS_ERR_ARG, "ivf_set_mode: bad argument");
+    if (!ivf || mode < 0 || mode > 2) return fail(VERS_ERR_ARG, "ivf_set_mode: bad argument");
     ivf->mode = mode;
     return VERS_OK;
 }

@@ -340,9 +340,11 @@ class IVFFlatIndex:
         return dict(distinct_list_rows=int(out[0]), pair_rows=int(out[1]), work_items=int(out[2]),
                     lists_touched=int(out[3]), uncertified_queries=int(out[4]), reranked=int(out[5]))
 
-    def set_mode(self, exact: bool):
-        """False (default): candidate pass + exact-order rerank + certificate; True: exact order everywhere"""
-        check(lib().vers_ivf_set_mode(self.h, int(bool(exact))))
+    def set_mode(self, mode):
+        """0 / False (default): tensor-core (TF32) candidate pass + exact-order rerank + certificate;
+        1 / True: exact order everywhere; 2: fp32 FMA candidate pass (SIMT) + rerank + certificate.
+        Every mode returns the reference's ids and distance bits."""
+        check(lib().vers_ivf_set_mode(self.h, int(mode)))
 
     @property
     def ids(self) -> List[np.ndarray]:

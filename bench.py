@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--recall-queries", type=int, default=100)
     ap.add_argument("--cpu-queries", type=int, default=256, help="queries in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", type=int, default=0, help="candidate pass: 0 tcgen05 split-TF32 (default), 1 exact "
+                    "order only, 2 fp32 FMA SIMT, 3 tcgen05 plain TF32")
     return ap.parse_args()
 
 
@@ -214,6 +216,7 @@ def main_ours(args):
     barrier()
     build_s = max_over_ranks(time.perf_counter() - t0)
 
+    index.ivf.set_mode(args.mode)
     qds = vb.Dataset.synth(ctx, SEED_QUERY, args.nq, args.dim, kind=1, n_centers=args.n_centers,
                            center_seed=SEED_CENTERS, row0=0, normalize=True)
     from vers_b200.sharded import device_view

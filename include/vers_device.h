@@ -142,11 +142,13 @@ int32_t vers_ivf_get_list(const vers_ivf* ivf, uint32_t list, uint64_t* ids, flo
  * out[0] = rows in the DISTINCT lists touched (the algorithmic HBM stream), out[1] = Σ over (query, list) pairs of
  * the list length (un-deduplicated rows x queries), out[2] = work items, out[3] = distinct lists touched,
  * out[4] = queries whose certificate failed and were redone by the exact-order scan, out[5] = candidates
- * re-ranked in exact order, out[6..7] reserved */
+ * re-ranked in exact order, out[6] = bit pattern (low 32 bits) of the largest observed |candidate value - exact
+ * value| among the re-ranked rows (validates the certificate's error allowance), out[7] reserved */
 int32_t vers_ivf_last_search_stats(const vers_ivf* ivf, uint64_t out[8]);
 /* nprobe >= 1 searches: 0 (default) = tensor-core candidate pass (TMA + tcgen05 kind::tf32 on the fp32 rows) +
  * exact-order rerank of the candidates + a rounding-error certificate, uncertified queries redone in exact order;
- * 1 = exact order everywhere; 2 = like 0 with an fp32 FMA (SIMT) candidate pass.
+ * (the default splits every operand into tf32 hi + lo parts: 3 MMAs per K step, fp32-grade candidate values);
+ * 1 = exact order everywhere; 2 = like 0 with an fp32 FMA (SIMT) candidate pass; 3 = like 0 with plain TF32.
  * Every mode returns the reference's ids and distance bits; the knob exists for tests and for timing. */
 int32_t vers_ivf_set_mode(vers_ivf* ivf, int32_t mode);
 /* Index::search_approximate (ivfflat.rs:153-198) for a batch.  nprobe == 0: the reference's semantics (nearest

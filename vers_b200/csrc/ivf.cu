@@ -533,7 +533,8 @@ static uint64_t ivf_max_chunks_per_query(const vers_ivf* ivf, uint32_t np) {
 __global__ void __launch_bounds__(128)
     cand_merge_kernel(const float* __restrict__ part_d, const uint32_t* __restrict__ part_p,
                       const uint64_t* __restrict__ pair_chunk_off, uint32_t nq, uint32_t np, uint32_t M,
-                      uint32_t nsplit, uint32_t* __restrict__ cand_pos, float* __restrict__ cand_bound) {
+                      uint32_t nsplit, uint32_t* __restrict__ cand_pos, float* __restrict__ cand_key,
+                      float* __restrict__ cand_bound) {
     extern __shared__ __align__(16) unsigned char csm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * 4 + warp;
@@ -566,7 +567,10 @@ __global__ void __launch_bounds__(128)
         }
     }
     for (int o = 16; o; o >>= 1) tfull = fminf(tfull, __shfl_xor_sync(FULL_MASK, tfull, o));
-    for (uint32_t e = lane; e < M; e += 32) cand_pos[(uint64_t)q * M + e] = sp[e];
+    for (uint32_t e = lane; e < M; e += 32) {
+        cand_pos[(uint64_t)q * M + e] = sp[e];
+        cand_key[(uint64_t)q * M + e] = sd[e];
+    }
     if (lane == 0) {
         float b = tfull;
         if (sp[M - 1] != 0xffffffffu) b = fminf(b, sd[M - 1]);
@@ -581,7 +585,8 @@ __global__ void __launch_bounds__(128)
     rerank_certify_kernel(const float* __restrict__ lm, const uint64_t* __restrict__ lm_ids, uint32_t ld,
                           const float* __restrict__ queries, uint32_t nq, uint32_t k, uint32_t M,
                           const uint32_t* __restrict__ cand_pos, const float* __restrict__ cand_bound,
-                          const uint32_t* __restrict__ nxmax_bits, int tf32_pass, uint64_t* out_ids, float* out_d,
+                          const uint32_t* __restrict__ nxmax_bits, const float* __restrict__ cand_key, int tf32_pass,
+                          uint64_t* out_ids, float* out_d,
                           uint32_t* out_cnt, uint32_t* fail_flag, unsigned long long* stats) {
     extern __shared__ __align__(16) unsigned char rsm2[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -597,6 +602,8 @@ __global__ void __launch_bounds__(128)
     const float* qrow = queries + (uint64_t)q * ld;
     float nq2 = 0.0f;  // ||q||^2, lane-partial
     uint32_t reranked = 0;
+    float my_key[4] = {0.f, 0.f, 0.f, 0.f}, my_d[4] = {0.f, 0.f, 0.f, 0.f};  // up to 128 candidates per query
+    bool my_live[4] = {false, false, false, false};
     for (uint32_t c0 = 0; c0 < M; c0 += 32) {
         const uint32_t pos = cand_pos[(uint64_t)q * M + c0 + lane];
         const bool live = pos != 0xffffffffu;
@@ -624,6 +631,11 @@ __global__ void __launch_bounds__(128)
             }
         }
         reranked += __popc(__ballot_sync(FULL_MASK, live));
+        if ((c0 >> 5) < 4) {
+            my_live[c0 >> 5] = live;
+            my_d[c0 >> 5] = s;
+            my_key[c0 >> 5] = live ? cand_key[(uint64_t)q * M + c0 + lane] : 0.f;
+        }
         uint64_t id = live ? lm_ids[pos] : 0xffffffffffffffffull;
         bool pend = live;
         while (true) {
@@ -638,6 +650,12 @@ __global__ void __launch_bounds__(128)
         }
     }
     for (int o = 16; o; o >>= 1) nq2 += __shfl_xor_sync(FULL_MASK, nq2, o);
+    // observed candidate-pass error |d~ - d_ref| (statistic only: validates the certificate's error allowance)
+    float err = 0.0f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+        if (my_live[g]) err = fmaxf(err, fabsf((my_key[g] + nq2) - my_d[g]));
+    for (int o = 16; o; o >>= 1) err = fmaxf(err, __shfl_xor_sync(FULL_MASK, err, o));
     uint32_t cnt = 0;
     for (uint32_t e0 = 0; e0 < k; e0 += 32) {
         uint32_t e = e0 + lane;
@@ -665,13 +683,17 @@ __global__ void __launch_bounds__(128)
             // x.q <= (||x||^2 + ||q||^2)/2, times the factor 2 of the key) and an accumulation allowance of
             // (n + 8) 2^-21 per unit of sum |x_i q_i| (4x the bound of a correctly rounded fp32 chain)
             double E = 1.01 * (2.0 * ld + 8.0) * u * (nxmax + (double)nq2);
-            if (tf32_pass) E += (1.001 / 512.0 + (ld + 8.0) * 4.76837158203125e-07) * (nxmax + (double)nq2);
+            if (tf32_pass == 1) E += (1.001 / 512.0 + (ld + 8.0) * 4.76837158203125e-07) * (nxmax + (double)nq2);
+            // split precision (hi.hi + lo.hi + hi.lo): dropped lo.lo and the truncation of lo are <= 3 * 2^-20 per
+            // product; accumulation allowance (n + 8) 2^-22 per unit of sum |x_i q_i|
+            if (tf32_pass == 2) E += (3.003 / 1048576.0 + (ld + 8.0) * 2.384185791015625e-07) * (nxmax + (double)nq2);
             const double lower = ((double)bound + (double)nq2 - E) * (1.0 - (ld + 3.0) * u);
             certified = lower > (double)sd[k - 1];
         }
         fail_flag[q] = certified ? 0u : 1u;
         if (!certified) atomicAdd(&stats[4], 1ull);
         atomicAdd(&stats[5], (unsigned long long)reranked);
+        atomicMax(&stats[6], (unsigned long long)__float_as_uint(err));  // non-negative floats order as uints
     }
 }
 
@@ -685,7 +707,9 @@ struct SearchBufs {
     float* cand_bound;
     float* part_d;
     uint32_t* part_p;
-    float* gq;  // [npairs + 16][ld] queries regrouped by list (tensor-core scan only)
+    float* gq;     // [npairs + 16][ld] queries regrouped by list (tensor-core scan only), tf32 hi part
+    float* gq_lo;  // [npairs + 16][ld] their tf32 lo part (split-precision scan)
+    float* cand_key;  // [nq][M] candidate keys (observed-error statistic)
 };
 
 static int32_t run_group(vers_ivf* ivf, const SearchBufs& b, uint32_t nq, uint32_t np, const uint32_t* used,
@@ -755,15 +779,18 @@ static int32_t run_list_scan(vers_ivf* ivf, const SearchBufs& b, const float* d_
     return VERS_OK;
 }
 
+template <bool SPLIT3>
 static int32_t run_list_scan_tc(vers_ivf* ivf, const SearchBufs& b, const float* d_queries, uint32_t nq, uint32_t np) {
+    using Cfg = TcCfg<SPLIT3>;
     vers_ctx* ctx = ivf->ctx;
     const uint64_t npairs = (uint64_t)nq * np;
     gather_queries_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_queries, b.lq_query, b.lq_off, ivf->C, ivf->ld,
-                                                                     b.gq);
+                                                                     b.gq, b.gq_lo, SPLIT3 ? 1 : 0);
     VERS_LAUNCH_CHECK(ctx);
-    CUtensorMap tm_rows, tm_q;
+    CUtensorMap tm_rows, tm_q, tm_ql;
     VERS_TRY(make_tmap_2d_f32(&tm_rows, ivf->d_lm, ivf->cap_total ? ivf->cap_total : 1, ivf->ld, ivf->ld, TC_M, TC_KC));
     VERS_TRY(make_tmap_2d_f32(&tm_q, b.gq, npairs + 16, ivf->ld, ivf->ld, TC_N, TC_KC));
+    VERS_TRY(make_tmap_2d_f32(&tm_ql, SPLIT3 ? b.gq_lo : b.gq, npairs + 16, ivf->ld, ivf->ld, TC_N, TC_KC));
     TcScanParams tp;
     tp.ld = ivf->ld;
     tp.C = ivf->C;
@@ -776,9 +803,11 @@ static int32_t run_list_scan_tc(vers_ivf* ivf, const SearchBufs& b, const float*
     tp.lm_norm = ivf->d_lm_norm;
     tp.part_d = b.part_d;
     tp.part_p = b.part_p;
-    VERS_CUDA(cudaFuncSetAttribute(tc_list_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    tp.counter = b.counter;
+    auto kern = tc_list_scan_kernel<SPLIT3>;
+    VERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     FamilyTimer ft(ctx, KF_CAND_SCAN);
-    tc_list_scan_kernel<<<ctx->sm_count, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(tm_rows, tm_q, tp);
+    kern<<<ctx->sm_count, Cfg::THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(tm_rows, tm_q, tm_ql, tp);
     VERS_LAUNCH_CHECK(ctx);
     return VERS_OK;
 }
@@ -792,7 +821,8 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
     // candidate list length of the approximate pass: the private lists are one register per lane
     const uint32_t M = 32;
     const bool approx = !ref_mode && ivf->mode != 1 && k <= 16;
-    const bool use_tc = approx && ivf->mode == 0 && ivf->ld >= TC_KC && ivf->cap_total < 0x7fffffffull;
+    const bool use_tc = approx && (ivf->mode == 0 || ivf->mode == 3) && ivf->ld >= TC_KC && ivf->cap_total < 0x7fffffffull;
+    const bool split3 = use_tc && ivf->mode == 0;
     const uint64_t npairs = (uint64_t)nq * np;
     const uint64_t max_chunks = std::max<uint64_t>((uint64_t)nq * ivf_max_chunks_per_query(ivf, np), 1);
     size_t entries = (size_t)max_chunks * ScanCfg::NSPLIT * k;
@@ -823,6 +853,8 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
         b.part_d = sc.take<float>(entries);
         b.part_p = sc.take<uint32_t>(entries);
         b.gq = sc.take<float>(use_tc ? (size_t)(npairs + 16) * ivf->ld : 4);
+        b.gq_lo = sc.take<float>(split3 ? (size_t)(npairs + 16) * ivf->ld : 4);
+        b.cand_key = sc.take<float>((size_t)nq * M);
     };
     {
         ScratchCarver plan(nullptr);
@@ -869,7 +901,10 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
         uint32_t nsplit;
         if (use_tc) {
             VERS_TRY(run_group(ivf, b, nq, np, nullptr, nullptr, true, TC_N));
-            VERS_TRY(run_list_scan_tc(ivf, b, d_queries, nq, np));
+            if (split3)
+                VERS_TRY(run_list_scan_tc<true>(ivf, b, d_queries, nq, np));
+            else
+                VERS_TRY(run_list_scan_tc<false>(ivf, b, d_queries, nq, np));
             nsplit = TC_EPI_WARPS;
         } else {
             VERS_TRY(run_group(ivf, b, nq, np, nullptr, nullptr, true));
@@ -877,12 +912,12 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
             nsplit = StreamCfg::NSPLIT;
         }
         cand_merge_kernel<<<(unsigned)ceil_div(nq, 4), 128, (size_t)4 * M * 8, ctx->stream>>>(
-            b.part_d, b.part_p, b.pair_chunk_off, nq, np, M, nsplit, b.cand_pos, b.cand_bound);
+            b.part_d, b.part_p, b.pair_chunk_off, nq, np, M, nsplit, b.cand_pos, b.cand_key, b.cand_bound);
         VERS_LAUNCH_CHECK(ctx);
         size_t rsm = (size_t)4 * RERANK_QCHUNK * 4 + (size_t)4 * k * 12;
         FamilyTimer ftr(ctx, KF_RERANK);
         rerank_certify_kernel<<<(unsigned)ceil_div(nq, 4), 128, rsm, ctx->stream>>>(
-            ivf->d_lm, ivf->d_lm_ids, ivf->ld, d_queries, nq, k, M, b.cand_pos, b.cand_bound, ivf->d_nxmax, use_tc ? 1 : 0,
+            ivf->d_lm, ivf->d_lm_ids, ivf->ld, d_queries, nq, k, M, b.cand_pos, b.cand_bound, ivf->d_nxmax, b.cand_key, use_tc ? (split3 ? 2 : 1) : 0,
             d_ids, d_d, d_cnt, b.fail_flag, ivf->d_stats);
         VERS_LAUNCH_CHECK(ctx);
         qmask = b.fail_flag;  // 2b. exact-order redo of the (rare) uncertified queries, no host round trip
@@ -1132,7 +1167,7 @@ extern "C" int32_t vers_ivf_get_list(const vers_ivf* ivf, uint32_t list, uint64_
 }
 
 extern "C" int32_t vers_ivf_set_mode(vers_ivf* ivf, int32_t mode) {
-    if (!ivf || mode < 0 || mode > 2) return fail(VERS_ERR_ARG, "ivf_set_mode: bad argument");
+    if (!ivf || mode < 0 || mode > 3) return fail(VERS_ERR_ARG, "ivf_set_mode: bad argument");
     ivf->mode = mode;
     return VERS_OK;
 }

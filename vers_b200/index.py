@@ -338,11 +338,13 @@ class IVFFlatIndex:
         out = np.zeros(8, np.uint64)
         check(lib().vers_ivf_last_search_stats(self.h, ptr(out)))
         return dict(distinct_list_rows=int(out[0]), pair_rows=int(out[1]), work_items=int(out[2]),
-                    lists_touched=int(out[3]), uncertified_queries=int(out[4]), reranked=int(out[5]))
+                    lists_touched=int(out[3]), uncertified_queries=int(out[4]), reranked=int(out[5]),
+                    max_candidate_error=float(np.array([out[6]], np.uint64).astype(np.uint32).view(np.float32)[0]))
 
     def set_mode(self, mode):
-        """0 / False (default): tensor-core (TF32) candidate pass + exact-order rerank + certificate;
-        1 / True: exact order everywhere; 2: fp32 FMA candidate pass (SIMT) + rerank + certificate.
+        """0 / False (default): tensor-core candidate pass (TMA + tcgen05 TF32, split precision hi/lo) + exact-order
+        rerank + certificate; 1 / True: exact order everywhere; 2: fp32 FMA candidate pass (SIMT) + rerank +
+        certificate; 3: tensor-core candidate pass with plain (unsplit) TF32.
         Every mode returns the reference's ids and distance bits."""
         check(lib().vers_ivf_set_mode(self.h, int(mode)))
 

@@ -101,6 +101,12 @@ int32_t vers_kmeans_get_assignments(vers_kmeans* km, uint64_t* assignments);
 int32_t vers_kmeans_centroids_device_ptr(vers_kmeans* km, void** ptr, uint32_t* ld);
 /* assign_to_clusters over the local rows with the current centroids (first minimum wins) */
 int32_t vers_kmeans_assign_step(vers_kmeans* km);
+/* 0 (default): tensor-core candidate argmin (TMA + tcgen05 kind::tf32, M=128 x N=256 tiles) + a rounding-error
+ * certificate on the gap between the two smallest values, uncertified rows re-assigned in exact order;
+ * 1: exact order everywhere.  Both give the reference's assignments bit for bit. */
+int32_t vers_kmeans_set_mode(vers_kmeans* km, int32_t mode);
+/* rows of the most recent assign step whose candidate argmin was not certified (redone in exact order) */
+int32_t vers_kmeans_last_assign_stats(vers_kmeans* km, uint64_t* uncertified_rows);
 /* the Σ of update_centroids over the LOCAL rows in row order, continuing from the running sums in
  * d_sums_io [C][ld] f32 / d_counts_io [C] u64 (device; pass zeros on the first shard).  Chaining shards in row
  * order reproduces the reference's global left-to-right association exactly. */

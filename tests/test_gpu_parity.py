@@ -103,6 +103,13 @@ def test_assign_first_minimum_on_duplicate_centroids(vb, vo, ctx):
     want = vo.assign(rows, cents)
     assert np.array_equal(got, want)
     assert not np.any(np.isin(got, [2, 3, 5]))
+    # the tensor-core candidate pass sees exact ties between the twins: every row whose nearest centroid has a twin
+    # must fail its certificate and be redone in exact order
+    km = vb.KMeans(ds, 6)
+    km.set_centroids(cents)
+    km.assign_step()
+    assert np.array_equal(km.assignments(), want)
+    assert km.last_uncertified_rows >= int((want != 4).sum()) > 0
 
 
 @pytest.mark.parametrize("n,dim,C", [(10000, 300, 16), (5000, 128, 64), (1000, 20, 7)])
@@ -119,12 +126,16 @@ def test_update_centroids_bit_exact(vb, vo, ctx, n, dim, C):
     assert counts[3] == 0 and not cents[3].any()
 
 
-def test_kmeans_fit_and_cost_bit_exact(vb, vo, ctx):
-    n, dim, C = 10000, 300, 16
+@pytest.mark.parametrize("km_mode", [0, 1])
+@pytest.mark.parametrize("n,dim,C", [(10000, 300, 16), (6000, 128, 300), (4097, 36, 129)])
+def test_kmeans_fit_and_cost_bit_exact(vb, vo, ctx, km_mode, n, dim, C):
+    """km_mode 0: tensor-core (tcgen05 split-TF32) candidate argmin + certificate + exact redo of uncertified rows;
+    km_mode 1: exact order only.  Iterations, assignments, centroid bits and cost bits must equal the oracle's."""
     rows = data(vo, n, dim)
     init = vo.init_rows(3, 1, C, n)[0]
     ds = vb.Dataset.upload(ctx, rows)
     km = vb.KMeans(ds, C)
+    km.set_mode(km_mode)
     km.init_from_rows(init)
     iters = km.fit(20)
     cents, assign, oit = vo.kmeans_fit(rows, init, 20)

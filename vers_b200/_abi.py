@@ -59,6 +59,8 @@ SIGNATURES = {
     "vers_kmeans_get_assignments": [vp, vp],
     "vers_kmeans_centroids_device_ptr": [vp, pvp, C.POINTER(u32)],
     "vers_kmeans_assign_step": [vp],
+    "vers_kmeans_set_mode": [vp, i32],
+    "vers_kmeans_last_assign_stats": [vp, C.POINTER(u64)],
     "vers_kmeans_sums_step_dev": [vp, vp, vp],
     "vers_kmeans_finalize_step_dev": [vp, vp, vp, C.POINTER(u32)],
     "vers_kmeans_cost_step": [vp, C.POINTER(f32)],

@@ -9,6 +9,7 @@
 
 #include "kmeans.cuh"
 #include "scan.cuh"
+#include "kmeans_tc.cuh"
 
 namespace vers {
 
@@ -278,6 +279,14 @@ extern "C" int32_t vers_kmeans_free(vers_kmeans* km) {
     cudaFree(km->d_rowdist);
     cudaFree(km->d_flag);
     cudaFree(km->d_cub);
+    cudaFree(km->d_row_norm);
+    cudaFree(km->d_cent_norm);
+    cudaFree(km->d_cent_hi);
+    cudaFree(km->d_cent_lo);
+    cudaFree(km->d_ncmax);
+    cudaFree(km->d_flagged);
+    cudaFree(km->d_nflagged);
+    cudaFree(km->d_exact);
     delete km;
     return VERS_OK;
 }
@@ -393,14 +402,88 @@ extern "C" int32_t vers_kmeans_centroids_device_ptr(vers_kmeans* km, void** ptr,
     return VERS_OK;
 }
 
+// tensor-core candidate argmin + certificate; uncertified rows redone by the exact-order kernel
+static int32_t kmeans_assign_tc(vers_kmeans* km) {
+    vers_dataset* ds = km->ds;
+    vers_ctx* ctx = ds->ctx;
+    cudaStream_t s = ctx->stream;
+    if (!km->d_row_norm) {
+        VERS_CUDA(cudaMalloc(&km->d_row_norm, ds->n * 4));
+        VERS_CUDA(cudaMalloc(&km->d_cent_norm, (size_t)km->C * 4));
+        VERS_CUDA(cudaMalloc(&km->d_cent_hi, (size_t)km->C * ds->ld * 4));
+        VERS_CUDA(cudaMalloc(&km->d_cent_lo, (size_t)km->C * ds->ld * 4));
+        VERS_CUDA(cudaMalloc(&km->d_ncmax, 4));
+        VERS_CUDA(cudaMalloc(&km->d_flagged, ds->n * 4));
+        VERS_CUDA(cudaMalloc(&km->d_nflagged, 4));
+        VERS_CUDA(cudaMalloc(&km->d_exact, ds->n * 4));
+        sqnorm_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(ds->d_rows, ds->ld, ds->n, km->d_row_norm, nullptr);
+        VERS_LAUNCH_CHECK(ctx);
+    }
+    VERS_CUDA(cudaMemsetAsync(km->d_ncmax, 0, 4, s));
+    VERS_CUDA(cudaMemsetAsync(km->d_nflagged, 0, 4, s));
+    sqnorm_kernel<<<(unsigned)ceil_div((uint64_t)km->C * 32, 256), 256, 0, s>>>(km->d_cents, ds->ld, km->C,
+                                                                               km->d_cent_norm, km->d_ncmax);
+    VERS_LAUNCH_CHECK(ctx);
+    split_tf32_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(km->d_cents, (uint64_t)km->C * (ds->ld >> 2), km->d_cent_hi,
+                                                        km->d_cent_lo);
+    VERS_LAUNCH_CHECK(ctx);
+    CUtensorMap tm_rows, tm_chi, tm_clo;
+    VERS_TRY(make_tmap_2d_f32(&tm_rows, ds->d_rows, ds->n, ds->ld, ds->ld, KA_M, KA_KC));
+    VERS_TRY(make_tmap_2d_f32(&tm_chi, km->d_cent_hi, km->C, ds->ld, ds->ld, KA_N, KA_KC));
+    VERS_TRY(make_tmap_2d_f32(&tm_clo, km->d_cent_lo, km->C, ds->ld, ds->ld, KA_N, KA_KC));
+    TcAssignParams p;
+    p.n_rows = ds->n;
+    p.C = km->C;
+    p.ld = ds->ld;
+    p.row_norm = km->d_row_norm;
+    p.cent_norm = km->d_cent_norm;
+    p.ncmax_bits = km->d_ncmax;
+    p.assign = km->d_assign;
+    p.flagged = km->d_flagged;
+    p.n_flagged = km->d_nflagged;
+    VERS_CUDA(cudaFuncSetAttribute(tc_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KA_SMEM_BYTES));
+    {
+        FamilyTimer ft(ctx, KF_ASSIGN);
+        const uint64_t nrb = ceil_div(ds->n, KA_M);
+        tc_assign_kernel<<<(unsigned)std::min<uint64_t>(nrb, ctx->sm_count), KA_THREADS, KA_SMEM_BYTES, s>>>(tm_rows,
+                                                                                                          tm_chi, tm_clo, p);
+        VERS_LAUNCH_CHECK(ctx);
+    }
+    uint32_t nf = 0;
+    VERS_CUDA(cudaMemcpyAsync(&nf, km->d_nflagged, 4, cudaMemcpyDeviceToHost, s));
+    VERS_CUDA(cudaStreamSynchronize(s));
+    km->last_flagged = nf;
+    if (nf) {
+        RowSrc A{ds->d_rows, km->d_flagged, ds->ld, nf};
+        VERS_TRY(kmeans_assign_rows(ctx, A, km->d_cents, km->C, ds->ld, km->d_exact));
+        scatter_assign_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(km->d_flagged, km->d_nflagged, km->d_exact, km->d_assign);
+        VERS_LAUNCH_CHECK(ctx);
+    }
+    return VERS_OK;
+}
+
 extern "C" int32_t vers_kmeans_assign_step(vers_kmeans* km) {
     if (!km) return fail(VERS_ERR_ARG, "kmeans_assign_step: null");
     vers_dataset* ds = km->ds;
     std::lock_guard<std::mutex> lk(ds->ctx->mu);
     VERS_CUDA(cudaSetDevice(ds->ctx->device));
     km->csr_valid = false;
+    if (km->mode == 0 && ds->ld >= KA_KC && ds->n >= 1 && ds->n < 0x7fffffffull) return kmeans_assign_tc(km);
+    km->last_flagged = 0;
     RowSrc A{ds->d_rows, nullptr, ds->ld, ds->n};
     return kmeans_assign_rows(ds->ctx, A, km->d_cents, km->C, ds->ld, km->d_assign);
+}
+
+extern "C" int32_t vers_kmeans_set_mode(vers_kmeans* km, int32_t mode) {
+    if (!km || mode < 0 || mode > 1) return fail(VERS_ERR_ARG, "kmeans_set_mode: bad argument");
+    km->mode = mode;
+    return VERS_OK;
+}
+
+extern "C" int32_t vers_kmeans_last_assign_stats(vers_kmeans* km, uint64_t* uncertified_rows) {
+    if (!km || !uncertified_rows) return fail(VERS_ERR_ARG, "kmeans_last_assign_stats: null");
+    *uncertified_rows = km->last_flagged;
+    return VERS_OK;
 }
 
 extern "C" int32_t vers_kmeans_sums_step_dev(vers_kmeans* km, float* d_sums_io, uint64_t* d_counts_io) {

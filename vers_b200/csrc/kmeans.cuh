@@ -20,6 +20,17 @@ struct vers_kmeans {
     void* d_cub = nullptr;
     size_t cub_bytes = 0;
     bool csr_valid = false;  // d_sorted_rows/d_off describe the current d_assign
+    // tensor-core candidate pass of assign (kmeans_tc.cuh)
+    int mode = 0;                    // 0 = tensor-core candidates + certificate + exact redo, 1 = exact order only
+    float* d_row_norm = nullptr;     // [n] ||x||^2, computed once (rows do not change)
+    float* d_cent_norm = nullptr;    // [C]
+    float* d_cent_hi = nullptr;      // [C][ld] tf32 hi part of the centroids
+    float* d_cent_lo = nullptr;      // [C][ld] tf32 lo part
+    uint32_t* d_ncmax = nullptr;     // [1] bits of max ||c||^2
+    uint32_t* d_flagged = nullptr;   // [n] rows whose candidate argmin was not certified
+    uint32_t* d_nflagged = nullptr;  // [1]
+    uint32_t* d_exact = nullptr;     // [n] exact re-assignments of the flagged rows
+    uint64_t last_flagged = 0;       // statistic of the most recent assign step
 };
 
 namespace vers {

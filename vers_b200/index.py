@@ -202,6 +202,16 @@ class KMeans:
     def assign_step(self):
         check(lib().vers_kmeans_assign_step(self.h))
 
+    def set_mode(self, mode: int):
+        """0 (default): tensor-core candidate argmin + certificate + exact redo; 1: exact order only"""
+        check(lib().vers_kmeans_set_mode(self.h, int(mode)))
+
+    @property
+    def last_uncertified_rows(self) -> int:
+        out = C.c_uint64(0)
+        check(lib().vers_kmeans_last_assign_stats(self.h, C.byref(out)))
+        return out.value
+
     def sums_step_dev(self, d_sums_ptr: int, d_counts_ptr: int):
         check(lib().vers_kmeans_sums_step_dev(self.h, C.c_void_p(d_sums_ptr), C.c_void_p(d_counts_ptr)))
 

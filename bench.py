@@ -46,7 +46,9 @@ def parse():
     ap.add_argument("--nprobe", type=int, default=32)
     ap.add_argument("--nq", type=int, default=1000)
     ap.add_argument("--k", type=int, default=10)
-    ap.add_argument("--n-centers", type=int, default=1024, help="natural clusters of the synthetic data")
+    ap.add_argument("--n-centers", type=int, default=65536,
+                    help="natural clusters of the synthetic data (65536 => ~150 rows each: k-means lists come out "
+                         "balanced and every probe opens a full-size list, ~78k rows scanned per query)")
     ap.add_argument("--kmeans-iters", type=int, default=2, help="max Lloyd iterations of the index build")
     ap.add_argument("--reduce", default="chained", choices=["chained", "allreduce"])
     ap.add_argument("--recall-queries", type=int, default=100)
@@ -154,7 +156,7 @@ def config_dict(args, n_gpus):
                         f"(BASELINE.json configs[3])",
             "rows": args.rows, "dim": args.dim, "nlist": args.nlist, "nprobe": args.nprobe, "top_k": args.k,
             "batch": args.nq, "sharding": f"rows/{n_gpus} per GPU, all-gather+merge of per-GPU top-k",
-            "kmeans_iters": args.kmeans_iters,
+            "kmeans_iters": args.kmeans_iters, "synthetic_natural_clusters": args.n_centers,
             "l2": "per-step scan (>= 3.8 GB per GPU) is far larger than the 126 MB L2; no flush needed"}
 
 
@@ -318,7 +320,11 @@ def main_ours(args):
     if dom_n:
         avg_ms = dom_ms / dom_n
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
-        kname = {"cand_scan": "list_scan_kernel<StreamCfg,1> (candidate pass: FMA dot, fp32 rows streamed once)",
+        cand_names = {0: "tc_list_scan_kernel<true> (candidate pass: TMA + tcgen05 kind::tf32 split hi/lo, fp32 rows "
+                         "streamed once)",
+                      3: "tc_list_scan_kernel<false> (candidate pass: TMA + tcgen05 kind::tf32)",
+                      2: "list_scan_kernel<StreamCfg,1> (candidate pass: fp32 FMA SIMT)"}
+        kname = {"cand_scan": cand_names.get(args.mode, "candidate pass"),
                  "list_scan": "list_scan_kernel<NarrowCfg,0> (exact-order scan)"}[dom]
         roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -327,7 +333,8 @@ def main_ours(args):
                 "family_ms_per_step": {k_: (v[0] / args.steps) for k_, v in fam.items()},
                 "pair_rows_per_launch": stats["pair_rows"], "lists_touched": stats["lists_touched"],
                 "uncertified_queries_last_step": stats["uncertified_queries"],
-                "reranked_candidates_last_step": stats["reranked"]}
+                "reranked_candidates_last_step": stats["reranked"],
+                "max_candidate_error_last_step": stats["max_candidate_error"]}
 
     cpu = None
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:

@@ -164,6 +164,12 @@ int32_t vers_ivf_search(vers_ivf* ivf, const float* queries, uint32_t nq, uint32
                         uint32_t nprobe, uint64_t* ids, float* dists, uint32_t* counts);
 int32_t vers_ivf_search_dev(vers_ivf* ivf, const float* d_queries, uint32_t nq, uint32_t top_k, uint32_t nprobe,
                             uint64_t* d_ids, float* d_dists, uint32_t* d_counts);
+/* The two halves of a nprobe >= 1 search, for drivers that split the centroid probe of a batch over several GPUs
+ * (the centroids are replicated, so any GPU can probe any query): probe_dev writes the nprobe nearest lists of each
+ * query by (distance, centroid index), exact order (ivfflat.rs:155-161); search_probed_dev scans exactly those lists. */
+int32_t vers_ivf_probe_dev(vers_ivf* ivf, const float* d_queries, uint32_t nq, uint32_t nprobe, uint64_t* d_probe_ids);
+int32_t vers_ivf_search_probed_dev(vers_ivf* ivf, const float* d_queries, uint32_t nq, uint32_t top_k, uint32_t nprobe,
+                                   const uint64_t* d_probe_ids, uint64_t* d_ids, float* d_dists, uint32_t* d_counts);
 /* Index::add (ivfflat.rs:200-213): nearest centroid by first minimum; vec_id is IGNORED like the reference
  * (the id is assignments.len()); *assigned_id / *cluster report what was stored. */
 int32_t vers_ivf_add(vers_ivf* ivf, const float* embedding, uint64_t vec_id, uint64_t* assigned_id,

@@ -80,6 +80,8 @@ SIGNATURES = {
     "vers_ivf_set_mode": [vp, i32],
     "vers_ivf_search": [vp, vp, u32, u32, u32, u32, vp, vp, vp],
     "vers_ivf_search_dev": [vp, vp, u32, u32, u32, vp, vp, vp],
+    "vers_ivf_probe_dev": [vp, vp, u32, u32, vp],
+    "vers_ivf_search_probed_dev": [vp, vp, u32, u32, u32, vp, vp, vp, vp],
     "vers_ivf_add": [vp, vp, u64, C.POINTER(u64), C.POINTER(u32)],
     "vers_topk_merge_dev": [vp, vp, vp, u32, u64, u64, u32, u32, vp, vp, vp],
     "vers_lsh_hash": [vp, vp, u32, u32, vp, vp],

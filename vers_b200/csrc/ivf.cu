@@ -813,7 +813,8 @@ static int32_t run_list_scan_tc(vers_ivf* ivf, const SearchBufs& b, const float*
 }
 
 static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint32_t nq, uint32_t k, uint32_t nprobe,
-                                     uint64_t* d_ids, float* d_d, uint32_t* d_cnt) {
+                                     uint64_t* d_ids, float* d_d, uint32_t* d_cnt,
+                                     const uint64_t* ext_probe = nullptr) {
     vers_ctx* ctx = ivf->ctx;
     const bool ref_mode = nprobe == 0;
     const uint32_t np = ref_mode ? std::min<uint32_t>(ivf->C, VERS_MAX_TOPK) : std::min<uint32_t>(nprobe, ivf->C);
@@ -865,10 +866,15 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
     carve(sc);
 
     // 1. probe: exact-order distances to every centroid, top-np by (distance, centroid index)
-    RowSrc CA{ivf->d_cents, nullptr, ivf->ld, ivf->C};
-    RowSrc QB{d_queries, nullptr, ivf->ld, nq};
-    VERS_TRY(scan_topk_run(ctx, probe_plan, ctx->scratch, CA, QB, nq, ivf->ld, np, VERS_METRIC_L2SQ, nullptr, 0,
-                           b.probe_ids, b.probe_d, nullptr, KF_PROBE));
+    //    (or the caller's probe lists: the multi-GPU driver splits the probe of a batch over the ranks)
+    if (ext_probe) {
+        VERS_CUDA(cudaMemcpyAsync(b.probe_ids, ext_probe, (size_t)npairs * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        RowSrc CA{ivf->d_cents, nullptr, ivf->ld, ivf->C};
+        RowSrc QB{d_queries, nullptr, ivf->ld, nq};
+        VERS_TRY(scan_topk_run(ctx, probe_plan, ctx->scratch, CA, QB, nq, ivf->ld, np, VERS_METRIC_L2SQ, nullptr, 0,
+                               b.probe_ids, b.probe_d, nullptr, KF_PROBE));
+    }
     VERS_CUDA(cudaMemsetAsync(ivf->d_stats, 0, 64, ctx->stream));
     VERS_CUDA(cudaMemsetAsync(b.counter, 0, 16, ctx->stream));
     uint32_t* short_flag = reinterpret_cast<uint32_t*>(b.counter + 1);
@@ -1108,6 +1114,37 @@ extern "C" int32_t vers_ivf_search_dev(vers_ivf* ivf, const float* d_queries, ui
 namespace vers {
 int32_t upload_queries(vers_ctx* ctx, const float* q, uint32_t nq, uint32_t stride, uint32_t dim, uint32_t ld,
                        float** d_q);
+}
+
+extern "C" int32_t vers_ivf_probe_dev(vers_ivf* ivf, const float* d_queries, uint32_t nq, uint32_t nprobe,
+                                      uint64_t* d_probe_ids) {
+    if (!ivf || (!d_queries && nq) || !d_probe_ids) return fail(VERS_ERR_ARG, "ivf_probe_dev: null argument");
+    if (nq == 0 || nprobe == 0) return VERS_OK;
+    if (nprobe > ivf->C || nprobe > VERS_MAX_TOPK) return fail(VERS_ERR_ARG, "ivf_probe_dev: nprobe %u out of range", nprobe);
+    vers_ctx* ctx = ivf->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    VERS_CUDA(cudaSetDevice(ctx->device));
+    const ScanPlan plan = scan_topk_plan(ctx, ivf->C, nq, nprobe);
+    const size_t off = (plan.bytes + 255) & ~size_t(255);
+    VERS_TRY(scratch_reserve(ctx, off + (size_t)nq * nprobe * 4 + 256));
+    float* d_pd = reinterpret_cast<float*>((char*)ctx->scratch + off);
+    RowSrc CA{ivf->d_cents, nullptr, ivf->ld, ivf->C};
+    RowSrc QB{d_queries, nullptr, ivf->ld, nq};
+    return scan_topk_run(ctx, plan, ctx->scratch, CA, QB, nq, ivf->ld, nprobe, VERS_METRIC_L2SQ, nullptr, 0, d_probe_ids,
+                         d_pd, nullptr, KF_PROBE);
+}
+
+extern "C" int32_t vers_ivf_search_probed_dev(vers_ivf* ivf, const float* d_queries, uint32_t nq, uint32_t top_k,
+                                              uint32_t nprobe, const uint64_t* d_probe_ids, uint64_t* d_ids,
+                                              float* d_dists, uint32_t* d_counts) {
+    if (!ivf || (!d_queries && nq) || !d_ids || !d_dists || !d_probe_ids)
+        return fail(VERS_ERR_ARG, "ivf_search_probed_dev: null argument");
+    if (top_k > VERS_MAX_TOPK) return fail(VERS_ERR_UNSUPPORTED, "top_k %u > %u", top_k, VERS_MAX_TOPK);
+    if (nprobe == 0 || nprobe > ivf->C) return fail(VERS_ERR_ARG, "ivf_search_probed_dev: nprobe %u out of range", nprobe);
+    if (nq == 0 || top_k == 0) return VERS_OK;
+    std::lock_guard<std::mutex> lk(ivf->ctx->mu);
+    VERS_CUDA(cudaSetDevice(ivf->ctx->device));
+    return ivf_search_dev_locked(ivf, d_queries, nq, top_k, nprobe, d_ids, d_dists, d_counts, d_probe_ids);
 }
 
 extern "C" int32_t vers_ivf_search(vers_ivf* ivf, const float* queries, uint32_t nq, uint32_t q_stride_floats,

@@ -182,7 +182,25 @@ class ShardedIVFFlat:
             self.ivf.search_batch_dev(d_queries.data_ptr(), nq, top_k, nprobe, out_ids.data_ptr(), out_d.data_ptr(),
                                       out_c.data_ptr())
             return out_ids, out_d, out_c
-        self.ivf.search_batch_dev(d_queries.data_ptr(), nq, top_k, nprobe, ids_ptr, d_ptr, out_c.data_ptr())
+        # the centroid probe is replicated work: every rank probes 1/world of the batch, the probe lists are
+        # all-gathered (nq x nprobe x 8 B), then every rank scans its row shard of exactly those lists
+        per = (nq + self.world - 1) // self.world
+        npb = min(nprobe, self.ivf.num_centroids)
+        key = ("probe", nq, npb)
+        if key not in self._bufs:
+            dev = d_queries.device
+            self._bufs[key] = (torch.full((per, npb), -1, dtype=torch.int64, device=dev),
+                               torch.empty((self.world * per, npb), dtype=torch.int64, device=dev))
+        p_local, p_all = self._bufs[key]
+        q0 = min(nq, self.rank * per)
+        nql = max(0, min(nq, q0 + per) - q0)
+        if nql:
+            check(lib().vers_ivf_probe_dev(self.ivf.h, C.c_void_p(d_queries.data_ptr() + q0 * d_queries.shape[1] * 4), nql,
+                                           npb, C.c_void_p(p_local.data_ptr())))
+        dist.all_gather_into_tensor(p_all, p_local)
+        check(lib().vers_ivf_search_probed_dev(self.ivf.h, C.c_void_p(d_queries.data_ptr()), nq, top_k, npb,
+                                               C.c_void_p(p_all.data_ptr()), C.c_void_p(ids_ptr), C.c_void_p(d_ptr),
+                                               C.c_void_p(out_c.data_ptr())))
         dist.all_gather_into_tensor(allb, local)
         base = allb.data_ptr()
         check(lib().vers_topk_merge_dev(self.ctx.h, C.c_void_p(base), C.c_void_p(base + nk * 8), self.world, L, 2 * L,

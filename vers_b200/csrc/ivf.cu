@@ -96,7 +96,7 @@ struct GroupParams {
     const uint32_t* used;       // optional [nq]: only slots s < used[q] are active (reference spill mode)
     const uint32_t* qmask;      // optional [nq]: only queries with a non-zero mask are active (exact fallback pass)
     uint32_t nq, np, C;
-    uint32_t tb;          // queries per work-item group (8 for the SIMT scans, 16 for the tensor-core scan)
+    uint32_t tb;          // queries per work-item group (8 for the SIMT scans, 32 for the tensor-core scan)
     uint32_t* lq_cnt;     // [C]   queries per list
     uint32_t* pair_nch;   // [nq*np] chunks of the pair's list (0 for inactive pairs / empty lists)
     uint32_t* item_cnt;   // [C]   work items per list
@@ -707,8 +707,8 @@ struct SearchBufs {
     float* cand_bound;
     float* part_d;
     uint32_t* part_p;
-    float* gq;     // [npairs + 16][ld] queries regrouped by list (tensor-core scan only), tf32 hi part
-    float* gq_lo;  // [npairs + 16][ld] their tf32 lo part (split-precision scan)
+    float* gq;     // [npairs + 32][ld] queries regrouped by list (tensor-core scan only), tf32 hi part
+    float* gq_lo;  // [npairs + 32][ld] their tf32 lo part (split-precision scan)
     float* cand_key;  // [nq][M] candidate keys (observed-error statistic)
 };
 
@@ -787,10 +787,13 @@ static int32_t run_list_scan_tc(vers_ivf* ivf, const SearchBufs& b, const float*
     gather_queries_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_queries, b.lq_query, b.lq_off, ivf->C, ivf->ld,
                                                                      b.gq, b.gq_lo, SPLIT3 ? 1 : 0);
     VERS_LAUNCH_CHECK(ctx);
-    CUtensorMap tm_rows, tm_q, tm_ql;
+    CUtensorMap tm_rows, tm_q16, tm_ql16, tm_q32, tm_ql32;
+    const float* lo_src = SPLIT3 ? b.gq_lo : b.gq;
     VERS_TRY(make_tmap_2d_f32(&tm_rows, ivf->d_lm, ivf->cap_total ? ivf->cap_total : 1, ivf->ld, ivf->ld, TC_M, TC_KC));
-    VERS_TRY(make_tmap_2d_f32(&tm_q, b.gq, npairs + 16, ivf->ld, ivf->ld, TC_N, TC_KC));
-    VERS_TRY(make_tmap_2d_f32(&tm_ql, SPLIT3 ? b.gq_lo : b.gq, npairs + 16, ivf->ld, ivf->ld, TC_N, TC_KC));
+    VERS_TRY(make_tmap_2d_f32(&tm_q16, b.gq, npairs + TC_NQ, ivf->ld, ivf->ld, 16, TC_KC));
+    VERS_TRY(make_tmap_2d_f32(&tm_ql16, lo_src, npairs + TC_NQ, ivf->ld, ivf->ld, 16, TC_KC));
+    VERS_TRY(make_tmap_2d_f32(&tm_q32, b.gq, npairs + TC_NQ, ivf->ld, ivf->ld, 32, TC_KC));
+    VERS_TRY(make_tmap_2d_f32(&tm_ql32, lo_src, npairs + TC_NQ, ivf->ld, ivf->ld, 32, TC_KC));
     TcScanParams tp;
     tp.ld = ivf->ld;
     tp.C = ivf->C;
@@ -807,7 +810,7 @@ static int32_t run_list_scan_tc(vers_ivf* ivf, const SearchBufs& b, const float*
     auto kern = tc_list_scan_kernel<SPLIT3>;
     VERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     FamilyTimer ft(ctx, KF_CAND_SCAN);
-    kern<<<ctx->sm_count, Cfg::THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(tm_rows, tm_q, tm_ql, tp);
+    kern<<<ctx->sm_count, Cfg::THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(tm_rows, tm_q16, tm_ql16, tm_q32, tm_ql32, tp);
     VERS_LAUNCH_CHECK(ctx);
     return VERS_OK;
 }
@@ -827,7 +830,7 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
     const uint64_t npairs = (uint64_t)nq * np;
     const uint64_t max_chunks = std::max<uint64_t>((uint64_t)nq * ivf_max_chunks_per_query(ivf, np), 1);
     size_t entries = (size_t)max_chunks * ScanCfg::NSPLIT * k;
-    if (approx) entries = std::max(entries, (size_t)max_chunks * std::max<size_t>(StreamCfg::NSPLIT, TC_EPI_WARPS) * M);
+    if (approx) entries = std::max(entries, (size_t)max_chunks * std::max<size_t>(StreamCfg::NSPLIT, TC_PARTS) * M);
 
     // the probe carves its partial buffers from the front of the arena, ours come after it
     const ScanPlan probe_plan = scan_topk_plan(ctx, ivf->C, nq, np);
@@ -853,8 +856,8 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
         b.counter = sc.take<unsigned long long>(2);
         b.part_d = sc.take<float>(entries);
         b.part_p = sc.take<uint32_t>(entries);
-        b.gq = sc.take<float>(use_tc ? (size_t)(npairs + 16) * ivf->ld : 4);
-        b.gq_lo = sc.take<float>(split3 ? (size_t)(npairs + 16) * ivf->ld : 4);
+        b.gq = sc.take<float>(use_tc ? (size_t)(npairs + TC_NQ) * ivf->ld : 4);
+        b.gq_lo = sc.take<float>(split3 ? (size_t)(npairs + TC_NQ) * ivf->ld : 4);
         b.cand_key = sc.take<float>((size_t)nq * M);
     };
     {
@@ -906,12 +909,12 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
         // 2a. candidate pass (FMA, HBM-streaming) -> top-M per query -> exact-order rerank -> certificate
         uint32_t nsplit;
         if (use_tc) {
-            VERS_TRY(run_group(ivf, b, nq, np, nullptr, nullptr, true, TC_N));
+            VERS_TRY(run_group(ivf, b, nq, np, nullptr, nullptr, true, TC_NQ));
             if (split3)
                 VERS_TRY(run_list_scan_tc<true>(ivf, b, d_queries, nq, np));
             else
                 VERS_TRY(run_list_scan_tc<false>(ivf, b, d_queries, nq, np));
-            nsplit = TC_EPI_WARPS;
+            nsplit = TC_PARTS;
         } else {
             VERS_TRY(run_group(ivf, b, nq, np, nullptr, nullptr, true));
             VERS_TRY((run_list_scan<StreamCfg, 1>(ivf, b, d_queries, nq, M)));

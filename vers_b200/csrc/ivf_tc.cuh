@@ -3,48 +3,60 @@
 // The dot products x.q of the candidate pass run on the 5th-generation tensor cores instead of the fp32 SIMT pipe:
 //   * TMA (cp.async.bulk.tensor, 128-byte swizzle) streams 128-row x 32-float tiles of a list straight from the fp32
 //     list-major rows into shared memory — no 16-bit copy of the database, no register staging;
-//   * tcgen05.mma kind::tf32 (M=128, N=16, K=8) multiplies them with the group's <= 16 queries, accumulators in TMEM
-//     (two 16-column buffers, so the MMAs of tile t+1 overlap the epilogue of tile t);
+//   * tcgen05.mma kind::tf32 (M=128, K=8) multiplies them with a group of the list's queries, accumulators in TMEM
+//     (two buffers, so the MMAs of tile t+1 overlap the epilogue of tile t).  A group holds up to 32 queries: lists
+//     probed by <= 16 queries run with N=16, busier lists with N=32, so a list is streamed from HBM once per 32 of its
+//     queries;
 //   * SPLIT3 (default): TF32 keeps 10 mantissa bits, too coarse for the rounding-error certificate to separate real
 //     neighbours, so every operand is split x = hi + lo (hi = x with the low 13 mantissa bits cleared, lo = x - hi,
-//     exact in fp32) and three MMAs are issued per K-step: hi.hi + lo.hi + hi.lo (the dropped lo.lo term and the
+//     exact in fp32) and three products are formed per K-step: hi.hi + lo.hi + hi.lo (the dropped lo.lo term and the
 //     truncation of lo are <= 3 * 2^-20 |x||q| per product).  The tensor core itself truncates fp32 -> tf32 (measured:
 //     bit-identical results with and without clearing the low bits first), so the row tile as loaded IS x_hi; four
 //     converter warps compute x_lo from the landed tile and park it in TENSOR MEMORY (tcgen05.st), from where the
 //     lo.hi MMA takes its A operand — shared memory sees each row byte only three times (TMA write, converter
-//     read, MMA read).  hi.hi and hi.lo are ONE MMA against the concatenated [q_hi; q_lo] tile (N = 32); the two
-//     16-column halves are summed in the epilogue.  The queries are split once by the gather kernel;
-//   * the epilogue warps pull the 128x16 tile with tcgen05.ld, form the key ||x||^2 - 2 x.q and keep a private
-//     top-32 per query in registers.
+//     read, MMA read).  hi.hi and hi.lo are ONE MMA against the concatenated [q_hi; q_lo] tile (N = 2 NQ); the
+//     column blocks are summed in the epilogue.  The queries are split once by the gather kernel;
+//   * the epilogue (8 warps: 4 TMEM lane groups x 2 column halves) forms the key ||x||^2 - 2 x.q per (row, query) and
+//     keeps the 32 smallest (key, row) per (lane group, query): rows that beat the query's current 32nd key are
+//     appended to a 32-entry shared-memory queue with one ballot; a full queue is sorted across the lanes (bitonic
+//     network) and merged into the sorted list, which tightens the threshold.  Selection cost is per batch of 32
+//     survivors, not per survivor, so the epilogue stays far below the HBM time of a tile.
 // What leaves the kernel is the same (key, position) partial lists as the SIMT candidate pass, so the merge ->
 // exact-order rerank -> certificate -> exact redo chain behind it is unchanged.  The kernel does no fp32 SIMT math
 // per (row, query, dim): it is an HBM stream.
 //
-// Warp roles: 0 = scheduler + TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue (warp w reads TMEM
-// lanes 32*(w%4)..+31 = tile rows), 6..9 = hi/lo converters (SPLIT3 only).  mbarriers: full / conv / empty per smem
-// stage, tmem_full / tmem_empty per accumulator buffer, sched_full / sched_empty for the work-item ring (work items
-// = (list, 16-query group, 4096-row chunk), handed out dynamically through an atomic counter).
+// Warp roles (16 warps): 0 = scheduler + TMA producer, 1 = TMEM allocator + main MMA issuer, 2 = x_lo MMA issuer,
+// 3 = idle, 4..11 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31 = tile rows; warps 4..7 take the first half of
+// the group's query columns, 8..11 the second), 12..15 = hi/lo converters (SPLIT3 only).  mbarriers: full / conv /
+// empty per smem stage, tmem_full / tmem_empty per accumulator buffer, sched_full / sched_empty for the work-item
+// ring (work items = (list, query group, 4096-row chunk), handed out dynamically through an atomic counter).
 #pragma once
 #include "tc.cuh"
 
 namespace vers {
 
-constexpr int TC_M = 128, TC_N = 16, TC_KC = 32, TC_EPI_WARPS = 4, TC_CONV_WARPS = 4, TC_CONV_GROUPS = 1, TC_SCHED = 4;
-constexpr int TC_A_BYTES = TC_M * TC_KC * 4, TC_B_BYTES = TC_N * TC_KC * 4;
+constexpr int TC_M = 128, TC_NQ = 32, TC_KC = 32, TC_SCHED = 4;
+constexpr int TC_PARTS = 4;       // partial lists per (pair, chunk): one per TMEM lane group
+constexpr int TC_EPI_WARP0 = 4, TC_EPI_WARPS = 8, TC_CONV_WARP0 = 12, TC_CONV_WARPS = 4;
+constexpr int TC_QPW = TC_NQ / 2;  // query columns per epilogue warp (at most)
+constexpr int TC_QCAP = 32;       // queue entries per (epilogue warp, query)
+constexpr int TC_A_BYTES = TC_M * TC_KC * 4;
 
 template <bool SPLIT3>
 struct TcCfg {
-    static constexpr int STAGES = 10;  // ~200 KB of row tiles in flight per SM: covers HBM latency + convert + MMA
-    static constexpr int THREADS = SPLIT3 ? (6 + TC_CONV_WARPS * TC_CONV_GROUPS + 1) * 32 : 192;  // + lo-MMA issuer warp
-    static constexpr int LO_WARP = 6 + TC_CONV_WARPS * TC_CONV_GROUPS;
-    static constexpr int NB = SPLIT3 ? 2 * TC_N : TC_N;         // B rows per stage: [q_hi; q_lo] or q
-    static constexpr int ACC_COLS = SPLIT3 ? 3 * TC_N : TC_N;    // per buffer: [hi.hi | hi.lo | lo.hi] or [x.q]
-    static constexpr int STAGE_BYTES = TC_A_BYTES + NB * TC_KC * 4;
-    static constexpr int TX_BYTES = STAGE_BYTES;
+    static constexpr int STAGES = 7;
+    static constexpr int THREADS = SPLIT3 ? 512 : 384;
+    static constexpr int B_ROWS = SPLIT3 ? 2 * TC_NQ : TC_NQ;      // B rows per stage at most: [q_hi; q_lo] or q
+    static constexpr int ACC_COLS = SPLIT3 ? 3 * TC_NQ : TC_NQ;    // per buffer: [hi.hi | hi.lo | lo.hi] or [x.q]
+    static constexpr int STAGE_BYTES = TC_A_BYTES + B_ROWS * TC_KC * 4;
     static constexpr int OFF_B = TC_A_BYTES;
-    static constexpr int ALO_COL0 = 2 * ACC_COLS;                // x_lo tiles live in TMEM after the accumulators
-    static constexpr uint32_t TMEM_COLS = SPLIT3 ? 512 : 32;     // 96 + 10*32 = 416 -> 512 / 2*16 = 32
-    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 512;
+    static constexpr int ALO_COL0 = 2 * ACC_COLS;                  // x_lo tiles live in TMEM after the accumulators
+    static constexpr uint32_t TMEM_COLS = SPLIT3 ? 512 : 64;       // 192 + 7*32 = 416 -> 512 / 2*32 = 64
+    // per epilogue warp: sorted list + queue, keys (fp32) and row offsets (u16), for TC_QPW queries
+    static constexpr int SEL_WARP_BYTES = TC_QPW * (32 + TC_QCAP) * 6;
+    static constexpr int OFF_SEL = STAGES * STAGE_BYTES;
+    static constexpr int OFF_BAR = OFF_SEL + TC_EPI_WARPS * SEL_WARP_BYTES;
+    static constexpr int SMEM_BYTES = 1024 + OFF_BAR + 1024;
 };
 
 // queries regrouped by list (row i = the i-th grouped (query, list) pair), split into tf32 hi and lo parts
@@ -72,6 +84,7 @@ __global__ void gather_queries_kernel(const float* __restrict__ queries, const u
     }
 }
 
+
 struct TcScanParams {
     uint32_t ld, C;
     const uint64_t* seg_off;
@@ -88,7 +101,8 @@ struct TcScanParams {
 
 struct TcItem {
     uint32_t list, chunk;
-    uint64_t q0, nB, base_pos, r0, r1;
+    uint32_t nB, nq;  // live queries of the group; MMA width of the group (16 or 32)
+    uint64_t q0, base_pos, r0, r1;
 };
 
 __device__ __forceinline__ TcItem tc_decode_item(const TcScanParams& p, uint64_t it) {
@@ -104,25 +118,74 @@ __device__ __forceinline__ TcItem tc_decode_item(const TcScanParams& p, uint64_t
     const uint32_t nch = (len + LIST_CHUNK_ROWS - 1) / LIST_CHUNK_ROWS;
     const uint32_t group = (uint32_t)(local / nch);
     t.chunk = (uint32_t)(local % nch);
-    t.q0 = p.lq_off[lo] + (uint64_t)group * TC_N;
+    t.q0 = p.lq_off[lo] + (uint64_t)group * TC_NQ;
     const uint64_t m_l = p.lq_off[lo + 1] - p.lq_off[lo];
-    t.nB = min((uint64_t)TC_N, m_l - (uint64_t)group * TC_N);
+    t.nB = (uint32_t)min((uint64_t)TC_NQ, m_l - (uint64_t)group * TC_NQ);
+    t.nq = t.nB <= 16 ? 16u : 32u;
     t.base_pos = p.seg_off[lo];
     t.r0 = (uint64_t)t.chunk * LIST_CHUNK_ROWS;
     t.r1 = min((uint64_t)len, t.r0 + LIST_CHUNK_ROWS);
     return t;
 }
 
+// ---- selection helpers of the epilogue: entries are (key, row offset in the item), ordered by key then offset
+__device__ __forceinline__ bool sel_less(float d0, uint32_t r0, float d1, uint32_t r1) {
+    return d0 < d1 || (d0 == d1 && r0 < r1);
+}
+// one compare-exchange step of a bitonic network across the lanes: partner = lane ^ j, keep the smaller entry when
+// keep_min, else the larger
+__device__ __forceinline__ void sel_cmpx(float& d, uint32_t& r, int j, bool keep_min) {
+    const float od = __shfl_xor_sync(FULL_MASK, d, j);
+    const uint32_t orr = __shfl_xor_sync(FULL_MASK, r, j);
+    const bool other_less = sel_less(od, orr, d, r);
+    const bool self_less = sel_less(d, r, od, orr);
+    if (keep_min ? other_less : self_less) {
+        d = od;
+        r = orr;
+    }
+}
+// Folds the c (<= 32) queued entries of one query into its sorted 32-entry list; returns the new 32nd key.
+//   lk/lr: the list (ascending, lane i = i-th smallest); qk/qr: the queue.  Whole warp, converged.
+__device__ __noinline__ float sel_flush(float* lk, uint16_t* lr, const float* qk, const uint16_t* qr, uint32_t c, int lane) {
+    __syncwarp();  // the queue writes of the other lanes are visible
+    float d = (uint32_t)lane < c ? qk[lane] : __int_as_float(0x7f800000);
+    uint32_t r = (uint32_t)lane < c ? (uint32_t)qr[lane] : 0xffffu;
+    // sort the batch DESCENDING across the lanes (bitonic sorting network, 15 steps)
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool desc_block = (lane & k) == 0 || k == 32;  // final pass: one descending run
+            const bool lower = (lane & j) == 0;
+            sel_cmpx(d, r, j, desc_block ? !lower : lower);
+        }
+    }
+    // list ascending, batch descending: the lane-wise minimum is the smaller half of the union, as a bitonic sequence
+    float ld_ = lk[lane];
+    uint32_t lrr = lr[lane];
+    if (sel_less(d, r, ld_, lrr)) {
+        ld_ = d;
+        lrr = r;
+    }
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) sel_cmpx(ld_, lrr, j, (lane & j) == 0);  // bitonic merge, ascending
+    lk[lane] = ld_;
+    lr[lane] = (uint16_t)lrr;
+    __syncwarp();
+    return __shfl_sync(FULL_MASK, ld_, 31);
+}
+
 template <bool SPLIT3>
 __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
-    tc_list_scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_qhi,
-                        const __grid_constant__ CUtensorMap tmap_qlo, TcScanParams p) {
+    tc_list_scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_qhi16,
+                        const __grid_constant__ CUtensorMap tmap_qlo16, const __grid_constant__ CUtensorMap tmap_qhi32,
+                        const __grid_constant__ CUtensorMap tmap_qlo32, TcScanParams p) {
     using Cfg = TcCfg<SPLIT3>;
     constexpr int S = Cfg::STAGES;
     extern __shared__ uint8_t tc_smem_raw[];
     const uint32_t raw = tc::smem_u32(tc_smem_raw);
     uint8_t* smem = tc_smem_raw + (((raw + 1023u) & ~1023u) - raw);  // SWIZZLE_128B tiles need 1024-byte alignment
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
     uint64_t* conv = full + S;
     uint64_t* empty = conv + S;
     uint64_t* tfull = empty + S;
@@ -135,8 +198,8 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t total_items = p.item_off[p.C];
     const uint32_t nk = (p.ld + TC_KC - 1) / TC_KC;
-    // consumers of a scheduled item besides the producer: MMA thread + epilogue warps (+ converter warps)
-    constexpr uint32_t SCHED_CONSUMERS = 1 + TC_EPI_WARPS + (SPLIT3 ? TC_CONV_WARPS * TC_CONV_GROUPS + 1 : 0);
+    // consumers of a scheduled item besides the producer: MMA thread + epilogue warps (+ lo MMA thread + converters)
+    constexpr uint32_t SCHED_CONSUMERS = 1 + TC_EPI_WARPS + (SPLIT3 ? 1 + TC_CONV_WARPS : 0);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -154,8 +217,12 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
         }
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&tmap_rows);
-        tc::tma_prefetch_desc(&tmap_qhi);
-        if (SPLIT3) tc::tma_prefetch_desc(&tmap_qlo);
+        tc::tma_prefetch_desc(&tmap_qhi16);
+        tc::tma_prefetch_desc(&tmap_qhi32);
+        if (SPLIT3) {
+            tc::tma_prefetch_desc(&tmap_qlo16);
+            tc::tma_prefetch_desc(&tmap_qlo32);
+        }
     }
     if (warp == 1) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tc::fence_before_thread_sync();
@@ -193,15 +260,20 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
                 }
                 if (it < 0) break;
                 const TcItem t = tc_decode_item(p, (uint64_t)it);
+                const bool wide = t.nq == 32;
+                const CUtensorMap* mhi = wide ? &tmap_qhi32 : &tmap_qhi16;
+                const CUtensorMap* mlo = wide ? &tmap_qlo32 : &tmap_qlo16;
+                const uint32_t b_bytes = t.nq * TC_KC * 4;
+                const uint32_t tx = TC_A_BYTES + (SPLIT3 ? 2 : 1) * b_bytes;
                 for (uint64_t a0 = t.r0; a0 < t.r1; a0 += TC_M) {
                     for (uint32_t kc = 0; kc < nk; ++kc) {
                         tc::mbar_wait(&empty[stage], phase ^ 1);
-                        tc::mbar_arrive_expect_tx(&full[stage], Cfg::TX_BYTES);
+                        tc::mbar_arrive_expect_tx(&full[stage], tx);
                         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                         tc::tma_load_2d(sa, &tmap_rows, &full[stage], (int32_t)(kc * TC_KC), (int32_t)(t.base_pos + a0));
-                        tc::tma_load_2d(sa + Cfg::OFF_B, &tmap_qhi, &full[stage], (int32_t)(kc * TC_KC), (int32_t)t.q0);
+                        tc::tma_load_2d(sa + Cfg::OFF_B, mhi, &full[stage], (int32_t)(kc * TC_KC), (int32_t)t.q0);
                         if (SPLIT3)
-                            tc::tma_load_2d(sa + Cfg::OFF_B + TC_B_BYTES, &tmap_qlo, &full[stage], (int32_t)(kc * TC_KC),
+                            tc::tma_load_2d(sa + Cfg::OFF_B + b_bytes, mlo, &full[stage], (int32_t)(kc * TC_KC),
                                             (int32_t)t.q0);
                         if (++stage == S) {
                             stage = 0;
@@ -214,12 +286,13 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc_main = tc::idesc_tf32(TC_M, Cfg::NB);  // x_hi . [q_hi; q_lo]  (or x . q unsplit)
             uint32_t stage = 0, phase = 0, tile_ctr = 0;
             while (true) {
                 const long long it = next_item(true, false);
                 if (it < 0) break;
                 const TcItem t = tc_decode_item(p, (uint64_t)it);
+                // x_hi . [q_hi; q_lo]  (or x . q unsplit)
+                const uint32_t idesc_main = tc::idesc_tf32(TC_M, SPLIT3 ? 2 * t.nq : t.nq);
                 for (uint64_t a0 = t.r0; a0 < t.r1; a0 += TC_M) {
                     const uint32_t buf = tile_ctr & 1, tphase = (tile_ctr >> 1) & 1;
                     tc::mbar_wait(&tempty[buf], tphase ^ 1);  // epilogue has drained this accumulator buffer
@@ -244,96 +317,21 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
                 }
             }
         }
-    } else if (warp < 2 + TC_EPI_WARPS) {
-        // ===================== epilogue: TMEM -> keys -> private top-32 per query =====================
-        const int lane_group = warp & 3;  // TMEM lanes this warp may touch
-        const int epi = warp - 2;         // partial-list slot of this warp
-        uint32_t tile_ctr = 0;
-        while (true) {
-            const long long it = next_item(lane == 0, true);
-            if (it < 0) break;
-            const TcItem t = tc_decode_item(p, (uint64_t)it);
-            float rl_d[TC_N], tau_d[TC_N];
-            uint32_t rl_p[TC_N], tau_p[TC_N];
-#pragma unroll
-            for (int j = 0; j < TC_N; ++j) {
-                rl_d[j] = tau_d[j] = __int_as_float(0x7f800000);
-                rl_p[j] = tau_p[j] = 0xffffffffu;
-            }
-            for (uint64_t a0 = t.r0; a0 < t.r1; a0 += TC_M) {
-                const uint32_t buf = tile_ctr & 1, tphase = (tile_ctr >> 1) & 1;
-                tc::mbar_wait(&tfull[buf], tphase);
-                tc::fence_after_thread_sync();
-                float v[TC_N];
-                const uint32_t tacc = tmem_base + ((uint32_t)(lane_group * 32) << 16) + buf * Cfg::ACC_COLS;
-                tc::tmem_ld_16(tacc, v);
-                if (SPLIT3) {
-                    float w[TC_N], z[TC_N];
-                    tc::tmem_ld_16(tacc + TC_N, w);      // x_hi . q_lo
-                    tc::tmem_ld_16(tacc + 2 * TC_N, z);  // x_lo . q_hi
-#pragma unroll
-                    for (int j = 0; j < TC_N; ++j) v[j] = __fadd_rn(v[j], __fadd_rn(w[j], z[j]));
-                }
-                tc::fence_before_thread_sync();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&tempty[buf]);
-                ++tile_ctr;
-                const uint64_t row = a0 + (uint64_t)(lane_group * 32 + lane);
-                const bool rowlive = row < t.r1;
-                const uint32_t pos = (uint32_t)(t.base_pos + row);
-                const float nx = rowlive ? __ldg(p.lm_norm + pos) : 0.0f;
-#pragma unroll
-                for (int j = 0; j < TC_N; ++j) {
-                    const float key = __fmaf_rn(-2.0f, v[j], nx);
-                    bool live = rowlive && (uint64_t)j < t.nB;
-                    while (true) {
-                        bool pass = live && entry_less<uint32_t>(key, pos, tau_d[j], tau_p[j]);
-                        unsigned m = __ballot_sync(FULL_MASK, pass);
-                        if (!m) break;
-                        int src = __ffs(m) - 1;
-                        float cv = __shfl_sync(FULL_MASK, key, src);
-                        uint32_t cp = __shfl_sync(FULL_MASK, pos, src);
-                        int ins = __popc(__ballot_sync(FULL_MASK, entry_less<uint32_t>(rl_d[j], rl_p[j], cv, cp)));
-                        float ud = __shfl_up_sync(FULL_MASK, rl_d[j], 1);
-                        uint32_t up = __shfl_up_sync(FULL_MASK, rl_p[j], 1);
-                        if (lane > ins) {
-                            rl_d[j] = ud;
-                            rl_p[j] = up;
-                        } else if (lane == ins) {
-                            rl_d[j] = cv;
-                            rl_p[j] = cp;
-                        }
-                        tau_d[j] = __shfl_sync(FULL_MASK, rl_d[j], 31);
-                        tau_p[j] = __shfl_sync(FULL_MASK, rl_p[j], 31);
-                        if (lane == src) live = false;
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < TC_N; ++j) {
-                if ((uint64_t)j < t.nB) {
-                    const uint32_t pair = p.lq_pair[t.q0 + j];
-                    const uint64_t base = ((p.pair_chunk_off[pair] + t.chunk) * TC_EPI_WARPS + epi) * 32;
-                    p.part_d[base + lane] = rl_d[j];
-                    p.part_p[base + lane] = rl_p[j];
-                }
-            }
-        }
-    } else if (SPLIT3 && warp == Cfg::LO_WARP) {
-        // ===================== second MMA issuer: x_lo (tensor memory) . q_hi -> its own 16 accumulator columns ====
+    } else if (warp == 2) {
+        // ===================== second MMA issuer: x_lo (tensor memory) . q_hi -> its own accumulator columns ========
         // (a separate thread so that neither issuer's instruction latency per stage exceeds the HBM time per stage)
-        if (lane == 0) {
-            const uint32_t idesc_lo = tc::idesc_tf32(TC_M, TC_N);
+        if (SPLIT3 && lane == 0) {
             uint32_t stage = 0, phase = 0, tile_ctr = 0;
             while (true) {
                 const long long it = next_item(true, false);
                 if (it < 0) break;
                 const TcItem t = tc_decode_item(p, (uint64_t)it);
+                const uint32_t idesc_lo = tc::idesc_tf32(TC_M, t.nq);
                 for (uint64_t a0 = t.r0; a0 < t.r1; a0 += TC_M) {
                     const uint32_t buf = tile_ctr & 1, tphase = (tile_ctr >> 1) & 1;
                     tc::mbar_wait(&tempty[buf], tphase ^ 1);
                     tc::fence_after_thread_sync();
-                    const uint32_t d_tmem = tmem_base + buf * Cfg::ACC_COLS + 2 * TC_N;
+                    const uint32_t d_tmem = tmem_base + buf * Cfg::ACC_COLS + 2 * t.nq;
                     for (uint32_t kc = 0; kc < nk; ++kc) {
                         tc::mbar_wait(&conv[stage], phase);  // x_lo of this stage is in tensor memory (implies full)
                         tc::fence_after_thread_sync();
@@ -353,26 +351,101 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
                 }
             }
         }
-    } else if (SPLIT3) {
+    } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_EPI_WARPS) {
+        // ===================== epilogue: TMEM -> keys -> 32 smallest (key, row) per (lane group, query) ==========
+        const int lane_group = warp & 3;                   // TMEM lanes this warp may touch
+        const uint32_t half = (uint32_t)(warp - TC_EPI_WARP0) >> 2;  // which half of the group's query columns
+        uint8_t* sel = smem + Cfg::OFF_SEL + (warp - TC_EPI_WARP0) * Cfg::SEL_WARP_BYTES;
+        float* lk = reinterpret_cast<float*>(sel);                       // [TC_QPW][32] sorted list keys
+        float* qk = lk + TC_QPW * 32;                                     // [TC_QPW][TC_QCAP] queue keys
+        uint16_t* lr = reinterpret_cast<uint16_t*>(qk + TC_QPW * TC_QCAP);  // [TC_QPW][32] list row offsets
+        uint16_t* qr = lr + TC_QPW * 32;                                  // [TC_QPW][TC_QCAP] queue row offsets
+        const uint32_t lt_mask = (1u << lane) - 1u;
+        uint32_t tile_ctr = 0;
+        while (true) {
+            const long long it = next_item(lane == 0, true);
+            if (it < 0) break;
+            const TcItem t = tc_decode_item(p, (uint64_t)it);
+            const uint32_t ncol = t.nq >> 1, col0 = half * ncol;
+            const uint32_t nlive = t.nB > col0 ? min(ncol, t.nB - col0) : 0u;  // this warp's live queries
+            // lane j keeps query j's threshold (its list's 32nd key) and queue fill
+            float my_tau = __int_as_float(0x7f800000);
+            uint32_t my_cnt = 0;
+            for (uint32_t j = 0; j < nlive; ++j) {
+                lk[j * 32 + lane] = __int_as_float(0x7f800000);
+                lr[j * 32 + lane] = 0xffffu;
+            }
+            __syncwarp();
+            const uint32_t c_hh = col0, c_hl = t.nq + col0, c_lh = 2 * t.nq + col0;
+            for (uint64_t a0 = t.r0; a0 < t.r1; a0 += TC_M) {
+                const uint32_t buf = tile_ctr & 1, tphase = (tile_ctr >> 1) & 1;
+                tc::mbar_wait(&tfull[buf], tphase);
+                tc::fence_after_thread_sync();
+                const uint32_t tacc = tmem_base + ((uint32_t)(lane_group * 32) << 16) + buf * Cfg::ACC_COLS;
+                const uint64_t row = a0 + (uint64_t)(lane_group * 32 + lane);
+                const bool rowlive = row < t.r1;
+                const uint32_t roff = (uint32_t)(row - t.r0);
+                const float nx = rowlive ? __ldg(p.lm_norm + t.base_pos + row) : 0.0f;
+                for (uint32_t j = 0; j < nlive; ++j) {
+                    float dot = tc::tmem_ld_1_nowait(tacc + c_hh + j);
+                    float w = 0.0f, z = 0.0f;
+                    if (SPLIT3) {
+                        w = tc::tmem_ld_1_nowait(tacc + c_hl + j);  // x_hi . q_lo
+                        z = tc::tmem_ld_1_nowait(tacc + c_lh + j);  // x_lo . q_hi
+                    }
+                    tc::tmem_ld_wait();
+                    if (SPLIT3) dot = __fadd_rn(dot, __fadd_rn(w, z));
+                    const float key = __fmaf_rn(-2.0f, dot, nx);
+                    float tau = __shfl_sync(FULL_MASK, my_tau, j);
+                    bool pass = rowlive && key <= tau;
+                    unsigned m = __ballot_sync(FULL_MASK, pass);
+                    if (m) {
+                        uint32_t c = __shfl_sync(FULL_MASK, my_cnt, j);
+                        uint32_t n = __popc(m);
+                        if (c + n > TC_QCAP) {  // make room: fold the queue into the list, which tightens tau
+                            tau = sel_flush(lk + j * 32, lr + j * 32, qk + j * TC_QCAP, qr + j * TC_QCAP, c, lane);
+                            if ((uint32_t)lane == j) my_tau = tau;
+                            c = 0;
+                            pass = pass && key <= tau;
+                            m = __ballot_sync(FULL_MASK, pass);
+                            n = __popc(m);
+                        }
+                        if (pass) {
+                            const uint32_t o = c + __popc(m & lt_mask);
+                            qk[j * TC_QCAP + o] = key;
+                            qr[j * TC_QCAP + o] = (uint16_t)roff;
+                        }
+                        if ((uint32_t)lane == j) my_cnt = c + n;
+                    }
+                }
+                tc::fence_before_thread_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&tempty[buf]);
+                ++tile_ctr;
+            }
+            const uint32_t pos0 = (uint32_t)(t.base_pos + t.r0);
+            for (uint32_t j = 0; j < nlive; ++j) {
+                const uint32_t c = __shfl_sync(FULL_MASK, my_cnt, j);
+                if (c) sel_flush(lk + j * 32, lr + j * 32, qk + j * TC_QCAP, qr + j * TC_QCAP, c, lane);
+                const uint32_t pair = p.lq_pair[t.q0 + col0 + j];
+                const uint64_t base = ((p.pair_chunk_off[pair] + t.chunk) * TC_PARTS + lane_group) * 32;
+                const uint32_t r = lr[j * 32 + lane];
+                p.part_d[base + lane] = lk[j * 32 + lane];
+                p.part_p[base + lane] = r == 0xffffu ? 0xffffffffu : pos0 + r;
+            }
+            __syncwarp();
+        }
+    } else if (SPLIT3 && warp >= TC_CONV_WARP0) {
         // ===================== converters: x_lo = x - trunc_tf32(x) of the landed tile -> tensor memory ==========
-        // TC_CONV_GROUPS groups of 4 warps take alternate stage uses, so two tiles are being split at any time
         const int lane_group = warp & 3;
-        const uint32_t cgroup = (uint32_t)(warp - (2 + TC_EPI_WARPS)) / TC_CONV_WARPS;
         const uint32_t row = (uint32_t)(lane_group * 32 + lane);  // tile row == TMEM lane of this thread
-        uint32_t stage = 0, phase = 0, use = 0;
+        uint32_t stage = 0, phase = 0;
         while (true) {
             const long long it = next_item(lane == 0, true);
             if (it < 0) break;
             const TcItem t = tc_decode_item(p, (uint64_t)it);
             for (uint64_t a0 = t.r0; a0 < t.r1; a0 += TC_M) {
-                for (uint32_t kc = 0; kc < nk; ++kc, ++use) {
-                    if (use % TC_CONV_GROUPS != cgroup) {
-                        if (++stage == S) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                        continue;
-                    }
+                for (uint32_t kc = 0; kc < nk; ++kc) {
                     tc::mbar_wait(&full[stage], phase);
                     const uint8_t* arow = smem + stage * Cfg::STAGE_BYTES + row * 128;
                     uint32_t lo[TC_KC];

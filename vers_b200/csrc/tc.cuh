@@ -124,6 +124,14 @@ __device__ __forceinline__ void tmem_ld_16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// one fp32 column per thread (lane base+t, column of taddr); issue only — pair with tmem_ld_wait()
+__device__ __forceinline__ float tmem_ld_1_nowait(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // thread t of warp w writes 32 consecutive 32-bit columns of TMEM lane 32*(w%4)+t
 __device__ __forceinline__ void tmem_st_32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(

@@ -149,7 +149,9 @@ int32_t vers_ivf_get_list(const vers_ivf* ivf, uint32_t list, uint64_t* ids, flo
  * the list length (un-deduplicated rows x queries), out[2] = work items, out[3] = distinct lists touched,
  * out[4] = queries whose certificate failed and were redone by the exact-order scan, out[5] = candidates
  * re-ranked in exact order, out[6] = bit pattern (low 32 bits) of the largest observed |candidate value - exact
- * value| among the re-ranked rows (validates the certificate's error allowance), out[7] reserved */
+ * value| among the re-ranked rows (validates the certificate's error allowance), out[7] = the tensor-core centroid
+ * probe: low 32 bits = queries whose probe certificate failed (redone by the exact-order engine), high 32 bits =
+ * candidate centroids re-ranked in exact order (0 when the exact-order probe ran) */
 int32_t vers_ivf_last_search_stats(const vers_ivf* ivf, uint64_t out[8]);
 /* nprobe >= 1 searches: 0 (default) = tensor-core candidate pass (TMA + tcgen05 kind::tf32 on the fp32 rows) +
  * exact-order rerank of the candidates + a rounding-error certificate, uncertified queries redone in exact order;

@@ -223,6 +223,60 @@ def test_ivf_search_bit_exact(vo, ivf_c1, k, nprobe, exact_mode):
         assert st["max_candidate_error"] < (3e-3 if exact_mode == 3 else 2e-5)
 
 
+@pytest.fixture(scope="module")
+def ivf_wide(vb, vo, ctx):
+    """enough lists (512) and queries (>= 32) for the tensor-core centroid probe"""
+    n, dim, C = 24000, 96, 512
+    rows = data(vo, n, dim, n_centers=300)
+    init = vo.init_rows(3, 1, C, n)
+    idx = vb.IVFFlatIndex.build_index(C, 1, 4, rows, init_rows=init, ctx=ctx)
+    cents, assign, _, _ = vo.ivf_build_index(rows, C, 1, 4, init)
+    assert np.array_equal(idx.assignments, assign)
+    return dict(rows=rows, idx=idx, cents=cents, assign=assign, C=C, dim=dim)
+
+
+@pytest.mark.parametrize("nprobe", [1, 8, 32, 64])
+@pytest.mark.parametrize("nq", [32, 200, 333])
+def test_ivf_tensor_core_probe_bit_exact(vo, ivf_wide, nq, nprobe):
+    """centroid probe on the tensor cores (top-M keys -> exact-order rerank -> certificate -> exact redo of the
+    uncertified queries): the probed lists, hence ids and distance bits, must equal the oracle's"""
+    s = ivf_wide
+    q = data(vo, nq, s["dim"], seed=2, n_centers=300)
+    off, lr = vo.ivf_lists(s["assign"], s["C"])
+    ids, d, cnt = s["idx"].search_batch(q, 10, nprobe=nprobe)
+    st = s["idx"].last_search_stats()
+    oi, od, oc = vo.ivf_search(s["rows"], s["cents"], off, lr, q, 10, nprobe=nprobe)
+    assert np.array_equal(cnt, oc)
+    assert np.array_equal(ids, oi)
+    assert np.array_equal(bits(d), bits(od))
+    assert st["probe_reranked"] > 0  # the tensor-core probe really ran
+    assert st["uncertified_probe_queries"] <= nq // 8
+
+
+def test_ivf_tensor_core_probe_falls_back_on_tied_centroids(vb, vo, ctx, ivf_wide):
+    """100 identical centroids (more than the candidate list holds) are the nearest ones: the certificate cannot
+    separate them, the exact redo must open the lowest-numbered ones like the reference's stable sort (ivfflat.rs:160)"""
+    s = ivf_wide
+    cents = s["cents"].copy()
+    big = int(np.argmax(np.bincount(s["assign"].astype(np.int64), minlength=s["C"])))
+    tied = np.array([c for c in range(100, 201) if c != big][:100])
+    cents[tied] = cents[big]
+    assign = vo.assign(s["rows"], cents).astype(np.uint64)
+    members = np.flatnonzero(assign == min(big, int(tied[0])))  # first minimum: the lowest-numbered copy gets the rows
+    assert members.size >= 60
+    assign[members] = tied[np.arange(members.size) % 100]  # spread those rows over the tied lists
+    idx = vb.IVFFlatIndex.from_parts(s["rows"], cents, assign, ctx=ctx)
+    q = data(vo, 64, s["dim"], seed=2, n_centers=300)
+    q[:8] = s["rows"][members[:8]]  # queries whose nearest centroids are the tied ones
+    off, lr = vo.ivf_lists(assign, s["C"])
+    for nprobe in (8, 32):
+        ids, d, cnt = idx.search_batch(q, 10, nprobe=nprobe)
+        st = idx.last_search_stats()
+        oi, od, oc = vo.ivf_search(s["rows"], cents, off, lr, q, 10, nprobe=nprobe)
+        assert np.array_equal(cnt, oc) and np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od))
+        assert st["uncertified_probe_queries"] >= 8
+
+
 def test_ivf_candidate_path_falls_back_on_ties(vb, vo, ctx):
     """more exact duplicates than the candidate list holds: the rounding-error certificate cannot separate them,
     the queries must be redone in exact order and still return the reference's (distance, id) order"""

@@ -109,8 +109,8 @@ struct FamilyTimer {
     vers_ctx* ctx;
     int fam;
     bool on;
-    FamilyTimer(vers_ctx* c, int f) : ctx(c), fam(f) {
-        on = ctx->timing && ctx->ev_used[fam] < (uint64_t)vers_ctx::EV_RING;
+    FamilyTimer(vers_ctx* c, int f) : ctx(c), fam(f) {  // f < 0: untimed (a launch inside an enclosing timer)
+        on = fam >= 0 && ctx->timing && ctx->ev_used[fam] < (uint64_t)vers_ctx::EV_RING;
         if (on) cudaEventRecord(ctx->ev0[fam][ctx->ev_used[fam]], ctx->stream);
     }
     ~FamilyTimer() {
@@ -118,7 +118,7 @@ struct FamilyTimer {
             cudaEventRecord(ctx->ev1[fam][ctx->ev_used[fam]], ctx->stream);
             ctx->ev_used[fam] += 1;
         }
-        ctx->fam_launches[fam] += 1;
+        if (fam >= 0) ctx->fam_launches[fam] += 1;
     }
 };
 

@@ -11,13 +11,18 @@ __global__ void __launch_bounds__(Cfg::NT, 2) flat_scan_kernel(FlatScanParams p)
     uint32_t* list_p = reinterpret_cast<uint32_t*>(list_d + Cfg::NLISTS * p.kpad);
     const uint64_t chunk = blockIdx.x;
     const uint64_t b0 = (uint64_t)blockIdx.y * Cfg::TB;
+    RowSrc B = p.B;
+    if (p.nB_dev) {
+        B.n = *p.nB_dev;
+        if (b0 >= B.n) return;
+    }
     const uint64_t r0 = chunk * p.rows_per_chunk;
     const uint64_t r1 = min(p.A.n, r0 + p.rows_per_chunk);
     lists_init<Cfg>(list_d, list_p, p.kpad);
     for (uint64_t a0 = r0; a0 < r1; a0 += Cfg::TA) {
         float acc[Cfg::MA][Cfg::MB];
-        tile_compute<Cfg, OP>(acc, p.A, a0, p.B, b0, p.ld, smem);
-        tile_select_topk<Cfg, XF>(acc, a0, r1, b0, p.B.n, p.k, p.kpad, list_d, list_p, 0);
+        tile_compute<Cfg, OP>(acc, p.A, a0, B, b0, p.ld, smem);
+        tile_select_topk<Cfg, XF>(acc, a0, r1, b0, B.n, p.k, p.kpad, list_d, list_p, 0);
     }
     __syncwarp();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -26,7 +31,7 @@ __global__ void __launch_bounds__(Cfg::NT, 2) flat_scan_kernel(FlatScanParams p)
         int slot = warp * SLOTS_PER_WARP + s, col, split;
         slot_to_col<Cfg>(slot, col, split);
         uint64_t q = b0 + (uint64_t)col;
-        if (q >= p.B.n) continue;
+        if (q >= B.n) continue;
         uint64_t base = (q * p.nparts + chunk * Cfg::NSPLIT + split) * p.k;
         for (uint32_t e = lane; e < p.k; e += 32) {
             p.part_d[base + e] = list_d[slot * p.kpad + e];
@@ -42,6 +47,7 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) merge_topk_kernel(MergeParam
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * MERGE_WARPS + warp;
     if (q >= p.nq) return;
+    if (p.nq_dev && q >= *p.nq_dev) return;
     if (p.qmask && p.qmask[q] == 0) return;
     uint64_t* sp = reinterpret_cast<uint64_t*>(msm) + (size_t)warp * p.k;
     float* sd = reinterpret_cast<float*>(msm + (size_t)MERGE_WARPS * p.k * 8) + (size_t)warp * p.k;
@@ -105,16 +111,29 @@ int32_t launch_merge(vers_ctx* ctx, const MergeParams& mp) {
     return VERS_OK;
 }
 
+// single block, 1024 threads x 8 consecutive elements per tile: thread-serial scan -> warp scan -> block scan
 __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const uint32_t* in, uint64_t n, uint64_t* out) {
+    constexpr int IT = 8;
     __shared__ uint64_t warp_tot[32];
     __shared__ uint64_t carry_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    for (uint64_t base = 0; base < n; base += 1024) {
-        uint64_t i = base + threadIdx.x;
-        uint64_t v = i < n ? in[i] : 0;
-        uint64_t x = v;
+    for (uint64_t base = 0; base < n; base += 1024 * IT) {
+        const uint64_t i0 = base + (uint64_t)threadIdx.x * IT;
+        uint32_t v[IT];
+        if (i0 + IT <= n && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+            const uint4 a = *reinterpret_cast<const uint4*>(in + i0), c = *reinterpret_cast<const uint4*>(in + i0 + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < IT; ++k) v[k] = i0 + k < n ? in[i0 + k] : 0u;
+        }
+        uint64_t tsum = 0;
+#pragma unroll
+        for (int k = 0; k < IT; ++k) tsum += v[k];
+        uint64_t x = tsum;
         for (int o = 1; o < 32; o <<= 1) {
             uint64_t y = __shfl_up_sync(FULL_MASK, x, o);
             if (lane >= o) x += y;
@@ -130,9 +149,13 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const uint32_t* in
             warp_tot[lane] = w;  // inclusive over warps
         }
         __syncthreads();
-        uint64_t carry = carry_s;
-        uint64_t prefix = carry + (warp ? warp_tot[warp - 1] : 0) + (x - v);
-        if (i < n) out[i] = prefix;
+        const uint64_t carry = carry_s;
+        uint64_t run = carry + (warp ? warp_tot[warp - 1] : 0) + (x - tsum);
+#pragma unroll
+        for (int k = 0; k < IT; ++k) {
+            if (i0 + k < n) out[i0 + k] = run;
+            run += v[k];
+        }
         __syncthreads();
         if (threadIdx.x == 1023) carry_s = carry + warp_tot[31];
         __syncthreads();
@@ -186,7 +209,7 @@ ScanPlan scan_topk_plan(const vers_ctx* ctx, uint64_t nA, uint32_t nq, uint32_t 
 
 int32_t scan_topk_run(vers_ctx* ctx, const ScanPlan& pl, void* scratch, const RowSrc& A, const RowSrc& B, uint32_t nq,
                       uint32_t ld, uint32_t k, uint32_t metric, const uint64_t* id_map, uint64_t id_base,
-                      uint64_t* d_ids, float* d_d, uint32_t* d_cnt, int family) {
+                      uint64_t* d_ids, float* d_d, uint32_t* d_cnt, int family, const uint32_t* nq_dev) {
     if (k == 0 || nq == 0) return VERS_OK;
     if (k > VERS_MAX_TOPK) return fail(VERS_ERR_UNSUPPORTED, "top_k %u > %u", k, VERS_MAX_TOPK);
     if (A.n >= 0xffffffffull) return fail(VERS_ERR_UNSUPPORTED, "more than 2^32-2 rows per GPU shard");
@@ -198,6 +221,7 @@ int32_t scan_topk_run(vers_ctx* ctx, const ScanPlan& pl, void* scratch, const Ro
     p.kpad = round_up(k, 32);
     p.rows_per_chunk = pl.rows_per_chunk;
     p.nparts = pl.nparts;
+    p.nB_dev = nq_dev;
     ScratchCarver sc(scratch);
     p.part_d = sc.take<float>(pl.entries);
     p.part_p = sc.take<uint32_t>(pl.entries);
@@ -230,6 +254,7 @@ int32_t scan_topk_run(vers_ctx* ctx, const ScanPlan& pl, void* scratch, const Ro
     mp.out_d = d_d;
     mp.out_cnt = d_cnt;
     mp.qmask = nullptr;
+    mp.nq_dev = nq_dev;
     return launch_merge(ctx, mp);
 }
 

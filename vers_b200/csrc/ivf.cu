@@ -38,9 +38,11 @@ struct vers_ivf {
     std::vector<uint32_t> assign_tail;  // assignments of rows added later
     float best_cost = 0.f;
     uint32_t best_attempt = 0;
-    unsigned long long* d_stats = nullptr;  // [8] counters of the most recent search (vers_ivf_last_search_stats)
+    unsigned long long* d_stats = nullptr;  // [16] counters of the most recent search (vers_ivf_last_search_stats)
     float* d_lm_norm = nullptr;             // [cap_total] ||row||^2 (any summation order; candidate pass only)
     uint32_t* d_nxmax = nullptr;            // [1] bit pattern of max ||row||^2 over the index (non-negative floats order as uints)
+    float* d_cent_norm = nullptr;           // [C] ||centroid||^2 (any order; tensor-core probe only)
+    uint32_t* d_ncmax = nullptr;            // [1] bit pattern of max ||centroid||^2
     int mode = 0;                           // 0 = candidate pass + exact rerank + certificate, 1 = exact-order everywhere
 };
 
@@ -418,16 +420,22 @@ static int32_t ivf_from_state(vers_kmeans* km, float cost, uint32_t attempt, ver
     VERS_CUDA(cudaMalloc(&ivf->d_seg_off, (size_t)km->C * 8));
     VERS_CUDA(cudaMalloc(&ivf->d_seg_len, (size_t)km->C * 4));
     VERS_CUDA(cudaMalloc(&ivf->d_assign, n1 * 4));
-    VERS_CUDA(cudaMalloc(&ivf->d_stats, 64));
+    VERS_CUDA(cudaMalloc(&ivf->d_stats, 128));
     VERS_CUDA(cudaMalloc(&ivf->d_lm_norm, n1 * 4));
     VERS_CUDA(cudaMalloc(&ivf->d_nxmax, 4));
     VERS_CUDA(cudaMemsetAsync(ivf->d_nxmax, 0, 4, ctx->stream));
+    VERS_CUDA(cudaMalloc(&ivf->d_cent_norm, (size_t)km->C * 4));
+    VERS_CUDA(cudaMalloc(&ivf->d_ncmax, 4));
+    VERS_CUDA(cudaMemsetAsync(ivf->d_ncmax, 0, 4, ctx->stream));
     ivf->cap_total = ds->n;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         VERS_TRY(kmeans_build_csr(km));
         VERS_CUDA(cudaMemcpyAsync(ivf->d_cents, km->d_cents, (size_t)km->C * ds->ld * 4, cudaMemcpyDeviceToDevice,
                                   ctx->stream));
+        rownorm_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(ivf->d_cents, ds->ld, 0, km->C, ivf->d_cent_norm,
+                                                                  ivf->d_ncmax);
+        VERS_LAUNCH_CHECK(ctx);
         if (ds->n) {
             VERS_CUDA(cudaMemcpyAsync(ivf->d_assign, km->d_assign, ds->n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
             gather_list_major_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
@@ -529,53 +537,121 @@ static uint64_t ivf_max_chunks_per_query(const vers_ivf* ivf, uint32_t np) {
 // Otherwise the query is flagged and redone by the exact-order scan.
 
 // one warp per query: top-M by (key, position) over the query's partial lists; bound = the smallest key any
-// non-selected row can have = min(last key of every FULL partial list, M-th merged key if the merged list is full)
+// non-selected row can have = min(last key of every FULL partial list, M-th merged key if the merged list is full).
+// The partial lists are sorted runs of 32, so the fold is a chain of bitonic merge-splits across the lanes: the
+// running top-M lives in R = M/32 sorted registers per lane; a run whose head does not beat the current M-th entry
+// is skipped after one comparison (most runs: far lists, late chunks).
+__device__ __forceinline__ bool cm_less(float d0, uint32_t p0, float d1, uint32_t p1) {
+    return d0 < d1 || (d0 == d1 && p0 < p1);
+}
+__device__ __forceinline__ void cm_merge_asc(float& d, uint32_t& p, int lane) {  // bitonic sequence -> ascending
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const float od = __shfl_xor_sync(FULL_MASK, d, j);
+        const uint32_t op = __shfl_xor_sync(FULL_MASK, p, j);
+        const bool keep_min = (lane & j) == 0;
+        const bool other_less = cm_less(od, op, d, p), self_less = cm_less(d, p, od, op);
+        if (keep_min ? other_less : self_less) {
+            d = od;
+            p = op;
+        }
+    }
+}
+
+template <int R>
 __global__ void __launch_bounds__(128)
     cand_merge_kernel(const float* __restrict__ part_d, const uint32_t* __restrict__ part_p,
-                      const uint64_t* __restrict__ pair_chunk_off, uint32_t nq, uint32_t np, uint32_t M,
-                      uint32_t nsplit, uint32_t* __restrict__ cand_pos, float* __restrict__ cand_key,
-                      float* __restrict__ cand_bound) {
-    extern __shared__ __align__(16) unsigned char csm[];
+                      const uint64_t* __restrict__ pair_chunk_off, uint32_t nq, uint32_t np, uint32_t nsplit,
+                      uint32_t* __restrict__ cand_pos, float* __restrict__ cand_key, float* __restrict__ cand_bound) {
+    constexpr uint32_t M = 32 * R;
+    constexpr int PF = 4;  // runs fetched together
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * 4 + warp;
     if (q >= nq) return;
-    uint32_t* sp = reinterpret_cast<uint32_t*>(csm) + (size_t)warp * M;
-    float* sd = reinterpret_cast<float*>(csm + (size_t)4 * M * 4) + (size_t)warp * M;
-    for (uint32_t e = lane; e < M; e += 32) {
-        sd[e] = __int_as_float(0x7f800000);
-        sp[e] = 0xffffffffu;
+    const float INF = __int_as_float(0x7f800000);
+    float ad[R];
+    uint32_t ap[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        ad[r] = INF;
+        ap[r] = 0xffffffffu;
     }
-    __syncwarp();
-    const uint64_t beg = pair_chunk_off[(uint64_t)q * np] * nsplit * M;
-    const uint64_t end = pair_chunk_off[(uint64_t)(q + 1) * np] * nsplit * M;
-    float tfull = __int_as_float(0x7f800000);
-    for (uint64_t e0 = beg; e0 < end; e0 += 32) {
-        uint64_t e = e0 + lane;  // (end - beg) is a multiple of M, M a multiple of 32
-        uint32_t pp = part_p[e];
-        float v = part_d[e];
-        bool live = pp != 0xffffffffu;
-        if (live && ((e - beg) % M) == M - 1) tfull = fminf(tfull, v);  // last slot of a full partial list
-        while (true) {
-            bool pass = live && entry_less<uint32_t>(v, pp, sd[M - 1], sp[M - 1]);
-            unsigned m = __ballot_sync(FULL_MASK, pass);
-            if (!m) break;
-            int src = __ffs(m) - 1;
-            float bv = __shfl_sync(FULL_MASK, v, src);
-            uint32_t bp = __shfl_sync(FULL_MASK, pp, src);
-            warp_topk_insert<uint32_t>(sd, sp, (int)M, bv, bp, lane);
-            if (lane == src) live = false;
+    const uint64_t beg = pair_chunk_off[(uint64_t)q * np] * nsplit * 32;  // partial lists hold 32 entries each
+    const uint64_t end = pair_chunk_off[(uint64_t)(q + 1) * np] * nsplit * 32;
+    float tfull = INF;
+    for (uint64_t e0 = beg; e0 < end; e0 += 32 * PF) {
+        float fd[PF];
+        uint32_t fp[PF];
+#pragma unroll
+        for (int f = 0; f < PF; ++f) {
+            const uint64_t e = e0 + (uint64_t)f * 32 + lane;
+            const bool in = e < end;
+            fd[f] = in ? part_d[e] : INF;
+            fp[f] = in ? part_p[e] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int f = 0; f < PF; ++f) {
+            float d = fd[f];
+            uint32_t pp = fp[f];
+            const float last_d = __shfl_sync(FULL_MASK, d, 31);
+            const uint32_t last_p = __shfl_sync(FULL_MASK, pp, 31);
+            if (last_p != 0xffffffffu) tfull = fminf(tfull, last_d);  // a full run: its dropped rows are >= last_d
+            const float first_d = __shfl_sync(FULL_MASK, d, 0);
+            const uint32_t first_p = __shfl_sync(FULL_MASK, pp, 0);
+            const float tau_d = __shfl_sync(FULL_MASK, ad[R - 1], 31);
+            const uint32_t tau_p = __shfl_sync(FULL_MASK, ap[R - 1], 31);
+            if (first_p == 0xffffffffu || !cm_less(first_d, first_p, tau_d, tau_p)) continue;  // warp-uniform
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                // incoming run ascending -> reversed; lane-wise min with the ascending register = lower half of the
+                // union (bitonic), lane-wise max = upper half (bitonic), which cascades into the next register
+                const float rd = __shfl_sync(FULL_MASK, d, 31 - lane);
+                const uint32_t rp = __shfl_sync(FULL_MASK, pp, 31 - lane);
+                const bool take = cm_less(rd, rp, ad[r], ap[r]);
+                float lo_d = take ? rd : ad[r], hi_d = take ? ad[r] : rd;
+                uint32_t lo_p = take ? rp : ap[r], hi_p = take ? ap[r] : rp;
+                cm_merge_asc(lo_d, lo_p, lane);
+                ad[r] = lo_d;
+                ap[r] = lo_p;
+                if (r + 1 < R) {
+                    cm_merge_asc(hi_d, hi_p, lane);
+                    d = hi_d;
+                    pp = hi_p;
+                }
+            }
         }
     }
-    for (int o = 16; o; o >>= 1) tfull = fminf(tfull, __shfl_xor_sync(FULL_MASK, tfull, o));
-    for (uint32_t e = lane; e < M; e += 32) {
-        cand_pos[(uint64_t)q * M + e] = sp[e];
-        cand_key[(uint64_t)q * M + e] = sd[e];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        cand_pos[(uint64_t)q * M + r * 32 + lane] = ap[r];
+        cand_key[(uint64_t)q * M + r * 32 + lane] = ad[r];
     }
+    const float mlast_d = __shfl_sync(FULL_MASK, ad[R - 1], 31);
+    const uint32_t mlast_p = __shfl_sync(FULL_MASK, ap[R - 1], 31);
     if (lane == 0) {
         float b = tfull;
-        if (sp[M - 1] != 0xffffffffu) b = fminf(b, sd[M - 1]);
+        if (mlast_p != 0xffffffffu) b = fminf(b, mlast_d);
         cand_bound[q] = b;
     }
+}
+
+static int32_t launch_cand_merge(vers_ctx* ctx, uint32_t M, const float* part_d, const uint32_t* part_p,
+                                 const uint64_t* pair_chunk_off, uint32_t nq, uint32_t np, uint32_t nsplit,
+                                 uint32_t* cand_pos, float* cand_key, float* cand_bound) {
+    const unsigned grid = (unsigned)ceil_div(nq, 4);
+    if (M == 32)
+        cand_merge_kernel<1><<<grid, 128, 0, ctx->stream>>>(part_d, part_p, pair_chunk_off, nq, np, nsplit, cand_pos,
+                                                           cand_key, cand_bound);
+    else if (M == 64)
+        cand_merge_kernel<2><<<grid, 128, 0, ctx->stream>>>(part_d, part_p, pair_chunk_off, nq, np, nsplit, cand_pos,
+                                                           cand_key, cand_bound);
+    else if (M == 128)
+        cand_merge_kernel<4><<<grid, 128, 0, ctx->stream>>>(part_d, part_p, pair_chunk_off, nq, np, nsplit, cand_pos,
+                                                           cand_key, cand_bound);
+    else
+        return fail(VERS_ERR_ARG, "cand_merge: unsupported candidate count %u", M);
+    VERS_LAUNCH_CHECK(ctx);
+    return VERS_OK;
 }
 
 // one warp per query: exact-order l2sq of the M candidates (lane = candidate, strictly sequential over the
@@ -587,7 +663,8 @@ __global__ void __launch_bounds__(128)
                           const uint32_t* __restrict__ cand_pos, const float* __restrict__ cand_bound,
                           const uint32_t* __restrict__ nxmax_bits, const float* __restrict__ cand_key, int tf32_pass,
                           uint64_t* out_ids, float* out_d,
-                          uint32_t* out_cnt, uint32_t* fail_flag, unsigned long long* stats) {
+                          uint32_t* out_cnt, uint32_t* fail_flag, unsigned long long* stats,
+                          uint32_t* fail_list = nullptr, uint32_t* n_fail = nullptr) {
     extern __shared__ __align__(16) unsigned char rsm2[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * 4 + warp;
@@ -636,7 +713,7 @@ __global__ void __launch_bounds__(128)
             my_d[c0 >> 5] = s;
             my_key[c0 >> 5] = live ? cand_key[(uint64_t)q * M + c0 + lane] : 0.f;
         }
-        uint64_t id = live ? lm_ids[pos] : 0xffffffffffffffffull;
+        uint64_t id = live ? (lm_ids ? lm_ids[pos] : (uint64_t)pos) : 0xffffffffffffffffull;
         bool pend = live;
         while (true) {
             bool pass = pend && entry_less<uint64_t>(s, id, sd[k - 1], sp[k - 1]);
@@ -691,6 +768,7 @@ __global__ void __launch_bounds__(128)
             certified = lower > (double)sd[k - 1];
         }
         fail_flag[q] = certified ? 0u : 1u;
+        if (!certified && fail_list) fail_list[atomicAdd(n_fail, 1u)] = q;
         if (!certified) atomicAdd(&stats[4], 1ull);
         atomicAdd(&stats[5], (unsigned long long)reranked);
         atomicMax(&stats[6], (unsigned long long)__float_as_uint(err));  // non-negative floats order as uints
@@ -779,24 +857,38 @@ static int32_t run_list_scan(vers_ivf* ivf, const SearchBufs& b, const float* d_
     return VERS_OK;
 }
 
+// launches the tensor-core scan over `rows` ([n_rows][ld], norms in tp.lm_norm) with the grouped queries gq / gq_lo
+// ([gq_rows][ld]); tp carries the work-item tables
+template <bool SPLIT3>
+static int32_t launch_tc_scan(vers_ctx* ctx, const float* rows, uint64_t n_rows, uint32_t ld, const float* gq,
+                              const float* gq_lo, uint64_t gq_rows, const TcScanParams& tp, int family) {
+    using Cfg = TcCfg<SPLIT3>;
+    CUtensorMap tm_rows, tm_q16, tm_ql16, tm_q32, tm_ql32;
+    const float* lo_src = SPLIT3 ? gq_lo : gq;
+    VERS_TRY(make_tmap_2d_f32(&tm_rows, rows, n_rows ? n_rows : 1, ld, ld, TC_M, TC_KC));
+    VERS_TRY(make_tmap_2d_f32(&tm_q16, gq, gq_rows, ld, ld, 16, TC_KC));
+    VERS_TRY(make_tmap_2d_f32(&tm_ql16, lo_src, gq_rows, ld, ld, 16, TC_KC));
+    VERS_TRY(make_tmap_2d_f32(&tm_q32, gq, gq_rows, ld, ld, 32, TC_KC));
+    VERS_TRY(make_tmap_2d_f32(&tm_ql32, lo_src, gq_rows, ld, ld, 32, TC_KC));
+    auto kern = tc_list_scan_kernel<SPLIT3>;
+    VERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    FamilyTimer ft(ctx, family);
+    kern<<<ctx->sm_count, Cfg::THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(tm_rows, tm_q16, tm_ql16, tm_q32, tm_ql32, tp);
+    VERS_LAUNCH_CHECK(ctx);
+    return VERS_OK;
+}
+
 template <bool SPLIT3>
 static int32_t run_list_scan_tc(vers_ivf* ivf, const SearchBufs& b, const float* d_queries, uint32_t nq, uint32_t np) {
-    using Cfg = TcCfg<SPLIT3>;
     vers_ctx* ctx = ivf->ctx;
     const uint64_t npairs = (uint64_t)nq * np;
     gather_queries_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_queries, b.lq_query, b.lq_off, ivf->C, ivf->ld,
                                                                      b.gq, b.gq_lo, SPLIT3 ? 1 : 0);
     VERS_LAUNCH_CHECK(ctx);
-    CUtensorMap tm_rows, tm_q16, tm_ql16, tm_q32, tm_ql32;
-    const float* lo_src = SPLIT3 ? b.gq_lo : b.gq;
-    VERS_TRY(make_tmap_2d_f32(&tm_rows, ivf->d_lm, ivf->cap_total ? ivf->cap_total : 1, ivf->ld, ivf->ld, TC_M, TC_KC));
-    VERS_TRY(make_tmap_2d_f32(&tm_q16, b.gq, npairs + TC_NQ, ivf->ld, ivf->ld, 16, TC_KC));
-    VERS_TRY(make_tmap_2d_f32(&tm_ql16, lo_src, npairs + TC_NQ, ivf->ld, ivf->ld, 16, TC_KC));
-    VERS_TRY(make_tmap_2d_f32(&tm_q32, b.gq, npairs + TC_NQ, ivf->ld, ivf->ld, 32, TC_KC));
-    VERS_TRY(make_tmap_2d_f32(&tm_ql32, lo_src, npairs + TC_NQ, ivf->ld, ivf->ld, 32, TC_KC));
     TcScanParams tp;
     tp.ld = ivf->ld;
     tp.C = ivf->C;
+    tp.chunk_rows = LIST_CHUNK_ROWS;
     tp.seg_off = ivf->d_seg_off;
     tp.seg_len = ivf->d_seg_len;
     tp.lq_pair = b.lq_pair;
@@ -807,10 +899,157 @@ static int32_t run_list_scan_tc(vers_ivf* ivf, const SearchBufs& b, const float*
     tp.part_d = b.part_d;
     tp.part_p = b.part_p;
     tp.counter = b.counter;
-    auto kern = tc_list_scan_kernel<SPLIT3>;
-    VERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    FamilyTimer ft(ctx, KF_CAND_SCAN);
-    kern<<<ctx->sm_count, Cfg::THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(tm_rows, tm_q16, tm_ql16, tm_q32, tm_ql32, tp);
+    return launch_tc_scan<SPLIT3>(ctx, ivf->d_lm, ivf->cap_total, ivf->ld, b.gq, b.gq_lo, npairs + TC_NQ, tp,
+                                  KF_CAND_SCAN);
+}
+
+// ---------------------------------------------------------------- centroid probe
+// nprobe nearest lists of every query by (distance, centroid index), exact order (ivfflat.rs:155-161).
+//   exact   : the exact-order tile engine over all C centroids (scan_topk_run), fp32-pipe bound
+//   tensor  : (mode 0, batches of >= 32 queries) the centroid table is scanned like one inverted list by the
+//             tensor-core candidate kernel -> top-M keys per query (M >= 2 nprobe) -> exact-order distances of the M
+//             candidates -> the same rounding-error certificate as the list scan proves that no other centroid can
+//             enter or tie the top-nprobe; queries that fail it are appended to a list on the device and redone by
+//             the exact engine in the same call (blocks of that launch exit at once when the list is empty).
+struct ProbePlan {
+    ScanPlan exact;
+    bool tc = false;
+    uint32_t nch = 0, chunk_rows = 0, M = 0;
+    size_t bytes = 0;
+};
+
+struct ProbeBufs {
+    uint64_t *seg_off, *lq_off, *item_off, *pair_chunk_off;
+    uint32_t *seg_len, *lq_pair, *cand_pos, *fail, *fail_idx, *n_fail, *part_p;
+    unsigned long long *counter, *pstats;
+    float *gq, *gq_lo, *part_d, *cand_key, *bound, *tmp_d;
+    uint64_t* tmp_ids;
+};
+
+static void probe_carve(ScratchCarver& sc, const vers_ivf* ivf, const ProbePlan& pp, uint32_t nq, uint32_t np,
+                        ProbeBufs& b) {
+    b.seg_off = sc.take<uint64_t>(1);
+    b.seg_len = sc.take<uint32_t>(1);
+    b.lq_off = sc.take<uint64_t>(2);
+    b.item_off = sc.take<uint64_t>(2);
+    b.pair_chunk_off = sc.take<uint64_t>((size_t)nq + 1);
+    b.lq_pair = sc.take<uint32_t>(nq);
+    b.counter = sc.take<unsigned long long>(2);
+    b.pstats = sc.take<unsigned long long>(8);
+    b.n_fail = sc.take<uint32_t>(1);
+    b.gq = sc.take<float>((size_t)(nq + TC_NQ) * ivf->ld);
+    b.gq_lo = sc.take<float>((size_t)(nq + TC_NQ) * ivf->ld);
+    b.part_d = sc.take<float>((size_t)nq * pp.nch * TC_PARTS * 32);
+    b.part_p = sc.take<uint32_t>((size_t)nq * pp.nch * TC_PARTS * 32);
+    b.cand_pos = sc.take<uint32_t>((size_t)nq * pp.M);
+    b.cand_key = sc.take<float>((size_t)nq * pp.M);
+    b.bound = sc.take<float>(nq);
+    b.fail = sc.take<uint32_t>(nq);
+    b.fail_idx = sc.take<uint32_t>(nq);
+    b.tmp_ids = sc.take<uint64_t>((size_t)nq * np);
+    b.tmp_d = sc.take<float>((size_t)nq * np);
+}
+
+static ProbePlan probe_plan(const vers_ivf* ivf, uint32_t nq, uint32_t np) {
+    const vers_ctx* ctx = ivf->ctx;
+    ProbePlan pp;
+    pp.exact = scan_topk_plan(ctx, ivf->C, nq, np);
+    pp.bytes = (pp.exact.bytes + 255) & ~size_t(255);
+    pp.tc = ivf->mode == 0 && nq >= 32 && np <= 64 && ivf->C >= 512 && ivf->C >= 4 * np && ivf->ld >= TC_KC;
+    if (pp.tc) {
+        pp.M = np <= 32 ? 64 : 128;
+        const uint32_t ngroups = (nq + TC_NQ - 1) / TC_NQ;
+        uint32_t nch = std::max<uint32_t>(1, (uint32_t)ctx->sm_count / ngroups);
+        nch = std::min<uint32_t>(nch, (ivf->C + TC_M - 1) / TC_M);
+        pp.chunk_rows = round_up((ivf->C + nch - 1) / nch, (uint32_t)TC_M);
+        pp.nch = (ivf->C + pp.chunk_rows - 1) / pp.chunk_rows;
+        ScratchCarver sc(nullptr);
+        sc.off = pp.bytes;
+        ProbeBufs b;
+        probe_carve(sc, ivf, pp, nq, np, b);
+        pp.bytes = (sc.off + 255) & ~size_t(255);
+    }
+    return pp;
+}
+
+// work-item tables of the probe: one "list" (the centroid table) probed by every query, nch chunks
+__global__ void probe_tables_kernel(uint32_t C, uint32_t nq, uint32_t nch, uint64_t* seg_off, uint32_t* seg_len,
+                                    uint64_t* lq_off, uint64_t* item_off, uint64_t* pair_chunk_off, uint32_t* lq_pair) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        seg_off[0] = 0;
+        seg_len[0] = C;
+        lq_off[0] = 0;
+        lq_off[1] = nq;
+        item_off[0] = 0;
+        item_off[1] = (uint64_t)((nq + TC_NQ - 1) / TC_NQ) * nch;
+    }
+    if (i <= nq) pair_chunk_off[i] = (uint64_t)i * nch;
+    if (i < nq) lq_pair[i] = i;
+}
+
+__global__ void probe_scatter_kernel(const uint32_t* __restrict__ fail_idx, const uint32_t* __restrict__ n_fail,
+                                     const uint64_t* __restrict__ tmp_ids, const float* __restrict__ tmp_d, uint32_t np,
+                                     uint64_t* __restrict__ out_ids, float* __restrict__ out_d) {
+    const uint32_t n = *n_fail;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n * np; i += gridDim.x * blockDim.x) {
+        const uint32_t r = i / np, e = i - r * np;
+        const uint64_t at = (uint64_t)fail_idx[r] * np + e;
+        out_ids[at] = tmp_ids[i];
+        out_d[at] = tmp_d[i];
+    }
+}
+
+// scratch: [0, pp.bytes) of the context arena.  out_ids / out_d: [nq][np]
+static int32_t probe_run(vers_ivf* ivf, const ProbePlan& pp, const float* d_queries, uint32_t nq, uint32_t np,
+                         uint64_t* out_ids, float* out_d) {
+    vers_ctx* ctx = ivf->ctx;
+    RowSrc CA{ivf->d_cents, nullptr, ivf->ld, ivf->C};
+    if (!pp.tc) {
+        RowSrc QB{d_queries, nullptr, ivf->ld, nq};
+        return scan_topk_run(ctx, pp.exact, ctx->scratch, CA, QB, nq, ivf->ld, np, VERS_METRIC_L2SQ, nullptr, 0, out_ids,
+                             out_d, nullptr, KF_PROBE);
+    }
+    ScratchCarver sc(ctx->scratch);
+    sc.off = (pp.exact.bytes + 255) & ~size_t(255);
+    ProbeBufs b;
+    probe_carve(sc, ivf, pp, nq, np, b);
+    FamilyTimer ft(ctx, KF_PROBE);
+    VERS_CUDA(cudaMemsetAsync(b.counter, 0, (size_t)((char*)b.n_fail - (char*)b.counter) + 4, ctx->stream));  // + pstats
+    probe_tables_kernel<<<(unsigned)ceil_div(nq + 1, 256), 256, 0, ctx->stream>>>(
+        ivf->C, nq, pp.nch, b.seg_off, b.seg_len, b.lq_off, b.item_off, b.pair_chunk_off, b.lq_pair);
+    VERS_LAUNCH_CHECK(ctx);
+    gather_queries_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_queries, nullptr, b.lq_off, 1, ivf->ld, b.gq,
+                                                                     b.gq_lo, 1);
+    VERS_LAUNCH_CHECK(ctx);
+    TcScanParams tp;
+    tp.ld = ivf->ld;
+    tp.C = 1;
+    tp.chunk_rows = pp.chunk_rows;
+    tp.seg_off = b.seg_off;
+    tp.seg_len = b.seg_len;
+    tp.lq_pair = b.lq_pair;
+    tp.lq_off = b.lq_off;
+    tp.item_off = b.item_off;
+    tp.pair_chunk_off = b.pair_chunk_off;
+    tp.lm_norm = ivf->d_cent_norm;
+    tp.part_d = b.part_d;
+    tp.part_p = b.part_p;
+    tp.counter = b.counter;
+    VERS_TRY(launch_tc_scan<true>(ctx, ivf->d_cents, ivf->C, ivf->ld, b.gq, b.gq_lo, (uint64_t)nq + TC_NQ, tp, -1));
+    VERS_TRY(launch_cand_merge(ctx, pp.M, b.part_d, b.part_p, b.pair_chunk_off, nq, 1, TC_PARTS, b.cand_pos, b.cand_key,
+                               b.bound));
+    const size_t rsm = (size_t)4 * RERANK_QCHUNK * 4 + (size_t)4 * np * 12;
+    rerank_certify_kernel<<<(unsigned)ceil_div(nq, 4), 128, rsm, ctx->stream>>>(
+        ivf->d_cents, nullptr, ivf->ld, d_queries, nq, np, pp.M, b.cand_pos, b.bound, ivf->d_ncmax, b.cand_key, 2, out_ids,
+        out_d, nullptr, b.fail, ivf->d_stats + 3, b.fail_idx, b.n_fail);  // stats[7] = uncertified probe queries
+    VERS_LAUNCH_CHECK(ctx);
+    // exact redo of the uncertified queries (none, typically): the launch is sized for nq, the blocks read n_fail
+    RowSrc QF{d_queries, b.fail_idx, ivf->ld, nq};
+    VERS_TRY(scan_topk_run(ctx, pp.exact, ctx->scratch, CA, QF, nq, ivf->ld, np, VERS_METRIC_L2SQ, nullptr, 0, b.tmp_ids,
+                           b.tmp_d, nullptr, -1, b.n_fail));
+    probe_scatter_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(b.fail_idx, b.n_fail, b.tmp_ids, b.tmp_d, np, out_ids,
+                                                               out_d);
     VERS_LAUNCH_CHECK(ctx);
     return VERS_OK;
 }
@@ -832,9 +1071,9 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
     size_t entries = (size_t)max_chunks * ScanCfg::NSPLIT * k;
     if (approx) entries = std::max(entries, (size_t)max_chunks * std::max<size_t>(StreamCfg::NSPLIT, TC_PARTS) * M);
 
-    // the probe carves its partial buffers from the front of the arena, ours come after it
-    const ScanPlan probe_plan = scan_topk_plan(ctx, ivf->C, nq, np);
-    const size_t probe_reserve = (probe_plan.bytes + 255) & ~size_t(255);
+    // the probe carves its buffers from the front of the arena, ours come after it
+    const ProbePlan pplan = probe_plan(ivf, nq, np);
+    const size_t probe_reserve = pplan.bytes;
     SearchBufs b;
     auto carve = [&](ScratchCarver& sc) {
         sc.off = probe_reserve;
@@ -868,17 +1107,14 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
     ScratchCarver sc(ctx->scratch);
     carve(sc);
 
+    VERS_CUDA(cudaMemsetAsync(ivf->d_stats, 0, 128, ctx->stream));
     // 1. probe: exact-order distances to every centroid, top-np by (distance, centroid index)
     //    (or the caller's probe lists: the multi-GPU driver splits the probe of a batch over the ranks)
     if (ext_probe) {
         VERS_CUDA(cudaMemcpyAsync(b.probe_ids, ext_probe, (size_t)npairs * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     } else {
-        RowSrc CA{ivf->d_cents, nullptr, ivf->ld, ivf->C};
-        RowSrc QB{d_queries, nullptr, ivf->ld, nq};
-        VERS_TRY(scan_topk_run(ctx, probe_plan, ctx->scratch, CA, QB, nq, ivf->ld, np, VERS_METRIC_L2SQ, nullptr, 0,
-                               b.probe_ids, b.probe_d, nullptr, KF_PROBE));
+        VERS_TRY(probe_run(ivf, pplan, d_queries, nq, np, b.probe_ids, b.probe_d));
     }
-    VERS_CUDA(cudaMemsetAsync(ivf->d_stats, 0, 64, ctx->stream));
     VERS_CUDA(cudaMemsetAsync(b.counter, 0, 16, ctx->stream));
     uint32_t* short_flag = reinterpret_cast<uint32_t*>(b.counter + 1);
 
@@ -920,9 +1156,8 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
             VERS_TRY((run_list_scan<StreamCfg, 1>(ivf, b, d_queries, nq, M)));
             nsplit = StreamCfg::NSPLIT;
         }
-        cand_merge_kernel<<<(unsigned)ceil_div(nq, 4), 128, (size_t)4 * M * 8, ctx->stream>>>(
-            b.part_d, b.part_p, b.pair_chunk_off, nq, np, M, nsplit, b.cand_pos, b.cand_key, b.cand_bound);
-        VERS_LAUNCH_CHECK(ctx);
+        VERS_TRY(launch_cand_merge(ctx, M, b.part_d, b.part_p, b.pair_chunk_off, nq, np, nsplit, b.cand_pos, b.cand_key,
+                                   b.cand_bound));
         size_t rsm = (size_t)4 * RERANK_QCHUNK * 4 + (size_t)4 * k * 12;
         FamilyTimer ftr(ctx, KF_RERANK);
         rerank_certify_kernel<<<(unsigned)ceil_div(nq, 4), 128, rsm, ctx->stream>>>(
@@ -969,6 +1204,8 @@ extern "C" int32_t vers_ivf_free(vers_ivf* ivf) {
     cudaFree(ivf->d_stats);
     cudaFree(ivf->d_lm_norm);
     cudaFree(ivf->d_nxmax);
+    cudaFree(ivf->d_cent_norm);
+    cudaFree(ivf->d_ncmax);
     delete ivf;
     return VERS_OK;
 }
@@ -1127,14 +1364,11 @@ extern "C" int32_t vers_ivf_probe_dev(vers_ivf* ivf, const float* d_queries, uin
     vers_ctx* ctx = ivf->ctx;
     std::lock_guard<std::mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
-    const ScanPlan plan = scan_topk_plan(ctx, ivf->C, nq, nprobe);
-    const size_t off = (plan.bytes + 255) & ~size_t(255);
-    VERS_TRY(scratch_reserve(ctx, off + (size_t)nq * nprobe * 4 + 256));
-    float* d_pd = reinterpret_cast<float*>((char*)ctx->scratch + off);
-    RowSrc CA{ivf->d_cents, nullptr, ivf->ld, ivf->C};
-    RowSrc QB{d_queries, nullptr, ivf->ld, nq};
-    return scan_topk_run(ctx, plan, ctx->scratch, CA, QB, nq, ivf->ld, nprobe, VERS_METRIC_L2SQ, nullptr, 0, d_probe_ids,
-                         d_pd, nullptr, KF_PROBE);
+    const ProbePlan pplan = probe_plan(ivf, nq, nprobe);
+    VERS_TRY(scratch_reserve(ctx, pplan.bytes + (size_t)nq * nprobe * 4 + 256));
+    VERS_CUDA(cudaMemsetAsync(ivf->d_stats, 0, 128, ctx->stream));
+    float* d_pd = reinterpret_cast<float*>((char*)ctx->scratch + pplan.bytes);
+    return probe_run(ivf, pplan, d_queries, nq, nprobe, d_probe_ids, d_pd);
 }
 
 extern "C" int32_t vers_ivf_search_probed_dev(vers_ivf* ivf, const float* d_queries, uint32_t nq, uint32_t top_k,
@@ -1215,8 +1449,11 @@ extern "C" int32_t vers_ivf_set_mode(vers_ivf* ivf, int32_t mode) {
 extern "C" int32_t vers_ivf_last_search_stats(const vers_ivf* ivf, uint64_t out[8]) {
     if (!ivf || !out) return fail(VERS_ERR_ARG, "ivf_last_search_stats: null");
     VERS_CUDA(cudaSetDevice(ivf->ctx->device));
-    VERS_CUDA(cudaMemcpyAsync(out, ivf->d_stats, 64, cudaMemcpyDeviceToHost, ivf->ctx->stream));
+    uint64_t tmp[16];
+    VERS_CUDA(cudaMemcpyAsync(tmp, ivf->d_stats, 128, cudaMemcpyDeviceToHost, ivf->ctx->stream));
     VERS_CUDA(cudaStreamSynchronize(ivf->ctx->stream));
+    for (int i = 0; i < 7; ++i) out[i] = tmp[i];
+    out[7] = (tmp[7] & 0xffffffffull) | (tmp[8] << 32);  // probe: uncertified queries | centroids re-ranked
     return VERS_OK;
 }
 

@@ -59,7 +59,8 @@ struct TcCfg {
     static constexpr int SMEM_BYTES = 1024 + OFF_BAR + 1024;
 };
 
-// queries regrouped by list (row i = the i-th grouped (query, list) pair), split into tf32 hi and lo parts
+// queries regrouped by list (row i = the i-th grouped (query, list) pair; lq_query == null: row i = query i), split
+// into tf32 hi and lo parts
 __global__ void gather_queries_kernel(const float* __restrict__ queries, const uint32_t* __restrict__ lq_query,
                                       const uint64_t* __restrict__ lq_off, uint32_t C, uint32_t ld,
                                       float* __restrict__ gq_hi, float* __restrict__ gq_lo, int split) {
@@ -69,7 +70,7 @@ __global__ void gather_queries_kernel(const float* __restrict__ queries, const u
          i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t r = i / ld4;
         uint32_t c = (uint32_t)(i - r * ld4);
-        float4 v = reinterpret_cast<const float4*>(queries)[(uint64_t)lq_query[r] * ld4 + c];
+        float4 v = reinterpret_cast<const float4*>(queries)[(uint64_t)(lq_query ? lq_query[r] : (uint32_t)r) * ld4 + c];
         if (split) {
             float4 h, l;
             h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = __fsub_rn(v.x, h.x);
@@ -87,6 +88,7 @@ __global__ void gather_queries_kernel(const float* __restrict__ queries, const u
 
 struct TcScanParams {
     uint32_t ld, C;
+    uint32_t chunk_rows;  // rows per work item (multiple of 128, <= 65535)
     const uint64_t* seg_off;
     const uint32_t* seg_len;
     const uint32_t* lq_pair;
@@ -115,7 +117,7 @@ __device__ __forceinline__ TcItem tc_decode_item(const TcScanParams& p, uint64_t
     t.list = lo;
     const uint64_t local = it - p.item_off[lo];
     const uint32_t len = p.seg_len[lo];
-    const uint32_t nch = (len + LIST_CHUNK_ROWS - 1) / LIST_CHUNK_ROWS;
+    const uint32_t nch = (len + p.chunk_rows - 1) / p.chunk_rows;
     const uint32_t group = (uint32_t)(local / nch);
     t.chunk = (uint32_t)(local % nch);
     t.q0 = p.lq_off[lo] + (uint64_t)group * TC_NQ;
@@ -123,8 +125,8 @@ __device__ __forceinline__ TcItem tc_decode_item(const TcScanParams& p, uint64_t
     t.nB = (uint32_t)min((uint64_t)TC_NQ, m_l - (uint64_t)group * TC_NQ);
     t.nq = t.nB <= 16 ? 16u : 32u;
     t.base_pos = p.seg_off[lo];
-    t.r0 = (uint64_t)t.chunk * LIST_CHUNK_ROWS;
-    t.r1 = min((uint64_t)len, t.r0 + LIST_CHUNK_ROWS);
+    t.r0 = (uint64_t)t.chunk * p.chunk_rows;
+    t.r1 = min((uint64_t)len, t.r0 + p.chunk_rows);
     return t;
 }
 

@@ -14,6 +14,7 @@ struct FlatScanParams {
     uint32_t nparts;  // gridDim.x * NSPLIT
     float* part_d;
     uint32_t* part_p;
+    const uint32_t* nB_dev;  // optional: the live query count is read on the device (blocks past it exit at once)
 };
 
 // Generic merge: one warp per query folds the entries [begin, end) of (d, p) into the final top-k by (d, id).
@@ -32,6 +33,7 @@ struct MergeParams {
     float* out_d;           // [nq][k]
     uint32_t* out_cnt;      // [nq] optional
     const uint32_t* qmask;  // optional [nq]: only queries with a non-zero mask are merged/written
+    const uint32_t* nq_dev = nullptr;  // optional: live query count read on the device
 };
 
 // scan rows [0, A.n) of A against nq queries (B), exact order; writes the global top-k per query.
@@ -51,7 +53,7 @@ ScanPlan scan_topk_plan(const vers_ctx* ctx, uint64_t nA, uint32_t nq, uint32_t 
 // same as scan_topk_dev but carves its partial buffers from `scratch` (>= pl.bytes, 256-byte aligned)
 int32_t scan_topk_run(vers_ctx* ctx, const ScanPlan& pl, void* scratch, const RowSrc& A, const RowSrc& B, uint32_t nq,
                       uint32_t ld, uint32_t k, uint32_t metric, const uint64_t* id_map, uint64_t id_base,
-                      uint64_t* d_ids, float* d_d, uint32_t* d_cnt, int family);
+                      uint64_t* d_ids, float* d_d, uint32_t* d_cnt, int family, const uint32_t* nq_dev = nullptr);
 
 int32_t launch_merge(vers_ctx* ctx, const MergeParams& mp);
 

@@ -349,7 +349,8 @@ class IVFFlatIndex:
         check(lib().vers_ivf_last_search_stats(self.h, ptr(out)))
         return dict(distinct_list_rows=int(out[0]), pair_rows=int(out[1]), work_items=int(out[2]),
                     lists_touched=int(out[3]), uncertified_queries=int(out[4]), reranked=int(out[5]),
-                    max_candidate_error=float(np.array([out[6]], np.uint64).astype(np.uint32).view(np.float32)[0]))
+                    max_candidate_error=float(np.array([out[6]], np.uint64).astype(np.uint32).view(np.float32)[0]),
+                    uncertified_probe_queries=int(out[7]) & 0xffffffff, probe_reranked=int(out[7]) >> 32)
 
     def set_mode(self, mode):
         """0 / False (default): tensor-core candidate pass (TMA + tcgen05 TF32, split precision hi/lo) + exact-order

@@ -51,6 +51,9 @@ def parse():
                          "balanced and every probe opens a full-size list, ~78k rows scanned per query)")
     ap.add_argument("--kmeans-iters", type=int, default=2, help="max Lloyd iterations of the index build")
     ap.add_argument("--reduce", default="chained", choices=["chained", "allreduce"])
+    ap.add_argument("--shard-by", default="lists", choices=["lists", "rows"],
+                    help="N > 1: every GPU owns whole inverted lists (rows exchanged once after k-means) or keeps its "
+                         "row block (1/N of every list)")
     ap.add_argument("--recall-queries", type=int, default=100)
     ap.add_argument("--cpu-queries", type=int, default=256, help="queries in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -155,7 +158,11 @@ def config_dict(args, n_gpus):
                         f"nlist {args.nlist}, nprobe {args.nprobe}, top_k {args.k}, {args.nq}-query batch "
                         f"(BASELINE.json configs[3])",
             "rows": args.rows, "dim": args.dim, "nlist": args.nlist, "nprobe": args.nprobe, "top_k": args.k,
-            "batch": args.nq, "sharding": f"rows/{n_gpus} per GPU, all-gather+merge of per-GPU top-k",
+            "batch": args.nq,
+            "sharding": ("1 GPU" if n_gpus == 1 else
+                         (f"inverted lists balanced over {n_gpus} GPUs (rows exchanged once after k-means)"
+                          if args.shard_by == "lists" else f"rows/{n_gpus} per GPU (1/{n_gpus} of every list)") +
+                         ", probe split over ranks, all-gather + merge of per-GPU top-k"),
             "kmeans_iters": args.kmeans_iters, "synthetic_natural_clusters": args.n_centers,
             "l2": "per-step scan (>= 3.8 GB per GPU) is far larger than the 126 MB L2; no flush needed"}
 
@@ -214,7 +221,7 @@ def main_ours(args):
     init = vb.synth_init_rows(SEED_INIT, 1, args.nlist, args.rows)[0]
     barrier()
     t0 = time.perf_counter()
-    index = ShardedIVFFlat.build(ds, args.nlist, args.kmeans_iters, init, reduce=args.reduce)
+    index = ShardedIVFFlat.build(ds, args.nlist, args.kmeans_iters, init, reduce=args.reduce, shard_by=args.shard_by)
     barrier()
     build_s = max_over_ranks(time.perf_counter() - t0)
 
@@ -282,6 +289,14 @@ def main_ours(args):
     ctx.enable_timing(False)
     stats = index.ivf.last_search_stats()
     qps = args.nq * args.steps / (dev_ms * 1e-3)
+    per_rank_cand = None
+    if ws > 1:
+        t = torch.tensor([fam["cand_scan"][0] / max(fam["cand_scan"][1], 1), float(stats["distinct_list_rows"])],
+                         dtype=torch.float64, device=dev)
+        allt = torch.empty((ws, 2), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allt, t)
+        per_rank_cand = {"cand_scan_ms": [round(x, 4) for x in allt[:, 0].cpu().tolist()],
+                         "distinct_list_rows": [int(x) for x in allt[:, 1].cpu().tolist()]}
 
     # ---- e2e: host (pinned) queries in, host ids+distances out, every step
     def e2e_step():
@@ -332,7 +347,9 @@ def main_ours(args):
                 "kernel_share_of_step": dom_ms / dev_ms if ws == 1 else None,
                 "family_ms_per_step": {k_: (v[0] / args.steps) for k_, v in fam.items()},
                 "pair_rows_per_launch": stats["pair_rows"], "lists_touched": stats["lists_touched"],
+                "per_rank": per_rank_cand,
                 "uncertified_queries_last_step": stats["uncertified_queries"],
+                "uncertified_probe_queries_last_step": stats["uncertified_probe_queries"],
                 "reranked_candidates_last_step": stats["reranked"],
                 "max_candidate_error_last_step": stats["max_candidate_error"]}
 

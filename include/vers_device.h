@@ -78,6 +78,11 @@ int32_t vers_dataset_info(const vers_dataset* ds, uint64_t* n, uint32_t* dim, ui
 int32_t vers_dataset_normalize(vers_dataset* ds);
 int32_t vers_dataset_download(const vers_dataset* ds, uint64_t row0, uint64_t n, float* out, uint32_t stride_floats);
 int32_t vers_dataset_device_ptr(const vers_dataset* ds, void** ptr);
+/* A dataset handle over rows that already live in device memory ([n][round_up(dim,4)] fp32, pad columns zero).  The
+ * caller keeps the memory alive for the life of the handle; nothing is copied (multi-GPU drivers hand the rows they
+ * received from their peers straight to the index build). */
+int32_t vers_dataset_wrap_device(vers_ctx* ctx, const float* d_rows, uint64_t n, uint32_t dim, uint64_t id_base,
+                                 vers_dataset** out);
 int32_t vers_dataset_free(vers_dataset* ds);
 
 /* ---- exhaustive search: utils::search_exhaustive (utils.rs:68-82) ----------------------------------------- */
@@ -99,6 +104,8 @@ int32_t vers_kmeans_set_centroids(vers_kmeans* km, const float* centroids, uint3
 int32_t vers_kmeans_get_centroids(vers_kmeans* km, float* centroids, uint32_t stride_floats);
 int32_t vers_kmeans_get_assignments(vers_kmeans* km, uint64_t* assignments);
 int32_t vers_kmeans_centroids_device_ptr(vers_kmeans* km, void** ptr, uint32_t* ld);
+/* device pointer of the current assignments: uint32 [n], cluster of every local row (ivfflat.rs:29-46) */
+int32_t vers_kmeans_assign_device_ptr(vers_kmeans* km, void** ptr);
 /* assign_to_clusters over the local rows with the current centroids (first minimum wins) */
 int32_t vers_kmeans_assign_step(vers_kmeans* km);
 /* 0 (default): tensor-core candidate argmin (TMA + tcgen05 kind::tf32, M=128 x N=256 tiles) + a rounding-error
@@ -136,6 +143,12 @@ int32_t vers_ivf_from_kmeans(vers_kmeans* km, vers_ivf** out);
  * assignments == NULL recomputes them on the device */
 int32_t vers_ivf_from_parts(vers_dataset* ds, const float* centroids, uint32_t num_clusters, uint32_t stride_floats,
                             const uint64_t* assignments, vers_ivf** out);
+/* The struct of ivfflat.rs:9-15 from parts that already live on the device: centroids [num_clusters][ld], the
+ * cluster of every row of `ds` (uint32) and, optionally, the GLOBAL id of every row (ascending; default
+ * id_base + row).  Multi-GPU drivers that shard by inverted list build each GPU's lists this way after exchanging
+ * rows; inside a list rows stay in ascending id order like `ids[c]` (ivfflat.rs:123-127). */
+int32_t vers_ivf_from_parts_dev(vers_dataset* ds, const float* d_centroids, uint32_t num_clusters,
+                                const uint32_t* d_assignments, const uint64_t* d_row_ids, vers_ivf** out);
 int32_t vers_ivf_free(vers_ivf* ivf);
 int32_t vers_ivf_info(const vers_ivf* ivf, uint64_t* n, uint32_t* dim, uint32_t* num_clusters, float* best_cost,
                       uint32_t* best_attempt);

@@ -14,7 +14,8 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import oracle as vo  # noqa: E402
 import vers_b200 as vb  # noqa: E402
-from vers_b200.sharded import ShardedIVFFlat, kmeans_cost_sharded, kmeans_fit_sharded, shard_bounds  # noqa: E402
+from vers_b200.sharded import (ShardedIVFFlat, build_list_sharded, kmeans_cost_sharded, kmeans_fit_sharded,  # noqa: E402
+                               shard_bounds)
 
 bits = lambda a: np.ascontiguousarray(a, np.float32).view(np.uint32)
 
@@ -43,18 +44,26 @@ def main():
     cost = kmeans_cost_sharded(km)
     assert bits(np.float32(cost)) == bits(vo.kmeans_cost(rows, cents, assign)), "chained cost differs"
 
-    # --- sharded search: all-gather + merge == oracle
-    ivf = vb.IVFFlatIndex.from_kmeans(km)
-    index = ShardedIVFFlat(ivf, ctx)
+    # --- sharded search (rows: every GPU holds 1/G of every list; lists: every GPU owns whole lists after an
+    #     all-to-all of the rows): all-gather + merge == oracle
     off, lrw = vo.ivf_lists(assign, C)
     d_q = torch.from_numpy(np.ascontiguousarray(q)).cuda()
-    for nprobe in (1, 8, C):
-        ids, d, cnt = index.search_dev(d_q, k, nprobe)
-        torch.cuda.synchronize()
-        oi, od, oc = vo.ivf_search(rows, cents, off, lrw, q, k, nprobe=nprobe)
-        assert np.array_equal(ids.cpu().numpy().view(np.uint64), oi), f"ids differ nprobe={nprobe}"
-        assert np.array_equal(bits(d.cpu().numpy()), bits(od)), f"distances differ nprobe={nprobe}"
-        assert np.array_equal(cnt.cpu().numpy().astype(np.uint32), oc)
+    for shard_by in ("rows", "lists"):
+        ivf = vb.IVFFlatIndex.from_kmeans(km) if shard_by == "rows" else build_list_sharded(km)
+        index = ShardedIVFFlat(ivf, ctx)
+        if shard_by == "lists":
+            sizes = torch.as_tensor(ivf.list_sizes.astype(np.int64)).cuda()
+            dist.all_reduce(sizes)
+            assert np.array_equal(sizes.cpu().numpy(), np.bincount(assign.astype(np.int64), minlength=C))
+            owned = int((ivf.list_sizes > 0).sum())
+            assert 0 < owned < C, "every rank must own some lists, not all"
+        for nprobe in (1, 8, C):
+            ids, d, cnt = index.search_dev(d_q, k, nprobe)
+            torch.cuda.synchronize()
+            oi, od, oc = vo.ivf_search(rows, cents, off, lrw, q, k, nprobe=nprobe)
+            assert np.array_equal(ids.cpu().numpy().view(np.uint64), oi), f"ids differ nprobe={nprobe} {shard_by}"
+            assert np.array_equal(bits(d.cpu().numpy()), bits(od)), f"distances differ nprobe={nprobe} {shard_by}"
+            assert np.array_equal(cnt.cpu().numpy().astype(np.uint32), oc)
 
     # --- all-reduce mode: same counts, centroids within tolerance of the oracle's sharded-order mode
     km2 = vb.KMeans(ds, C)
@@ -66,7 +75,7 @@ def main():
     dist.barrier()
     if rank == 0:
         print(f"mgpu_check ok: world={ws}, chained k-means bit-identical to the single-process oracle "
-              f"({iters} iterations), sharded search ids+distances identical")
+              f"({iters} iterations), sharded search (row shards and list shards) ids+distances identical")
     dist.destroy_process_group()
 
 

@@ -48,6 +48,7 @@ SIGNATURES = {
     "vers_dataset_normalize": [vp],
     "vers_dataset_download": [vp, u64, u64, vp, u32],
     "vers_dataset_device_ptr": [vp, pvp],
+    "vers_dataset_wrap_device": [vp, vp, u64, u32, u64, pvp],
     "vers_dataset_free": [vp],
     "vers_flat_search": [vp, vp, u32, u32, u32, u32, vp, vp, vp],
     "vers_flat_search_dev": [vp, vp, u32, u32, u32, vp, vp, vp],
@@ -58,6 +59,7 @@ SIGNATURES = {
     "vers_kmeans_get_centroids": [vp, vp, u32],
     "vers_kmeans_get_assignments": [vp, vp],
     "vers_kmeans_centroids_device_ptr": [vp, pvp, C.POINTER(u32)],
+    "vers_kmeans_assign_device_ptr": [vp, pvp],
     "vers_kmeans_assign_step": [vp],
     "vers_kmeans_set_mode": [vp, i32],
     "vers_kmeans_last_assign_stats": [vp, C.POINTER(u64)],
@@ -77,6 +79,7 @@ SIGNATURES = {
     "vers_ivf_get_list_sizes": [vp, vp],
     "vers_ivf_get_list": [vp, u32, vp, vp, u32],
     "vers_ivf_last_search_stats": [vp, vp],
+    "vers_ivf_from_parts_dev": [vp, vp, u32, vp, vp, pvp],
     "vers_ivf_set_mode": [vp, i32],
     "vers_ivf_search": [vp, vp, u32, u32, u32, u32, vp, vp, vp],
     "vers_ivf_search_dev": [vp, vp, u32, u32, u32, vp, vp, vp],

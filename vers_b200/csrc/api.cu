@@ -332,6 +332,22 @@ extern "C" int32_t vers_dataset_device_ptr(const vers_dataset* ds, void** ptr) {
     return VERS_OK;
 }
 
+extern "C" int32_t vers_dataset_wrap_device(vers_ctx* ctx, const float* d_rows, uint64_t n, uint32_t dim,
+                                            uint64_t id_base, vers_dataset** out) {
+    if (!ctx || !out || (!d_rows && n)) return fail(VERS_ERR_ARG, "dataset_wrap_device: null argument");
+    if (dim == 0) return fail(VERS_ERR_ARG, "dataset_wrap_device: dim == 0");
+    vers_dataset* ds = new vers_dataset();
+    ds->ctx = ctx;
+    ds->d_rows = const_cast<float*>(d_rows);
+    ds->n = n;
+    ds->dim = dim;
+    ds->ld = round_up(dim, 4);
+    ds->id_base = id_base;
+    ds->owned = false;  // the caller keeps the memory alive for the life of the handle
+    *out = ds;
+    return VERS_OK;
+}
+
 extern "C" int32_t vers_dataset_free(vers_dataset* ds) {
     if (!ds) return VERS_OK;
     cudaSetDevice(ds->ctx->device);

@@ -44,11 +44,19 @@ struct vers_ivf {
     float* d_cent_norm = nullptr;           // [C] ||centroid||^2 (any order; tensor-core probe only)
     uint32_t* d_ncmax = nullptr;            // [1] bit pattern of max ||centroid||^2
     int mode = 0;                           // 0 = candidate pass + exact rerank + certificate, 1 = exact-order everywhere
+    // cache of ivf_max_chunks_per_query (host loop over the lists): valid while seg_epoch == mc_epoch
+    uint64_t seg_epoch = 1, mc_epoch = 0;
+    uint32_t mc_np = 0;
+    uint64_t mc_val[2] = {0, 0};
 };
 
 namespace vers {
 
 constexpr uint32_t LIST_CHUNK_ROWS = 4096;  // rows per work item; multiple of NarrowCfg::TA
+// tensor-core scan: the last sixth of the lists (the work items handed out last) is cut into small items so that the
+// persistent CTAs drain together; everything before keeps whole-list items (one partial list per (query, list))
+constexpr uint32_t TC_TAIL_CHUNK_ROWS = 512;
+inline uint32_t tc_tail_list0(uint32_t C) { return C - C / 6; }
 using ScanCfg = NarrowCfg;
 
 // ---------------------------------------------------------------- layout
@@ -99,6 +107,8 @@ struct GroupParams {
     const uint32_t* qmask;      // optional [nq]: only queries with a non-zero mask are active (exact fallback pass)
     uint32_t nq, np, C;
     uint32_t tb;          // queries per work-item group (8 for the SIMT scans, 32 for the tensor-core scan)
+    uint32_t chunk_rows, chunk_rows_tail, tail_list0;  // rows per work item: lists >= tail_list0 use chunk_rows_tail
+    uint32_t* qtau;       // optional [nq]: per-query shared bound of the tensor-core scan, reset here
     uint32_t* lq_cnt;     // [C]   queries per list
     uint32_t* pair_nch;   // [nq*np] chunks of the pair's list (0 for inactive pairs / empty lists)
     uint32_t* item_cnt;   // [C]   work items per list
@@ -113,11 +123,13 @@ __global__ void group_count_kernel(GroupParams g) {
     uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
     if (pi >= g.nq * g.np) return;
     uint32_t q = pi / g.np, s = pi % g.np;
+    if (g.qtau && pi < g.nq) g.qtau[pi] = 0xff800000u;  // TAU_INF (ivf_tc.cuh): +inf in the ordered encoding
     uint32_t nch = 0;
     if ((!g.used || s < g.used[q]) && (!g.qmask || g.qmask[q] != 0)) {
         uint32_t l = (uint32_t)g.probe_ids[pi];
         uint32_t len = g.seg_len[l];
-        nch = (len + LIST_CHUNK_ROWS - 1) / LIST_CHUNK_ROWS;
+        uint32_t cr = l >= g.tail_list0 ? g.chunk_rows_tail : g.chunk_rows;
+        nch = (len + cr - 1) / cr;
         if (nch) atomicAdd(&g.lq_cnt[l], 1u);
     }
     g.pair_nch[pi] = nch;
@@ -127,7 +139,8 @@ __global__ void group_items_kernel(GroupParams g) {
     uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= g.C) return;
     uint32_t m = g.lq_cnt[l];
-    uint32_t nch = (g.seg_len[l] + LIST_CHUNK_ROWS - 1) / LIST_CHUNK_ROWS;
+    uint32_t cr = l >= g.tail_list0 ? g.chunk_rows_tail : g.chunk_rows;
+    uint32_t nch = (g.seg_len[l] + cr - 1) / cr;
     uint32_t items = ((m + g.tb - 1) / g.tb) * nch;
     g.item_cnt[l] = items;
     if (m && g.stats) {
@@ -455,6 +468,7 @@ static int32_t ivf_from_state(vers_kmeans* km, float cost, uint32_t attempt, ver
             ivf->seg_off[c] = off[c];
             ivf->seg_len[c] = (uint32_t)(off[c + 1] - off[c]);
             ivf->seg_cap[c] = ivf->seg_len[c];
+            ivf->seg_epoch += 1;
         }
     }
     return ivf_upload_segments(ivf);
@@ -517,14 +531,27 @@ static int32_t ivf_relayout(vers_ivf* ivf) {
 }
 
 // upper bound on the number of (pair, chunk) partial lists one query can produce when it opens np lists
-static uint64_t ivf_max_chunks_per_query(const vers_ivf* ivf, uint32_t np) {
+static uint64_t ivf_max_chunks_per_query_uncached(const vers_ivf* ivf, uint32_t np, uint32_t chunk_rows) {
     std::vector<uint32_t> nch(ivf->C);
-    for (uint32_t c = 0; c < ivf->C; ++c) nch[c] = (ivf->seg_len[c] + LIST_CHUNK_ROWS - 1) / LIST_CHUNK_ROWS;
+    for (uint32_t c = 0; c < ivf->C; ++c) nch[c] = (ivf->seg_len[c] + chunk_rows - 1) / chunk_rows;
     np = std::min(np, ivf->C);
     std::partial_sort(nch.begin(), nch.begin() + np, nch.end(), std::greater<uint32_t>());
     uint64_t s = 0;
     for (uint32_t i = 0; i < np; ++i) s += nch[i];
     return s;
+}
+
+// [0]: whole-list items (LIST_CHUNK_ROWS), [1]: every list cut into TC_TAIL_CHUNK_ROWS items (upper bound of the
+// tensor-core scan's mixed chunking)
+static void ivf_max_chunks(vers_ivf* ivf, uint32_t np, uint64_t out[2]) {
+    if (ivf->mc_epoch != ivf->seg_epoch || ivf->mc_np != np) {
+        ivf->mc_val[0] = ivf_max_chunks_per_query_uncached(ivf, np, LIST_CHUNK_ROWS);
+        ivf->mc_val[1] = ivf_max_chunks_per_query_uncached(ivf, np, TC_TAIL_CHUNK_ROWS);
+        ivf->mc_epoch = ivf->seg_epoch;
+        ivf->mc_np = np;
+    }
+    out[0] = ivf->mc_val[0];
+    out[1] = ivf->mc_val[1];
 }
 
 // ---------------------------------------------------------------- candidate pass: merge, exact rerank, certificate
@@ -788,10 +815,13 @@ struct SearchBufs {
     float* gq;     // [npairs + 32][ld] queries regrouped by list (tensor-core scan only), tf32 hi part
     float* gq_lo;  // [npairs + 32][ld] their tf32 lo part (split-precision scan)
     float* cand_key;  // [nq][M] candidate keys (observed-error statistic)
+    uint32_t* qtau;   // [nq] shared per-query bound of the tensor-core scan
 };
 
 static int32_t run_group(vers_ivf* ivf, const SearchBufs& b, uint32_t nq, uint32_t np, const uint32_t* used,
-                         const uint32_t* qmask, bool record_stats, uint32_t tb = ScanCfg::TB) {
+                         const uint32_t* qmask, bool record_stats, uint32_t tb = ScanCfg::TB,
+                         uint32_t chunk_rows_tail = LIST_CHUNK_ROWS, uint32_t tail_list0 = 0xffffffffu,
+                         uint32_t* qtau = nullptr) {
     vers_ctx* ctx = ivf->ctx;
     const uint64_t npairs = (uint64_t)nq * np;
     VERS_CUDA(cudaMemsetAsync(b.lq_cnt, 0, (size_t)ivf->C * 4, ctx->stream));
@@ -806,6 +836,10 @@ static int32_t run_group(vers_ivf* ivf, const SearchBufs& b, uint32_t nq, uint32
     g.np = np;
     g.C = ivf->C;
     g.tb = tb;
+    g.chunk_rows = LIST_CHUNK_ROWS;
+    g.chunk_rows_tail = chunk_rows_tail;
+    g.tail_list0 = tail_list0;
+    g.qtau = qtau;
     g.lq_cnt = b.lq_cnt;
     g.pair_nch = b.pair_nch;
     g.item_cnt = b.item_cnt;
@@ -889,6 +923,8 @@ static int32_t run_list_scan_tc(vers_ivf* ivf, const SearchBufs& b, const float*
     tp.ld = ivf->ld;
     tp.C = ivf->C;
     tp.chunk_rows = LIST_CHUNK_ROWS;
+    tp.chunk_rows_tail = TC_TAIL_CHUNK_ROWS;
+    tp.tail_list0 = tc_tail_list0(ivf->C);
     tp.seg_off = ivf->d_seg_off;
     tp.seg_len = ivf->d_seg_len;
     tp.lq_pair = b.lq_pair;
@@ -899,6 +935,8 @@ static int32_t run_list_scan_tc(vers_ivf* ivf, const SearchBufs& b, const float*
     tp.part_d = b.part_d;
     tp.part_p = b.part_p;
     tp.counter = b.counter;
+    tp.qtau = b.qtau;
+    tp.lq_query = b.lq_query;
     return launch_tc_scan<SPLIT3>(ctx, ivf->d_lm, ivf->cap_total, ivf->ld, b.gq, b.gq_lo, npairs + TC_NQ, tp,
                                   KF_CAND_SCAN);
 }
@@ -1026,6 +1064,8 @@ static int32_t probe_run(vers_ivf* ivf, const ProbePlan& pp, const float* d_quer
     tp.ld = ivf->ld;
     tp.C = 1;
     tp.chunk_rows = pp.chunk_rows;
+    tp.chunk_rows_tail = pp.chunk_rows;
+    tp.tail_list0 = 0xffffffffu;
     tp.seg_off = b.seg_off;
     tp.seg_len = b.seg_len;
     tp.lq_pair = b.lq_pair;
@@ -1036,6 +1076,8 @@ static int32_t probe_run(vers_ivf* ivf, const ProbePlan& pp, const float* d_quer
     tp.part_d = b.part_d;
     tp.part_p = b.part_p;
     tp.counter = b.counter;
+    tp.qtau = nullptr;  // the probe keeps M = 64 > 32 candidates: no shared bound
+    tp.lq_query = nullptr;
     VERS_TRY(launch_tc_scan<true>(ctx, ivf->d_cents, ivf->C, ivf->ld, b.gq, b.gq_lo, (uint64_t)nq + TC_NQ, tp, -1));
     VERS_TRY(launch_cand_merge(ctx, pp.M, b.part_d, b.part_p, b.pair_chunk_off, nq, 1, TC_PARTS, b.cand_pos, b.cand_key,
                                b.bound));
@@ -1067,9 +1109,12 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
     const bool use_tc = approx && (ivf->mode == 0 || ivf->mode == 3) && ivf->ld >= TC_KC && ivf->cap_total < 0x7fffffffull;
     const bool split3 = use_tc && ivf->mode == 0;
     const uint64_t npairs = (uint64_t)nq * np;
-    const uint64_t max_chunks = std::max<uint64_t>((uint64_t)nq * ivf_max_chunks_per_query(ivf, np), 1);
+    uint64_t mc[2];
+    ivf_max_chunks(ivf, np, mc);
+    const uint64_t max_chunks = std::max<uint64_t>((uint64_t)nq * mc[0], 1);
     size_t entries = (size_t)max_chunks * ScanCfg::NSPLIT * k;
-    if (approx) entries = std::max(entries, (size_t)max_chunks * std::max<size_t>(StreamCfg::NSPLIT, TC_PARTS) * M);
+    if (approx) entries = std::max(entries, (size_t)max_chunks * StreamCfg::NSPLIT * M);
+    if (use_tc) entries = std::max(entries, (size_t)nq * std::max<uint64_t>(mc[1], 1) * TC_PARTS * M);
 
     // the probe carves its buffers from the front of the arena, ours come after it
     const ProbePlan pplan = probe_plan(ivf, nq, np);
@@ -1098,6 +1143,7 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
         b.gq = sc.take<float>(use_tc ? (size_t)(npairs + TC_NQ) * ivf->ld : 4);
         b.gq_lo = sc.take<float>(split3 ? (size_t)(npairs + TC_NQ) * ivf->ld : 4);
         b.cand_key = sc.take<float>((size_t)nq * M);
+        b.qtau = sc.take<uint32_t>(nq);
     };
     {
         ScratchCarver plan(nullptr);
@@ -1145,7 +1191,8 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
         // 2a. candidate pass (FMA, HBM-streaming) -> top-M per query -> exact-order rerank -> certificate
         uint32_t nsplit;
         if (use_tc) {
-            VERS_TRY(run_group(ivf, b, nq, np, nullptr, nullptr, true, TC_NQ));
+            VERS_TRY(run_group(ivf, b, nq, np, nullptr, nullptr, true, TC_NQ, TC_TAIL_CHUNK_ROWS, tc_tail_list0(ivf->C),
+                               b.qtau));
             if (split3)
                 VERS_TRY(run_list_scan_tc<true>(ivf, b, d_queries, nq, np));
             else
@@ -1296,6 +1343,44 @@ extern "C" int32_t vers_ivf_from_parts(vers_dataset* ds, const float* centroids,
             vers_ivf_free(*out);
             *out = nullptr;
         }
+    }
+    vers_kmeans_free(km);
+    return rc;
+}
+
+namespace vers {
+__global__ void remap_ids_kernel(uint64_t* __restrict__ lm_ids, uint64_t n, uint64_t id_base,
+                                 const uint64_t* __restrict__ row_ids) {
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x)
+        lm_ids[j] = row_ids[lm_ids[j] - id_base];
+}
+}  // namespace vers
+
+extern "C" int32_t vers_ivf_from_parts_dev(vers_dataset* ds, const float* d_centroids, uint32_t num_clusters,
+                                           const uint32_t* d_assignments, const uint64_t* d_row_ids, vers_ivf** out) {
+    if (!ds || !d_centroids || !out || (!d_assignments && ds->n))
+        return fail(VERS_ERR_ARG, "ivf_from_parts_dev: null argument");
+    *out = nullptr;
+    vers_ctx* ctx = ds->ctx;
+    VERS_CUDA(cudaSetDevice(ctx->device));
+    vers_kmeans* km = nullptr;
+    VERS_TRY(vers_kmeans_create(ds, num_clusters, &km));
+    cudaError_t e = cudaMemcpyAsync(km->d_cents, d_centroids, (size_t)num_clusters * ds->ld * 4, cudaMemcpyDeviceToDevice,
+                                    ctx->stream);
+    if (e == cudaSuccess && ds->n)
+        e = cudaMemcpyAsync(km->d_assign, d_assignments, ds->n * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+    km->csr_valid = false;
+    int32_t rc = e == cudaSuccess ? VERS_OK : fail(VERS_ERR_CUDA, "ivf_from_parts_dev: %s", cudaGetErrorString(e));
+    if (rc == VERS_OK) rc = ivf_from_state(km, 0.f, 0, out);
+    if (rc == VERS_OK && d_row_ids && ds->n) {
+        remap_ids_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>((*out)->d_lm_ids, ds->n, ds->id_base, d_row_ids);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(VERS_ERR_CUDA, "ivf_from_parts_dev: %s", cudaGetErrorString(e));
+    }
+    if (rc != VERS_OK) {
+        vers_ivf_free(*out);
+        *out = nullptr;
     }
     vers_kmeans_free(km);
     return rc;
@@ -1499,6 +1584,7 @@ extern "C" int32_t vers_ivf_add(vers_ivf* ivf, const float* embedding, uint64_t 
                 e = cudaGetLastError();
             }
             ivf->seg_len[c] += 1;
+            ivf->seg_epoch += 1;
             if (e == cudaSuccess)
                 e = cudaMemcpyAsync(ivf->d_seg_len + c, &ivf->seg_len[c], 4, cudaMemcpyHostToDevice, ctx->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -88,7 +88,9 @@ __global__ void gather_queries_kernel(const float* __restrict__ queries, const u
 
 struct TcScanParams {
     uint32_t ld, C;
-    uint32_t chunk_rows;  // rows per work item (multiple of 128, <= 65535)
+    uint32_t chunk_rows;       // rows per work item (multiple of 128, <= 65535)
+    uint32_t chunk_rows_tail;  // ... for the lists >= tail_list0: the items handed out last are small, so the
+    uint32_t tail_list0;       //     persistent CTAs finish within a fraction of a full item of each other
     const uint64_t* seg_off;
     const uint32_t* seg_len;
     const uint32_t* lq_pair;
@@ -99,7 +101,23 @@ struct TcScanParams {
     float* part_d;
     uint32_t* part_p;
     unsigned long long* counter;
+    // optional (null: off): per-query running bound shared by all work items of the launch.  qtau[q] holds, in an
+    // order-preserving uint32 encoding, the smallest 32nd key any (lane group, item) list of query q has reached.
+    // A row whose key exceeds it cannot be among the query's 32 best keys (that list alone holds 32 better rows and
+    // only improves), so later items start selective instead of re-learning the threshold from +inf.  The merged
+    // top-32 and its bound do not depend on the timing of these updates.  Requires merged M == 32.
+    uint32_t* qtau;
+    const uint32_t* lq_query;  // grouped pair -> query
 };
+
+__device__ __forceinline__ uint32_t tau_encode(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float tau_decode(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+constexpr uint32_t TAU_INF = 0xff800000u;  // tau_encode(+inf)
 
 struct TcItem {
     uint32_t list, chunk;
@@ -117,7 +135,8 @@ __device__ __forceinline__ TcItem tc_decode_item(const TcScanParams& p, uint64_t
     t.list = lo;
     const uint64_t local = it - p.item_off[lo];
     const uint32_t len = p.seg_len[lo];
-    const uint32_t nch = (len + p.chunk_rows - 1) / p.chunk_rows;
+    const uint32_t cr = lo >= p.tail_list0 ? p.chunk_rows_tail : p.chunk_rows;
+    const uint32_t nch = (len + cr - 1) / cr;
     const uint32_t group = (uint32_t)(local / nch);
     t.chunk = (uint32_t)(local % nch);
     t.q0 = p.lq_off[lo] + (uint64_t)group * TC_NQ;
@@ -125,8 +144,8 @@ __device__ __forceinline__ TcItem tc_decode_item(const TcScanParams& p, uint64_t
     t.nB = (uint32_t)min((uint64_t)TC_NQ, m_l - (uint64_t)group * TC_NQ);
     t.nq = t.nB <= 16 ? 16u : 32u;
     t.base_pos = p.seg_off[lo];
-    t.r0 = (uint64_t)t.chunk * p.chunk_rows;
-    t.r1 = min((uint64_t)len, t.r0 + p.chunk_rows);
+    t.r0 = (uint64_t)t.chunk * cr;
+    t.r1 = min((uint64_t)len, t.r0 + cr);
     return t;
 }
 
@@ -370,9 +389,13 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
             const TcItem t = tc_decode_item(p, (uint64_t)it);
             const uint32_t ncol = t.nq >> 1, col0 = half * ncol;
             const uint32_t nlive = t.nB > col0 ? min(ncol, t.nB - col0) : 0u;  // this warp's live queries
-            // lane j keeps query j's threshold (its list's 32nd key) and queue fill
+            // lane j keeps query j's threshold (its list's 32nd key, or the query's shared bound) and queue fill
             float my_tau = __int_as_float(0x7f800000);
-            uint32_t my_cnt = 0;
+            uint32_t my_cnt = 0, my_q = 0;
+            if (p.qtau && (uint32_t)lane < nlive) {
+                my_q = p.lq_query[t.q0 + col0 + lane];
+                my_tau = tau_decode(__ldcg(p.qtau + my_q));
+            }
             for (uint32_t j = 0; j < nlive; ++j) {
                 lk[j * 32 + lane] = __int_as_float(0x7f800000);
                 lr[j * 32 + lane] = 0xffffu;
@@ -388,6 +411,8 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
                 const bool rowlive = row < t.r1;
                 const uint32_t roff = (uint32_t)(row - t.r0);
                 const float nx = rowlive ? __ldg(p.lm_norm + t.base_pos + row) : 0.0f;
+                if (p.qtau && (uint32_t)lane < nlive && a0 != t.r0)  // bounds published by other CTAs meanwhile
+                    my_tau = fminf(my_tau, tau_decode(__ldcg(p.qtau + my_q)));
                 for (uint32_t j = 0; j < nlive; ++j) {
                     float dot = tc::tmem_ld_1_nowait(tacc + c_hh + j);
                     float w = 0.0f, z = 0.0f;
@@ -405,8 +430,11 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
                         uint32_t c = __shfl_sync(FULL_MASK, my_cnt, j);
                         uint32_t n = __popc(m);
                         if (c + n > TC_QCAP) {  // make room: fold the queue into the list, which tightens tau
-                            tau = sel_flush(lk + j * 32, lr + j * 32, qk + j * TC_QCAP, qr + j * TC_QCAP, c, lane);
-                            if ((uint32_t)lane == j) my_tau = tau;
+                            tau = fminf(tau, sel_flush(lk + j * 32, lr + j * 32, qk + j * TC_QCAP, qr + j * TC_QCAP, c, lane));
+                            if ((uint32_t)lane == j) {
+                                if (p.qtau && tau < my_tau) atomicMin(p.qtau + my_q, tau_encode(tau));
+                                my_tau = tau;
+                            }
                             c = 0;
                             pass = pass && key <= tau;
                             m = __ballot_sync(FULL_MASK, pass);
@@ -428,7 +456,10 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
             const uint32_t pos0 = (uint32_t)(t.base_pos + t.r0);
             for (uint32_t j = 0; j < nlive; ++j) {
                 const uint32_t c = __shfl_sync(FULL_MASK, my_cnt, j);
-                if (c) sel_flush(lk + j * 32, lr + j * 32, qk + j * TC_QCAP, qr + j * TC_QCAP, c, lane);
+                if (c) {
+                    const float tau = sel_flush(lk + j * 32, lr + j * 32, qk + j * TC_QCAP, qr + j * TC_QCAP, c, lane);
+                    if (p.qtau && (uint32_t)lane == j && tau < my_tau) atomicMin(p.qtau + my_q, tau_encode(tau));
+                }
                 const uint32_t pair = p.lq_pair[t.q0 + col0 + j];
                 const uint64_t base = ((p.pair_chunk_off[pair] + t.chunk) * TC_PARTS + lane_group) * 32;
                 const uint32_t r = lr[j * 32 + lane];

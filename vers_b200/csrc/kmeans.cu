@@ -402,6 +402,12 @@ extern "C" int32_t vers_kmeans_centroids_device_ptr(vers_kmeans* km, void** ptr,
     return VERS_OK;
 }
 
+extern "C" int32_t vers_kmeans_assign_device_ptr(vers_kmeans* km, void** ptr) {
+    if (!km || !ptr) return fail(VERS_ERR_ARG, "kmeans_assign_device_ptr: null argument");
+    *ptr = km->d_assign;
+    return VERS_OK;
+}
+
 // tensor-core candidate argmin + certificate; uncertified rows redone by the exact-order kernel
 static int32_t kmeans_assign_tc(vers_kmeans* km) {
     vers_dataset* ds = km->ds;

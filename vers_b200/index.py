@@ -113,6 +113,16 @@ class Dataset:
                                        C.byref(h)))
         return cls(ctx, h)
 
+    @classmethod
+    def wrap_device(cls, ctx: Context, d_rows_ptr: int, n: int, dim: int, id_base: int = 0, keepalive=None) -> "Dataset":
+        """non-owning handle over rows already in device memory ([n][round_up(dim, 4)] fp32); ``keepalive`` (e.g. the
+        torch tensor that owns the memory) is held for the life of the handle"""
+        h = C.c_void_p()
+        check(lib().vers_dataset_wrap_device(ctx.h, C.c_void_p(d_rows_ptr), n, dim, id_base, C.byref(h)))
+        ds = cls(ctx, h)
+        ds._keepalive = keepalive
+        return ds
+
     def normalize(self):
         check(lib().vers_dataset_normalize(self.h))
 
@@ -298,6 +308,18 @@ class IVFFlatIndex:
         check(lib().vers_ivf_from_parts(dataset.h, ptr(c), c.shape[0], c.shape[1], None if a is None else ptr(a),
                                         C.byref(h)))
         return cls(ctx, h, values, dataset)
+
+    @classmethod
+    def from_parts_dev(cls, dataset: Dataset, d_centroids_ptr: int, num_clusters: int, d_assign_ptr: int,
+                       d_row_ids_ptr: Optional[int] = None) -> "IVFFlatIndex":
+        """the index struct from parts resident on the device: centroids [C][ld] fp32, uint32 cluster per row of
+        ``dataset`` and (optionally) the uint64 GLOBAL id of every row — how a list-sharded multi-GPU build hands each
+        GPU the rows of the lists it owns"""
+        h = C.c_void_p()
+        check(lib().vers_ivf_from_parts_dev(dataset.h, C.c_void_p(d_centroids_ptr), num_clusters,
+                                            C.c_void_p(d_assign_ptr),
+                                            C.c_void_p(d_row_ids_ptr) if d_row_ids_ptr else None, C.byref(h)))
+        return cls(dataset.ctx, h, None, dataset)
 
     @classmethod
     def from_kmeans(cls, km: KMeans, values: Optional[np.ndarray] = None) -> "IVFFlatIndex":

@@ -1,5 +1,8 @@
-"""Multi-GPU driver: one process per GPU (torch.distributed, NCCL over NVLink), rows sharded in contiguous blocks so
-every GPU holds 1/G of every inverted list.
+"""Multi-GPU driver: one process per GPU (torch.distributed, NCCL over NVLink).  k-means runs on contiguous row
+blocks; the search index is sharded either by ROWS (every GPU keeps the rows it already has = 1/G of every inverted
+list) or by LISTS (default for G > 1: after k-means the rows are exchanged once with an all-to-all so every GPU owns
+whole lists, balanced by size — the per-list work items keep their single-GPU size, so the scan scales with G
+instead of shrinking every list to a few tiles).
 
   k-means : assign is embarrassingly parallel.  update needs Σ over ALL rows in row order (ivfflat.rs:52-55):
             reduce="chained" passes the running (sums, counts) from rank r-1 to rank r, which continues the
@@ -138,6 +141,66 @@ def kmeans_cost_sharded(km: KMeans, group=None) -> np.float32:
     return np.float32(acc.item())
 
 
+def balanced_list_owners(sizes: np.ndarray, world_size: int) -> np.ndarray:
+    """owner rank of every inverted list: largest list first onto the least-loaded rank (ties: lowest rank, lowest
+    list), the same table on every rank"""
+    order = np.lexsort((np.arange(sizes.shape[0]), -sizes.astype(np.int64)))
+    load = np.zeros(world_size, np.int64)
+    owner = np.zeros(sizes.shape[0], np.int64)
+    for c in order:
+        r = int(np.argmin(load))
+        owner[c] = r
+        load[r] += int(sizes[c])
+    return owner
+
+
+def build_list_sharded(km: KMeans, group=None) -> IVFFlatIndex:
+    """After k-means on row blocks: every rank sends each of its rows (with its global id and cluster) to the rank that
+    owns the row's list (one all-to-all over NVLink) and builds its lists from what it receives.  Blocks arrive in
+    rank order and ranks hold ascending id blocks, so inside a list the rows stay in ascending id order like
+    `ids[c]` (ivfflat.rs:123-127).  Lists a rank does not own are empty there; the centroid table is whole."""
+    rank, ws = world()
+    ds = km.ds
+    Cn, ld, n = km.C, ds.ld, ds.n
+    dev = torch.device("cuda", torch.cuda.current_device())
+    p = C.c_void_p()
+    check(lib().vers_kmeans_assign_device_ptr(km.h, C.byref(p)))
+    ds.ctx.sync()
+    assign = device_view(p.value, (max(n, 1),), torch.int32)[:n].to(torch.int64)
+    sizes = torch.bincount(assign, minlength=Cn)
+    dist.all_reduce(sizes, group=group)
+    owner = torch.as_tensor(balanced_list_owners(sizes.cpu().numpy(), ws), device=dev)
+    dest = owner[assign]
+    order = torch.argsort(dest, stable=True)  # by destination, ascending local row (= ascending id) inside each
+    send_counts = torch.bincount(dest, minlength=ws)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    sc, rc = send_counts.cpu().tolist(), recv_counts.cpu().tolist()
+    n_recv = int(sum(rc))
+    rows = device_view(ds.device_ptr, (max(n, 1), ld))[:n]
+    send_rows = rows.index_select(0, order)
+    recv_rows = torch.empty((max(n_recv, 1), ld), dtype=torch.float32, device=dev)
+    dist.all_to_all_single(recv_rows[:n_recv], send_rows, rc, sc, group=group)
+    del send_rows
+    send_ids = order + ds.id_base
+    recv_ids = torch.empty(max(n_recv, 1), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv_ids[:n_recv], send_ids, rc, sc, group=group)
+    send_assign = assign.index_select(0, order).to(torch.int32)
+    recv_assign = torch.empty(max(n_recv, 1), dtype=torch.int32, device=dev)
+    dist.all_to_all_single(recv_assign[:n_recv], send_assign, rc, sc, group=group)
+    cp, cl = C.c_void_p(), C.c_uint32()
+    check(lib().vers_kmeans_centroids_device_ptr(km.h, C.byref(cp), C.byref(cl)))
+    torch.cuda.synchronize()
+    local = Dataset.wrap_device(ds.ctx, recv_rows.data_ptr(), n_recv, ds.dim, 0, keepalive=recv_rows)
+    ivf = IVFFlatIndex.from_parts_dev(local, cp.value, Cn, recv_assign.data_ptr(), recv_ids.data_ptr())
+    ds.ctx.sync()
+    # the list-major copy is built; the received row-major rows are no longer needed
+    local.close()
+    ivf._ds = None
+    del recv_rows, local
+    return ivf
+
+
 class ShardedIVFFlat:
     """IVFFlatIndex whose rows are sharded over the ranks of the default process group."""
 
@@ -149,10 +212,16 @@ class ShardedIVFFlat:
 
     @classmethod
     def build(cls, ds: Dataset, num_clusters: int, max_iterations: int, init_rows_global: np.ndarray,
-              reduce: str = "chained") -> "ShardedIVFFlat":
+              reduce: str = "chained", shard_by: str = "lists") -> "ShardedIVFFlat":
         km = KMeans(ds, num_clusters)
         kmeans_fit_sharded(km, init_rows_global, max_iterations, reduce)
-        ivf = IVFFlatIndex.from_kmeans(km)
+        _, ws = world()
+        if ws == 1 or shard_by == "rows":
+            ivf = IVFFlatIndex.from_kmeans(km)
+        elif shard_by == "lists":
+            ivf = build_list_sharded(km)
+        else:
+            raise ValueError(shard_by)
         km.close()
         return cls(ivf, ds.ctx)
 

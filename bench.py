@@ -62,6 +62,18 @@ def parse():
     return ap.parse_args()
 
 
+def committed_traffic(args, ws):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json);
+    None when no capture exists for this workload"""
+    key = (f"ivf_{args.rows}x{args.dim}_nlist{args.nlist}_nprobe{args.nprobe}_nq{args.nq}_k{args.k}_gpus{ws}"
+           f"_mode{args.mode}")
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t[key]["dram_bytes_per_launch"], t[key]["source"]
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -341,8 +353,9 @@ def main_ours(args):
                       2: "list_scan_kernel<StreamCfg,1> (candidate pass: fp32 FMA SIMT)"}
         kname = {"cand_scan": cand_names.get(args.mode, "candidate pass"),
                  "list_scan": "list_scan_kernel<NarrowCfg,0> (exact-order scan)"}[dom]
+        traffic, traffic_src = committed_traffic(args, ws)
         roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
                 "kernel_share_of_step": dom_ms / dev_ms if ws == 1 else None,
                 "family_ms_per_step": {k_: (v[0] / args.steps) for k_, v in fam.items()},

@@ -55,6 +55,7 @@ namespace vers {
 constexpr uint32_t LIST_CHUNK_ROWS = 4096;  // rows per work item; multiple of NarrowCfg::TA
 // tensor-core scan: the last sixth of the lists (the work items handed out last) is cut into small items so that the
 // persistent CTAs drain together; everything before keeps whole-list items (one partial list per (query, list))
+// (measured on the bench workload: 256..2048 rows and 1/10..1/3 of the lists are all within 1 % of each other)
 constexpr uint32_t TC_TAIL_CHUNK_ROWS = 512;
 inline uint32_t tc_tail_list0(uint32_t C) { return C - C / 6; }
 using ScanCfg = NarrowCfg;

@@ -57,6 +57,13 @@ def parse():
     ap.add_argument("--recall-queries", type=int, default=100)
     ap.add_argument("--cpu-queries", type=int, default=256, help="queries in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="ivf", choices=["ivf", "kmeans"],
+                    help="ivf (default): the QPS line; kmeans: BASELINE.json configs[4], k-means build seconds on "
+                         "50M x 128, 16384 centroids, --steps Lloyd iterations (default 20), rows sharded over the GPUs")
+    ap.add_argument("--km-rows", type=int, default=50_000_000)
+    ap.add_argument("--km-dim", type=int, default=128)
+    ap.add_argument("--km-clusters", type=int, default=16384)
+    ap.add_argument("--km-mode", type=int, default=0, help="0 tcgen05 candidate argmin + certificate, 1 exact order only")
     ap.add_argument("--mode", type=int, default=0, help="candidate pass: 0 tcgen05 split-TF32 (default), 1 exact "
                     "order only, 2 fp32 FMA SIMT, 3 tcgen05 plain TF32")
     return ap.parse_args()
@@ -385,9 +392,111 @@ def main_ours(args):
         dist.destroy_process_group()
 
 
+def main_kmeans(args):
+    """k-means build seconds (BASELINE.json configs[4]): --steps Lloyd iterations (assign + ordered update + bitwise
+    convergence test) + the final assign of build_kmeans (ivfflat.rs:73-100), rows sharded over the GPUs."""
+    import torch
+    import torch.distributed as dist
+
+    import vers_b200 as vb
+    from vers_b200 import _abi
+    from vers_b200.sharded import kmeans_fit_sharded, shard_bounds
+
+    rank = int(os.environ.get("RANK", "0"))
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if ws > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    iters = args.steps if args.steps != 10 else 20
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = vb.Context(local_rank)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    row0, n_local = shard_bounds(args.km_rows, rank, ws)
+    ds = vb.Dataset.synth(ctx, SEED_DATA, n_local, args.km_dim, kind=1, n_centers=args.n_centers,
+                          center_seed=SEED_CENTERS, row0=row0, normalize=False)
+    init = vb.synth_init_rows(SEED_INIT, 1, args.km_clusters, args.km_rows)[0]
+    km = vb.KMeans(ds, args.km_clusters)
+    km.set_mode(args.km_mode)
+    kmeans_fit_sharded(km, init, min(args.warmup, 3), reduce=args.reduce)  # warm-up iterations (allocations, clocks)
+    barrier()
+    ctx.enable_timing(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    t0 = time.perf_counter()
+    ran = kmeans_fit_sharded(km, init, iters, reduce=args.reduce)
+    ev1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_s = ev0.elapsed_time(ev1) * 1e-3
+    if ws > 1:
+        t = torch.tensor([dev_s, wall], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, wall = float(t[0].item()), float(t[1].item())
+    clocks = sampler.stop() if rank == 0 else None
+    a_ms, a_n = ctx.kernel_ms(_abi.KF_ASSIGN)
+    s_ms, s_n = ctx.kernel_ms(_abi.KF_SUMS)
+    ctx.enable_timing(False)
+    flagged = km.last_uncertified_rows
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        # kind::tf32 issue floor of tcgen05 (M=128: 128*N*8 MACs per N/2 cycles = 2048 MAC/clk/SM, B300_MICROARCH.md
+        # "tcgen05 floor") at the maximum SM clock: 148 * 2048 * 2 * 1.965 GHz = 1191 TFLOP/s.  MEASURED_PEAKS.json only
+        # carries a cuBLAS bf16 figure (1639 TF/s => 819 for tf32), which this kernel exceeds, so it is not a ceiling.
+        sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+        tf32_peak = 148 * 2048 * 2 * sm_mhz * 1e6 / 1e12
+        passes = ran + 1
+        flop_pass = 2.0 * args.km_rows * args.km_clusters * args.km_dim  # the GEMM form of one assign pass
+        split = 3 if args.km_mode == 0 else 1
+        avg_assign_ms = a_ms / max(a_n, 1)
+        achieved = split * flop_pass / ws / (avg_assign_ms * 1e-3) / 1e12 if a_n else None
+        line = {"metric": "k-means build seconds (50Mx128, 16384 centroids, 20 iterations)", "value": dev_s, "unit": "s",
+                "n_gpus": ws, "steps": ran, "warmup": min(args.warmup, 3), "ms_per_step": dev_s / max(ran, 1) * 1e3,
+                "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"IVFFlatIndex::build_kmeans: {args.km_rows}x{args.km_dim} fp32 synthetic clustered "
+                                       f"(unnormalized), {args.km_clusters} centroids, {ran} Lloyd iterations + final "
+                                       f"assign (BASELINE.json configs[4])",
+                           "rows": args.km_rows, "dim": args.km_dim, "clusters": args.km_clusters, "iterations": ran,
+                           "reduce": args.reduce, "sharding": f"rows/{ws} per GPU",
+                           "l2": "every assign pass streams the row shard (>= 3 GB) once: far larger than L2"},
+                "wall_s": wall, "assign_passes": passes, "uncertified_rows_last_pass": flagged,
+                "gpu_launches": ctx.launch_count, "clocks": clocks,
+                "roofline": {"bound": "tensor", "kernel": "tc_assign_kernel (tcgen05 kind::tf32, split hi/lo: 3 MMAs per "
+                             "K step)" if args.km_mode == 0 else "assign_kernel (exact order, fp32 pipe)",
+                             "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                             "frac": (achieved / tf32_peak) if achieved else None, "traffic": None,
+                             "peak_source": "tcgen05 kind::tf32 issue floor: 148 SMs x 2048 MAC/clk x 2 x sm_max_mhz "
+                                            "(MEASURED_PEAKS.json has no tf32 figure; its cuBLAS bf16 / 2 = "
+                                            f"{float(peaks.get('bf16_tflops', 1638.9)) / 2:.0f} TF/s is exceeded)",
+                             "algorithmic_flop_per_launch": split * flop_pass / ws, "avg_launch_ms": avg_assign_ms,
+                             "kernel_share_of_step": a_ms * 1e-3 / dev_s if dev_s else None,
+                             "sums_ms_per_iteration": s_ms / max(s_n, 1)},
+                "cpu_baseline": None}
+        print(json.dumps(line))
+    if ws > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         main_reference(a)
+    elif a.workload == "kmeans":
+        main_kmeans(a)
     else:
         main_ours(a)

@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
                         w = tc::tmem_ld_1_nowait(tacc + c_hl + j);  // x_hi . q_lo
                         z = tc::tmem_ld_1_nowait(tacc + c_lh + j);  // x_lo . q_hi
                     }
-                    tc::tmem_ld_wait();
+                    tc::tmem_ld_wait3(dot, w, z);
                     if (SPLIT3) dot = __fadd_rn(dot, __fadd_rn(w, z));
                     const float key = __fmaf_rn(-2.0f, dot, nx);
                     float tau = __shfl_sync(FULL_MASK, my_tau, j);

@@ -415,7 +415,12 @@ static int32_t kmeans_assign_tc(vers_kmeans* km) {
     cudaStream_t s = ctx->stream;
     if (!km->d_row_norm) {
         VERS_CUDA(cudaMalloc(&km->d_row_norm, ds->n * 4));
-        VERS_CUDA(cudaMalloc(&km->d_cent_norm, (size_t)km->C * 4));
+        VERS_CUDA(cudaMalloc(&km->d_cent_norm, ((size_t)km->C + KA_N) * 4));
+        {   // +inf past C: the epilogue reads whole 128-centroid tiles of norms; a padded column can never win
+            std::vector<float> inf(KA_N, __builtin_inff());
+            VERS_CUDA(cudaMemcpyAsync(km->d_cent_norm + km->C, inf.data(), KA_N * 4, cudaMemcpyHostToDevice, s));
+            VERS_CUDA(cudaStreamSynchronize(s));
+        }
         VERS_CUDA(cudaMalloc(&km->d_cent_hi, (size_t)km->C * ds->ld * 4));
         VERS_CUDA(cudaMalloc(&km->d_cent_lo, (size_t)km->C * ds->ld * 4));
         VERS_CUDA(cudaMalloc(&km->d_ncmax, 4));

@@ -18,7 +18,9 @@ constexpr int KA_M = 128, KA_N = 128, KA_KC = 32, KA_STAGES = 4, KA_EPI_WARPS = 
 constexpr int KA_THREADS = (2 + KA_EPI_WARPS + KA_CONV_WARPS) * 32;
 constexpr int KA_A_BYTES = KA_M * KA_KC * 4, KA_B_BYTES = KA_N * KA_KC * 4;
 constexpr int KA_STAGE_BYTES = KA_A_BYTES + 2 * KA_B_BYTES;  // x | c_hi | c_lo
-constexpr int KA_SMEM_BYTES = 1024 + KA_STAGES * KA_STAGE_BYTES + 256;
+constexpr int KA_OFF_NRM = KA_STAGES * KA_STAGE_BYTES;         // [2][KA_N] ||c||^2 of the centroid tile per accumulator
+constexpr int KA_OFF_BAR = KA_OFF_NRM + 2 * KA_N * 4;
+constexpr int KA_SMEM_BYTES = 1024 + KA_OFF_BAR + 256;
 constexpr uint32_t KA_ALO_COL0 = 2 * KA_N;                    // x_lo tiles live in TMEM after the two accumulators
 constexpr uint32_t KA_TMEM_COLS = 512;                        // 2*128 + 4*32 = 384 -> 512
 
@@ -26,7 +28,7 @@ struct TcAssignParams {
     uint64_t n_rows;
     uint32_t C, ld;
     const float* row_norm;   // [n] ||x||^2 (any order)
-    const float* cent_norm;  // [C] ||c||^2 (any order)
+    const float* cent_norm;  // [round_up(C, 128)] ||c||^2 (any order), +inf past C
     const uint32_t* ncmax_bits;  // max ||c||^2
     uint32_t* assign;        // [n] candidate argmin
     uint32_t* flagged;       // [n] compacted list of uncertified rows
@@ -56,12 +58,14 @@ __global__ void __launch_bounds__(KA_THREADS, 1)
     extern __shared__ uint8_t ka_smem_raw[];
     const uint32_t raw = tc::smem_u32(ka_smem_raw);
     uint8_t* smem = ka_smem_raw + (((raw + 1023u) & ~1023u) - raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + KA_STAGES * KA_STAGE_BYTES);
+    float* nrm = reinterpret_cast<float*>(smem + KA_OFF_NRM);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + KA_OFF_BAR);
     uint64_t* conv = full + KA_STAGES;
     uint64_t* empty = conv + KA_STAGES;
     uint64_t* tfull = empty + KA_STAGES;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* nbar = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(nbar + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t nk = (p.ld + KA_KC - 1) / KA_KC;
     const uint32_t nct = (p.C + KA_N - 1) / KA_N;
@@ -76,6 +80,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1)
         for (int b = 0; b < 2; ++b) {
             tc::mbar_init(&tfull[b], 1);
             tc::mbar_init(&tempty[b], KA_EPI_WARPS);
+            tc::mbar_init(&nbar[b], 1);
         }
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&tmap_rows);
@@ -119,6 +124,10 @@ __global__ void __launch_bounds__(KA_THREADS, 1)
                     const uint32_t buf = tile_ctr & 1, tphase = (tile_ctr >> 1) & 1;
                     tc::mbar_wait(&tempty[buf], tphase ^ 1);
                     tc::fence_after_thread_sync();
+                    // the tile's ||c||^2 ride along into shared memory for the epilogue (the buffer is free: the
+                    // epilogue released it together with the accumulator)
+                    tc::mbar_arrive_expect_tx(&nbar[buf], KA_N * 4);
+                    tc::bulk_load(nrm + buf * KA_N, p.cent_norm + (size_t)ct * KA_N, KA_N * 4, &nbar[buf]);
                     const uint32_t d_tmem = tmem_base + buf * KA_N;
                     for (uint32_t kc = 0; kc < nk; ++kc) {
                         tc::mbar_wait(&full[stage], phase);
@@ -161,30 +170,41 @@ __global__ void __launch_bounds__(KA_THREADS, 1)
             uint32_t c1 = 0xffffffffu;
             for (uint32_t ct = 0; ct < nct; ++ct) {
                 const uint32_t buf = tile_ctr & 1, tphase = (tile_ctr >> 1) & 1;
+                tc::mbar_wait(&nbar[buf], tphase);
                 tc::mbar_wait(&tfull[buf], tphase);
                 tc::fence_after_thread_sync();
                 const uint32_t tacc = tmem_base + ((uint32_t)(lane_group * 32) << 16) + buf * KA_N;
-#pragma unroll 1
-                for (uint32_t cc = 0; cc < KA_N; cc += 16) {
-                    const uint32_t cbase = ct * KA_N + cc;
-                    if (cbase >= p.C) break;  // warp-uniform
-                    float v[16];
-                    tc::tmem_ld_16(tacc + cc, v);
+                const float* nr = nrm + buf * KA_N;
+                // branch-free running (smallest, second smallest, index of the smallest) over the 128 columns; two
+                // 32-column register buffers so the next tcgen05.ld is in flight while one is consumed.  Strict `<`:
+                // the lowest index among equal keys stays first; an equal key lands in b2 (gap 0 => uncertified)
+                const float b1_in = b1;
+                uint32_t loc = 0;
+                uint32_t va[32], vb[32];
+                tc::tmem_ld_32_nowait(tacc, va);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const uint32_t c = cbase + j;
-                        if (c < p.C) {
-                            const float key = __fmaf_rn(-2.0f, v[j], __ldg(p.cent_norm + c));
-                            if (key < b1) {  // strict: the lowest index among equal keys stays first
-                                b2 = b1;
-                                b1 = key;
-                                c1 = c;
-                            } else if (key < b2) {
-                                b2 = key;
-                            }
+                for (int h = 0; h < KA_N / 32; ++h) {
+                    if (h & 1) tc::tmem_ld_wait_32(vb); else tc::tmem_ld_wait_32(va);
+                    if (h + 1 < KA_N / 32) {
+                        if (h & 1) tc::tmem_ld_32_nowait(tacc + 32 * (h + 1), va);
+                        else tc::tmem_ld_32_nowait(tacc + 32 * (h + 1), vb);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 n4 = *reinterpret_cast<const float4*>(nr + 32 * h + j);
+                        const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float acc = __uint_as_float((h & 1) ? vb[j + e] : va[j + e]);
+                            const float key = __fmaf_rn(-2.0f, acc, nn[e]);
+                            b2 = fminf(b2, fmaxf(b1, key));
+                            const bool lt = key < b1;
+                            b1 = lt ? key : b1;
+                            loc = lt ? (uint32_t)(32 * h + j + e) : loc;
                         }
                     }
                 }
+                if (b1 < b1_in) c1 = ct * KA_N + loc;
                 tc::fence_before_thread_sync();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&tempty[buf]);

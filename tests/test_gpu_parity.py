@@ -253,6 +253,23 @@ def test_ivf_tensor_core_probe_bit_exact(vo, ivf_wide, nq, nprobe):
     assert st["uncertified_probe_queries"] <= nq // 8
 
 
+def test_ivf_tensor_core_probe_large_centroid_table(vb, vo, ctx):
+    """more than 8192 lists: the probe keeps per-chunk top-32 lists in the scan kernel (no dense key matrix)"""
+    n, dim, C = 30000, 32, 9000
+    rows = data(vo, n, dim, n_centers=500)
+    cents = rows[::3][:C].copy()  # 9000 distinct rows as centroids
+    assign = vo.assign(rows, cents).astype(np.uint64)
+    idx = vb.IVFFlatIndex.from_parts(rows, cents, assign, ctx=ctx)
+    q = data(vo, 96, dim, seed=2, n_centers=500)
+    off, lr = vo.ivf_lists(assign, C)
+    for nprobe in (4, 32):
+        ids, d, cnt = idx.search_batch(q, 10, nprobe=nprobe)
+        st = idx.last_search_stats()
+        oi, od, oc = vo.ivf_search(rows, cents, off, lr, q, 10, nprobe=nprobe)
+        assert np.array_equal(cnt, oc) and np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od))
+        assert st["probe_reranked"] > 0
+
+
 def test_ivf_tensor_core_probe_falls_back_on_tied_centroids(vb, vo, ctx, ivf_wide):
     """100 identical centroids (more than the candidate list holds) are the nearest ones: the certificate cannot
     separate them, the exact redo must open the lowest-numbered ones like the reference's stable sort (ivfflat.rs:160)"""

@@ -170,6 +170,7 @@ extern "C" int32_t vers_ctx_destroy(vers_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->scan_flags) cudaFree(ctx->scan_flags);
     if (ctx->io) cudaFree(ctx->io);
     for (int i = 0; i < KF_COUNT; ++i) {
         for (cudaEvent_t e : ctx->ev0[i]) cudaEventDestroy(e);

@@ -59,6 +59,7 @@ struct vers_ctx {
     // scratch arena (grow-only), owned by ctx, used by search calls; guarded by mu
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    unsigned long long* scan_flags = nullptr;  // [256] inter-block carries of the chained exclusive scan
     std::mutex mu;
 };
 

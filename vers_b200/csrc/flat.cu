@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) merge_topk_kernel(MergeParam
     const uint32_t q = blockIdx.x * MERGE_WARPS + warp;
     if (q >= p.nq) return;
     if (p.nq_dev && q >= *p.nq_dev) return;
+    if (p.skip_if_zero && *p.skip_if_zero == 0) return;
     if (p.qmask && p.qmask[q] == 0) return;
     uint64_t* sp = reinterpret_cast<uint64_t*>(msm) + (size_t)warp * p.k;
     float* sd = reinterpret_cast<float*>(msm + (size_t)MERGE_WARPS * p.k * 8) + (size_t)warp * p.k;
@@ -111,9 +112,11 @@ int32_t launch_merge(vers_ctx* ctx, const MergeParams& mp) {
     return VERS_OK;
 }
 
-// single block, 1024 threads x 8 consecutive elements per tile: thread-serial scan -> warp scan -> block scan
-__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const uint32_t* in, uint64_t n, uint64_t* out) {
-    constexpr int IT = 8;
+// single block, 1024 threads x IT consecutive elements per tile: thread-serial scan -> warp scan -> block scan
+template <int IT>
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const uint32_t* in, uint64_t n, uint64_t* out,
+                                                              const uint32_t* skip_if_zero) {
+    if (skip_if_zero && *skip_if_zero == 0) return;
     __shared__ uint64_t warp_tot[32];
     __shared__ uint64_t carry_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -123,9 +126,11 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const uint32_t* in
         const uint64_t i0 = base + (uint64_t)threadIdx.x * IT;
         uint32_t v[IT];
         if (i0 + IT <= n && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
-            const uint4 a = *reinterpret_cast<const uint4*>(in + i0), c = *reinterpret_cast<const uint4*>(in + i0 + 4);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-            v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+#pragma unroll
+            for (int k = 0; k < IT; k += 4) {
+                const uint4 a = *reinterpret_cast<const uint4*>(in + i0 + k);
+                v[k] = a.x; v[k + 1] = a.y; v[k + 2] = a.z; v[k + 3] = a.w;
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < IT; ++k) v[k] = i0 + k < n ? in[i0 + k] : 0u;
@@ -163,8 +168,86 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const uint32_t* in
     if (threadIdx.x == 0) out[n] = carry_s;
 }
 
-int32_t launch_exclusive_scan(vers_ctx* ctx, const uint32_t* d_in, uint64_t n, uint64_t* d_out) {
-    exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_in, n, d_out);
+// several blocks, one 8192-element tile each, carries chained through flags[] (flags[b] = inclusive total of the
+// tiles 0..b, plus 1; 0 = not published yet).  The grid never exceeds the SM count, so every block is resident and
+// the spin on the predecessor terminates.
+__global__ void __launch_bounds__(1024) exclusive_scan_chained_kernel(const uint32_t* in, uint64_t n, uint64_t* out,
+                                                                      unsigned long long* flags,
+                                                                      const uint32_t* skip_if_zero) {
+    constexpr int IT = 8;
+    if (skip_if_zero && *skip_if_zero == 0) return;
+    __shared__ uint64_t warp_tot[32];
+    __shared__ uint64_t carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t i0 = ((uint64_t)blockIdx.x * 1024 + threadIdx.x) * IT;
+    uint32_t v[IT];
+    if (i0 + IT <= n && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+#pragma unroll
+        for (int k = 0; k < IT; k += 4) {
+            const uint4 a = *reinterpret_cast<const uint4*>(in + i0 + k);
+            v[k] = a.x; v[k + 1] = a.y; v[k + 2] = a.z; v[k + 3] = a.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < IT; ++k) v[k] = i0 + k < n ? in[i0 + k] : 0u;
+    }
+    uint64_t tsum = 0;
+#pragma unroll
+    for (int k = 0; k < IT; ++k) tsum += v[k];
+    uint64_t x = tsum;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint64_t y = __shfl_up_sync(FULL_MASK, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t w = warp_tot[lane];
+        for (int o = 1; o < 32; o <<= 1) {
+            uint64_t y = __shfl_up_sync(FULL_MASK, w, o);
+            if (lane >= o) w += y;
+        }
+        warp_tot[lane] = w;  // inclusive over warps
+        if (lane == 31) {
+            uint64_t carry = 0;
+            if (blockIdx.x > 0) {
+                volatile unsigned long long* f = flags + blockIdx.x - 1;
+                unsigned long long got;
+                while ((got = *f) == 0ull) {
+                }
+                carry = got - 1;
+            }
+            carry_s = carry;
+            __threadfence();
+            *(volatile unsigned long long*)(flags + blockIdx.x) = carry + w + 1;
+            if (blockIdx.x == gridDim.x - 1) out[n] = carry + w;
+        }
+    }
+    __syncthreads();
+    uint64_t run = carry_s + (warp ? warp_tot[warp - 1] : 0) + (x - tsum);
+#pragma unroll
+    for (int k = 0; k < IT; ++k) {
+        if (i0 + k < n) out[i0 + k] = run;
+        run += v[k];
+    }
+}
+
+int32_t launch_exclusive_scan(vers_ctx* ctx, const uint32_t* d_in, uint64_t n, uint64_t* d_out,
+                              const uint32_t* skip_if_zero) {
+    const uint64_t tiles = ceil_div(n, 8192);
+    if (tiles > 1 && tiles <= (uint64_t)std::min(ctx->sm_count, 256)) {
+        if (!ctx->scan_flags) VERS_CUDA(cudaMalloc(&ctx->scan_flags, 256 * 8));
+        VERS_CUDA(cudaMemsetAsync(ctx->scan_flags, 0, 256 * 8, ctx->stream));
+        exclusive_scan_chained_kernel<<<(unsigned)tiles, 1024, 0, ctx->stream>>>(d_in, n, d_out, ctx->scan_flags,
+                                                                                skip_if_zero);
+        VERS_LAUNCH_CHECK(ctx);
+        return VERS_OK;
+    }
+    // one tile when it fits: 1024 threads x 8 or 32 consecutive elements
+    if (n <= 8192)
+        exclusive_scan_kernel<8><<<1, 1024, 0, ctx->stream>>>(d_in, n, d_out, skip_if_zero);
+    else
+        exclusive_scan_kernel<32><<<1, 1024, 0, ctx->stream>>>(d_in, n, d_out, skip_if_zero);
     VERS_LAUNCH_CHECK(ctx);
     return VERS_OK;
 }

@@ -110,6 +110,7 @@ struct GroupParams {
     uint32_t tb;          // queries per work-item group (8 for the SIMT scans, 32 for the tensor-core scan)
     uint32_t chunk_rows, chunk_rows_tail, tail_list0;  // rows per work item: lists >= tail_list0 use chunk_rows_tail
     uint32_t* qtau;       // optional [nq]: per-query shared bound of the tensor-core scan, reset here
+    const uint32_t* skip_if_zero;  // optional: the whole pass is a no-op when this device word is 0 (no query to redo)
     uint32_t* lq_cnt;     // [C]   queries per list
     uint32_t* pair_nch;   // [nq*np] chunks of the pair's list (0 for inactive pairs / empty lists)
     uint32_t* item_cnt;   // [C]   work items per list
@@ -121,6 +122,7 @@ struct GroupParams {
 };
 
 __global__ void group_count_kernel(GroupParams g) {
+    if (g.skip_if_zero && *g.skip_if_zero == 0) return;
     uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
     if (pi >= g.nq * g.np) return;
     uint32_t q = pi / g.np, s = pi % g.np;
@@ -137,22 +139,34 @@ __global__ void group_count_kernel(GroupParams g) {
 }
 
 __global__ void group_items_kernel(GroupParams g) {
+    if (g.skip_if_zero && *g.skip_if_zero == 0) return;
     uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= g.C) return;
-    uint32_t m = g.lq_cnt[l];
+    const bool in = l < g.C;
+    uint32_t m = in ? g.lq_cnt[l] : 0u;
     uint32_t cr = l >= g.tail_list0 ? g.chunk_rows_tail : g.chunk_rows;
-    uint32_t nch = (g.seg_len[l] + cr - 1) / cr;
+    uint32_t len = in ? g.seg_len[l] : 0u;
+    uint32_t nch = (len + cr - 1) / cr;
     uint32_t items = ((m + g.tb - 1) / g.tb) * nch;
-    g.item_cnt[l] = items;
-    if (m && g.stats) {
-        atomicAdd(&g.stats[0], (unsigned long long)g.seg_len[l]);
-        atomicAdd(&g.stats[1], (unsigned long long)g.seg_len[l] * m);
-        atomicAdd(&g.stats[2], (unsigned long long)items);
-        atomicAdd(&g.stats[3], 1ull);
+    if (in) g.item_cnt[l] = items;
+    if (g.stats) {  // warp-aggregated: one atomic per counter per warp
+        unsigned long long v0 = m ? len : 0ull, v1 = (unsigned long long)len * m, v2 = m ? items : 0ull, v3 = m ? 1ull : 0ull;
+        for (int o = 16; o; o >>= 1) {
+            v0 += __shfl_xor_sync(FULL_MASK, v0, o);
+            v1 += __shfl_xor_sync(FULL_MASK, v1, o);
+            v2 += __shfl_xor_sync(FULL_MASK, v2, o);
+            v3 += __shfl_xor_sync(FULL_MASK, v3, o);
+        }
+        if ((threadIdx.x & 31) == 0 && v3) {
+            atomicAdd(&g.stats[0], v0);
+            atomicAdd(&g.stats[1], v1);
+            atomicAdd(&g.stats[2], v2);
+            atomicAdd(&g.stats[3], v3);
+        }
     }
 }
 
 __global__ void group_fill_kernel(GroupParams g) {
+    if (g.skip_if_zero && *g.skip_if_zero == 0) return;
     uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
     if (pi >= g.nq * g.np) return;
     if (g.pair_nch[pi] == 0) return;
@@ -180,6 +194,7 @@ struct ListScanParams {
     uint32_t* part_p;
     unsigned long long* counter;
     const float* lm_norm;  // MODE 1 only
+    const uint32_t* skip_if_zero;  // optional: no-op launch when this device word is 0
 };
 
 // MODE 0: exact order (OP_L2SQ), private top-k by (distance, position)
@@ -193,6 +208,7 @@ __global__ void __launch_bounds__(Cfg::NT, (Cfg::TILE_FLOATS * 4 > 110 * 1024) ?
     __shared__ uint32_t s_list;
     const uint64_t total_items = p.item_off[p.C];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (p.skip_if_zero && *p.skip_if_zero == 0) return;
     while (true) {
         if (threadIdx.x == 0) {
             unsigned long long it = atomicAdd(p.counter, 1ull);
@@ -586,6 +602,8 @@ __device__ __forceinline__ void cm_merge_asc(float& d, uint32_t& p, int lane) { 
     }
 }
 
+// one BLOCK (4 warps) per query: each warp folds every 4th group of runs into its own top-M, then warp 0 folds the
+// other three warps' sorted results (handed over through shared memory) into the final list
 template <int R>
 __global__ void __launch_bounds__(128)
     cand_merge_kernel(const float* __restrict__ part_d, const uint32_t* __restrict__ part_p,
@@ -593,9 +611,11 @@ __global__ void __launch_bounds__(128)
                       uint32_t* __restrict__ cand_pos, float* __restrict__ cand_key, float* __restrict__ cand_bound) {
     constexpr uint32_t M = 32 * R;
     constexpr int PF = 4;  // runs fetched together
+    __shared__ float xd[3][R][32];
+    __shared__ uint32_t xp[3][R][32];
+    __shared__ float xfull[3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t q = blockIdx.x * 4 + warp;
-    if (q >= nq) return;
+    const uint32_t q = blockIdx.x;
     const float INF = __int_as_float(0x7f800000);
     float ad[R];
     uint32_t ap[R];
@@ -604,10 +624,36 @@ __global__ void __launch_bounds__(128)
         ad[r] = INF;
         ap[r] = 0xffffffffu;
     }
+    // folds one sorted run (d, pp: lane i = i-th smallest, empties last) into the running top-M
+    auto fold = [&](float d, uint32_t pp) {
+        const float first_d = __shfl_sync(FULL_MASK, d, 0);
+        const uint32_t first_p = __shfl_sync(FULL_MASK, pp, 0);
+        const float tau_d = __shfl_sync(FULL_MASK, ad[R - 1], 31);
+        const uint32_t tau_p = __shfl_sync(FULL_MASK, ap[R - 1], 31);
+        if (first_p == 0xffffffffu || !cm_less(first_d, first_p, tau_d, tau_p)) return;  // warp-uniform
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            // incoming run ascending -> reversed; lane-wise min with the ascending register = lower half of the
+            // union (bitonic), lane-wise max = upper half (bitonic), which cascades into the next register
+            const float rd = __shfl_sync(FULL_MASK, d, 31 - lane);
+            const uint32_t rp = __shfl_sync(FULL_MASK, pp, 31 - lane);
+            const bool take = cm_less(rd, rp, ad[r], ap[r]);
+            float lo_d = take ? rd : ad[r], hi_d = take ? ad[r] : rd;
+            uint32_t lo_p = take ? rp : ap[r], hi_p = take ? ap[r] : rp;
+            cm_merge_asc(lo_d, lo_p, lane);
+            ad[r] = lo_d;
+            ap[r] = lo_p;
+            if (r + 1 < R) {
+                cm_merge_asc(hi_d, hi_p, lane);
+                d = hi_d;
+                pp = hi_p;
+            }
+        }
+    };
     const uint64_t beg = pair_chunk_off[(uint64_t)q * np] * nsplit * 32;  // partial lists hold 32 entries each
     const uint64_t end = pair_chunk_off[(uint64_t)(q + 1) * np] * nsplit * 32;
     float tfull = INF;
-    for (uint64_t e0 = beg; e0 < end; e0 += 32 * PF) {
+    for (uint64_t e0 = beg + (uint64_t)warp * 32 * PF; e0 < end; e0 += 4 * 32 * PF) {
         float fd[PF];
         uint32_t fp[PF];
 #pragma unroll
@@ -619,35 +665,26 @@ __global__ void __launch_bounds__(128)
         }
 #pragma unroll
         for (int f = 0; f < PF; ++f) {
-            float d = fd[f];
-            uint32_t pp = fp[f];
-            const float last_d = __shfl_sync(FULL_MASK, d, 31);
-            const uint32_t last_p = __shfl_sync(FULL_MASK, pp, 31);
+            const float last_d = __shfl_sync(FULL_MASK, fd[f], 31);
+            const uint32_t last_p = __shfl_sync(FULL_MASK, fp[f], 31);
             if (last_p != 0xffffffffu) tfull = fminf(tfull, last_d);  // a full run: its dropped rows are >= last_d
-            const float first_d = __shfl_sync(FULL_MASK, d, 0);
-            const uint32_t first_p = __shfl_sync(FULL_MASK, pp, 0);
-            const float tau_d = __shfl_sync(FULL_MASK, ad[R - 1], 31);
-            const uint32_t tau_p = __shfl_sync(FULL_MASK, ap[R - 1], 31);
-            if (first_p == 0xffffffffu || !cm_less(first_d, first_p, tau_d, tau_p)) continue;  // warp-uniform
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                // incoming run ascending -> reversed; lane-wise min with the ascending register = lower half of the
-                // union (bitonic), lane-wise max = upper half (bitonic), which cascades into the next register
-                const float rd = __shfl_sync(FULL_MASK, d, 31 - lane);
-                const uint32_t rp = __shfl_sync(FULL_MASK, pp, 31 - lane);
-                const bool take = cm_less(rd, rp, ad[r], ap[r]);
-                float lo_d = take ? rd : ad[r], hi_d = take ? ad[r] : rd;
-                uint32_t lo_p = take ? rp : ap[r], hi_p = take ? ap[r] : rp;
-                cm_merge_asc(lo_d, lo_p, lane);
-                ad[r] = lo_d;
-                ap[r] = lo_p;
-                if (r + 1 < R) {
-                    cm_merge_asc(hi_d, hi_p, lane);
-                    d = hi_d;
-                    pp = hi_p;
-                }
-            }
+            fold(fd[f], fp[f]);
         }
+    }
+    if (warp > 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            xd[warp - 1][r][lane] = ad[r];
+            xp[warp - 1][r][lane] = ap[r];
+        }
+        if (lane == 0) xfull[warp - 1] = tfull;
+    }
+    __syncthreads();
+    if (warp > 0) return;
+    for (int w = 0; w < 3; ++w) {
+        tfull = fminf(tfull, xfull[w]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) fold(xd[w][r][lane], xp[w][r][lane]);  // sorted runs of 32, ascending overall
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -666,7 +703,7 @@ __global__ void __launch_bounds__(128)
 static int32_t launch_cand_merge(vers_ctx* ctx, uint32_t M, const float* part_d, const uint32_t* part_p,
                                  const uint64_t* pair_chunk_off, uint32_t nq, uint32_t np, uint32_t nsplit,
                                  uint32_t* cand_pos, float* cand_key, float* cand_bound) {
-    const unsigned grid = (unsigned)ceil_div(nq, 4);
+    const unsigned grid = nq;
     if (M == 32)
         cand_merge_kernel<1><<<grid, 128, 0, ctx->stream>>>(part_d, part_p, pair_chunk_off, nq, np, nsplit, cand_pos,
                                                            cand_key, cand_bound);
@@ -682,84 +719,112 @@ static int32_t launch_cand_merge(vers_ctx* ctx, uint32_t M, const float* part_d,
     return VERS_OK;
 }
 
-// one warp per query: exact-order l2sq of the M candidates (lane = candidate, strictly sequential over the
-// dimensions like base.rs:119-126), top-k by (distance, id), certificate.
-constexpr int RERANK_QCHUNK = 256;  // query floats staged per step
+// Exact-order l2sq of the M = 32 R candidates of every query (lane = candidate, strictly sequential over the
+// dimensions like base.rs:119-126), top-k by (distance, id), certificate.  R warps per query, 4 warps per block.
+// The candidate rows are scattered over the index, so each warp stages them chunk by chunk: 16 coalesced 16-byte
+// loads per lane (two candidates' 64-float chunks per instruction, all in flight together, the next chunk fetched
+// while the current one is consumed) into a padded shared-memory tile that lane c then walks sequentially.
+constexpr int RR_KCH = 64;          // dimensions per staged chunk
+constexpr int RR_LDS = RR_KCH + 4;  // padded tile row (floats): lanes walking their own rows stay conflict-free
+template <int R>
 __global__ void __launch_bounds__(128)
     rerank_certify_kernel(const float* __restrict__ lm, const uint64_t* __restrict__ lm_ids, uint32_t ld,
-                          const float* __restrict__ queries, uint32_t nq, uint32_t k, uint32_t M,
+                          const float* __restrict__ queries, uint32_t nq, uint32_t k,
                           const uint32_t* __restrict__ cand_pos, const float* __restrict__ cand_bound,
                           const uint32_t* __restrict__ nxmax_bits, const float* __restrict__ cand_key, int tf32_pass,
-                          uint64_t* out_ids, float* out_d,
-                          uint32_t* out_cnt, uint32_t* fail_flag, unsigned long long* stats,
-                          uint32_t* fail_list = nullptr, uint32_t* n_fail = nullptr) {
-    extern __shared__ __align__(16) unsigned char rsm2[];
+                          uint64_t* out_ids, float* out_d, uint32_t* out_cnt, uint32_t* fail_flag,
+                          unsigned long long* stats, uint32_t* fail_list, uint32_t* n_fail) {
+    constexpr uint32_t M = 32 * R;
+    constexpr int QPB = 4 / R;  // queries per block
+    __shared__ __align__(16) float tile[4][32][RR_LDS];
+    __shared__ __align__(16) float qs[4][RR_KCH];
+    __shared__ float sdist[4][32], skey[4][32];
+    __shared__ uint64_t sid[4][32];
+    extern __shared__ __align__(16) unsigned char rsm2[];  // per query of the block: k ids (u64) then k distances
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t q = blockIdx.x * 4 + warp;
-    if (q >= nq) return;
-    float* qs = reinterpret_cast<float*>(rsm2) + (size_t)warp * RERANK_QCHUNK;
-    uint64_t* sp = reinterpret_cast<uint64_t*>(rsm2 + (size_t)4 * RERANK_QCHUNK * 4) + (size_t)warp * k;
-    float* sd = reinterpret_cast<float*>(rsm2 + (size_t)4 * RERANK_QCHUNK * 4 + (size_t)4 * k * 8) + (size_t)warp * k;
+    const int wq = warp / R, wr = warp % R;
+    const uint32_t q = blockIdx.x * QPB + wq;
+    const bool active = q < nq;
+    const uint32_t pos = active ? cand_pos[(uint64_t)q * M + wr * 32 + lane] : 0xffffffffu;
+    const bool live = pos != 0xffffffffu;
+    const float* qrow = queries + (uint64_t)(active ? q : 0) * ld;
+    const int half = lane >> 4, sub = lane & 15;
+    float4 nxt[16];
+    auto fetch = [&](uint32_t k0) {
+        const uint32_t col = k0 + sub * 4;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t cpos = __shfl_sync(FULL_MASK, pos, 2 * i + half);
+            nxt[i] = (cpos != 0xffffffffu && col < ld)
+                         ? __ldg(reinterpret_cast<const float4*>(lm + (uint64_t)cpos * ld + col))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    float s = 0.0f, nq2 = 0.0f;
+    fetch(0);
+    for (uint32_t k0 = 0; k0 < ld; k0 += RR_KCH) {
+        const uint32_t kn = min((uint32_t)RR_KCH, ld - k0);  // multiple of 4
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) *reinterpret_cast<float4*>(&tile[warp][2 * i + half][sub * 4]) = nxt[i];
+        {
+            const uint32_t c = k0 + lane * 2;
+            float2 v = make_float2(0.f, 0.f);
+            if (active && c < ld) v = *reinterpret_cast<const float2*>(qrow + c);  // ld % 4 == 0: the pair is in range
+            *reinterpret_cast<float2*>(&qs[warp][lane * 2]) = v;
+            nq2 = __fmaf_rn(v.x, v.x, nq2);
+            nq2 = __fmaf_rn(v.y, v.y, nq2);
+        }
+        __syncwarp();
+        if (k0 + RR_KCH < ld) fetch(k0 + RR_KCH);
+        if (live) {
+            for (uint32_t i = 0; i < kn; i += 4) {
+                const float4 a = *reinterpret_cast<const float4*>(&tile[warp][lane][i]);
+                const float4 b = *reinterpret_cast<const float4*>(&qs[warp][i]);
+                float t;
+                t = __fsub_rn(a.x, b.x); s = __fadd_rn(s, __fmul_rn(t, t));
+                t = __fsub_rn(a.y, b.y); s = __fadd_rn(s, __fmul_rn(t, t));
+                t = __fsub_rn(a.z, b.z); s = __fadd_rn(s, __fmul_rn(t, t));
+                t = __fsub_rn(a.w, b.w); s = __fadd_rn(s, __fmul_rn(t, t));
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) nq2 += __shfl_xor_sync(FULL_MASK, nq2, o);
+    sdist[warp][lane] = s;
+    skey[warp][lane] = live ? cand_key[(uint64_t)q * M + wr * 32 + lane] : 0.f;
+    sid[warp][lane] = live ? (lm_ids ? lm_ids[pos] : (uint64_t)pos) : 0xffffffffffffffffull;
+    __syncthreads();
+    if (!active || wr != 0) return;
+
+    // ---- one warp per query: top-k by (distance, id) over its M exact distances, certificate
+    uint64_t* sp = reinterpret_cast<uint64_t*>(rsm2) + (size_t)wq * k;
+    float* sd = reinterpret_cast<float*>(rsm2 + (size_t)QPB * k * 8) + (size_t)wq * k;
     for (uint32_t e = lane; e < k; e += 32) {
         sd[e] = __int_as_float(0x7f800000);
         sp[e] = 0xffffffffffffffffull;
     }
-    const float* qrow = queries + (uint64_t)q * ld;
-    float nq2 = 0.0f;  // ||q||^2, lane-partial
+    __syncwarp();
     uint32_t reranked = 0;
-    float my_key[4] = {0.f, 0.f, 0.f, 0.f}, my_d[4] = {0.f, 0.f, 0.f, 0.f};  // up to 128 candidates per query
-    bool my_live[4] = {false, false, false, false};
-    for (uint32_t c0 = 0; c0 < M; c0 += 32) {
-        const uint32_t pos = cand_pos[(uint64_t)q * M + c0 + lane];
-        const bool live = pos != 0xffffffffu;
-        const float4* row = reinterpret_cast<const float4*>(lm + (uint64_t)(live ? pos : 0) * ld);
-        float s = 0.0f;
-        for (uint32_t k0 = 0; k0 < ld; k0 += RERANK_QCHUNK) {
-            const uint32_t kn = min((uint32_t)RERANK_QCHUNK, ld - k0);  // multiple of 4
-            __syncwarp();
-            for (uint32_t i = lane; i < kn; i += 32) {
-                float v = qrow[k0 + i];
-                qs[i] = v;
-                if (c0 == 0) nq2 = __fmaf_rn(v, v, nq2);
-            }
-            __syncwarp();
-            if (live) {
-                for (uint32_t i = 0; i < kn; i += 4) {
-                    float4 a = row[(k0 + i) >> 2];
-                    float4 b = *reinterpret_cast<const float4*>(qs + i);
-                    float t;
-                    t = __fsub_rn(a.x, b.x); s = __fadd_rn(s, __fmul_rn(t, t));
-                    t = __fsub_rn(a.y, b.y); s = __fadd_rn(s, __fmul_rn(t, t));
-                    t = __fsub_rn(a.z, b.z); s = __fadd_rn(s, __fmul_rn(t, t));
-                    t = __fsub_rn(a.w, b.w); s = __fadd_rn(s, __fmul_rn(t, t));
-                }
-            }
-        }
-        reranked += __popc(__ballot_sync(FULL_MASK, live));
-        if ((c0 >> 5) < 4) {
-            my_live[c0 >> 5] = live;
-            my_d[c0 >> 5] = s;
-            my_key[c0 >> 5] = live ? cand_key[(uint64_t)q * M + c0 + lane] : 0.f;
-        }
-        uint64_t id = live ? (lm_ids ? lm_ids[pos] : (uint64_t)pos) : 0xffffffffffffffffull;
-        bool pend = live;
+    float err = 0.0f;
+    for (int g = 0; g < R; ++g) {
+        const float v = sdist[wq * R + g][lane];
+        const uint64_t id = sid[wq * R + g][lane];
+        const bool lv = id != 0xffffffffffffffffull;
+        reranked += __popc(__ballot_sync(FULL_MASK, lv));
+        // observed candidate-pass error |d~ - d_ref| (statistic only: validates the certificate's error allowance)
+        if (lv) err = fmaxf(err, fabsf((skey[wq * R + g][lane] + nq2) - v));
+        bool pend = lv;
         while (true) {
-            bool pass = pend && entry_less<uint64_t>(s, id, sd[k - 1], sp[k - 1]);
+            bool pass = pend && entry_less<uint64_t>(v, id, sd[k - 1], sp[k - 1]);
             unsigned m = __ballot_sync(FULL_MASK, pass);
             if (!m) break;
             int src = __ffs(m) - 1;
-            float bv = __shfl_sync(FULL_MASK, s, src);
+            float bv = __shfl_sync(FULL_MASK, v, src);
             uint64_t bid = __shfl_sync(FULL_MASK, id, src);
             warp_topk_insert<uint64_t>(sd, sp, (int)k, bv, bid, lane);
             if (lane == src) pend = false;
         }
     }
-    for (int o = 16; o; o >>= 1) nq2 += __shfl_xor_sync(FULL_MASK, nq2, o);
-    // observed candidate-pass error |d~ - d_ref| (statistic only: validates the certificate's error allowance)
-    float err = 0.0f;
-#pragma unroll
-    for (int g = 0; g < 4; ++g)
-        if (my_live[g]) err = fmaxf(err, fabsf((my_key[g] + nq2) - my_d[g]));
     for (int o = 16; o; o >>= 1) err = fmaxf(err, __shfl_xor_sync(FULL_MASK, err, o));
     uint32_t cnt = 0;
     for (uint32_t e0 = 0; e0 < k; e0 += 32) {
@@ -803,6 +868,25 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+static int32_t launch_rerank(vers_ctx* ctx, uint32_t M, const float* lm, const uint64_t* lm_ids, uint32_t ld,
+                             const float* queries, uint32_t nq, uint32_t k, const uint32_t* cand_pos,
+                             const float* cand_bound, const uint32_t* nxmax_bits, const float* cand_key, int tf32_pass,
+                             uint64_t* out_ids, float* out_d, uint32_t* out_cnt, uint32_t* fail_flag,
+                             unsigned long long* stats, uint32_t* fail_list, uint32_t* n_fail) {
+    if (k > M) return fail(VERS_ERR_ARG, "rerank: k %u > %u candidates", k, M);
+#define VERS_RR(R)                                                                                                  \
+    rerank_certify_kernel<R><<<(unsigned)ceil_div(nq, 4 / R), 128, (size_t)(4 / R) * k * 12, ctx->stream>>>(       \
+        lm, lm_ids, ld, queries, nq, k, cand_pos, cand_bound, nxmax_bits, cand_key, tf32_pass, out_ids, out_d,      \
+        out_cnt, fail_flag, stats, fail_list, n_fail)
+    if (M == 32) VERS_RR(1);
+    else if (M == 64) VERS_RR(2);
+    else if (M == 128) VERS_RR(4);
+    else return fail(VERS_ERR_ARG, "rerank: unsupported candidate count %u", M);
+#undef VERS_RR
+    VERS_LAUNCH_CHECK(ctx);
+    return VERS_OK;
+}
+
 // ---------------------------------------------------------------- host: one batched search
 struct SearchBufs {
     uint64_t* probe_ids;
@@ -822,7 +906,7 @@ struct SearchBufs {
 static int32_t run_group(vers_ivf* ivf, const SearchBufs& b, uint32_t nq, uint32_t np, const uint32_t* used,
                          const uint32_t* qmask, bool record_stats, uint32_t tb = ScanCfg::TB,
                          uint32_t chunk_rows_tail = LIST_CHUNK_ROWS, uint32_t tail_list0 = 0xffffffffu,
-                         uint32_t* qtau = nullptr) {
+                         uint32_t* qtau = nullptr, const uint32_t* skip_if_zero = nullptr) {
     vers_ctx* ctx = ivf->ctx;
     const uint64_t npairs = (uint64_t)nq * np;
     VERS_CUDA(cudaMemsetAsync(b.lq_cnt, 0, (size_t)ivf->C * 4, ctx->stream));
@@ -841,6 +925,7 @@ static int32_t run_group(vers_ivf* ivf, const SearchBufs& b, uint32_t nq, uint32
     g.chunk_rows_tail = chunk_rows_tail;
     g.tail_list0 = tail_list0;
     g.qtau = qtau;
+    g.skip_if_zero = skip_if_zero;
     g.lq_cnt = b.lq_cnt;
     g.pair_nch = b.pair_nch;
     g.item_cnt = b.item_cnt;
@@ -853,16 +938,17 @@ static int32_t run_group(vers_ivf* ivf, const SearchBufs& b, uint32_t nq, uint32
     VERS_LAUNCH_CHECK(ctx);
     group_items_kernel<<<(unsigned)ceil_div(ivf->C, 256), 256, 0, ctx->stream>>>(g);
     VERS_LAUNCH_CHECK(ctx);
-    VERS_TRY(launch_exclusive_scan(ctx, b.lq_cnt, ivf->C, b.lq_off));
-    VERS_TRY(launch_exclusive_scan(ctx, b.item_cnt, ivf->C, b.item_off));
-    VERS_TRY(launch_exclusive_scan(ctx, b.pair_nch, npairs, b.pair_chunk_off));
+    VERS_TRY(launch_exclusive_scan(ctx, b.lq_cnt, ivf->C, b.lq_off, skip_if_zero));
+    VERS_TRY(launch_exclusive_scan(ctx, b.item_cnt, ivf->C, b.item_off, skip_if_zero));
+    VERS_TRY(launch_exclusive_scan(ctx, b.pair_nch, npairs, b.pair_chunk_off, skip_if_zero));
     group_fill_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, ctx->stream>>>(g);
     VERS_LAUNCH_CHECK(ctx);
     return VERS_OK;
 }
 
 template <class Cfg, int MODE>
-static int32_t run_list_scan(vers_ivf* ivf, const SearchBufs& b, const float* d_queries, uint32_t nq, uint32_t klist) {
+static int32_t run_list_scan(vers_ivf* ivf, const SearchBufs& b, const float* d_queries, uint32_t nq, uint32_t klist,
+                             const uint32_t* skip_if_zero = nullptr) {
     vers_ctx* ctx = ivf->ctx;
     ListScanParams lp;
     lp.lm = ivf->d_lm;
@@ -883,6 +969,7 @@ static int32_t run_list_scan(vers_ivf* ivf, const SearchBufs& b, const float* d_
     lp.part_p = b.part_p;
     lp.counter = b.counter;
     lp.lm_norm = ivf->d_lm_norm;
+    lp.skip_if_zero = skip_if_zero;
     auto kern = list_scan_kernel<Cfg, MODE>;
     size_t smem = scan_smem_bytes(Cfg::TILE_FLOATS, Cfg::NLISTS, lp.kpad);
     VERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -938,6 +1025,8 @@ static int32_t run_list_scan_tc(vers_ivf* ivf, const SearchBufs& b, const float*
     tp.counter = b.counter;
     tp.qtau = b.qtau;
     tp.lq_query = b.lq_query;
+    tp.dense_out = nullptr;
+    tp.dense_ld = 0;
     return launch_tc_scan<SPLIT3>(ctx, ivf->d_lm, ivf->cap_total, ivf->ld, b.gq, b.gq_lo, npairs + TC_NQ, tp,
                                   KF_CAND_SCAN);
 }
@@ -950,9 +1039,11 @@ static int32_t run_list_scan_tc(vers_ivf* ivf, const SearchBufs& b, const float*
 //             candidates -> the same rounding-error certificate as the list scan proves that no other centroid can
 //             enter or tie the top-nprobe; queries that fail it are appended to a list on the device and redone by
 //             the exact engine in the same call (blocks of that launch exit at once when the list is empty).
+constexpr uint32_t PROBE_DENSE_MAX_C = 8192;  // C keys of one query fit the select kernel's shared memory
 struct ProbePlan {
     ScanPlan exact;
     bool tc = false;
+    bool dense = false;  // tc && C small: all C keys per query are written out and selected by probe_select_kernel
     uint32_t nch = 0, chunk_rows = 0, M = 0;
     size_t bytes = 0;
 };
@@ -961,7 +1052,7 @@ struct ProbeBufs {
     uint64_t *seg_off, *lq_off, *item_off, *pair_chunk_off;
     uint32_t *seg_len, *lq_pair, *cand_pos, *fail, *fail_idx, *n_fail, *part_p;
     unsigned long long *counter, *pstats;
-    float *gq, *gq_lo, *part_d, *cand_key, *bound, *tmp_d;
+    float *gq, *gq_lo, *part_d, *cand_key, *bound, *tmp_d, *dense;
     uint64_t* tmp_ids;
 };
 
@@ -978,8 +1069,9 @@ static void probe_carve(ScratchCarver& sc, const vers_ivf* ivf, const ProbePlan&
     b.n_fail = sc.take<uint32_t>(1);
     b.gq = sc.take<float>((size_t)(nq + TC_NQ) * ivf->ld);
     b.gq_lo = sc.take<float>((size_t)(nq + TC_NQ) * ivf->ld);
-    b.part_d = sc.take<float>((size_t)nq * pp.nch * TC_PARTS * 32);
-    b.part_p = sc.take<uint32_t>((size_t)nq * pp.nch * TC_PARTS * 32);
+    b.part_d = sc.take<float>(pp.dense ? 4 : (size_t)nq * pp.nch * TC_PARTS * 32);
+    b.part_p = sc.take<uint32_t>(pp.dense ? 4 : (size_t)nq * pp.nch * TC_PARTS * 32);
+    b.dense = sc.take<float>(pp.dense ? (size_t)nq * ivf->C : 4);
     b.cand_pos = sc.take<uint32_t>((size_t)nq * pp.M);
     b.cand_key = sc.take<float>((size_t)nq * pp.M);
     b.bound = sc.take<float>(nq);
@@ -997,6 +1089,7 @@ static ProbePlan probe_plan(const vers_ivf* ivf, uint32_t nq, uint32_t np) {
     pp.tc = ivf->mode == 0 && nq >= 32 && np <= 64 && ivf->C >= 512 && ivf->C >= 4 * np && ivf->ld >= TC_KC;
     if (pp.tc) {
         pp.M = np <= 32 ? 64 : 128;
+        pp.dense = ivf->C <= PROBE_DENSE_MAX_C;
         const uint32_t ngroups = (nq + TC_NQ - 1) / TC_NQ;
         uint32_t nch = std::max<uint32_t>(1, (uint32_t)ctx->sm_count / ngroups);
         nch = std::min<uint32_t>(nch, (ivf->C + TC_M - 1) / TC_M);
@@ -1009,6 +1102,89 @@ static ProbePlan probe_plan(const vers_ivf* ivf, uint32_t nq, uint32_t np) {
         pp.bytes = (sc.off + 255) & ~size_t(255);
     }
     return pp;
+}
+
+// ---- dense probe: exact selection of the M smallest (key, centroid) pairs of one query out of its C keys.
+// One block per query, keys staged in shared memory in the order-preserving uint32 encoding; 4 radix passes (8 bits
+// each, most significant first) find the M-th smallest value T; everything below T is a candidate, ties at T are
+// taken in centroid order (the (key, position) order of the other paths).  bound = T: no other centroid has a
+// smaller key.  Candidates come out unsorted: the exact rerank orders them.
+__global__ void __launch_bounds__(256)
+    probe_select_kernel(const float* __restrict__ dense, uint32_t C, uint32_t M, uint32_t* __restrict__ cand_pos,
+                        float* __restrict__ cand_key, float* __restrict__ cand_bound) {
+    extern __shared__ uint32_t ps_keys[];  // [C]
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_need, s_cnt;
+    const uint32_t q = blockIdx.x, tid = threadIdx.x;
+    const float* row = dense + (uint64_t)q * C;
+    for (uint32_t i = tid; i < C; i += 256) ps_keys[i] = tau_encode(row[i]);
+    if (tid == 0) {
+        s_prefix = 0;
+        s_need = M;
+        s_cnt = 0;
+    }
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        hist[tid] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        for (uint32_t i = tid; i < C; i += 256) {
+            const uint32_t u = ps_keys[i];
+            if (pass == 0 || (u >> (shift + 8)) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {  // 256-bin exclusive scan by one warp (8 bins per lane), find the bin holding the need-th element
+            uint32_t h[8], sum = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                h[e] = hist[tid * 8 + e];
+                sum += h[e];
+            }
+            uint32_t incl = sum;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y = __shfl_up_sync(FULL_MASK, incl, o);
+                if ((int)tid >= o) incl += y;
+            }
+            uint32_t before = incl - sum;
+            const uint32_t need = s_need;
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (need > before && need <= before + h[e]) {  // exactly one (lane, e) matches
+                    s_prefix = (prefix << 8) | (uint32_t)(tid * 8 + e);
+                    s_need = need - before;
+                }
+                before += h[e];
+            }
+        }
+        __syncthreads();
+    }
+    const uint32_t T = s_prefix, need_eq = s_need;  // take every u < T and the first need_eq entries with u == T
+    const uint32_t n_less = M - need_eq;
+    for (uint32_t i = tid; i < C; i += 256) {
+        const uint32_t u = ps_keys[i];
+        if (u < T) {
+            const uint32_t slot = atomicAdd(&s_cnt, 1u);
+            cand_pos[(uint64_t)q * M + slot] = i;
+            cand_key[(uint64_t)q * M + slot] = tau_decode(u);
+        }
+    }
+    if (tid < 32) {  // ties at T in centroid order
+        uint32_t taken = 0;
+        for (uint32_t i0 = 0; i0 < C && taken < need_eq; i0 += 32) {
+            const uint32_t i = i0 + tid;
+            const bool eq = i < C && ps_keys[i] == T;
+            const unsigned m = __ballot_sync(FULL_MASK, eq);
+            const uint32_t rank = taken + __popc(m & ((1u << tid) - 1u));
+            if (eq && rank < need_eq) {
+                cand_pos[(uint64_t)q * M + n_less + rank] = i;
+                cand_key[(uint64_t)q * M + n_less + rank] = tau_decode(T);
+            }
+            taken += __popc(m);
+        }
+        if (tid == 0) cand_bound[q] = tau_decode(T);
+    }
 }
 
 // work-item tables of the probe: one "list" (the centroid table) probed by every query, nch chunks
@@ -1079,14 +1255,20 @@ static int32_t probe_run(vers_ivf* ivf, const ProbePlan& pp, const float* d_quer
     tp.counter = b.counter;
     tp.qtau = nullptr;  // the probe keeps M = 64 > 32 candidates: no shared bound
     tp.lq_query = nullptr;
+    tp.dense_out = pp.dense ? b.dense : nullptr;
+    tp.dense_ld = ivf->C;
     VERS_TRY(launch_tc_scan<true>(ctx, ivf->d_cents, ivf->C, ivf->ld, b.gq, b.gq_lo, (uint64_t)nq + TC_NQ, tp, -1));
-    VERS_TRY(launch_cand_merge(ctx, pp.M, b.part_d, b.part_p, b.pair_chunk_off, nq, 1, TC_PARTS, b.cand_pos, b.cand_key,
-                               b.bound));
-    const size_t rsm = (size_t)4 * RERANK_QCHUNK * 4 + (size_t)4 * np * 12;
-    rerank_certify_kernel<<<(unsigned)ceil_div(nq, 4), 128, rsm, ctx->stream>>>(
-        ivf->d_cents, nullptr, ivf->ld, d_queries, nq, np, pp.M, b.cand_pos, b.bound, ivf->d_ncmax, b.cand_key, 2, out_ids,
-        out_d, nullptr, b.fail, ivf->d_stats + 3, b.fail_idx, b.n_fail);  // stats[7] = uncertified probe queries
-    VERS_LAUNCH_CHECK(ctx);
+    if (pp.dense) {
+        probe_select_kernel<<<nq, 256, (size_t)ivf->C * 4, ctx->stream>>>(b.dense, ivf->C, pp.M, b.cand_pos, b.cand_key,
+                                                                         b.bound);
+        VERS_LAUNCH_CHECK(ctx);
+    } else {
+        VERS_TRY(launch_cand_merge(ctx, pp.M, b.part_d, b.part_p, b.pair_chunk_off, nq, 1, TC_PARTS, b.cand_pos,
+                                   b.cand_key, b.bound));
+    }
+    VERS_TRY(launch_rerank(ctx, pp.M, ivf->d_cents, nullptr, ivf->ld, d_queries, nq, np, b.cand_pos, b.bound, ivf->d_ncmax,
+                           b.cand_key, 2, out_ids, out_d, nullptr, b.fail, ivf->d_stats + 3, b.fail_idx,
+                           b.n_fail));  // stats[7] = uncertified probe queries
     // exact redo of the uncertified queries (none, typically): the launch is sized for nq, the blocks read n_fail
     RowSrc QF{d_queries, b.fail_idx, ivf->ld, nq};
     VERS_TRY(scan_topk_run(ctx, pp.exact, ctx->scratch, CA, QF, nq, ivf->ld, np, VERS_METRIC_L2SQ, nullptr, 0, b.tmp_ids,
@@ -1206,17 +1388,19 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
         }
         VERS_TRY(launch_cand_merge(ctx, M, b.part_d, b.part_p, b.pair_chunk_off, nq, np, nsplit, b.cand_pos, b.cand_key,
                                    b.cand_bound));
-        size_t rsm = (size_t)4 * RERANK_QCHUNK * 4 + (size_t)4 * k * 12;
-        FamilyTimer ftr(ctx, KF_RERANK);
-        rerank_certify_kernel<<<(unsigned)ceil_div(nq, 4), 128, rsm, ctx->stream>>>(
-            ivf->d_lm, ivf->d_lm_ids, ivf->ld, d_queries, nq, k, M, b.cand_pos, b.cand_bound, ivf->d_nxmax, b.cand_key, use_tc ? (split3 ? 2 : 1) : 0,
-            d_ids, d_d, d_cnt, b.fail_flag, ivf->d_stats);
-        VERS_LAUNCH_CHECK(ctx);
+        {
+            FamilyTimer ftr(ctx, KF_RERANK);
+            VERS_TRY(launch_rerank(ctx, M, ivf->d_lm, ivf->d_lm_ids, ivf->ld, d_queries, nq, k, b.cand_pos, b.cand_bound,
+                                   ivf->d_nxmax, b.cand_key, use_tc ? (split3 ? 2 : 1) : 0, d_ids, d_d, d_cnt,
+                                   b.fail_flag, ivf->d_stats, nullptr, nullptr));
+        }
         qmask = b.fail_flag;  // 2b. exact-order redo of the (rare) uncertified queries, no host round trip
     }
     // 2b / exact mode: exact-order scan of the probed lists, merge by (distance, id)
-    VERS_TRY(run_group(ivf, b, nq, np, nullptr, qmask, !approx));
-    VERS_TRY((run_list_scan<ScanCfg, 0>(ivf, b, d_queries, nq, k)));
+    // (approximate path: every kernel of this pass returns at once when no query failed its certificate)
+    const uint32_t* skip = approx ? reinterpret_cast<const uint32_t*>(ivf->d_stats + 4) : nullptr;
+    VERS_TRY(run_group(ivf, b, nq, np, nullptr, qmask, !approx, ScanCfg::TB, LIST_CHUNK_ROWS, 0xffffffffu, nullptr, skip));
+    VERS_TRY((run_list_scan<ScanCfg, 0>(ivf, b, d_queries, nq, k, skip)));
     MergeParams mp;
     mp.part_d = b.part_d;
     mp.part_p = b.part_p;
@@ -1232,6 +1416,7 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
     mp.out_d = d_d;
     mp.out_cnt = d_cnt;
     mp.qmask = qmask;
+    mp.skip_if_zero = skip;
     return launch_merge(ctx, mp);
 }
 

@@ -108,6 +108,10 @@ struct TcScanParams {
     // top-32 and its bound do not depend on the timing of these updates.  Requires merged M == 32.
     uint32_t* qtau;
     const uint32_t* lq_query;  // grouped pair -> query
+    // optional (null: off): no selection at all, every key is written to dense_out[grouped pair][row position]
+    // (the centroid probe of small tables: C keys per query, selected afterwards by probe_select_kernel)
+    float* dense_out;
+    uint64_t dense_ld;
 };
 
 __device__ __forceinline__ uint32_t tau_encode(float f) {
@@ -389,6 +393,35 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
             const TcItem t = tc_decode_item(p, (uint64_t)it);
             const uint32_t ncol = t.nq >> 1, col0 = half * ncol;
             const uint32_t nlive = t.nB > col0 ? min(ncol, t.nB - col0) : 0u;  // this warp's live queries
+            if (p.dense_out) {
+                // dense mode: keys straight to global memory, lanes = consecutive rows => coalesced
+                for (uint64_t a0 = t.r0; a0 < t.r1; a0 += TC_M) {
+                    const uint32_t buf = tile_ctr & 1, tphase = (tile_ctr >> 1) & 1;
+                    tc::mbar_wait(&tfull[buf], tphase);
+                    tc::fence_after_thread_sync();
+                    const uint32_t tacc = tmem_base + ((uint32_t)(lane_group * 32) << 16) + buf * Cfg::ACC_COLS;
+                    const uint64_t row = a0 + (uint64_t)(lane_group * 32 + lane);
+                    const bool rowlive = row < t.r1;
+                    const float nx = rowlive ? __ldg(p.lm_norm + t.base_pos + row) : 0.0f;
+                    for (uint32_t j = 0; j < nlive; ++j) {
+                        float dot = tc::tmem_ld_1_nowait(tacc + col0 + j);
+                        float w = 0.0f, z = 0.0f;
+                        if (SPLIT3) {
+                            w = tc::tmem_ld_1_nowait(tacc + t.nq + col0 + j);
+                            z = tc::tmem_ld_1_nowait(tacc + 2 * t.nq + col0 + j);
+                        }
+                        tc::tmem_ld_wait3(dot, w, z);
+                        if (SPLIT3) dot = __fadd_rn(dot, __fadd_rn(w, z));
+                        if (rowlive)
+                            p.dense_out[(t.q0 + col0 + j) * p.dense_ld + t.base_pos + row] = __fmaf_rn(-2.0f, dot, nx);
+                    }
+                    tc::fence_before_thread_sync();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&tempty[buf]);
+                    ++tile_ctr;
+                }
+                continue;
+            }
             // lane j keeps query j's threshold (its list's 32nd key, or the query's shared bound) and queue fill
             float my_tau = __int_as_float(0x7f800000);
             uint32_t my_cnt = 0, my_q = 0;

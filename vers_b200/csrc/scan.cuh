@@ -34,6 +34,7 @@ struct MergeParams {
     uint32_t* out_cnt;      // [nq] optional
     const uint32_t* qmask;  // optional [nq]: only queries with a non-zero mask are merged/written
     const uint32_t* nq_dev = nullptr;  // optional: live query count read on the device
+    const uint32_t* skip_if_zero = nullptr;  // optional: no-op launch when this device word is 0
 };
 
 // scan rows [0, A.n) of A against nq queries (B), exact order; writes the global top-k per query.
@@ -58,6 +59,7 @@ int32_t scan_topk_run(vers_ctx* ctx, const ScanPlan& pl, void* scratch, const Ro
 int32_t launch_merge(vers_ctx* ctx, const MergeParams& mp);
 
 // exclusive scan of n uint32 -> uint64 out[n+1] (single block; n up to a few million is fine)
-int32_t launch_exclusive_scan(vers_ctx* ctx, const uint32_t* d_in, uint64_t n, uint64_t* d_out);
+int32_t launch_exclusive_scan(vers_ctx* ctx, const uint32_t* d_in, uint64_t n, uint64_t* d_out,
+                              const uint32_t* skip_if_zero = nullptr);
 
 }  // namespace vers

@@ -184,8 +184,15 @@ extern "C" int32_t vers_ctx_destroy(vers_ctx* ctx) {
 extern "C" int32_t vers_ctx_set_stream(vers_ctx* ctx, void* cuda_stream) {
     if (!ctx) return fail(VERS_ERR_ARG, "ctx_set_stream: null ctx");
     std::lock_guard<std::mutex> lk(ctx->mu);
-    cudaStreamSynchronize(ctx->stream);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    // switching INTO a capturing stream (CUDA graph capture of a search step): a synchronize would invalidate the
+    // capture; the caller has drained the old stream before starting the capture
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing((cudaStream_t)cuda_stream, &cap) != cudaSuccess) {
+        cudaGetLastError();
+        cap = cudaStreamCaptureStatusNone;
+    }
+    if (cap == cudaStreamCaptureStatusNone) cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream && cap == cudaStreamCaptureStatusNone) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)cuda_stream;
     ctx->own_stream = false;
     return VERS_OK;

@@ -216,11 +216,15 @@ __global__ void __launch_bounds__(1024) exclusive_scan_chained_kernel(const uint
                 while ((got = *f) == 0ull) {
                 }
                 carry = got - 1;
+                *f = 0ull;  // consumed exactly once: the flags are all zero again when the kernel ends
             }
             carry_s = carry;
-            __threadfence();
-            *(volatile unsigned long long*)(flags + blockIdx.x) = carry + w + 1;
-            if (blockIdx.x == gridDim.x - 1) out[n] = carry + w;
+            if (blockIdx.x == gridDim.x - 1) {
+                out[n] = carry + w;
+            } else {
+                __threadfence();
+                *(volatile unsigned long long*)(flags + blockIdx.x) = carry + w + 1;
+            }
         }
     }
     __syncthreads();
@@ -236,8 +240,10 @@ int32_t launch_exclusive_scan(vers_ctx* ctx, const uint32_t* d_in, uint64_t n, u
                               const uint32_t* skip_if_zero) {
     const uint64_t tiles = ceil_div(n, 8192);
     if (tiles > 1 && tiles <= (uint64_t)std::min(ctx->sm_count, 256)) {
-        if (!ctx->scan_flags) VERS_CUDA(cudaMalloc(&ctx->scan_flags, 256 * 8));
-        VERS_CUDA(cudaMemsetAsync(ctx->scan_flags, 0, 256 * 8, ctx->stream));
+        if (!ctx->scan_flags) {
+            VERS_CUDA(cudaMalloc(&ctx->scan_flags, 256 * 8));
+            VERS_CUDA(cudaMemsetAsync(ctx->scan_flags, 0, 256 * 8, ctx->stream));  // the kernel leaves them zero
+        }
         exclusive_scan_chained_kernel<<<(unsigned)tiles, 1024, 0, ctx->stream>>>(d_in, n, d_out, ctx->scan_flags,
                                                                                 skip_if_zero);
         VERS_LAUNCH_CHECK(ctx);

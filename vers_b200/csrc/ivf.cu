@@ -58,6 +58,15 @@ constexpr uint32_t LIST_CHUNK_ROWS = 4096;  // rows per work item; multiple of N
 // (measured on the bench workload: 256..2048 rows and 1/10..1/3 of the lists are all within 1 % of each other)
 constexpr uint32_t TC_TAIL_CHUNK_ROWS = 512;
 inline uint32_t tc_tail_list0(uint32_t C) { return C - C / 6; }
+// ... and when this GPU's share of the batch is small (many GPUs, few queries) every item shrinks so that each SM
+// still gets >= ~8 of them: rows the batch will stream ~ min(rows held, nq * nprobe * mean list length)
+inline uint32_t tc_chunk_rows(const vers_ivf* ivf, uint32_t nq, uint32_t np) {
+    const double mean_len = ivf->C ? (double)ivf->n / ivf->C : 0.0;
+    const double est_rows = std::min((double)ivf->n, (double)nq * np * mean_len);
+    const double per_sm = est_rows / std::max(ivf->ctx->sm_count, 1);
+    uint32_t cr = (uint32_t)(per_sm / 8.0) / 128u * 128u;
+    return std::min<uint32_t>(LIST_CHUNK_ROWS, std::max<uint32_t>(TC_TAIL_CHUNK_ROWS, cr));
+}
 using ScanCfg = NarrowCfg;
 
 // ---------------------------------------------------------------- layout
@@ -905,13 +914,13 @@ struct SearchBufs {
 
 static int32_t run_group(vers_ivf* ivf, const SearchBufs& b, uint32_t nq, uint32_t np, const uint32_t* used,
                          const uint32_t* qmask, bool record_stats, uint32_t tb = ScanCfg::TB,
-                         uint32_t chunk_rows_tail = LIST_CHUNK_ROWS, uint32_t tail_list0 = 0xffffffffu,
+                         uint32_t chunk_rows = LIST_CHUNK_ROWS, uint32_t chunk_rows_tail = LIST_CHUNK_ROWS,
+                         uint32_t tail_list0 = 0xffffffffu,
                          uint32_t* qtau = nullptr, const uint32_t* skip_if_zero = nullptr) {
     vers_ctx* ctx = ivf->ctx;
     const uint64_t npairs = (uint64_t)nq * np;
-    VERS_CUDA(cudaMemsetAsync(b.lq_cnt, 0, (size_t)ivf->C * 4, ctx->stream));
-    VERS_CUDA(cudaMemsetAsync(b.cursor, 0, (size_t)ivf->C * 4, ctx->stream));
-    VERS_CUDA(cudaMemsetAsync(b.counter, 0, 8, ctx->stream));
+    // lq_cnt, cursor and the work counter are carved back to back: one memset (counter[1], the short flag, survives)
+    VERS_CUDA(cudaMemsetAsync(b.lq_cnt, 0, (size_t)((char*)b.counter - (char*)b.lq_cnt) + 8, ctx->stream));
     GroupParams g;
     g.probe_ids = b.probe_ids;
     g.seg_len = ivf->d_seg_len;
@@ -921,7 +930,7 @@ static int32_t run_group(vers_ivf* ivf, const SearchBufs& b, uint32_t nq, uint32
     g.np = np;
     g.C = ivf->C;
     g.tb = tb;
-    g.chunk_rows = LIST_CHUNK_ROWS;
+    g.chunk_rows = chunk_rows;
     g.chunk_rows_tail = chunk_rows_tail;
     g.tail_list0 = tail_list0;
     g.qtau = qtau;
@@ -1001,7 +1010,8 @@ static int32_t launch_tc_scan(vers_ctx* ctx, const float* rows, uint64_t n_rows,
 }
 
 template <bool SPLIT3>
-static int32_t run_list_scan_tc(vers_ivf* ivf, const SearchBufs& b, const float* d_queries, uint32_t nq, uint32_t np) {
+static int32_t run_list_scan_tc(vers_ivf* ivf, const SearchBufs& b, const float* d_queries, uint32_t nq, uint32_t np,
+                                uint32_t chunk_rows) {
     vers_ctx* ctx = ivf->ctx;
     const uint64_t npairs = (uint64_t)nq * np;
     gather_queries_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_queries, b.lq_query, b.lq_off, ivf->C, ivf->ld,
@@ -1010,7 +1020,7 @@ static int32_t run_list_scan_tc(vers_ivf* ivf, const SearchBufs& b, const float*
     TcScanParams tp;
     tp.ld = ivf->ld;
     tp.C = ivf->C;
-    tp.chunk_rows = LIST_CHUNK_ROWS;
+    tp.chunk_rows = chunk_rows;
     tp.chunk_rows_tail = TC_TAIL_CHUNK_ROWS;
     tp.tail_list0 = tc_tail_list0(ivf->C);
     tp.seg_off = ivf->d_seg_off;
@@ -1309,6 +1319,7 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
         b.probe_d = sc.take<float>(npairs);
         b.lq_cnt = sc.take<uint32_t>(ivf->C);
         b.cursor = sc.take<uint32_t>(ivf->C);
+        b.counter = sc.take<unsigned long long>(2);
         b.item_cnt = sc.take<uint32_t>(ivf->C);
         b.pair_nch = sc.take<uint32_t>(npairs);
         b.lq_off = sc.take<uint64_t>((size_t)ivf->C + 1);
@@ -1320,7 +1331,6 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
         b.fail_flag = sc.take<uint32_t>(nq);
         b.cand_pos = sc.take<uint32_t>((size_t)nq * M);
         b.cand_bound = sc.take<float>(nq);
-        b.counter = sc.take<unsigned long long>(2);
         b.part_d = sc.take<float>(entries);
         b.part_p = sc.take<uint32_t>(entries);
         b.gq = sc.take<float>(use_tc ? (size_t)(npairs + TC_NQ) * ivf->ld : 4);
@@ -1374,12 +1384,13 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
         // 2a. candidate pass (FMA, HBM-streaming) -> top-M per query -> exact-order rerank -> certificate
         uint32_t nsplit;
         if (use_tc) {
-            VERS_TRY(run_group(ivf, b, nq, np, nullptr, nullptr, true, TC_NQ, TC_TAIL_CHUNK_ROWS, tc_tail_list0(ivf->C),
-                               b.qtau));
+            const uint32_t cr = tc_chunk_rows(ivf, nq, np);
+            VERS_TRY(run_group(ivf, b, nq, np, nullptr, nullptr, true, TC_NQ, cr, TC_TAIL_CHUNK_ROWS,
+                               tc_tail_list0(ivf->C), b.qtau));
             if (split3)
-                VERS_TRY(run_list_scan_tc<true>(ivf, b, d_queries, nq, np));
+                VERS_TRY(run_list_scan_tc<true>(ivf, b, d_queries, nq, np, cr));
             else
-                VERS_TRY(run_list_scan_tc<false>(ivf, b, d_queries, nq, np));
+                VERS_TRY(run_list_scan_tc<false>(ivf, b, d_queries, nq, np, cr));
             nsplit = TC_PARTS;
         } else {
             VERS_TRY(run_group(ivf, b, nq, np, nullptr, nullptr, true));
@@ -1399,7 +1410,8 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
     // 2b / exact mode: exact-order scan of the probed lists, merge by (distance, id)
     // (approximate path: every kernel of this pass returns at once when no query failed its certificate)
     const uint32_t* skip = approx ? reinterpret_cast<const uint32_t*>(ivf->d_stats + 4) : nullptr;
-    VERS_TRY(run_group(ivf, b, nq, np, nullptr, qmask, !approx, ScanCfg::TB, LIST_CHUNK_ROWS, 0xffffffffu, nullptr, skip));
+    VERS_TRY(run_group(ivf, b, nq, np, nullptr, qmask, !approx, ScanCfg::TB, LIST_CHUNK_ROWS, LIST_CHUNK_ROWS, 0xffffffffu,
+                       nullptr, skip));
     VERS_TRY((run_list_scan<ScanCfg, 0>(ivf, b, d_queries, nq, k, skip)));
     MergeParams mp;
     mp.part_d = b.part_d;

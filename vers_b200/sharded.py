@@ -239,6 +239,27 @@ class ShardedIVFFlat:
             self._bufs[key] = (local, allb, out_ids, out_d, out_c, L)
         return self._bufs[key]
 
+    def capture_search(self, d_queries: torch.Tensor, top_k: int, nprobe: int):
+        """Single GPU: captures one search_dev call on this batch buffer into a CUDA graph (the ~45 small launches of
+        a step become one graph launch).  Returns (graph, outputs): refill ``d_queries`` in place and
+        ``graph.replay()``; the outputs are the same device tensors every time.  The library makes no host
+        synchronisation and no allocation on this path once it has run eagerly with the same shapes."""
+        if self.world > 1:
+            raise RuntimeError("capture_search: capturing the NCCL all-gathers of the multi-GPU step is not supported "
+                               "(it deadlocked with torch 2.11 / NCCL 2.28 in this image)")
+        for _ in range(2):
+            self.search_dev(d_queries, top_k, nprobe)
+        torch.cuda.synchronize()
+        eager_stream = torch.cuda.current_stream()
+        g = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(g):
+                self.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+                out = self.search_dev(d_queries, top_k, nprobe)
+        finally:
+            self.ctx.set_stream(eager_stream.cuda_stream)
+        return g, out
+
     def search_dev(self, d_queries: torch.Tensor, top_k: int, nprobe: int):
         """d_queries: [nq, ld] float32 on this rank's GPU (the same batch on every rank).  Returns device tensors
         (ids int64 [nq,k] holding u64 bit patterns, dists [nq,k], counts [nq]) — the global result on every rank."""

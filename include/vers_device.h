@@ -92,6 +92,14 @@ int32_t vers_flat_search(vers_dataset* ds, const float* queries, uint32_t nq, ui
 /* d_queries: device, nq rows of ld floats (ld = dataset ld, zero padded); outputs device [nq][top_k] */
 int32_t vers_flat_search_dev(vers_dataset* ds, const float* d_queries, uint32_t nq, uint32_t top_k, uint32_t metric,
                              uint64_t* d_ids, float* d_dists, uint32_t* d_counts);
+/* Batches of >= 32 queries with top_k <= 64 and the L2 metric take the two-stage path of the inverted-list scan over
+ * the whole dataset: tensor-core candidate keys (TMA + tcgen05 kind::tf32, split hi/lo) -> exact-order rerank of the
+ * 64/128 best -> rounding-error certificate -> exact-order redo of uncertified queries.  ids and distance bits are
+ * the reference's either way.  mode 1 forces the exact-order engine (tests, timing).  Stats of the last tensor-core
+ * search: out[4] = uncertified queries, out[5] = rows re-ranked, out[6] = bit pattern of the largest observed
+ * |candidate value - exact value|; all zero when the exact-order engine ran. */
+int32_t vers_flat_set_mode(vers_dataset* ds, int32_t mode);
+int32_t vers_flat_last_search_stats(const vers_dataset* ds, uint64_t out[8]);
 
 /* ---- k-means: IVFFlatIndex::{assign_to_clusters, update_centroids, build_kmeans, calculate_kmeans_cost}
  *      (indexes/ivfflat.rs:29-46, :47-71, :73-100, :138-149) ------------------------------------------------ */

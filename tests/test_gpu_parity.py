@@ -176,6 +176,39 @@ def test_kmeans_chained_shards_reproduce_global_order(vb, vo, ctx):
     assert np.array_equal(bits(kms[0].centroids()), bits(want))
 
 
+@pytest.mark.parametrize("n,dim,nq,k", [(50000, 300, 100, 10), (20000, 768, 33, 10), (70000, 128, 257, 1),
+                                        (6000, 96, 64, 37), (150000, 64, 40, 64)])
+def test_flat_search_tensor_core_path_bit_exact(vb, vo, ctx, n, dim, nq, k):
+    """large batches take tensor-core candidate keys -> exact rerank -> certificate (-> exact redo): same ids and
+    distance bits as search_exhaustive, and the same as the exact-order engine (mode 1)"""
+    rows = data(vo, n, dim, n_centers=64)
+    q = data(vo, nq, dim, seed=2, n_centers=64)
+    ds = vb.Dataset.upload(ctx, rows, id_base=77)
+    ids, d, cnt = vb.search_exhaustive_batch(ds, q, k, 0)
+    st = ds.last_flat_search_stats()
+    oi, od, oc = vo.exhaustive(rows, q, k, 0, id_base=77)
+    assert np.array_equal(cnt, oc) and np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od))
+    assert st["reranked"] > 0 and st["uncertified_queries"] <= nq // 4 and st["max_candidate_error"] < 2e-5
+    ds.set_flat_mode(1)
+    ids1, d1, cnt1 = vb.search_exhaustive_batch(ds, q, k, 0)
+    assert np.array_equal(ids1, oi) and np.array_equal(bits(d1), bits(od))
+    assert ds.last_flat_search_stats()["reranked"] == 0
+
+
+def test_flat_search_tensor_core_path_ties_fall_back(vb, vo, ctx):
+    """200 copies of one row: more ties than candidates, the certificate must fail and the exact redo order them by id"""
+    rows = data(vo, 30000, 96, n_centers=32)
+    rows[5000:5200] = rows[11]
+    q = data(vo, 48, 96, seed=2, n_centers=32)
+    q[0] = rows[11]
+    ds = vb.Dataset.upload(ctx, rows)
+    ids, d, cnt = vb.search_exhaustive_batch(ds, q, 10, 0)
+    oi, od, oc = vo.exhaustive(rows, q, 10, 0)
+    assert np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od))
+    assert list(ids[0]) == [11] + list(range(5000, 5009))
+    assert ds.last_flat_search_stats()["uncertified_queries"] >= 1
+
+
 # ---------------------------------------------------------------------------------------------- IVFFlat
 @pytest.fixture(scope="module")
 def ivf_c1(vb, vo, ctx):

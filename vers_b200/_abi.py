@@ -52,6 +52,8 @@ SIGNATURES = {
     "vers_dataset_free": [vp],
     "vers_flat_search": [vp, vp, u32, u32, u32, u32, vp, vp, vp],
     "vers_flat_search_dev": [vp, vp, u32, u32, u32, vp, vp, vp],
+    "vers_flat_set_mode": [vp, i32],
+    "vers_flat_last_search_stats": [vp, vp],
     "vers_kmeans_create": [vp, u32, pvp],
     "vers_kmeans_free": [vp],
     "vers_kmeans_init_from_rows": [vp, vp],

@@ -307,6 +307,15 @@ extern "C" int32_t vers_dataset_normalize(vers_dataset* ds) {
     normalize_kernel<<<(unsigned)ceil_div(ds->n, NORM_ROWS), NORM_ROWS, 0, ctx->stream>>>(ds->d_rows, ds->n, ds->dim,
                                                                                          ds->ld);
     VERS_LAUNCH_CHECK(ctx);
+    if (ds->d_norm) {  // cached ||row||^2 of the tensor-core exhaustive search are stale now
+        VERS_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ds->d_norm);
+        cudaFree(ds->d_nmax);
+        cudaFree(ds->d_stats);
+        ds->d_norm = nullptr;
+        ds->d_nmax = nullptr;
+        ds->d_stats = nullptr;
+    }
     return VERS_OK;
 }
 
@@ -361,6 +370,9 @@ extern "C" int32_t vers_dataset_free(vers_dataset* ds) {
     cudaSetDevice(ds->ctx->device);
     cudaStreamSynchronize(ds->ctx->stream);
     if (ds->owned && ds->d_rows) cudaFree(ds->d_rows);
+    cudaFree(ds->d_norm);
+    cudaFree(ds->d_nmax);
+    cudaFree(ds->d_stats);
     delete ds;
     return VERS_OK;
 }

@@ -71,6 +71,12 @@ struct vers_dataset {
     uint32_t ld = 0;  // round_up(dim, 4), pad columns are zero
     uint64_t id_base = 0;
     bool owned = true;
+    // tensor-core exhaustive search: ||row||^2 (any order), their max, 8 counters; built on first use, dropped when the
+    // rows change (normalize)
+    float* d_norm = nullptr;
+    uint32_t* d_nmax = nullptr;
+    unsigned long long* d_stats = nullptr;
+    int flat_mode = 0;  // 0: tensor-core candidate path for eligible batches, 1: exact-order engine only
 };
 
 namespace vers {

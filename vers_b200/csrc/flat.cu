@@ -419,10 +419,41 @@ extern "C" int32_t vers_flat_search_dev(vers_dataset* ds, const float* d_queries
     vers_ctx* ctx = ds->ctx;
     std::lock_guard<std::mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
+    if (metric == VERS_METRIC_L2SQ && ds->flat_mode == 0 && nq >= 32 && top_k >= 1 && top_k <= 64) {
+        // large batches: tensor-core candidate keys -> exact-order rerank -> certificate -> exact redo (ivf.cu)
+        if (!ds->d_norm) {
+            VERS_CUDA(cudaMalloc(&ds->d_norm, (ds->n ? ds->n : 1) * 4));
+            VERS_CUDA(cudaMalloc(&ds->d_nmax, 4));
+            VERS_CUDA(cudaMalloc(&ds->d_stats, 128));
+            VERS_TRY(launch_rownorm(ctx, ds->d_rows, ds->ld, ds->n, ds->d_norm, ds->d_nmax));
+        }
+        bool used = false;
+        int32_t rc = flat_search_tc_plan_and_run(ctx, ds->d_rows, ds->n, ds->ld, ds->d_norm, ds->d_nmax, ds->id_base,
+                                                 ds->d_stats, d_queries, nq, top_k, d_ids, d_dists, d_counts, &used);
+        if (used || rc != VERS_ERR_UNSUPPORTED) return rc;
+    }
+    if (ds->d_stats) VERS_CUDA(cudaMemsetAsync(ds->d_stats, 0, 64, ctx->stream));  // the exact-order engine ran
     RowSrc A{ds->d_rows, nullptr, ds->ld, ds->n};
     RowSrc B{d_queries, nullptr, ds->ld, nq};
     return scan_topk_dev(ctx, A, B, nq, ds->ld, top_k, metric, nullptr, ds->id_base, d_ids, d_dists, d_counts,
                          KF_FLAT_SCAN);
+}
+
+extern "C" int32_t vers_flat_set_mode(vers_dataset* ds, int32_t mode) {
+    if (!ds) return fail(VERS_ERR_ARG, "flat_set_mode: null");
+    if (mode < 0 || mode > 1) return fail(VERS_ERR_ARG, "flat_set_mode: mode %d", mode);
+    ds->flat_mode = mode;
+    return VERS_OK;
+}
+
+extern "C" int32_t vers_flat_last_search_stats(const vers_dataset* ds, uint64_t out[8]) {
+    if (!ds || !out) return fail(VERS_ERR_ARG, "flat_last_search_stats: null");
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    if (!ds->d_stats) return VERS_OK;
+    VERS_CUDA(cudaSetDevice(ds->ctx->device));
+    VERS_CUDA(cudaMemcpyAsync(out, ds->d_stats, 64, cudaMemcpyDeviceToHost, ds->ctx->stream));
+    VERS_CUDA(cudaStreamSynchronize(ds->ctx->stream));
+    return VERS_OK;
 }
 
 namespace vers {

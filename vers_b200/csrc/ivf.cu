@@ -737,8 +737,8 @@ constexpr int RR_KCH = 64;          // dimensions per staged chunk
 constexpr int RR_LDS = RR_KCH + 4;  // padded tile row (floats): lanes walking their own rows stay conflict-free
 template <int R>
 __global__ void __launch_bounds__(128)
-    rerank_certify_kernel(const float* __restrict__ lm, const uint64_t* __restrict__ lm_ids, uint32_t ld,
-                          const float* __restrict__ queries, uint32_t nq, uint32_t k,
+    rerank_certify_kernel(const float* __restrict__ lm, const uint64_t* __restrict__ lm_ids, uint64_t id_base,
+                          uint32_t ld, const float* __restrict__ queries, uint32_t nq, uint32_t k,
                           const uint32_t* __restrict__ cand_pos, const float* __restrict__ cand_bound,
                           const uint32_t* __restrict__ nxmax_bits, const float* __restrict__ cand_key, int tf32_pass,
                           uint64_t* out_ids, float* out_d, uint32_t* out_cnt, uint32_t* fail_flag,
@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(128)
     for (int o = 16; o; o >>= 1) nq2 += __shfl_xor_sync(FULL_MASK, nq2, o);
     sdist[warp][lane] = s;
     skey[warp][lane] = live ? cand_key[(uint64_t)q * M + wr * 32 + lane] : 0.f;
-    sid[warp][lane] = live ? (lm_ids ? lm_ids[pos] : (uint64_t)pos) : 0xffffffffffffffffull;
+    sid[warp][lane] = live ? (lm_ids ? lm_ids[pos] : id_base + pos) : 0xffffffffffffffffull;
     __syncthreads();
     if (!active || wr != 0) return;
 
@@ -877,15 +877,15 @@ __global__ void __launch_bounds__(128)
     }
 }
 
-static int32_t launch_rerank(vers_ctx* ctx, uint32_t M, const float* lm, const uint64_t* lm_ids, uint32_t ld,
-                             const float* queries, uint32_t nq, uint32_t k, const uint32_t* cand_pos,
+static int32_t launch_rerank(vers_ctx* ctx, uint32_t M, const float* lm, const uint64_t* lm_ids, uint64_t id_base,
+                             uint32_t ld, const float* queries, uint32_t nq, uint32_t k, const uint32_t* cand_pos,
                              const float* cand_bound, const uint32_t* nxmax_bits, const float* cand_key, int tf32_pass,
                              uint64_t* out_ids, float* out_d, uint32_t* out_cnt, uint32_t* fail_flag,
                              unsigned long long* stats, uint32_t* fail_list, uint32_t* n_fail) {
     if (k > M) return fail(VERS_ERR_ARG, "rerank: k %u > %u candidates", k, M);
 #define VERS_RR(R)                                                                                                  \
     rerank_certify_kernel<R><<<(unsigned)ceil_div(nq, 4 / R), 128, (size_t)(4 / R) * k * 12, ctx->stream>>>(       \
-        lm, lm_ids, ld, queries, nq, k, cand_pos, cand_bound, nxmax_bits, cand_key, tf32_pass, out_ids, out_d,      \
+        lm, lm_ids, id_base, ld, queries, nq, k, cand_pos, cand_bound, nxmax_bits, cand_key, tf32_pass, out_ids, out_d, \
         out_cnt, fail_flag, stats, fail_list, n_fail)
     if (M == 32) VERS_RR(1);
     else if (M == 64) VERS_RR(2);
@@ -1050,6 +1050,17 @@ static int32_t run_list_scan_tc(vers_ivf* ivf, const SearchBufs& b, const float*
 //             enter or tie the top-nprobe; queries that fail it are appended to a list on the device and redone by
 //             the exact engine in the same call (blocks of that launch exit at once when the list is empty).
 constexpr uint32_t PROBE_DENSE_MAX_C = 8192;  // C keys of one query fit the select kernel's shared memory
+// the table the queries are ranked against: the centroids (probe) or a whole dataset (exhaustive search)
+struct RankTable {
+    const float* rows;          // [n][ld]
+    uint64_t n;
+    uint32_t ld;
+    const float* norm;          // [n] ||row||^2, any order
+    const uint32_t* nmax_bits;  // max ||row||^2
+    uint64_t id_base;           // reported id = id_base + row
+    bool allow_tc;
+    unsigned long long* stats;  // stats[4] uncertified queries, [5] re-ranked rows, [6] max observed candidate error
+};
 struct ProbePlan {
     ScanPlan exact;
     bool tc = false;
@@ -1066,7 +1077,7 @@ struct ProbeBufs {
     uint64_t* tmp_ids;
 };
 
-static void probe_carve(ScratchCarver& sc, const vers_ivf* ivf, const ProbePlan& pp, uint32_t nq, uint32_t np,
+static void probe_carve(ScratchCarver& sc, const RankTable& tb, const ProbePlan& pp, uint32_t nq, uint32_t np,
                         ProbeBufs& b) {
     b.seg_off = sc.take<uint64_t>(1);
     b.seg_len = sc.take<uint32_t>(1);
@@ -1077,11 +1088,11 @@ static void probe_carve(ScratchCarver& sc, const vers_ivf* ivf, const ProbePlan&
     b.counter = sc.take<unsigned long long>(2);
     b.pstats = sc.take<unsigned long long>(8);
     b.n_fail = sc.take<uint32_t>(1);
-    b.gq = sc.take<float>((size_t)(nq + TC_NQ) * ivf->ld);
-    b.gq_lo = sc.take<float>((size_t)(nq + TC_NQ) * ivf->ld);
+    b.gq = sc.take<float>((size_t)(nq + TC_NQ) * tb.ld);
+    b.gq_lo = sc.take<float>((size_t)(nq + TC_NQ) * tb.ld);
     b.part_d = sc.take<float>(pp.dense ? 4 : (size_t)nq * pp.nch * TC_PARTS * 32);
     b.part_p = sc.take<uint32_t>(pp.dense ? 4 : (size_t)nq * pp.nch * TC_PARTS * 32);
-    b.dense = sc.take<float>(pp.dense ? (size_t)nq * ivf->C : 4);
+    b.dense = sc.take<float>(pp.dense ? (size_t)nq * tb.n : 4);
     b.cand_pos = sc.take<uint32_t>((size_t)nq * pp.M);
     b.cand_key = sc.take<float>((size_t)nq * pp.M);
     b.bound = sc.take<float>(nq);
@@ -1091,27 +1102,45 @@ static void probe_carve(ScratchCarver& sc, const vers_ivf* ivf, const ProbePlan&
     b.tmp_d = sc.take<float>((size_t)nq * np);
 }
 
-static ProbePlan probe_plan(const vers_ivf* ivf, uint32_t nq, uint32_t np) {
-    const vers_ctx* ctx = ivf->ctx;
+static ProbePlan probe_plan(const vers_ctx* ctx, const RankTable& tb, uint32_t nq, uint32_t np) {
     ProbePlan pp;
-    pp.exact = scan_topk_plan(ctx, ivf->C, nq, np);
+    pp.exact = scan_topk_plan(ctx, tb.n, nq, np);
     pp.bytes = (pp.exact.bytes + 255) & ~size_t(255);
-    pp.tc = ivf->mode == 0 && nq >= 32 && np <= 64 && ivf->C >= 512 && ivf->C >= 4 * np && ivf->ld >= TC_KC;
+    pp.tc = tb.allow_tc && nq >= 32 && np <= 64 && tb.n >= 512 && tb.n >= 4ull * np && tb.ld >= TC_KC &&
+            tb.n < 0x7fffffffull;
     if (pp.tc) {
         pp.M = np <= 32 ? 64 : 128;
-        pp.dense = ivf->C <= PROBE_DENSE_MAX_C;
+        pp.dense = tb.n <= PROBE_DENSE_MAX_C;
         const uint32_t ngroups = (nq + TC_NQ - 1) / TC_NQ;
-        uint32_t nch = std::max<uint32_t>(1, (uint32_t)ctx->sm_count / ngroups);
-        nch = std::min<uint32_t>(nch, (ivf->C + TC_M - 1) / TC_M);
-        pp.chunk_rows = round_up((ivf->C + nch - 1) / nch, (uint32_t)TC_M);
-        pp.nch = (ivf->C + pp.chunk_rows - 1) / pp.chunk_rows;
+        // small tables (the centroids): one wave of work items; large ones (a dataset): ~8 items per SM, and a chunk
+        // must keep its row offsets in 16 bits
+        const uint32_t target = tb.n <= 65536 ? (uint32_t)ctx->sm_count : (uint32_t)ctx->sm_count * 8;
+        uint64_t nch = std::max<uint32_t>(1, target / ngroups);
+        nch = std::min<uint64_t>(nch, (tb.n + TC_M - 1) / TC_M);
+        uint64_t cr = round_up((uint32_t)((tb.n + nch - 1) / nch), (uint32_t)TC_M);
+        cr = std::min<uint64_t>(cr, 32768);
+        pp.chunk_rows = (uint32_t)cr;
+        pp.nch = (uint32_t)((tb.n + cr - 1) / cr);
         ScratchCarver sc(nullptr);
         sc.off = pp.bytes;
         ProbeBufs b;
-        probe_carve(sc, ivf, pp, nq, np, b);
+        probe_carve(sc, tb, pp, nq, np, b);
         pp.bytes = (sc.off + 255) & ~size_t(255);
     }
     return pp;
+}
+
+static RankTable centroid_table(const vers_ivf* ivf) {
+    RankTable tb;
+    tb.rows = ivf->d_cents;
+    tb.n = ivf->C;
+    tb.ld = ivf->ld;
+    tb.norm = ivf->d_cent_norm;
+    tb.nmax_bits = ivf->d_ncmax;
+    tb.id_base = 0;
+    tb.allow_tc = ivf->mode == 0;
+    tb.stats = ivf->d_stats + 3;  // stats[7] = uncertified probe queries, [8] = re-ranked centroids
+    return tb;
 }
 
 // ---- dense probe: exact selection of the M smallest (key, centroid) pairs of one query out of its C keys.
@@ -1226,29 +1255,28 @@ __global__ void probe_scatter_kernel(const uint32_t* __restrict__ fail_idx, cons
 }
 
 // scratch: [0, pp.bytes) of the context arena.  out_ids / out_d: [nq][np]
-static int32_t probe_run(vers_ivf* ivf, const ProbePlan& pp, const float* d_queries, uint32_t nq, uint32_t np,
-                         uint64_t* out_ids, float* out_d) {
-    vers_ctx* ctx = ivf->ctx;
-    RowSrc CA{ivf->d_cents, nullptr, ivf->ld, ivf->C};
+static int32_t probe_run(vers_ctx* ctx, const RankTable& tb, const ProbePlan& pp, const float* d_queries, uint32_t nq,
+                         uint32_t np, uint64_t* out_ids, float* out_d, uint32_t* out_cnt, int family) {
+    RowSrc CA{tb.rows, nullptr, tb.ld, tb.n};
     if (!pp.tc) {
-        RowSrc QB{d_queries, nullptr, ivf->ld, nq};
-        return scan_topk_run(ctx, pp.exact, ctx->scratch, CA, QB, nq, ivf->ld, np, VERS_METRIC_L2SQ, nullptr, 0, out_ids,
-                             out_d, nullptr, KF_PROBE);
+        RowSrc QB{d_queries, nullptr, tb.ld, nq};
+        return scan_topk_run(ctx, pp.exact, ctx->scratch, CA, QB, nq, tb.ld, np, VERS_METRIC_L2SQ, nullptr, tb.id_base,
+                             out_ids, out_d, out_cnt, family);
     }
     ScratchCarver sc(ctx->scratch);
     sc.off = (pp.exact.bytes + 255) & ~size_t(255);
     ProbeBufs b;
-    probe_carve(sc, ivf, pp, nq, np, b);
-    FamilyTimer ft(ctx, KF_PROBE);
+    probe_carve(sc, tb, pp, nq, np, b);
+    FamilyTimer ft(ctx, family);
     VERS_CUDA(cudaMemsetAsync(b.counter, 0, (size_t)((char*)b.n_fail - (char*)b.counter) + 4, ctx->stream));  // + pstats
     probe_tables_kernel<<<(unsigned)ceil_div(nq + 1, 256), 256, 0, ctx->stream>>>(
-        ivf->C, nq, pp.nch, b.seg_off, b.seg_len, b.lq_off, b.item_off, b.pair_chunk_off, b.lq_pair);
+        (uint32_t)tb.n, nq, pp.nch, b.seg_off, b.seg_len, b.lq_off, b.item_off, b.pair_chunk_off, b.lq_pair);
     VERS_LAUNCH_CHECK(ctx);
-    gather_queries_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_queries, nullptr, b.lq_off, 1, ivf->ld, b.gq,
+    gather_queries_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_queries, nullptr, b.lq_off, 1, tb.ld, b.gq,
                                                                      b.gq_lo, 1);
     VERS_LAUNCH_CHECK(ctx);
     TcScanParams tp;
-    tp.ld = ivf->ld;
+    tp.ld = tb.ld;
     tp.C = 1;
     tp.chunk_rows = pp.chunk_rows;
     tp.chunk_rows_tail = pp.chunk_rows;
@@ -1259,32 +1287,62 @@ static int32_t probe_run(vers_ivf* ivf, const ProbePlan& pp, const float* d_quer
     tp.lq_off = b.lq_off;
     tp.item_off = b.item_off;
     tp.pair_chunk_off = b.pair_chunk_off;
-    tp.lm_norm = ivf->d_cent_norm;
+    tp.lm_norm = tb.norm;
     tp.part_d = b.part_d;
     tp.part_p = b.part_p;
     tp.counter = b.counter;
-    tp.qtau = nullptr;  // the probe keeps M = 64 > 32 candidates: no shared bound
+    tp.qtau = nullptr;  // M = 64 > 32 candidates are kept: no shared bound
     tp.lq_query = nullptr;
     tp.dense_out = pp.dense ? b.dense : nullptr;
-    tp.dense_ld = ivf->C;
-    VERS_TRY(launch_tc_scan<true>(ctx, ivf->d_cents, ivf->C, ivf->ld, b.gq, b.gq_lo, (uint64_t)nq + TC_NQ, tp, -1));
+    tp.dense_ld = tb.n;
+    VERS_TRY(launch_tc_scan<true>(ctx, tb.rows, tb.n, tb.ld, b.gq, b.gq_lo, (uint64_t)nq + TC_NQ, tp, -1));
     if (pp.dense) {
-        probe_select_kernel<<<nq, 256, (size_t)ivf->C * 4, ctx->stream>>>(b.dense, ivf->C, pp.M, b.cand_pos, b.cand_key,
-                                                                         b.bound);
+        probe_select_kernel<<<nq, 256, (size_t)tb.n * 4, ctx->stream>>>(b.dense, (uint32_t)tb.n, pp.M, b.cand_pos,
+                                                                       b.cand_key, b.bound);
         VERS_LAUNCH_CHECK(ctx);
     } else {
         VERS_TRY(launch_cand_merge(ctx, pp.M, b.part_d, b.part_p, b.pair_chunk_off, nq, 1, TC_PARTS, b.cand_pos,
                                    b.cand_key, b.bound));
     }
-    VERS_TRY(launch_rerank(ctx, pp.M, ivf->d_cents, nullptr, ivf->ld, d_queries, nq, np, b.cand_pos, b.bound, ivf->d_ncmax,
-                           b.cand_key, 2, out_ids, out_d, nullptr, b.fail, ivf->d_stats + 3, b.fail_idx,
-                           b.n_fail));  // stats[7] = uncertified probe queries
+    VERS_TRY(launch_rerank(ctx, pp.M, tb.rows, nullptr, tb.id_base, tb.ld, d_queries, nq, np, b.cand_pos, b.bound,
+                           tb.nmax_bits, b.cand_key, 2, out_ids, out_d, out_cnt, b.fail, tb.stats, b.fail_idx, b.n_fail));
     // exact redo of the uncertified queries (none, typically): the launch is sized for nq, the blocks read n_fail
-    RowSrc QF{d_queries, b.fail_idx, ivf->ld, nq};
-    VERS_TRY(scan_topk_run(ctx, pp.exact, ctx->scratch, CA, QF, nq, ivf->ld, np, VERS_METRIC_L2SQ, nullptr, 0, b.tmp_ids,
-                           b.tmp_d, nullptr, -1, b.n_fail));
+    RowSrc QF{d_queries, b.fail_idx, tb.ld, nq};
+    VERS_TRY(scan_topk_run(ctx, pp.exact, ctx->scratch, CA, QF, nq, tb.ld, np, VERS_METRIC_L2SQ, nullptr, tb.id_base,
+                           b.tmp_ids, b.tmp_d, nullptr, -1, b.n_fail));
     probe_scatter_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(b.fail_idx, b.n_fail, b.tmp_ids, b.tmp_d, np, out_ids,
                                                                out_d);
+    VERS_LAUNCH_CHECK(ctx);
+    return VERS_OK;
+}
+
+// exhaustive search (utils.rs:68-82) of a query batch through the same tensor-core candidate path: the dataset is the
+// table.  Declared in scan.cuh, called by vers_flat_search_dev (caller holds ctx->mu).
+int32_t flat_search_tc_plan_and_run(vers_ctx* ctx, const float* rows, uint64_t n, uint32_t ld, const float* norm,
+                                    const uint32_t* nmax_bits, uint64_t id_base, unsigned long long* stats,
+                                    const float* d_queries, uint32_t nq, uint32_t k, uint64_t* d_ids, float* d_d,
+                                    uint32_t* d_cnt, bool* used_tc) {
+    RankTable tb;
+    tb.rows = rows;
+    tb.n = n;
+    tb.ld = ld;
+    tb.norm = norm;
+    tb.nmax_bits = nmax_bits;
+    tb.id_base = id_base;
+    tb.allow_tc = true;
+    tb.stats = stats;
+    const ProbePlan pp = probe_plan(ctx, tb, nq, k);
+    if (used_tc) *used_tc = pp.tc;
+    if (!pp.tc) return VERS_ERR_UNSUPPORTED;  // the caller runs the exact-order engine
+    VERS_TRY(scratch_reserve(ctx, pp.bytes));
+    VERS_CUDA(cudaMemsetAsync(stats, 0, 64, ctx->stream));
+    return probe_run(ctx, tb, pp, d_queries, nq, k, d_ids, d_d, d_cnt, KF_FLAT_SCAN);
+}
+
+// ||row||^2 of n rows + running max (exported for flat.cu)
+int32_t launch_rownorm(vers_ctx* ctx, const float* rows, uint32_t ld, uint64_t n, float* norm, uint32_t* nmax_bits) {
+    VERS_CUDA(cudaMemsetAsync(nmax_bits, 0, 4, ctx->stream));
+    rownorm_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(rows, ld, 0, n, norm, nmax_bits);
     VERS_LAUNCH_CHECK(ctx);
     return VERS_OK;
 }
@@ -1310,7 +1368,8 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
     if (use_tc) entries = std::max(entries, (size_t)nq * std::max<uint64_t>(mc[1], 1) * TC_PARTS * M);
 
     // the probe carves its buffers from the front of the arena, ours come after it
-    const ProbePlan pplan = probe_plan(ivf, nq, np);
+    const RankTable ctab = centroid_table(ivf);
+    const ProbePlan pplan = probe_plan(ctx, ctab, nq, np);
     const size_t probe_reserve = pplan.bytes;
     SearchBufs b;
     auto carve = [&](ScratchCarver& sc) {
@@ -1352,7 +1411,7 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
     if (ext_probe) {
         VERS_CUDA(cudaMemcpyAsync(b.probe_ids, ext_probe, (size_t)npairs * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     } else {
-        VERS_TRY(probe_run(ivf, pplan, d_queries, nq, np, b.probe_ids, b.probe_d));
+        VERS_TRY(probe_run(ctx, ctab, pplan, d_queries, nq, np, b.probe_ids, b.probe_d, nullptr, KF_PROBE));
     }
     VERS_CUDA(cudaMemsetAsync(b.counter, 0, 16, ctx->stream));
     uint32_t* short_flag = reinterpret_cast<uint32_t*>(b.counter + 1);
@@ -1401,7 +1460,7 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
                                    b.cand_bound));
         {
             FamilyTimer ftr(ctx, KF_RERANK);
-            VERS_TRY(launch_rerank(ctx, M, ivf->d_lm, ivf->d_lm_ids, ivf->ld, d_queries, nq, k, b.cand_pos, b.cand_bound,
+            VERS_TRY(launch_rerank(ctx, M, ivf->d_lm, ivf->d_lm_ids, 0, ivf->ld, d_queries, nq, k, b.cand_pos, b.cand_bound,
                                    ivf->d_nxmax, b.cand_key, use_tc ? (split3 ? 2 : 1) : 0, d_ids, d_d, d_cnt,
                                    b.fail_flag, ivf->d_stats, nullptr, nullptr));
         }
@@ -1647,11 +1706,12 @@ extern "C" int32_t vers_ivf_probe_dev(vers_ivf* ivf, const float* d_queries, uin
     vers_ctx* ctx = ivf->ctx;
     std::lock_guard<std::mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
-    const ProbePlan pplan = probe_plan(ivf, nq, nprobe);
+    const RankTable ctab = centroid_table(ivf);
+    const ProbePlan pplan = probe_plan(ctx, ctab, nq, nprobe);
     VERS_TRY(scratch_reserve(ctx, pplan.bytes + (size_t)nq * nprobe * 4 + 256));
     VERS_CUDA(cudaMemsetAsync(ivf->d_stats, 0, 128, ctx->stream));
     float* d_pd = reinterpret_cast<float*>((char*)ctx->scratch + pplan.bytes);
-    return probe_run(ivf, pplan, d_queries, nq, nprobe, d_probe_ids, d_pd);
+    return probe_run(ctx, ctab, pplan, d_queries, nq, nprobe, d_probe_ids, d_pd, nullptr, KF_PROBE);
 }
 
 extern "C" int32_t vers_ivf_search_probed_dev(vers_ivf* ivf, const float* d_queries, uint32_t nq, uint32_t top_k,

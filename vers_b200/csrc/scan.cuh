@@ -58,6 +58,15 @@ int32_t scan_topk_run(vers_ctx* ctx, const ScanPlan& pl, void* scratch, const Ro
 
 int32_t launch_merge(vers_ctx* ctx, const MergeParams& mp);
 
+// ivf.cu: exhaustive L2 search of a batch through the tensor-core candidate path (top-M keys -> exact-order rerank ->
+// certificate -> exact redo of uncertified queries).  Returns VERS_ERR_UNSUPPORTED (and *used_tc = false) when the
+// batch is not eligible; the caller then runs the exact-order engine.  stats: >= 8 device counters.
+int32_t flat_search_tc_plan_and_run(vers_ctx* ctx, const float* rows, uint64_t n, uint32_t ld, const float* norm,
+                                    const uint32_t* nmax_bits, uint64_t id_base, unsigned long long* stats,
+                                    const float* d_queries, uint32_t nq, uint32_t k, uint64_t* d_ids, float* d_d,
+                                    uint32_t* d_cnt, bool* used_tc);
+int32_t launch_rownorm(vers_ctx* ctx, const float* rows, uint32_t ld, uint64_t n, float* norm, uint32_t* nmax_bits);
+
 // exclusive scan of n uint32 -> uint64 out[n+1] (single block; n up to a few million is fine)
 int32_t launch_exclusive_scan(vers_ctx* ctx, const uint32_t* d_in, uint64_t n, uint64_t* d_out,
                               const uint32_t* skip_if_zero = nullptr);

@@ -138,6 +138,16 @@ class Dataset:
         check(lib().vers_dataset_device_ptr(self.h, C.byref(p)))
         return p.value
 
+    def set_flat_mode(self, mode: int):
+        """exhaustive search: 0 (default) tensor-core candidate path for batches >= 32 queries, 1 exact-order only"""
+        check(lib().vers_flat_set_mode(self.h, int(mode)))
+
+    def last_flat_search_stats(self) -> dict:
+        out = np.zeros(8, np.uint64)
+        check(lib().vers_flat_last_search_stats(self.h, ptr(out)))
+        return dict(uncertified_queries=int(out[4]), reranked=int(out[5]),
+                    max_candidate_error=float(np.array([out[6]], np.uint64).astype(np.uint32).view(np.float32)[0]))
+
     def close(self):
         if getattr(self, "h", None) and self.h:
             lib().vers_dataset_free(self.h)

@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--recall-queries", type=int, default=100)
     ap.add_argument("--cpu-queries", type=int, default=256, help="queries in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="ivf", choices=["ivf", "kmeans", "flat"],
+    ap.add_argument("--workload", default="ivf", choices=["ivf", "kmeans", "flat", "lsh"],
                     help="ivf (default): the QPS line; kmeans: BASELINE.json configs[4], k-means build seconds on "
                          "50M x 128, 16384 centroids, --steps Lloyd iterations (default 20), rows sharded over the GPUs")
     ap.add_argument("--flat-rows", type=int, default=1_000_000, help="--workload flat: BASELINE.json configs[1]")
@@ -662,6 +662,53 @@ def main_flat(args):
     print(json.dumps(line))
 
 
+def main_lsh(args):
+    """BASELINE.json configs[2]: the hyperplane forest ("LSH", indexes/lsh.rs) on 1M x 300, 16 trees, max_size 100,
+    1000-query batches, 1 GPU.  build = level-synchronous split of every tree on the device; search = batched
+    traversal + leaf scan + exact rerank.  The search entry point takes host buffers, so value == e2e here."""
+    import vers_b200 as vb
+
+    n, dim = args.flat_rows, args.flat_dim
+    ctx = vb.Context(0)
+    ds = vb.Dataset.synth(ctx, SEED_DATA, n, dim, kind=1, n_centers=args.n_centers, center_seed=SEED_CENTERS, row0=0,
+                          normalize=True)
+    rows = ds.download()
+    qds = vb.Dataset.synth(ctx, SEED_QUERY, args.nq, dim, kind=1, n_centers=args.n_centers, center_seed=SEED_CENTERS,
+                           row0=0, normalize=True)
+    q = qds.download()
+    t0 = time.perf_counter()
+    idx = vb.ANNIndex.build_index(16, 100, rows, None, seed=4, ctx=ctx)
+    ctx.sync()
+    build_s = time.perf_counter() - t0
+    for _ in range(args.warmup):
+        idx.search_batch(q, args.k)
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = ctx.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ids, d, cnt = idx.search_batch(q, args.k)
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    nrec = min(args.recall_queries, args.nq)
+    gi, _, _ = vb.search_exhaustive_batch(ds, q[:nrec], args.k, 0)
+    recall = float(np.mean([len(set(ids[i][: cnt[i]]) & set(gi[i])) / args.k for i in range(nrec)]))
+    qps = args.nq * args.steps / dt
+    info = idx.info()
+    line = {"metric": "hyperplane-forest (LSH) search QPS (1Mx300, 16 trees, batch 1k)", "value": qps, "unit": "queries/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"ANNIndex build_index + search_approximate batch: {n}x{dim}, 16 trees, max_size 100, "
+                                   f"top_k {args.k}, {args.nq}-query batch (BASELINE.json configs[2])",
+                       "rows": n, "dim": dim, "trees": 16, "max_size": 100, "nodes": info["num_nodes"]},
+            "build_s": build_s, "recall_at_10": recall,
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": args.nq * dim * 4,
+                    "d2h_bytes_per_step": args.nq * args.k * 12 + args.nq * 4},
+            "gpu_launches": launches, "clocks": clocks, "roofline": None, "cpu_baseline": None}
+    print(json.dumps(line))
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
@@ -670,5 +717,7 @@ if __name__ == "__main__":
         main_kmeans(a)
     elif a.workload == "flat":
         main_flat(a)
+    elif a.workload == "lsh":
+        main_lsh(a)
     else:
         main_ours(a)

@@ -20,12 +20,18 @@ extern "C" {
     pub fn vers_dataset_upload(ctx: *mut vers_ctx, rows: *const f32, n: u64, dim: u32, stride_floats: u32, id_base: u64, out: *mut *mut vers_dataset) -> i32;
     pub fn vers_dataset_normalize(ds: *mut vers_dataset) -> i32;
     pub fn vers_dataset_download(ds: *const vers_dataset, row0: u64, n: u64, out: *mut f32, stride_floats: u32) -> i32;
+    pub fn vers_dataset_wrap_device(ctx: *mut vers_ctx, d_rows: *const f32, n: u64, dim: u32, id_base: u64, out: *mut *mut vers_dataset) -> i32;
     pub fn vers_dataset_free(ds: *mut vers_dataset) -> i32;
     pub fn vers_flat_search(ds: *mut vers_dataset, queries: *const f32, nq: u32, q_stride_floats: u32, top_k: u32, metric: u32, ids: *mut u64, dists: *mut f32, counts: *mut u32) -> i32;
+    pub fn vers_flat_set_mode(ds: *mut vers_dataset, mode: i32) -> i32;
+    pub fn vers_flat_last_search_stats(ds: *const vers_dataset, out: *mut u64) -> i32;
     pub fn vers_kmeans_assign(ds: *mut vers_dataset, centroids: *const f32, num_clusters: u32, stride_floats: u32, assignments: *mut u64) -> i32;
     pub fn vers_kmeans_update(ds: *mut vers_dataset, assignments: *const u64, num_clusters: u32, centroids: *mut f32, counts: *mut u64) -> i32;
     pub fn vers_ivf_build_index(ds: *mut vers_dataset, num_clusters: u32, num_attempts: u32, max_iterations: u32, init_rows: *const u64, out: *mut *mut vers_ivf) -> i32;
     pub fn vers_ivf_from_parts(ds: *mut vers_dataset, centroids: *const f32, num_clusters: u32, stride_floats: u32, assignments: *const u64, out: *mut *mut vers_ivf) -> i32;
+    pub fn vers_ivf_from_parts_dev(ds: *mut vers_dataset, d_centroids: *const f32, num_clusters: u32, d_assignments: *const u32, d_row_ids: *const u64, out: *mut *mut vers_ivf) -> i32;
+    pub fn vers_ivf_set_mode(ivf: *mut vers_ivf, mode: i32) -> i32;
+    pub fn vers_ivf_last_search_stats(ivf: *const vers_ivf, out: *mut u64) -> i32;
     pub fn vers_ivf_free(ivf: *mut vers_ivf) -> i32;
     pub fn vers_ivf_get_centroids(ivf: *const vers_ivf, centroids: *mut f32, stride_floats: u32) -> i32;
     pub fn vers_ivf_get_assignments(ivf: *const vers_ivf, assignments: *mut u64) -> i32;

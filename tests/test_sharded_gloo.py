@@ -58,6 +58,21 @@ def _worker(rank, ws, port, out_dir):
         sharded, _ = vo.update(rows, assign, C, shards=ws)
         assert np.array_equal(ar.view(np.uint32), sharded.view(np.uint32))  # == the oracle's sharded-order mode
         assert not np.array_equal(ar.view(np.uint32), want.view(np.uint32))
+
+        # list-sharded index build: the all-to-all hands every rank whole lists, in ascending id order, balanced
+        from vers_b200.sharded import balanced_list_owners, exchange_rows_by_list
+
+        a_local = torch.from_numpy(assign[r0:r0 + nl].astype(np.int64))
+        rr, rid, ras, owner = exchange_rows_by_list(local, a_local, r0, C)
+        owner = owner.numpy()
+        sizes = np.bincount(assign.astype(np.int64), minlength=C)
+        assert np.array_equal(owner, balanced_list_owners(sizes, ws))
+        mine = np.flatnonzero(owner[assign.astype(np.int64)] == rank)  # global ids this rank must end up with
+        assert np.array_equal(rid.numpy(), mine), "received ids are not the owned lists' rows in ascending order"
+        assert np.array_equal(ras.numpy().astype(np.int64), assign[mine].astype(np.int64))
+        assert np.array_equal(rr.numpy().view(np.uint32), rows[mine].view(np.uint32))
+        loads = np.array([sizes[owner == r].sum() for r in range(ws)])
+        assert loads.max() - loads.min() <= sizes.max(), "largest-first placement keeps the ranks within one list"
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

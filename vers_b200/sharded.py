@@ -154,40 +154,61 @@ def balanced_list_owners(sizes: np.ndarray, world_size: int) -> np.ndarray:
     return owner
 
 
-def build_list_sharded(km: KMeans, group=None) -> IVFFlatIndex:
-    """After k-means on row blocks: every rank sends each of its rows (with its global id and cluster) to the rank that
-    owns the row's list (one all-to-all over NVLink) and builds its lists from what it receives.  Blocks arrive in
-    rank order and ranks hold ascending id blocks, so inside a list the rows stay in ascending id order like
-    `ids[c]` (ivfflat.rs:123-127).  Lists a rank does not own are empty there; the centroid table is whole."""
-    rank, ws = world()
-    ds = km.ds
-    Cn, ld, n = km.C, ds.ld, ds.n
-    dev = torch.device("cuda", torch.cuda.current_device())
-    p = C.c_void_p()
-    check(lib().vers_kmeans_assign_device_ptr(km.h, C.byref(p)))
-    ds.ctx.sync()
-    assign = device_view(p.value, (max(n, 1),), torch.int32)[:n].to(torch.int64)
-    sizes = torch.bincount(assign, minlength=Cn)
-    dist.all_reduce(sizes, group=group)
+def exchange_rows_by_list(rows: torch.Tensor, assign: torch.Tensor, id_base: int, num_clusters: int, group=None):
+    """The all-to-all of a list-sharded build, on whatever device the tensors live (NCCL on GPUs, gloo in the CPU
+    tests).  rows [n, ld] fp32 and assign [n] int64 are this rank's contiguous block (global ids id_base ..).
+    Returns (recv_rows, recv_ids int64, recv_assign int32, owner int64 [C]): the rows of the lists this rank owns, in
+    ascending global id order (blocks arrive in rank order and ranks hold ascending id blocks)."""
+    _, ws = world()
+    dev = rows.device
+    n, ld = rows.shape
+    sizes = torch.bincount(assign, minlength=num_clusters)
+    if ws > 1:
+        dist.all_reduce(sizes, group=group)
     owner = torch.as_tensor(balanced_list_owners(sizes.cpu().numpy(), ws), device=dev)
     dest = owner[assign]
     order = torch.argsort(dest, stable=True)  # by destination, ascending local row (= ascending id) inside each
     send_counts = torch.bincount(dest, minlength=ws)
     recv_counts = torch.empty_like(send_counts)
-    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    if ws > 1:
+        dist.all_to_all_single(recv_counts, send_counts, group=group)
+    else:
+        recv_counts.copy_(send_counts)
     sc, rc = send_counts.cpu().tolist(), recv_counts.cpu().tolist()
     n_recv = int(sum(rc))
+
+    def a2a(send: torch.Tensor) -> torch.Tensor:
+        recv = torch.empty((n_recv,) + tuple(send.shape[1:]), dtype=send.dtype, device=dev)
+        if ws > 1:
+            dist.all_to_all_single(recv, send, rc, sc, group=group)
+        else:
+            recv.copy_(send)
+        return recv
+
+    recv_rows = a2a(rows.index_select(0, order))
+    recv_ids = a2a(order + id_base)
+    recv_assign = a2a(assign.index_select(0, order).to(torch.int32))
+    return recv_rows, recv_ids, recv_assign, owner
+
+
+def build_list_sharded(km: KMeans, group=None) -> IVFFlatIndex:
+    """After k-means on row blocks: every rank sends each of its rows (with its global id and cluster) to the rank that
+    owns the row's list (one all-to-all over NVLink) and builds its lists from what it receives.  Inside a list the
+    rows stay in ascending id order like `ids[c]` (ivfflat.rs:123-127).  Lists a rank does not own are empty there;
+    the centroid table is whole."""
+    ds = km.ds
+    Cn, ld, n = km.C, ds.ld, ds.n
+    p = C.c_void_p()
+    check(lib().vers_kmeans_assign_device_ptr(km.h, C.byref(p)))
+    ds.ctx.sync()
+    assign = device_view(p.value, (max(n, 1),), torch.int32)[:n].to(torch.int64)
     rows = device_view(ds.device_ptr, (max(n, 1), ld))[:n]
-    send_rows = rows.index_select(0, order)
-    recv_rows = torch.empty((max(n_recv, 1), ld), dtype=torch.float32, device=dev)
-    dist.all_to_all_single(recv_rows[:n_recv], send_rows, rc, sc, group=group)
-    del send_rows
-    send_ids = order + ds.id_base
-    recv_ids = torch.empty(max(n_recv, 1), dtype=torch.int64, device=dev)
-    dist.all_to_all_single(recv_ids[:n_recv], send_ids, rc, sc, group=group)
-    send_assign = assign.index_select(0, order).to(torch.int32)
-    recv_assign = torch.empty(max(n_recv, 1), dtype=torch.int32, device=dev)
-    dist.all_to_all_single(recv_assign[:n_recv], send_assign, rc, sc, group=group)
+    recv_rows, recv_ids, recv_assign, _ = exchange_rows_by_list(rows, assign, ds.id_base, Cn, group)
+    n_recv = recv_rows.shape[0]
+    if n_recv == 0:  # keep the pointers valid
+        recv_rows = torch.zeros((1, ld), dtype=torch.float32, device=rows.device)
+        recv_ids = torch.zeros(1, dtype=torch.int64, device=rows.device)
+        recv_assign = torch.zeros(1, dtype=torch.int32, device=rows.device)
     cp, cl = C.c_void_p(), C.c_uint32()
     check(lib().vers_kmeans_centroids_device_ptr(km.h, C.byref(cp), C.byref(cl)))
     torch.cuda.synchronize()

@@ -511,6 +511,7 @@ def main_kmeans(args):
         dev_s, wall = float(t[0].item()), float(t[1].item())
     clocks = sampler.stop() if rank == 0 else None
     a_ms, a_n = ctx.kernel_ms(_abi.KF_ASSIGN)
+    r_ms, r_n = ctx.kernel_ms(_abi.KF_LIST_SCAN)  # the exact-order redo of uncertified rows is timed in this family
     s_ms, s_n = ctx.kernel_ms(_abi.KF_SUMS)
     ctx.enable_timing(False)
     flagged = km.last_uncertified_rows
@@ -550,7 +551,8 @@ def main_kmeans(args):
                                             f"{float(peaks.get('bf16_tflops', 1638.9)) / 2:.0f} TF/s is exceeded)",
                              "algorithmic_flop_per_launch": split * flop_pass / ws, "avg_launch_ms": avg_assign_ms,
                              "kernel_share_of_step": a_ms * 1e-3 / dev_s if dev_s else None,
-                             "sums_ms_per_iteration": s_ms / max(s_n, 1)},
+                             "sums_ms_per_iteration": s_ms / max(s_n, 1),
+                             "exact_redo_ms_per_pass": (r_ms / r_n) if r_n else 0.0},
                 "cpu_baseline": None}
         print(json.dumps(line))
     if ws > 1:

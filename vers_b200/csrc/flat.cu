@@ -412,13 +412,10 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32)
 
 using namespace vers;
 
-extern "C" int32_t vers_flat_search_dev(vers_dataset* ds, const float* d_queries, uint32_t nq, uint32_t top_k,
-                                        uint32_t metric, uint64_t* d_ids, float* d_dists, uint32_t* d_counts) {
-    if (!ds || (!d_queries && nq) || !d_ids || !d_dists) return fail(VERS_ERR_ARG, "flat_search_dev: null argument");
-    if (metric > VERS_METRIC_COSINE) return fail(VERS_ERR_ARG, "flat_search_dev: unknown metric %u", metric);
+// caller holds ctx->mu
+static int32_t flat_search_dev_locked(vers_dataset* ds, const float* d_queries, uint32_t nq, uint32_t top_k,
+                                      uint32_t metric, uint64_t* d_ids, float* d_dists, uint32_t* d_counts) {
     vers_ctx* ctx = ds->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    VERS_CUDA(cudaSetDevice(ctx->device));
     if (metric == VERS_METRIC_L2SQ && ds->flat_mode == 0 && nq >= 32 && top_k >= 1 && top_k <= 64) {
         // large batches: tensor-core candidate keys -> exact-order rerank -> certificate -> exact redo (ivf.cu)
         if (!ds->d_norm) {
@@ -437,6 +434,15 @@ extern "C" int32_t vers_flat_search_dev(vers_dataset* ds, const float* d_queries
     RowSrc B{d_queries, nullptr, ds->ld, nq};
     return scan_topk_dev(ctx, A, B, nq, ds->ld, top_k, metric, nullptr, ds->id_base, d_ids, d_dists, d_counts,
                          KF_FLAT_SCAN);
+}
+
+extern "C" int32_t vers_flat_search_dev(vers_dataset* ds, const float* d_queries, uint32_t nq, uint32_t top_k,
+                                        uint32_t metric, uint64_t* d_ids, float* d_dists, uint32_t* d_counts) {
+    if (!ds || (!d_queries && nq) || !d_ids || !d_dists) return fail(VERS_ERR_ARG, "flat_search_dev: null argument");
+    if (metric > VERS_METRIC_COSINE) return fail(VERS_ERR_ARG, "flat_search_dev: unknown metric %u", metric);
+    std::lock_guard<std::mutex> lk(ds->ctx->mu);
+    VERS_CUDA(cudaSetDevice(ds->ctx->device));
+    return flat_search_dev_locked(ds, d_queries, nq, top_k, metric, d_ids, d_dists, d_counts);
 }
 
 extern "C" int32_t vers_flat_set_mode(vers_dataset* ds, int32_t mode) {
@@ -475,16 +481,34 @@ extern "C" int32_t vers_flat_search(vers_dataset* ds, const float* queries, uint
     }
     vers_ctx* ctx = ds->ctx;
     VERS_CUDA(cudaSetDevice(ctx->device));
-    float* d_q = nullptr;
-    uint64_t* d_ids = nullptr;
-    float* d_d = nullptr;
-    uint32_t* d_c = nullptr;
-    size_t nk = (size_t)nq * top_k;
-    int32_t rc = upload_queries(ctx, queries, nq, q_stride_floats, ds->dim, ds->ld, &d_q);
-    if (rc == VERS_OK && cudaMalloc(&d_ids, nk * 8) != cudaSuccess) rc = fail(VERS_ERR_NOMEM, "cudaMalloc ids");
-    if (rc == VERS_OK && cudaMalloc(&d_d, nk * 4) != cudaSuccess) rc = fail(VERS_ERR_NOMEM, "cudaMalloc dists");
-    if (rc == VERS_OK && cudaMalloc(&d_c, (size_t)nq * 4) != cudaSuccess) rc = fail(VERS_ERR_NOMEM, "cudaMalloc cnt");
-    if (rc == VERS_OK) rc = vers_flat_search_dev(ds, d_q, nq, top_k, metric, d_ids, d_d, d_c);
+    const size_t nk = (size_t)nq * top_k;
+    float* d_q;
+    uint64_t* d_ids;
+    float* d_d;
+    uint32_t* d_c;
+    if (metric > VERS_METRIC_COSINE) return fail(VERS_ERR_ARG, "flat_search: unknown metric %u", metric);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    {   // device staging from the context's grow-only I/O arena: no allocation on the steady-state path
+        ScratchCarver plan(nullptr);
+        plan.plan<float>((size_t)nq * ds->ld);
+        plan.plan<uint64_t>(nk);
+        plan.plan<float>(nk);
+        plan.plan<uint32_t>(nq);
+        VERS_TRY(io_reserve(ctx, plan.off + 256));
+        ScratchCarver io(ctx->io);
+        d_q = io.take<float>((size_t)nq * ds->ld);
+        d_ids = io.take<uint64_t>(nk);
+        d_d = io.take<float>(nk);
+        d_c = io.take<uint32_t>(nq);
+        if (q_stride_floats == ds->ld && ds->ld == ds->dim) {
+            VERS_CUDA(cudaMemcpyAsync(d_q, queries, (size_t)nq * ds->ld * 4, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            if (ds->ld != ds->dim) VERS_CUDA(cudaMemsetAsync(d_q, 0, (size_t)nq * ds->ld * 4, ctx->stream));
+            VERS_CUDA(cudaMemcpy2DAsync(d_q, (size_t)ds->ld * 4, queries, (size_t)q_stride_floats * 4,
+                                        (size_t)ds->dim * 4, nq, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    int32_t rc = flat_search_dev_locked(ds, d_q, nq, top_k, metric, d_ids, d_d, d_c);
     if (rc == VERS_OK) {
         cudaError_t e = cudaMemcpyAsync(ids, d_ids, nk * 8, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(dists, d_d, nk * 4, cudaMemcpyDeviceToHost, ctx->stream);
@@ -493,10 +517,6 @@ extern "C" int32_t vers_flat_search(vers_dataset* ds, const float* queries, uint
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = fail(VERS_ERR_CUDA, "flat_search copy back: %s", cudaGetErrorString(e));
     }
-    cudaFree(d_q);
-    cudaFree(d_ids);
-    cudaFree(d_d);
-    cudaFree(d_c);
     return rc;
 }
 

@@ -1753,9 +1753,13 @@ extern "C" int32_t vers_ivf_search(vers_ivf* ivf, const float* queries, uint32_t
     uint64_t* d_ids = io.take<uint64_t>(nk);
     float* d_d = io.take<float>(nk);
     uint32_t* d_c = io.take<uint32_t>(nq);
-    if (ivf->ld != ivf->dim) VERS_CUDA(cudaMemsetAsync(d_q, 0, (size_t)nq * ivf->ld * 4, ctx->stream));
-    VERS_CUDA(cudaMemcpy2DAsync(d_q, (size_t)ivf->ld * 4, queries, (size_t)q_stride_floats * 4, (size_t)ivf->dim * 4,
-                                nq, cudaMemcpyHostToDevice, ctx->stream));
+    if (q_stride_floats == ivf->ld && ivf->ld == ivf->dim) {  // dense rows: one linear copy
+        VERS_CUDA(cudaMemcpyAsync(d_q, queries, (size_t)nq * ivf->ld * 4, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        if (ivf->ld != ivf->dim) VERS_CUDA(cudaMemsetAsync(d_q, 0, (size_t)nq * ivf->ld * 4, ctx->stream));
+        VERS_CUDA(cudaMemcpy2DAsync(d_q, (size_t)ivf->ld * 4, queries, (size_t)q_stride_floats * 4,
+                                    (size_t)ivf->dim * 4, nq, cudaMemcpyHostToDevice, ctx->stream));
+    }
     VERS_TRY(ivf_search_dev_locked(ivf, d_q, nq, top_k, nprobe, d_ids, d_d, d_c));
     VERS_CUDA(cudaMemcpyAsync(ids, d_ids, nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
     VERS_CUDA(cudaMemcpyAsync(dists, d_d, nk * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -82,10 +82,10 @@ static int32_t launch_assign(vers_ctx* ctx, const RowSrc& A, const RowSrc& B, ui
 }
 
 int32_t kmeans_assign_rows(vers_ctx* ctx, const RowSrc& rows, const float* d_cents, uint32_t C, uint32_t ld,
-                           uint32_t* d_assign) {
+                           uint32_t* d_assign, int family) {
     if (rows.n == 0) return VERS_OK;
     RowSrc B{d_cents, nullptr, ld, C};
-    FamilyTimer ft(ctx, KF_ASSIGN);
+    FamilyTimer ft(ctx, family);
     if (C <= 8) return launch_assign<NarrowCfg>(ctx, rows, B, ld, d_assign);
     return launch_assign<WideCfg>(ctx, rows, B, ld, d_assign);
 }
@@ -466,7 +466,7 @@ static int32_t kmeans_assign_tc(vers_kmeans* km) {
     km->last_flagged = nf;
     if (nf) {
         RowSrc A{ds->d_rows, km->d_flagged, ds->ld, nf};
-        VERS_TRY(kmeans_assign_rows(ctx, A, km->d_cents, km->C, ds->ld, km->d_exact));
+        VERS_TRY(kmeans_assign_rows(ctx, A, km->d_cents, km->C, ds->ld, km->d_exact, KF_LIST_SCAN));  // own family: the redo
         scatter_assign_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(km->d_flagged, km->d_nflagged, km->d_exact, km->d_assign);
         VERS_LAUNCH_CHECK(ctx);
     }

@@ -37,5 +37,5 @@ namespace vers {
 // groups the local rows by cluster in ascending row order (stable): fills d_sorted_rows and d_off
 int32_t kmeans_build_csr(vers_kmeans* km);
 int32_t kmeans_assign_rows(vers_ctx* ctx, const RowSrc& rows, const float* d_cents, uint32_t C, uint32_t ld,
-                           uint32_t* d_assign);
+                           uint32_t* d_assign, int family = KF_ASSIGN);
 }  // namespace vers

@@ -21,8 +21,9 @@ constexpr int KA_STAGE_BYTES = KA_A_BYTES + 2 * KA_B_BYTES;  // x | c_hi | c_lo
 constexpr int KA_OFF_NRM = KA_STAGES * KA_STAGE_BYTES;         // [2][KA_N] ||c||^2 of the centroid tile per accumulator
 constexpr int KA_OFF_BAR = KA_OFF_NRM + 2 * KA_N * 4;
 constexpr int KA_SMEM_BYTES = 1024 + KA_OFF_BAR + 256;
-constexpr uint32_t KA_ALO_COL0 = 2 * KA_N;                    // x_lo tiles live in TMEM after the two accumulators
-constexpr uint32_t KA_TMEM_COLS = 512;                        // 2*128 + 4*32 = 384 -> 512
+constexpr uint32_t KA_ALO_COL0 = 2 * KA_N;                    // x_lo tiles live in TMEM after the two accumulators,
+constexpr uint32_t KA_AHI_COL0 = KA_ALO_COL0 + KA_STAGES * KA_KC;  // then the row tiles themselves (x_hi after truncation)
+constexpr uint32_t KA_TMEM_COLS = 512;                        // 2*128 + 4*32 + 4*32 = 512
 
 struct TcAssignParams {
     uint64_t n_rows;
@@ -49,9 +50,12 @@ __global__ void split_tf32_kernel(const float* __restrict__ in, uint64_t n4, flo
     }
 }
 
-// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = argmin epilogue, 6..9 = x_lo converters.
-// Per 32-wide K chunk: x_hi.c_hi + x_hi.c_lo (A from shared memory) + x_lo.c_hi (A from tensor memory), all three
-// accumulated into the same 128-column accumulator.
+// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = argmin epilogue, 6..9 = converters.
+// Per 32-wide K chunk: x_hi.c_hi + x_hi.c_lo + x_lo.c_hi, all three accumulated into the same 128-column accumulator.
+// ALL THREE take their A operand from TENSOR MEMORY: the converter warps park the landed row tile (the tensor core
+// truncates it to x_hi) next to x_lo.  With M = N = 128 an MMA that reads A and B from shared memory needs
+// 8 KB / 64 cycles = the whole 128 B/clk of the SM, and the TMA writes and converter reads come on top: measured 67 %
+// tensor-pipe activity.  With A in TMEM shared memory only serves the B tiles.
 __global__ void __launch_bounds__(KA_THREADS, 1)
     tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_chi,
                      const __grid_constant__ CUtensorMap tmap_clo, TcAssignParams p) {
@@ -133,20 +137,18 @@ __global__ void __launch_bounds__(KA_THREADS, 1)
                         tc::mbar_wait(&full[stage], phase);
                         tc::fence_after_thread_sync();
                         const uint32_t sa = tc::smem_u32(smem + stage * KA_STAGE_BYTES);
-                        const uint64_t da = tc::smem_desc_k_sw128(sa);
                         const uint64_t dbh = tc::smem_desc_k_sw128(sa + KA_A_BYTES);
                         const uint64_t dbl = tc::smem_desc_k_sw128(sa + KA_A_BYTES + KA_B_BYTES);
-#pragma unroll
-                        for (uint32_t kk = 0; kk < KA_KC / 8; ++kk) {
-                            tc::mma_tf32(d_tmem, da + 2 * kk, dbh + 2 * kk, idesc, (kc | kk) != 0);
-                            tc::mma_tf32(d_tmem, da + 2 * kk, dbl + 2 * kk, idesc, 1);
-                        }
-                        tc::mbar_wait(&conv[stage], phase);  // x_lo of this stage is in tensor memory
+                        tc::mbar_wait(&conv[stage], phase);  // x and x_lo of this stage are in tensor memory
                         tc::fence_after_thread_sync();
+                        const uint32_t a_hi = tmem_base + KA_AHI_COL0 + stage * KA_KC;
                         const uint32_t a_lo = tmem_base + KA_ALO_COL0 + stage * KA_KC;
 #pragma unroll
-                        for (uint32_t kk = 0; kk < KA_KC / 8; ++kk)
+                        for (uint32_t kk = 0; kk < KA_KC / 8; ++kk) {
+                            tc::mma_tf32_ts(d_tmem, a_hi + 8 * kk, dbh + 2 * kk, idesc, (kc | kk) != 0);
+                            tc::mma_tf32_ts(d_tmem, a_hi + 8 * kk, dbl + 2 * kk, idesc, 1);
                             tc::mma_tf32_ts(d_tmem, a_lo + 8 * kk, dbh + 2 * kk, idesc, 1);
+                        }
                         tc::mma_commit(&empty[stage]);
                         if (++stage == KA_STAGES) {
                             stage = 0;
@@ -236,16 +238,22 @@ __global__ void __launch_bounds__(KA_THREADS, 1)
                 for (uint32_t kc = 0; kc < nk; ++kc) {
                     tc::mbar_wait(&full[stage], phase);
                     const uint8_t* arow = smem + stage * KA_STAGE_BYTES + row * 128;
-                    uint32_t lo[KA_KC];
+                    uint32_t lo[KA_KC], hi[KA_KC];
 #pragma unroll
                     for (uint32_t c = 0; c < 8; ++c) {
                         const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7u)) << 4));
+                        hi[4 * c + 0] = __float_as_uint(v.x);
+                        hi[4 * c + 1] = __float_as_uint(v.y);
+                        hi[4 * c + 2] = __float_as_uint(v.z);
+                        hi[4 * c + 3] = __float_as_uint(v.w);
                         lo[4 * c + 0] = __float_as_uint(__fsub_rn(v.x, __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u)));
                         lo[4 * c + 1] = __float_as_uint(__fsub_rn(v.y, __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u)));
                         lo[4 * c + 2] = __float_as_uint(__fsub_rn(v.z, __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u)));
                         lo[4 * c + 3] = __float_as_uint(__fsub_rn(v.w, __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u)));
                     }
-                    tc::tmem_st_32(tmem_base + ((uint32_t)(lane_group * 32) << 16) + KA_ALO_COL0 + stage * KA_KC, lo);
+                    const uint32_t tl = tmem_base + ((uint32_t)(lane_group * 32) << 16);
+                    tc::tmem_st_32(tl + KA_AHI_COL0 + stage * KA_KC, hi);  // the tensor core truncates it to x_hi
+                    tc::tmem_st_32(tl + KA_ALO_COL0 + stage * KA_KC, lo);
                     tc::fence_before_thread_sync();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&conv[stage]);

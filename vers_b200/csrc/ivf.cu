@@ -994,9 +994,10 @@ template <bool SPLIT3>
 static int32_t launch_tc_scan(vers_ctx* ctx, const float* rows, uint64_t n_rows, uint32_t ld, const float* gq,
                               const float* gq_lo, uint64_t gq_rows, const TcScanParams& tp, int family) {
     using Cfg = TcCfg<SPLIT3>;
-    CUtensorMap tm_rows, tm_q16, tm_ql16, tm_q32, tm_ql32;
+    CUtensorMap tm_rows, tm_rows32, tm_q16, tm_ql16, tm_q32, tm_ql32;
     const float* lo_src = SPLIT3 ? gq_lo : gq;
     VERS_TRY(make_tmap_2d_f32(&tm_rows, rows, n_rows ? n_rows : 1, ld, ld, TC_M, TC_KC));
+    VERS_TRY(make_tmap_2d_f32(&tm_rows32, rows, n_rows ? n_rows : 1, ld, ld, 32, TC_KC));
     VERS_TRY(make_tmap_2d_f32(&tm_q16, gq, gq_rows, ld, ld, 16, TC_KC));
     VERS_TRY(make_tmap_2d_f32(&tm_ql16, lo_src, gq_rows, ld, ld, 16, TC_KC));
     VERS_TRY(make_tmap_2d_f32(&tm_q32, gq, gq_rows, ld, ld, 32, TC_KC));
@@ -1004,7 +1005,8 @@ static int32_t launch_tc_scan(vers_ctx* ctx, const float* rows, uint64_t n_rows,
     auto kern = tc_list_scan_kernel<SPLIT3>;
     VERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     FamilyTimer ft(ctx, family);
-    kern<<<ctx->sm_count, Cfg::THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(tm_rows, tm_q16, tm_ql16, tm_q32, tm_ql32, tp);
+    kern<<<ctx->sm_count, Cfg::THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(tm_rows, tm_rows32, tm_q16, tm_ql16, tm_q32,
+                                                                        tm_ql32, tp);
     VERS_LAUNCH_CHECK(ctx);
     return VERS_OK;
 }

@@ -202,7 +202,8 @@ __device__ __noinline__ float sel_flush(float* lk, uint16_t* lr, const float* qk
 
 template <bool SPLIT3>
 __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
-    tc_list_scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_qhi16,
+    tc_list_scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_rows32,
+                        const __grid_constant__ CUtensorMap tmap_qhi16,
                         const __grid_constant__ CUtensorMap tmap_qlo16, const __grid_constant__ CUtensorMap tmap_qhi32,
                         const __grid_constant__ CUtensorMap tmap_qlo32, TcScanParams p) {
     using Cfg = TcCfg<SPLIT3>;
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
         }
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&tmap_rows);
+        tc::tma_prefetch_desc(&tmap_rows32);
         tc::tma_prefetch_desc(&tmap_qhi16);
         tc::tma_prefetch_desc(&tmap_qhi32);
         if (SPLIT3) {
@@ -289,13 +291,24 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
                 const CUtensorMap* mhi = wide ? &tmap_qhi32 : &tmap_qhi16;
                 const CUtensorMap* mlo = wide ? &tmap_qlo32 : &tmap_qlo16;
                 const uint32_t b_bytes = t.nq * TC_KC * 4;
-                const uint32_t tx = TC_A_BYTES + (SPLIT3 ? 2 : 1) * b_bytes;
                 for (uint64_t a0 = t.r0; a0 < t.r1; a0 += TC_M) {
+                    // the last tile of an item fetches only the 32-row boxes it needs (the rows behind them belong
+                    // to the next list: streaming them would be pure waste); the rest of the stage keeps stale,
+                    // finite row data whose products land in accumulator rows nobody reads
+                    const uint32_t rem = (uint32_t)min((uint64_t)TC_M, t.r1 - a0);
+                    const uint32_t nbox = rem > 96 ? 0u : (rem + 31) / 32;  // 0: one full 128-row box
+                    const uint32_t tx = (nbox ? nbox * (TC_A_BYTES / 4) : TC_A_BYTES) + (SPLIT3 ? 2 : 1) * b_bytes;
                     for (uint32_t kc = 0; kc < nk; ++kc) {
                         tc::mbar_wait(&empty[stage], phase ^ 1);
                         tc::mbar_arrive_expect_tx(&full[stage], tx);
                         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                        tc::tma_load_2d(sa, &tmap_rows, &full[stage], (int32_t)(kc * TC_KC), (int32_t)(t.base_pos + a0));
+                        if (nbox == 0) {
+                            tc::tma_load_2d(sa, &tmap_rows, &full[stage], (int32_t)(kc * TC_KC), (int32_t)(t.base_pos + a0));
+                        } else {
+                            for (uint32_t bx = 0; bx < nbox; ++bx)
+                                tc::tma_load_2d(sa + bx * (TC_A_BYTES / 4), &tmap_rows32, &full[stage],
+                                                (int32_t)(kc * TC_KC), (int32_t)(t.base_pos + a0 + bx * 32));
+                        }
                         tc::tma_load_2d(sa + Cfg::OFF_B, mhi, &full[stage], (int32_t)(kc * TC_KC), (int32_t)t.q0);
                         if (SPLIT3)
                             tc::tma_load_2d(sa + Cfg::OFF_B + b_bytes, mlo, &full[stage], (int32_t)(kc * TC_KC),

@@ -450,6 +450,8 @@ def main_ours(args):
                 "build_s": build_s, "kmeans_reduce": args.reduce,
                 "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": args.nq * qds.ld * 4,
                         "d2h_bytes_per_step": args.nq * args.k * 12 + args.nq * 4, "ids_match_device_path": e2e_matches},
+                "exchange": ("peer-memory gather+merge kernel" if getattr(index, "_want_peer", False) else
+                             ("nccl all-gather + merge kernel" if ws > 1 else None)),
                 "gpu_launches": launches, "launch_mode": "cuda_graph_replay" if graph is not None else "eager",
                 "eager_ms_per_step": eager_ms / args.steps, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line))

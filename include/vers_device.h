@@ -205,6 +205,19 @@ int32_t vers_topk_merge_dev(vers_ctx* ctx, const uint64_t* d_ids_all, const floa
                             uint64_t part_stride_ids, uint64_t part_stride_dists, uint32_t nq, uint32_t top_k,
                             uint64_t* d_ids, float* d_dists, uint32_t* d_counts);
 
+/* The same exchange as ONE kernel over NVLink peer memory instead of all-gather + merge (multi-GPU hosts, one
+ * process per GPU): every rank creates an exchange buffer, the 64-byte CUDA IPC handles are swapped by the host
+ * (any transport), vers_peer_connect maps the peers' buffers.  vers_peer_gather_merge_dev then stores this rank's
+ * local top-k into every peer's buffer, raises a flag, waits for all ranks' flags and merges by (distance, id).
+ * Every rank must call it once per batch, in the same order; slot_bytes >= nq * top_k * 12. */
+typedef struct vers_peer vers_peer;
+int32_t vers_peer_create(vers_ctx* ctx, uint32_t world, uint32_t rank, uint64_t slot_bytes, vers_peer** out,
+                         uint8_t ipc_handle_out[64]);
+int32_t vers_peer_connect(vers_peer* peer, const uint8_t* all_handles /* [world][64], rank order */);
+int32_t vers_peer_gather_merge_dev(vers_peer* peer, const uint64_t* d_local_ids, const float* d_local_dists,
+                                   uint32_t nq, uint32_t top_k, uint64_t* d_ids, float* d_dists, uint32_t* d_counts);
+int32_t vers_peer_free(vers_peer* peer);
+
 /* ---- "LSH" random-hyperplane forest (indexes/lsh.rs) -------------------------------------------------------- */
 /* Hyperplane::point_is_above (lsh.rs:27-29) for every row x every plane: bits[r*P + p] = dot(plane_p, row_r) +
  * consts[p] >= 0.0 */

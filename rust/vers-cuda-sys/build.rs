@@ -12,7 +12,7 @@ fn main() {
         .flag("-lineinfo")
         .flag("-fmad=false") // exact-order contract (vers/src/indexes/base.rs:91-93, 119-126): never contract a*b+c
         .include(root.join("include"));
-    for f in ["api.cu", "flat.cu", "kmeans.cu", "ivf.cu", "lsh.cu", "lsh_forest.cu"] {
+    for f in ["api.cu", "flat.cu", "kmeans.cu", "ivf.cu", "lsh.cu", "lsh_forest.cu", "peer.cu"] {
         b.file(csrc.join(f));
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }

@@ -50,7 +50,7 @@ def main():
     d_q = torch.from_numpy(np.ascontiguousarray(q)).cuda()
     for shard_by in ("rows", "lists"):
         ivf = vb.IVFFlatIndex.from_kmeans(km) if shard_by == "rows" else build_list_sharded(km)
-        index = ShardedIVFFlat(ivf, ctx)
+        index = ShardedIVFFlat(ivf, ctx, peer_exchange=(shard_by == "lists" and os.environ.get("VERS_PEER_GATHER") == "1"))
         if shard_by == "lists":
             sizes = torch.as_tensor(ivf.list_sizes.astype(np.int64)).cuda()
             dist.all_reduce(sizes)

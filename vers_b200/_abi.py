@@ -89,6 +89,10 @@ SIGNATURES = {
     "vers_ivf_search_probed_dev": [vp, vp, u32, u32, u32, vp, vp, vp, vp],
     "vers_ivf_add": [vp, vp, u64, C.POINTER(u64), C.POINTER(u32)],
     "vers_topk_merge_dev": [vp, vp, vp, u32, u64, u64, u32, u32, vp, vp, vp],
+    "vers_peer_create": [vp, u32, u32, u64, pvp, vp],
+    "vers_peer_connect": [vp, vp],
+    "vers_peer_gather_merge_dev": [vp, vp, vp, u32, u32, vp, vp, vp],
+    "vers_peer_free": [vp],
     "vers_lsh_hash": [vp, vp, u32, u32, vp, vp],
     "vers_lsh_hash_dev": [vp, vp, u32, vp, vp],
     "vers_lsh_build_index": [vp, vp, u64, u32, u32, vp, u32, u32, u64, pvp],

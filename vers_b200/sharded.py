@@ -16,6 +16,7 @@ torch is used for what it is here for: device buffers, streams and the process g
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -225,11 +226,44 @@ def build_list_sharded(km: KMeans, group=None) -> IVFFlatIndex:
 class ShardedIVFFlat:
     """IVFFlatIndex whose rows are sharded over the ranks of the default process group."""
 
-    def __init__(self, ivf: IVFFlatIndex, ctx: Context):
+    def __init__(self, ivf: IVFFlatIndex, ctx: Context, peer_exchange: Optional[bool] = None):
+        """peer_exchange: merge the per-GPU top-k with ONE kernel over NVLink peer memory (vers_peer_*: every rank
+        stores its results into every peer's buffer, flags, waits, merges) instead of NCCL all-gather + merge kernel.
+        Default: the environment variable VERS_PEER_GATHER=1 turns it on (opt-in this round: validated on 2 GPUs)."""
         self.ivf = ivf
         self.ctx = ctx
         self.rank, self.world = world()
         self._bufs = {}
+        if peer_exchange is None:
+            peer_exchange = os.environ.get("VERS_PEER_GATHER", "0") == "1"
+        self._want_peer = bool(peer_exchange) and self.world > 1
+        self._peer = None
+        self._peer_slot = 0
+
+    def _peer_handle(self, nq: int, k: int):
+        """(re)creates the exchange buffers when the batch shape needs a larger slot; collective over all ranks"""
+        need = nq * k * 12
+        if self._peer is not None and need <= self._peer_slot:
+            return self._peer
+        if self._peer is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+            check(lib().vers_peer_free(self._peer))
+            self._peer = None
+        h = C.c_void_p()
+        mine = (C.c_ubyte * 64)()
+        check(lib().vers_peer_create(self.ctx.h, self.world, self.rank, need, C.byref(h), mine))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+        allh = torch.empty(self.world * 64, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, t)
+        raw = bytes(allh.cpu().numpy().tobytes())
+        buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        check(lib().vers_peer_connect(h, buf))
+        torch.cuda.synchronize()
+        dist.barrier()  # every rank has mapped every buffer before anyone stores into a peer
+        self._peer, self._peer_slot = h, need
+        return h
 
     @classmethod
     def build(cls, ds: Dataset, num_clusters: int, max_iterations: int, init_rows_global: np.ndarray,
@@ -312,6 +346,13 @@ class ShardedIVFFlat:
         check(lib().vers_ivf_search_probed_dev(self.ivf.h, C.c_void_p(d_queries.data_ptr()), nq, top_k, npb,
                                                C.c_void_p(p_all.data_ptr()), C.c_void_p(ids_ptr), C.c_void_p(d_ptr),
                                                C.c_void_p(out_c.data_ptr())))
+        if self._want_peer:
+            # exchange + merge as one kernel over NVLink peer memory
+            peer = self._peer_handle(nq, top_k)
+            check(lib().vers_peer_gather_merge_dev(peer, C.c_void_p(ids_ptr), C.c_void_p(d_ptr), nq, top_k,
+                                                   C.c_void_p(out_ids.data_ptr()), C.c_void_p(out_d.data_ptr()),
+                                                   C.c_void_p(out_c.data_ptr())))
+            return out_ids, out_d, out_c
         dist.all_gather_into_tensor(allb, local)
         base = allb.data_ptr()
         check(lib().vers_topk_merge_dev(self.ctx.h, C.c_void_p(base), C.c_void_p(base + nk * 8), self.world, L, 2 * L,

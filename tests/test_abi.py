@@ -100,3 +100,69 @@ def test_cpp_host_mirror_compiles_and_links(vb, tmp_path):
     subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "host", "host_check.cpp"), "-o", exe, "-L" + libdir,
                     "-lvers_b200", "-Wl,-rpath," + libdir], check=True)
     assert os.path.exists(exe)
+
+
+def test_bincode_ann_index_layout(tmp_path, vo):
+    """ANNIndex (lsh.rs:13-55) in the reference's bincode layout: written from the flattened forest (the oracle's here,
+    the device forest is compared with it bit for bit in the GPU tests), read back, and checked node by node against
+    an independent walk of the flattened preorder (node, above, below) -> serialized order (node, left=below,
+    right=above)."""
+    import struct
+
+    from vers_b200.bincode import read_ann, write_ann
+
+    n, dim, T, max_size = 700, 12, 3, 9
+    rows = vo.synth(1, n, dim, kind=1, n_centers=8, center_seed=7)
+    rows[50] = rows[3]  # dropped by deduplicate (lsh.rs:113-130)
+    ids = np.arange(n, dtype=np.uint64) + 100
+    forest = vo.LSH(rows, ids, T, max_size, 4)
+    keep = np.array([i for i in range(n) if i != 50])
+    assert forest.num_values == keep.shape[0]
+    flats = [forest.flatten(t) for t in range(T)]
+    path = str(tmp_path / "ann.bin")
+    write_ann(path, max_size, flats, rows[keep], ids[keep])
+    mns, trees, values, rid = read_ann(path, dim)
+    assert mns == max_size and len(trees) == T
+    assert np.array_equal(values.view(np.uint32), rows[keep].view(np.uint32)) and np.array_equal(rid, ids[keep])
+
+    def walk(flat):
+        pos = {"node": 0, "plane": 0, "item": 0}
+
+        def rec():
+            i = pos["node"]
+            pos["node"] += 1
+            if flat["kind"][i] == 1:
+                ln = int(flat["leaf_len"][i])
+                it = flat["items"][pos["item"]:pos["item"] + ln].astype(np.uint64)
+                pos["item"] += ln
+                return ("leaf", it)
+            p = pos["plane"]
+            pos["plane"] += 1
+            above = rec()
+            below = rec()
+            return ("inner", flat["planes"][p], flat["consts"][p], below, above)  # left = below, right = above
+
+        return rec()
+
+    def same(a, b):
+        if a[0] != b[0]:
+            return False
+        if a[0] == "leaf":
+            return np.array_equal(a[1], b[1])
+        return (np.array_equal(np.asarray(a[1], np.float32).view(np.uint32), np.asarray(b[1], np.float32).view(np.uint32))
+                and np.float32(a[2]).view(np.uint32) == np.float32(b[2]).view(np.uint32) and same(a[3], b[3])
+                and same(a[4], b[4]))
+
+    for t in range(T):
+        assert same(trees[t], walk(flats[t])), f"tree {t}"
+    # header bytes: max_node_size, number of trees, then the first Node's variant tag (u32)
+    raw = open(path, "rb").read()
+    assert struct.unpack_from("<QQI", raw, 0) == (max_size, T, int(flats[0]["kind"][0]))
+    # every leaf holds fewer than max_size rows (lsh.rs:97-98) and every row appears exactly once per tree
+    def leaves(nd):
+        return [nd[1]] if nd[0] == "leaf" else leaves(nd[3]) + leaves(nd[4])
+
+    for t in range(T):
+        ls = leaves(trees[t])
+        assert all(l.shape[0] < max_size for l in ls)
+        assert np.array_equal(np.sort(np.concatenate(ls)), np.arange(keep.shape[0], dtype=np.uint64))

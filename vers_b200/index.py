@@ -492,7 +492,9 @@ class ANNIndex:
         h = C.c_void_p()
         check(lib().vers_lsh_build_index(ctx.h, ptr(v), v.shape[0], v.shape[1], v.shape[1],
                                          None if ids is None else ptr(ids), num_trees, max_size, seed, C.byref(h)))
-        return cls(ctx, h, v.shape[1])
+        self = cls(ctx, h, v.shape[1])
+        self.max_node_size, self._src, self._src_ids = max_size, v, ids
+        return self
 
     def close(self):
         if getattr(self, "h", None) and self.h:
@@ -518,6 +520,22 @@ class ANNIndex:
         check(lib().vers_lsh_flatten(self.h, tree, ptr(kind), ptr(leaf_len), ptr(planes), ptr(consts), ptr(items),
                                      C.byref(nn), C.byref(ni), C.byref(nit)))
         return dict(kind=kind, leaf_len=leaf_len, planes=planes, consts=consts, items=items)
+
+    def save_index(self, file_path: str):
+        """Index::save_index (base.rs:31-43): the reference's bincode layout of ANNIndex (lsh.rs:47-55).  `values` /
+        `ids` are the deduplicated rows (lsh.rs:113-130: first occurrence of every bit pattern, original order).
+        Only valid for an index that has not been modified by add() since build_index."""
+        from . import bincode
+
+        v = self._src
+        _, first = np.unique(np.ascontiguousarray(v).view(np.uint32).reshape(v.shape[0], -1), axis=0, return_index=True)
+        keep = np.sort(first)
+        ids = np.arange(v.shape[0], dtype=np.uint64) if self._src_ids is None else self._src_ids
+        info = self.info()
+        if info["num_values"] != keep.shape[0]:
+            raise ValueError("save_index: the index was modified after build_index")
+        bincode.write_ann(file_path, self.max_node_size, [self.flatten(t) for t in range(info["num_trees"])], v[keep],
+                          ids[keep])
 
     def add(self, embedding, vec_id: int):
         """Index::add (lsh.rs:255-263)"""

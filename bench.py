@@ -459,6 +459,28 @@ def main_ours(args):
         dist.destroy_process_group()
 
 
+def kmeans_cpu_sample(args, passes):
+    """the reference's assign_to_clusters (ivfflat.rs:29-46, rayon over rows => all host cores) timed on a row sample of
+    the same shape, extrapolated linearly to the full build (assign is > 99 % of the reference's build time)"""
+    try:
+        import oracle as vo
+
+        n_s = max(1000, min(args.km_rows, 100_000))
+        rows = vo.synth(SEED_DATA, n_s, args.km_dim, kind=1, n_centers=args.n_centers, center_seed=SEED_CENTERS,
+                        normalize=False)
+        cents = vo.synth(SEED_INIT, args.km_clusters, args.km_dim, kind=1, n_centers=args.n_centers,
+                         center_seed=SEED_CENTERS, normalize=False)
+        t0 = time.perf_counter()
+        vo.assign(rows, cents)
+        dt = time.perf_counter() - t0
+        est = dt * (args.km_rows / n_s) * passes
+        return {"value": est, "unit": "s", "cores": vo.num_threads(), "kind": "port",
+                "sample": f"one assign pass of {n_s} rows x {args.km_clusters} centroids x {args.km_dim} dims took {dt:.2f} s; "
+                          f"extrapolated linearly to {args.km_rows} rows x {passes} passes (update/cost not included)"}
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "unit": "s", "cores": 0, "kind": "port", "sample": f"failed: {type(e).__name__}: {e}"}
+
+
 def main_kmeans(args):
     """k-means build seconds (BASELINE.json configs[4]): --steps Lloyd iterations (assign + ordered update + bitwise
     convergence test) + the final assign of build_kmeans (ivfflat.rs:73-100), rows sharded over the GPUs."""
@@ -517,6 +539,9 @@ def main_kmeans(args):
     s_ms, s_n = ctx.kernel_ms(_abi.KF_SUMS)
     ctx.enable_timing(False)
     flagged = km.last_uncertified_rows
+    cpu = None
+    if rank == 0 and ws == 1 and not args.no_cpu_baseline:
+        cpu = kmeans_cpu_sample(args, ran + 1)
     if rank == 0:
         peaks = {}
         try:
@@ -555,7 +580,7 @@ def main_kmeans(args):
                              "kernel_share_of_step": a_ms * 1e-3 / dev_s if dev_s else None,
                              "sums_ms_per_iteration": s_ms / max(s_n, 1),
                              "exact_redo_ms_per_pass": (r_ms / r_n) if r_n else 0.0},
-                "cpu_baseline": None}
+                "cpu_baseline": cpu}
         print(json.dumps(line))
     if ws > 1:
         dist.destroy_process_group()

@@ -491,8 +491,10 @@ def test_no_cpu_fallback_symbols(vb):
     assert "oracle" not in out
 
 
-def test_multi_gpu_sharded_parity_when_two_gpus_present():
-    """runs tests/mgpu_check.py under torchrun on 2 GPUs (skipped on a 1-GPU box)"""
+@pytest.mark.parametrize("peer_exchange", ["0", "1"])
+def test_multi_gpu_sharded_parity_when_two_gpus_present(peer_exchange):
+    """runs tests/mgpu_check.py under torchrun on 2 GPUs (skipped on a 1-GPU box); peer_exchange=1: the per-GPU top-k
+    are exchanged and merged by the peer-memory kernel (csrc/peer.cu) instead of NCCL all-gather + merge"""
     import os
     import subprocess
     import sys
@@ -502,9 +504,11 @@ def test_multi_gpu_sharded_parity_when_two_gpus_present():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VERS_PEER_GATHER=peer_exchange)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "mgpu_check.py")],
-                       capture_output=True, text=True, timeout=600)
+                        "--master-addr", "127.0.0.1", "--master-port", "29517" if peer_exchange == "0" else "29518",
+                        os.path.join(root, "tests", "mgpu_check.py")],
+                       capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "mgpu_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
@@ -605,3 +609,23 @@ def test_cpp_host_mirror(vb, tmp_path):
                     "-lvers_b200", "-Wl,-rpath," + libdir], check=True)
     r = subprocess.run([exe, str(tmp_path / "ivf.bin")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "host_check ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_lsh_save_index_writes_the_reference_layout(vb, vo, ctx, tmp_path):
+    """ANNIndex.save_index: the device forest serialized in the reference's bincode layout (lsh.rs:13-55) equals the
+    oracle's forest serialized the same way, byte for byte"""
+    from vers_b200.bincode import read_ann, write_ann
+
+    n, dim, T, max_size = 3000, 24, 4, 12
+    rows = data(vo, n, dim, n_centers=20)
+    rows[100] = rows[7]
+    ids = np.arange(n, dtype=np.uint64) + 1000
+    g = vb.ANNIndex.build_index(T, max_size, rows, ids, seed=4, ctx=ctx)
+    o = vo.LSH(rows, ids, T, max_size, 4)
+    pg, po = str(tmp_path / "g.bin"), str(tmp_path / "o.bin")
+    g.save_index(pg)
+    keep = np.array([i for i in range(n) if i != 100])
+    write_ann(po, max_size, [o.flatten(t) for t in range(T)], rows[keep], ids[keep])
+    assert open(pg, "rb").read() == open(po, "rb").read()
+    mns, trees, values, rid = read_ann(pg, dim)
+    assert mns == max_size and len(trees) == T and values.shape == (n - 1, dim) and np.array_equal(rid, ids[keep])

@@ -131,6 +131,22 @@ class IVFFlatIndex : public Index<N> {
         for (uint32_t i = 0; i < cnt; ++i) out.emplace_back((size_t)ids[i], d[i]);
         return out;
     }
+    // Extension the trait lacks (BASELINE config 4): a batch of queries, global top_k by (distance, id) over the nprobe
+    // nearest lists of each query; nprobe == 0 keeps the reference's nearest-list-plus-spill semantics per query.
+    std::vector<std::vector<std::pair<size_t, float>>> search_batch(const std::vector<Vector<N>>& queries, size_t top_k,
+                                                                    size_t nprobe) const {
+        const size_t nq = queries.size(), kk = top_k ? top_k : 1;
+        std::vector<uint64_t> ids(nq * kk);
+        std::vector<float> d(nq * kk);
+        std::vector<uint32_t> cnt(nq ? nq : 1);
+        if (nq)
+            check(vers_ivf_search(ivf_, &queries[0].v[0], (uint32_t)nq, vector_stride<N>(), (uint32_t)top_k,
+                                  (uint32_t)nprobe, ids.data(), d.data(), cnt.data()));
+        std::vector<std::vector<std::pair<size_t, float>>> out(nq);
+        for (size_t q = 0; q < nq; ++q)
+            for (uint32_t i = 0; i < cnt[q]; ++i) out[q].emplace_back((size_t)ids[q * top_k + i], d[q * top_k + i]);
+        return out;
+    }
     std::vector<uint64_t> assignments() const {
         std::vector<uint64_t> a(values_.size());
         check(vers_ivf_get_assignments(ivf_, a.data()));

@@ -153,10 +153,21 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+def use_all_host_threads(vo):
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arms are meant to use every host core this process
+    may run on (the reference's rayon pool defaults to all logical CPUs)"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    vo.set_threads(max(1, n))
+
+
 def cpu_arm(args, steps, warmup, nq_sample):
     """the reference's CPU search path (oracle port) on the bounded sample; returns (qps, ms_per_step, info)"""
     import oracle as vo
 
+    use_all_host_threads(vo)
     rows_n = max(args.rows // CPU_SCALE, 1000)
     nlist = max(args.nlist // CPU_SCALE, 1)
     nprobe = min(args.nprobe, nlist)
@@ -465,6 +476,7 @@ def kmeans_cpu_sample(args, passes):
     try:
         import oracle as vo
 
+        use_all_host_threads(vo)
         n_s = max(1000, min(args.km_rows, 100_000))
         rows = vo.synth(SEED_DATA, n_s, args.km_dim, kind=1, n_centers=args.n_centers, center_seed=SEED_CENTERS,
                         normalize=False)
@@ -660,6 +672,7 @@ def main_flat(args):
     if not args.no_cpu_baseline:
         import oracle as vo
 
+        use_all_host_threads(vo)
         rows_s = vo.synth(SEED_DATA, n // 8, dim, kind=1, n_centers=args.n_centers, center_seed=SEED_CENTERS)
         qs = vo.synth(SEED_QUERY, 64, dim, kind=1, n_centers=args.n_centers, center_seed=SEED_CENTERS)
         t0 = time.perf_counter()

@@ -52,6 +52,7 @@ def lib():
         "vo_cosine_distance": (f32, [_f32p, _f32p, u32]),
         "vo_normalize_rows": (None, [_f32p, u64, u32, u32]),
         "vo_synth": (None, [u64, u64, u32, u32, u64, u64, u32, u32, i32, _f32p]),
+        "vo_synth_rows": (None, [u64, u64, u32, u32, _u64p, u64, u32, u32, i32, _f32p]),
         "vo_assign": (i32, [_f32p, u64, u32, u32, _f32p, u32, u32, _u64p]),
         "vo_partial_sums": (None, [_f32p, u64, u32, u32, _u64p, u32, _f32p, _u64p]),
         "vo_finalize_centroids": (None, [_f32p, _u64p, u32, u32, _f32p]),
@@ -139,6 +140,14 @@ def synth(seed, n, dim, kind=0, n_centers=1, center_seed=0, row0=0, normalize=Tr
     out = np.empty((n, stride), np.float32)
     lib().vo_synth(seed, center_seed, kind, n_centers, row0, n, dim, stride, int(normalize), out)
     return out if stride != dim else out
+
+
+def synth_rows(seed, row_ids, dim, kind=0, n_centers=1, center_seed=0, normalize=True) -> np.ndarray:
+    """rows `row_ids` of the synthetic matrix (same bits as synth(...)[row_ids])"""
+    ids = np.ascontiguousarray(row_ids, np.uint64)
+    out = np.empty((ids.shape[0], dim), np.float32)
+    lib().vo_synth_rows(seed, center_seed, kind, n_centers, ids, ids.shape[0], dim, dim, int(normalize), out)
+    return out
 
 
 def init_rows(seed, attempts, C_, n) -> np.ndarray:

@@ -103,13 +103,55 @@ def test_assign_first_minimum_on_duplicate_centroids(vb, vo, ctx):
     want = vo.assign(rows, cents)
     assert np.array_equal(got, want)
     assert not np.any(np.isin(got, [2, 3, 5]))
-    # the tensor-core candidate pass sees exact ties between the twins: every row whose nearest centroid has a twin
-    # must fail its certificate and be redone in exact order
-    km = vb.KMeans(ds, 6)
+    # the split-precision candidate pass (mode 2) keeps (best, second best): it sees exact ties between the twins, so
+    # every row whose nearest centroid has a twin must fail its certificate and be redone in exact order.  The
+    # tf32-first pass (mode 0, ld <= 128) re-ranks its four best candidates in exact order inside the kernel: twins and
+    # triplets are resolved there (first minimum wins) without a redo.
+    for mode in (0, 2):
+        km = vb.KMeans(ds, 6)
+        km.set_mode(mode)
+        km.set_centroids(cents)
+        km.assign_step()
+        assert np.array_equal(km.assignments(), want)
+        if mode == 2:
+            assert km.last_uncertified_rows >= int((want != 4).sum()) > 0
+        km.close()
+
+
+@pytest.mark.parametrize("n,dim,C,normalize", [(5000, 128, 1000, False), (3001, 100, 65, True), (777, 36, 3, True),
+                                               (2048, 64, 1, True), (1500, 128, 5, False), (513, 32, 200, True)])
+def test_assign_tf32_first_kernel_bit_exact(vb, vo, ctx, n, dim, C, normalize):
+    """tc_assign1_kernel (ld <= 128): one tf32 MMA per K step, top-4 + exact rerank + certificate; tile edges (C not a
+    multiple of 64, fewer than five centroids, a last row-block pair that is half empty), duplicated centroids"""
+    rows = data(vo, n, dim, normalize=normalize)
+    pick = vo.init_rows(5, 1, C, n)[0].astype(np.int64)
+    cents = rows[pick].copy()
+    if C >= 8:
+        cents[C // 2] = cents[0]  # an exact twin
+        cents[1] = 0.5 * (cents[2] + cents[3])  # and a centroid that is not a data row
+    ds = vb.Dataset.upload(ctx, rows)
+    km = vb.KMeans(ds, C)
     km.set_centroids(cents)
     km.assign_step()
-    assert np.array_equal(km.assignments(), want)
-    assert km.last_uncertified_rows >= int((want != 4).sum()) > 0
+    assert np.array_equal(km.assignments(), vo.assign(rows, cents))
+    assert km.last_uncertified_rows <= n // 4
+    km.close()
+
+
+def test_assign_nan_row_panics_like_the_reference(vb, vo, ctx):
+    """partial_cmp(..).unwrap() on a NaN distance panics (ivfflat.rs:39): both assign paths must report it instead of
+    writing an out-of-range cluster"""
+    rows = data(vo, 1000, 64)
+    rows[123, 7] = np.nan
+    cents = rows[[1, 2, 3, 4, 5, 6, 7, 8]].copy()
+    ds = vb.Dataset.upload(ctx, rows)
+    for mode in (0, 1, 2):
+        km = vb.KMeans(ds, 8)
+        km.set_mode(mode)
+        km.set_centroids(cents)
+        with pytest.raises(vb.VersPanic):
+            km.assign_step()
+        km.close()
 
 
 @pytest.mark.parametrize("n,dim,C", [(10000, 300, 16), (5000, 128, 64), (1000, 20, 7)])
@@ -126,11 +168,11 @@ def test_update_centroids_bit_exact(vb, vo, ctx, n, dim, C):
     assert counts[3] == 0 and not cents[3].any()
 
 
-@pytest.mark.parametrize("km_mode", [0, 1])
+@pytest.mark.parametrize("km_mode", [0, 1, 2])
 @pytest.mark.parametrize("n,dim,C", [(10000, 300, 16), (6000, 128, 300), (4097, 36, 129)])
 def test_kmeans_fit_and_cost_bit_exact(vb, vo, ctx, km_mode, n, dim, C):
-    """km_mode 0: tensor-core (tcgen05 split-TF32) candidate argmin + certificate + exact redo of uncertified rows;
-    km_mode 1: exact order only.  Iterations, assignments, centroid bits and cost bits must equal the oracle's."""
+    """km_mode 0: tensor-core candidate argmin + certificate + exact redo of uncertified rows (tf32-first kernel for
+    ld <= 128, split-precision kernel otherwise); km_mode 1: exact order only; km_mode 2: split-precision kernel.  Iterations, assignments, centroid bits and cost bits must equal the oracle's."""
     rows = data(vo, n, dim)
     init = vo.init_rows(3, 1, C, n)[0]
     ds = vb.Dataset.upload(ctx, rows)

@@ -307,6 +307,7 @@ extern "C" int32_t vers_dataset_normalize(vers_dataset* ds) {
     normalize_kernel<<<(unsigned)ceil_div(ds->n, NORM_ROWS), NORM_ROWS, 0, ctx->stream>>>(ds->d_rows, ds->n, ds->dim,
                                                                                          ds->ld);
     VERS_LAUNCH_CHECK(ctx);
+    ds->epoch += 1;    // k-means states over this dataset recompute their ||row||^2 on the next assign
     if (ds->d_norm) {  // cached ||row||^2 of the tensor-core exhaustive search are stale now
         VERS_CUDA(cudaStreamSynchronize(ctx->stream));
         cudaFree(ds->d_norm);

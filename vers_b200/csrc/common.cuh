@@ -71,6 +71,7 @@ struct vers_dataset {
     uint32_t ld = 0;  // round_up(dim, 4), pad columns are zero
     uint64_t id_base = 0;
     bool owned = true;
+    uint64_t epoch = 1;  // bumped whenever the rows are rewritten in place (normalize): cached ||row||^2 become stale
     // tensor-core exhaustive search: ||row||^2 (any order), their max, 8 counters; built on first use, dropped when the
     // rows change (normalize)
     float* d_norm = nullptr;

@@ -1832,6 +1832,8 @@ extern "C" int32_t vers_ivf_add(vers_ivf* ivf, const float* embedding, uint64_t 
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = fail(VERS_ERR_CUDA, "ivf_add: %s", cudaGetErrorString(e));
     }
+    if (rc == VERS_OK && best >= ivf->C)  // every distance compared false (NaN / inf - inf in the embedding)
+        rc = fail(VERS_ERR_PANIC, "ivf_add: a distance is NaN (partial_cmp(..).unwrap() panics, ivfflat.rs:207)");
     if (rc == VERS_OK) {
         uint32_t c = (uint32_t)best;
         if (ivf->seg_len[c] == ivf->seg_cap[c]) rc = ivf_relayout(ivf);

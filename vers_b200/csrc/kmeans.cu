@@ -16,7 +16,7 @@ namespace vers {
 // ---------------------------------------------------------------- assign
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::NT, 2)
-    assign_kernel(RowSrc A, RowSrc B, uint32_t ld, uint32_t* __restrict__ out_assign) {
+    assign_kernel(RowSrc A, RowSrc B, uint32_t ld, uint32_t* __restrict__ out_assign, uint32_t* __restrict__ bad) {
     extern __shared__ __align__(16) float smem[];
     constexpr int MA = Cfg::MA, MB = Cfg::MB, NTA = Cfg::NTA, NTB = Cfg::NTB, TA = Cfg::TA, TB = Cfg::TB;
     const int tid = threadIdx.x, ta = tid % NTA, tb = tid / NTA;
@@ -66,28 +66,45 @@ __global__ void __launch_bounds__(Cfg::NT, 2)
                 bc = c;
             }
         }
-        if (a0 + r < A.n) out_assign[a0 + r] = bc;
+        if (a0 + r < A.n) {
+            out_assign[a0 + r] = bc;
+            // every distance of this row compared false (NaN, or inf - inf): the reference panics on
+            // partial_cmp(..).unwrap() (ivfflat.rs:39); flag it instead of handing out an index past the table
+            if (bc == 0xffffffffu && bad) atomicOr(bad, 1u);
+        }
     }
 }
 
 template <class Cfg>
-static int32_t launch_assign(vers_ctx* ctx, const RowSrc& A, const RowSrc& B, uint32_t ld, uint32_t* d_assign) {
+static int32_t launch_assign(vers_ctx* ctx, const RowSrc& A, const RowSrc& B, uint32_t ld, uint32_t* d_assign,
+                             uint32_t* d_bad) {
     static_assert(Cfg::TILE_FLOATS >= Cfg::TA * Cfg::NTB * 2, "reduction fits in the staging buffers");
     auto kern = assign_kernel<Cfg>;
     size_t smem = (size_t)Cfg::TILE_FLOATS * 4;
     VERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)ceil_div(A.n, Cfg::TA), Cfg::NT, smem, ctx->stream>>>(A, B, ld, d_assign);
+    kern<<<(unsigned)ceil_div(A.n, Cfg::TA), Cfg::NT, smem, ctx->stream>>>(A, B, ld, d_assign, d_bad);
     VERS_LAUNCH_CHECK(ctx);
     return VERS_OK;
 }
 
 int32_t kmeans_assign_rows(vers_ctx* ctx, const RowSrc& rows, const float* d_cents, uint32_t C, uint32_t ld,
-                           uint32_t* d_assign, int family) {
+                           uint32_t* d_assign, int family, uint32_t* d_bad) {
     if (rows.n == 0) return VERS_OK;
     RowSrc B{d_cents, nullptr, ld, C};
     FamilyTimer ft(ctx, family);
-    if (C <= 8) return launch_assign<NarrowCfg>(ctx, rows, B, ld, d_assign);
-    return launch_assign<WideCfg>(ctx, rows, B, ld, d_assign);
+    if (C <= 8) return launch_assign<NarrowCfg>(ctx, rows, B, ld, d_assign, d_bad);
+    return launch_assign<WideCfg>(ctx, rows, B, ld, d_assign, d_bad);
+}
+
+// reads the "a row compared false against every centroid" flag of the assign kernels (synchronises)
+static int32_t kmeans_check_bad(vers_kmeans* km) {
+    uint32_t bad = 0;
+    VERS_CUDA(cudaMemcpyAsync(&bad, km->d_bad, 4, cudaMemcpyDeviceToHost, km->ds->ctx->stream));
+    VERS_CUDA(cudaStreamSynchronize(km->ds->ctx->stream));
+    if (bad)
+        return fail(VERS_ERR_PANIC, "assign_to_clusters: a distance is NaN (partial_cmp(..).unwrap() panics, "
+                                    "ivfflat.rs:39)");
+    return VERS_OK;
 }
 
 // ---------------------------------------------------------------- CSR (rows grouped by cluster, stable)
@@ -278,6 +295,7 @@ extern "C" int32_t vers_kmeans_free(vers_kmeans* km) {
     cudaFree(km->d_counts);
     cudaFree(km->d_rowdist);
     cudaFree(km->d_flag);
+    cudaFree(km->d_bad);
     cudaFree(km->d_cub);
     cudaFree(km->d_row_norm);
     cudaFree(km->d_cent_norm);
@@ -317,6 +335,7 @@ extern "C" int32_t vers_kmeans_create(vers_dataset* ds, uint32_t num_clusters, v
     A((void**)&km->d_hist, (size_t)num_clusters * 4);
     A((void**)&km->d_off, ((size_t)num_clusters + 1) * 8);
     A((void**)&km->d_flag, 4);
+    A((void**)&km->d_bad, 4);
     if (e != cudaSuccess) {
         vers_kmeans_free(km);
         return fail(VERS_ERR_NOMEM, "kmeans_create: cudaMalloc failed: %s", cudaGetErrorString(e));
@@ -408,52 +427,106 @@ extern "C" int32_t vers_kmeans_assign_device_ptr(vers_kmeans* km, void** ptr) {
     return VERS_OK;
 }
 
-// tensor-core candidate argmin + certificate; uncertified rows redone by the exact-order kernel
+// tensor-core candidate argmin + certificate; uncertified rows redone by the exact-order kernel.
+// ld <= 128 (mode 0): tc_assign1_kernel (one tf32 MMA per K step, rows resident in tensor memory, top-4 + exact rerank
+// inside the kernel); otherwise / mode 2: tc_assign_kernel (split precision, three MMAs per K step, top-2 gap).
+static int32_t kmeans_tc_buffers(vers_kmeans* km) {
+    vers_dataset* ds = km->ds;
+    vers_ctx* ctx = ds->ctx;
+    cudaStream_t s = ctx->stream;
+    if (km->d_row_norm && km->norm_epoch == ds->epoch) return VERS_OK;
+    if (!km->d_row_norm) {
+        // all or nothing: a failed allocation must not leave a half-initialised state behind
+        float *row_norm = nullptr, *cent_norm = nullptr, *cent_hi = nullptr, *cent_lo = nullptr;
+        uint32_t *ncmax = nullptr, *flagged = nullptr, *nflagged = nullptr, *exact = nullptr;
+        cudaError_t e = cudaSuccess;
+        auto A = [&](void** p, size_t bytes) {
+            if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+        };
+        A((void**)&row_norm, ds->n * 4);
+        A((void**)&cent_norm, ((size_t)km->C + KA_N) * 4);
+        A((void**)&cent_hi, (size_t)km->C * ds->ld * 4);
+        A((void**)&cent_lo, (size_t)km->C * ds->ld * 4);
+        A((void**)&ncmax, 4);
+        A((void**)&flagged, ds->n * 4);
+        A((void**)&nflagged, 4);
+        A((void**)&exact, ds->n * 4);
+        if (e == cudaSuccess) {  // +inf past C: the epilogue reads whole tiles of norms; a padded column can never win
+            std::vector<float> inf(KA_N, __builtin_inff());
+            e = cudaMemcpyAsync(cent_norm + km->C, inf.data(), KA_N * 4, cudaMemcpyHostToDevice, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        }
+        if (e != cudaSuccess) {
+            cudaFree(row_norm), cudaFree(cent_norm), cudaFree(cent_hi), cudaFree(cent_lo);
+            cudaFree(ncmax), cudaFree(flagged), cudaFree(nflagged), cudaFree(exact);
+            return fail(e == cudaErrorMemoryAllocation ? VERS_ERR_NOMEM : VERS_ERR_CUDA, "kmeans assign buffers: %s",
+                        cudaGetErrorString(e));
+        }
+        km->d_row_norm = row_norm, km->d_cent_norm = cent_norm, km->d_cent_hi = cent_hi, km->d_cent_lo = cent_lo;
+        km->d_ncmax = ncmax, km->d_flagged = flagged, km->d_nflagged = nflagged, km->d_exact = exact;
+    }
+    // (re)computed whenever the rows changed since (vers_dataset_normalize bumps ds->epoch)
+    sqnorm_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(ds->d_rows, ds->ld, ds->n, km->d_row_norm, nullptr);
+    VERS_LAUNCH_CHECK(ctx);
+    km->norm_epoch = ds->epoch;
+    return VERS_OK;
+}
+
 static int32_t kmeans_assign_tc(vers_kmeans* km) {
     vers_dataset* ds = km->ds;
     vers_ctx* ctx = ds->ctx;
     cudaStream_t s = ctx->stream;
-    if (!km->d_row_norm) {
-        VERS_CUDA(cudaMalloc(&km->d_row_norm, ds->n * 4));
-        VERS_CUDA(cudaMalloc(&km->d_cent_norm, ((size_t)km->C + KA_N) * 4));
-        {   // +inf past C: the epilogue reads whole 128-centroid tiles of norms; a padded column can never win
-            std::vector<float> inf(KA_N, __builtin_inff());
-            VERS_CUDA(cudaMemcpyAsync(km->d_cent_norm + km->C, inf.data(), KA_N * 4, cudaMemcpyHostToDevice, s));
-            VERS_CUDA(cudaStreamSynchronize(s));
-        }
-        VERS_CUDA(cudaMalloc(&km->d_cent_hi, (size_t)km->C * ds->ld * 4));
-        VERS_CUDA(cudaMalloc(&km->d_cent_lo, (size_t)km->C * ds->ld * 4));
-        VERS_CUDA(cudaMalloc(&km->d_ncmax, 4));
-        VERS_CUDA(cudaMalloc(&km->d_flagged, ds->n * 4));
-        VERS_CUDA(cudaMalloc(&km->d_nflagged, 4));
-        VERS_CUDA(cudaMalloc(&km->d_exact, ds->n * 4));
-        sqnorm_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(ds->d_rows, ds->ld, ds->n, km->d_row_norm, nullptr);
-        VERS_LAUNCH_CHECK(ctx);
-    }
+    VERS_TRY(kmeans_tc_buffers(km));
+    const bool tf32_first = km->mode == 0 && ds->ld <= K1_MAX_KCH * K1_KC;
     VERS_CUDA(cudaMemsetAsync(km->d_ncmax, 0, 4, s));
     VERS_CUDA(cudaMemsetAsync(km->d_nflagged, 0, 4, s));
+    VERS_CUDA(cudaMemsetAsync(km->d_bad, 0, 4, s));
     sqnorm_kernel<<<(unsigned)ceil_div((uint64_t)km->C * 32, 256), 256, 0, s>>>(km->d_cents, ds->ld, km->C,
                                                                                km->d_cent_norm, km->d_ncmax);
     VERS_LAUNCH_CHECK(ctx);
-    split_tf32_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(km->d_cents, (uint64_t)km->C * (ds->ld >> 2), km->d_cent_hi,
-                                                        km->d_cent_lo);
-    VERS_LAUNCH_CHECK(ctx);
-    CUtensorMap tm_rows, tm_chi, tm_clo;
-    VERS_TRY(make_tmap_2d_f32(&tm_rows, ds->d_rows, ds->n, ds->ld, ds->ld, KA_M, KA_KC));
-    VERS_TRY(make_tmap_2d_f32(&tm_chi, km->d_cent_hi, km->C, ds->ld, ds->ld, KA_N, KA_KC));
-    VERS_TRY(make_tmap_2d_f32(&tm_clo, km->d_cent_lo, km->C, ds->ld, ds->ld, KA_N, KA_KC));
-    TcAssignParams p;
-    p.n_rows = ds->n;
-    p.C = km->C;
-    p.ld = ds->ld;
-    p.row_norm = km->d_row_norm;
-    p.cent_norm = km->d_cent_norm;
-    p.ncmax_bits = km->d_ncmax;
-    p.assign = km->d_assign;
-    p.flagged = km->d_flagged;
-    p.n_flagged = km->d_nflagged;
-    VERS_CUDA(cudaFuncSetAttribute(tc_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KA_SMEM_BYTES));
-    {
+    if (tf32_first) {
+        round_tf32_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(km->d_cents, (uint64_t)km->C * (ds->ld >> 2), km->d_cent_hi);
+        VERS_LAUNCH_CHECK(ctx);
+        CUtensorMap tm_rows, tm_c;
+        VERS_TRY(make_tmap_2d_f32(&tm_rows, ds->d_rows, ds->n, ds->ld, ds->ld, K1_M, K1_KC));
+        VERS_TRY(make_tmap_2d_f32(&tm_c, km->d_cent_hi, km->C, ds->ld, ds->ld, K1_N, K1_KC));
+        TcAssign1Params p;
+        p.n_rows = ds->n;
+        p.C = km->C;
+        p.ld = ds->ld;
+        p.rows = ds->d_rows;
+        p.cents = km->d_cents;
+        p.row_norm = km->d_row_norm;
+        p.cent_norm = km->d_cent_norm;
+        p.ncmax_bits = km->d_ncmax;
+        p.assign = km->d_assign;
+        p.flagged = km->d_flagged;
+        p.n_flagged = km->d_nflagged;
+        VERS_CUDA(cudaFuncSetAttribute(tc_assign1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES));
+        FamilyTimer ft(ctx, KF_ASSIGN);
+        const uint64_t nrbp = ceil_div(ds->n, 2 * K1_M);
+        tc_assign1_kernel<<<(unsigned)std::min<uint64_t>(nrbp, ctx->sm_count), K1_THREADS, K1_SMEM_BYTES, s>>>(tm_rows, tm_c,
+                                                                                                           p);
+        VERS_LAUNCH_CHECK(ctx);
+    } else {
+        split_tf32_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(km->d_cents, (uint64_t)km->C * (ds->ld >> 2), km->d_cent_hi,
+                                                            km->d_cent_lo);
+        VERS_LAUNCH_CHECK(ctx);
+        CUtensorMap tm_rows, tm_chi, tm_clo;
+        VERS_TRY(make_tmap_2d_f32(&tm_rows, ds->d_rows, ds->n, ds->ld, ds->ld, KA_M, KA_KC));
+        VERS_TRY(make_tmap_2d_f32(&tm_chi, km->d_cent_hi, km->C, ds->ld, ds->ld, KA_N, KA_KC));
+        VERS_TRY(make_tmap_2d_f32(&tm_clo, km->d_cent_lo, km->C, ds->ld, ds->ld, KA_N, KA_KC));
+        TcAssignParams p;
+        p.n_rows = ds->n;
+        p.C = km->C;
+        p.ld = ds->ld;
+        p.row_norm = km->d_row_norm;
+        p.cent_norm = km->d_cent_norm;
+        p.ncmax_bits = km->d_ncmax;
+        p.assign = km->d_assign;
+        p.flagged = km->d_flagged;
+        p.n_flagged = km->d_nflagged;
+        VERS_CUDA(cudaFuncSetAttribute(tc_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KA_SMEM_BYTES));
         FamilyTimer ft(ctx, KF_ASSIGN);
         const uint64_t nrb = ceil_div(ds->n, KA_M);
         tc_assign_kernel<<<(unsigned)std::min<uint64_t>(nrb, ctx->sm_count), KA_THREADS, KA_SMEM_BYTES, s>>>(tm_rows,
@@ -466,9 +539,10 @@ static int32_t kmeans_assign_tc(vers_kmeans* km) {
     km->last_flagged = nf;
     if (nf) {
         RowSrc A{ds->d_rows, km->d_flagged, ds->ld, nf};
-        VERS_TRY(kmeans_assign_rows(ctx, A, km->d_cents, km->C, ds->ld, km->d_exact, KF_LIST_SCAN));  // own family: the redo
+        VERS_TRY(kmeans_assign_rows(ctx, A, km->d_cents, km->C, ds->ld, km->d_exact, KF_LIST_SCAN, km->d_bad));  // own family: the redo
         scatter_assign_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(km->d_flagged, km->d_nflagged, km->d_exact, km->d_assign);
         VERS_LAUNCH_CHECK(ctx);
+        VERS_TRY(kmeans_check_bad(km));
     }
     return VERS_OK;
 }
@@ -479,14 +553,16 @@ extern "C" int32_t vers_kmeans_assign_step(vers_kmeans* km) {
     std::lock_guard<std::mutex> lk(ds->ctx->mu);
     VERS_CUDA(cudaSetDevice(ds->ctx->device));
     km->csr_valid = false;
-    if (km->mode == 0 && ds->ld >= KA_KC && ds->n >= 1 && ds->n < 0x7fffffffull) return kmeans_assign_tc(km);
+    if (km->mode != 1 && ds->ld >= KA_KC && ds->n >= 1 && ds->n < 0x7fffffffull) return kmeans_assign_tc(km);
     km->last_flagged = 0;
+    VERS_CUDA(cudaMemsetAsync(km->d_bad, 0, 4, ds->ctx->stream));
     RowSrc A{ds->d_rows, nullptr, ds->ld, ds->n};
-    return kmeans_assign_rows(ds->ctx, A, km->d_cents, km->C, ds->ld, km->d_assign);
+    VERS_TRY(kmeans_assign_rows(ds->ctx, A, km->d_cents, km->C, ds->ld, km->d_assign, KF_ASSIGN, km->d_bad));
+    return kmeans_check_bad(km);
 }
 
 extern "C" int32_t vers_kmeans_set_mode(vers_kmeans* km, int32_t mode) {
-    if (!km || mode < 0 || mode > 1) return fail(VERS_ERR_ARG, "kmeans_set_mode: bad argument");
+    if (!km || mode < 0 || mode > 2) return fail(VERS_ERR_ARG, "kmeans_set_mode: bad argument");
     km->mode = mode;
     return VERS_OK;
 }

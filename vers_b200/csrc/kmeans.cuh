@@ -17,12 +17,15 @@ struct vers_kmeans {
     uint64_t* d_counts = nullptr;       // [C]
     float* d_rowdist = nullptr;         // [n] cost scratch (allocated lazily)
     uint32_t* d_flag = nullptr;         // [1]
+    uint32_t* d_bad = nullptr;          // [1] set by the exact-order assign when a row has no comparable distance (NaN)
     void* d_cub = nullptr;
     size_t cub_bytes = 0;
     bool csr_valid = false;  // d_sorted_rows/d_off describe the current d_assign
     // tensor-core candidate pass of assign (kmeans_tc.cuh)
-    int mode = 0;                    // 0 = tensor-core candidates + certificate + exact redo, 1 = exact order only
-    float* d_row_norm = nullptr;     // [n] ||x||^2, computed once (rows do not change)
+    int mode = 0;                    // 0 = tensor-core candidates + certificate + exact redo (tf32-first kernel when
+                                     // ld <= 128), 1 = exact order only, 2 = like 0 with the split-precision kernel
+    float* d_row_norm = nullptr;     // [n] ||x||^2, recomputed when the rows change (ds->epoch)
+    uint64_t norm_epoch = 0;         // ds->epoch d_row_norm was computed for
     float* d_cent_norm = nullptr;    // [C]
     float* d_cent_hi = nullptr;      // [C][ld] tf32 hi part of the centroids
     float* d_cent_lo = nullptr;      // [C][ld] tf32 lo part
@@ -37,5 +40,5 @@ namespace vers {
 // groups the local rows by cluster in ascending row order (stable): fills d_sorted_rows and d_off
 int32_t kmeans_build_csr(vers_kmeans* km);
 int32_t kmeans_assign_rows(vers_ctx* ctx, const RowSrc& rows, const float* d_cents, uint32_t C, uint32_t ld,
-                           uint32_t* d_assign, int family = KF_ASSIGN);
+                           uint32_t* d_assign, int family = KF_ASSIGN, uint32_t* d_bad = nullptr);
 }  // namespace vers

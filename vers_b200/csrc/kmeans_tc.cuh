@@ -270,6 +270,354 @@ __global__ void __launch_bounds__(KA_THREADS, 1)
     if (warp == 1) tc::tmem_dealloc(tmem_base, KA_TMEM_COLS);
 }
 
+// =====================================================================================================================
+// tc_assign1_kernel — TF32-FIRST candidate pass for ld <= 128 (BASELINE configs[4]: 50M x 128, 16384 centroids).
+//
+// The split-precision kernel above is bound by L2 -> SM operand traffic, not by the tensor pipe: per 128 x 128 tile it
+// moves 192 KB (the row tile re-fetched per K chunk + c_hi + c_lo) against an L2 delivery of ~42 B/clk/SM, i.e.
+// ~4500 clk for 3072 clk of MMAs (ncu: 67 % tensor-pipe activity).  This kernel removes both factors:
+//   * ONE tcgen05.mma kind::tf32 per K step instead of three.  Both operands are rounded to nearest tf32 (centroids by
+//     a prep kernel, rows by the converter warps), so |x.c - x~.c~| <= 2^-10 (1 + 2^-12) |x||c|.  That is too coarse
+//     to certify the argmin from the candidate values alone, so per row the FOUR smallest keys are kept (+ the fifth
+//     key as the bound), the four candidates are re-ranked with the reference's exact-order arithmetic
+//     (indexes/base.rs:119-126) inside the same kernel, and the certificate compares the exact best distance with the
+//     fifth key: (k5 + ||x||^2 - E)(1 - rho) > d_ref(best)  =>  no centroid outside the four can win or tie.
+//     Uncertified rows (near-ties within the tf32 error) are appended to the flagged list and redone exactly.
+//   * the rows are loaded and converted ONCE per row block and stay resident in TENSOR MEMORY as the A operand
+//     (ld <= 128 fp32 columns); a CTA owns TWO 128-row blocks (2 x 128 A columns + 2 x 2 x 64 accumulator columns =
+//     all 512 TMEM columns), so a 64-centroid B tile (32 KB, the only thing streamed from L2) feeds 2 x 16 MMAs of
+//     M=128 N=64 K=8: 32 B/clk/SM at full tensor rate.
+//   * epilogue: key = ||c||^2 - 2 acc per element (one FFMA), a min-tree per 16 columns and ONE compare against the
+//     row's current fifth key; the insertion code runs only for groups that contain a new top-5 entry.
+// Warp roles (14 warps): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = epilogue (warps 2..5 row block 0,
+// 6..9 row block 1; warp w reads TMEM lanes 32*(w%4)..+31), 10..13 = converters.
+constexpr int K1_M = 128, K1_N = 64, K1_KC = 32, K1_STAGES = 5, K1_MAX_KCH = 4;
+constexpr int K1_EPI_WARP0 = 2, K1_EPI_WARPS = 8, K1_CONV_WARP0 = 10, K1_CONV_WARPS = 4;
+constexpr int K1_THREADS = (2 + K1_EPI_WARPS + K1_CONV_WARPS) * 32;
+constexpr int K1_BOX_BYTES = K1_N * K1_KC * 4;                 // one [64 centroids x 32 floats] box
+constexpr int K1_STAGE_BYTES = K1_MAX_KCH * K1_BOX_BYTES;      // a whole 64-centroid tile (all K chunks)
+constexpr int K1_ASLOT_BYTES = K1_M * K1_KC * 4;               // one [128 rows x 32 floats] staging slot
+constexpr int K1_OFF_ASLOT = K1_STAGES * K1_STAGE_BYTES;
+constexpr int K1_OFF_NRM = K1_OFF_ASLOT + 2 * K1_ASLOT_BYTES;  // [4][64] ||c||^2 ring
+constexpr int K1_OFF_BAR = K1_OFF_NRM + 4 * K1_N * 4;
+constexpr int K1_SMEM_BYTES = 1024 + K1_OFF_BAR + 512;
+constexpr uint32_t K1_ACC_COL0 = 0;      // accumulator of (row block rb, buffer b) at column (2 rb + b) * 64
+constexpr uint32_t K1_A_COL0 = 256;      // rows of row block rb at column 256 + 128 rb
+constexpr uint32_t K1_TMEM_COLS = 512;
+
+struct TcAssign1Params {
+    uint64_t n_rows;
+    uint32_t C, ld;
+    const float* rows;       // [n][ld] the rows themselves (exact rerank)
+    const float* cents;      // [C][ld] the centroids themselves (exact rerank)
+    const float* row_norm;   // [n] ||x||^2 (any order)
+    const float* cent_norm;  // [round_up(C, 128)] ||c||^2 (any order), +inf past C
+    const uint32_t* ncmax_bits;
+    uint32_t* assign;
+    uint32_t* flagged;
+    uint32_t* n_flagged;
+};
+
+__device__ __forceinline__ uint32_t round_tf32_bits(uint32_t u) {  // round to nearest even at bit 13
+    return (u + 0xFFFu + ((u >> 13) & 1u)) & 0xFFFFE000u;
+}
+
+// centroids rounded to nearest tf32 (the tensor core would truncate; rounding halves the error term)
+__global__ void round_tf32_kernel(const float* __restrict__ in, uint64_t n4, float* __restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<const float4*>(in)[i];
+        v.x = __uint_as_float(round_tf32_bits(__float_as_uint(v.x)));
+        v.y = __uint_as_float(round_tf32_bits(__float_as_uint(v.y)));
+        v.z = __uint_as_float(round_tf32_bits(__float_as_uint(v.z)));
+        v.w = __uint_as_float(round_tf32_bits(__float_as_uint(v.w)));
+        reinterpret_cast<float4*>(out)[i] = v;
+    }
+}
+
+// sorted insertion into the five smallest keys (ids for the first four); strict `<`: an equal key stays behind
+__device__ __forceinline__ void k1_insert(float (&k)[5], uint32_t (&id)[4], float key, uint32_t idx) {
+    const bool c3 = key < k[3], c2 = key < k[2], c1 = key < k[1], c0 = key < k[0];
+    k[4] = c3 ? k[3] : key;
+    k[3] = c3 ? (c2 ? k[2] : key) : k[3];
+    id[3] = c3 ? (c2 ? id[2] : idx) : id[3];
+    k[2] = c2 ? (c1 ? k[1] : key) : k[2];
+    id[2] = c2 ? (c1 ? id[1] : idx) : id[2];
+    k[1] = c1 ? (c0 ? k[0] : key) : k[1];
+    id[1] = c1 ? (c0 ? id[0] : idx) : id[1];
+    k[0] = c0 ? key : k[0];
+    id[0] = c0 ? idx : id[0];
+}
+
+__global__ void __launch_bounds__(K1_THREADS, 1)
+    tc_assign1_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_c,
+                      TcAssign1Params p) {
+    extern __shared__ uint8_t k1_smem_raw[];
+    const uint32_t raw = tc::smem_u32(k1_smem_raw);
+    uint8_t* smem = k1_smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    float* nrm = reinterpret_cast<float*>(smem + K1_OFF_NRM);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + K1_OFF_BAR);
+    uint64_t* empty = full + K1_STAGES;
+    uint64_t* afull = empty + K1_STAGES;   // [2] staging slot landed
+    uint64_t* aempty = afull + 2;          // [2] staging slot read by all converter warps
+    uint64_t* aready = aempty + 2;         // [1] both row blocks of this pair are in tensor memory
+    uint64_t* afree = aready + 1;          // [1] every MMA of the pair has completed: A may be overwritten
+    uint64_t* tfull = afree + 1;           // [2 rb][2 buf]
+    uint64_t* tempty = tfull + 4;          // [2 rb][2 buf]
+    uint64_t* nbar = tempty + 4;           // [4] norm ring
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(nbar + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t nk = (p.ld + K1_KC - 1) / K1_KC;            // <= 4
+    const uint32_t nct = (p.C + K1_N - 1) / K1_N;
+    const uint64_t nrbp = (p.n_rows + 2 * K1_M - 1) / (2 * K1_M);
+    const uint64_t my_pairs = blockIdx.x < nrbp ? (nrbp - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint64_t total_tiles = my_pairs * nct;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < K1_STAGES; ++s) {
+            tc::mbar_init(&full[s], 1);
+            tc::mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&afull[s], 1);
+            tc::mbar_init(&aempty[s], K1_CONV_WARPS);
+        }
+        tc::mbar_init(aready, K1_CONV_WARPS);
+        tc::mbar_init(afree, 1);
+        for (int b = 0; b < 4; ++b) {
+            tc::mbar_init(&tfull[b], 1);
+            tc::mbar_init(&tempty[b], K1_EPI_WARPS / 2);
+            tc::mbar_init(&nbar[b], 1);
+        }
+        tc::fence_barrier_init();
+        tc::tma_prefetch_desc(&tmap_rows);
+        tc::tma_prefetch_desc(&tmap_c);
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, K1_TMEM_COLS);
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, chunk = 0;
+            for (uint64_t rbp = blockIdx.x; rbp < nrbp; rbp += gridDim.x) {
+                for (uint32_t rb = 0; rb < 2; ++rb) {
+                    for (uint32_t kc = 0; kc < nk; ++kc, ++chunk) {
+                        const uint32_t slot = chunk & 1, ph = (chunk >> 1) & 1;
+                        tc::mbar_wait(&aempty[slot], ph ^ 1);
+                        tc::mbar_arrive_expect_tx(&afull[slot], K1_ASLOT_BYTES);
+                        tc::tma_load_2d(smem + K1_OFF_ASLOT + slot * K1_ASLOT_BYTES, &tmap_rows, &afull[slot],
+                                        (int32_t)(kc * K1_KC), (int32_t)((rbp * 2 + rb) * K1_M));
+                    }
+                }
+                for (uint32_t ct = 0; ct < nct; ++ct) {
+                    tc::mbar_wait(&empty[stage], phase ^ 1);
+                    tc::mbar_arrive_expect_tx(&full[stage], nk * K1_BOX_BYTES);
+                    uint8_t* sb = smem + stage * K1_STAGE_BYTES;
+                    for (uint32_t kc = 0; kc < nk; ++kc)
+                        tc::tma_load_2d(sb + kc * K1_BOX_BYTES, &tmap_c, &full[stage], (int32_t)(kc * K1_KC),
+                                        (int32_t)(ct * K1_N));
+                    if (++stage == K1_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = tc::idesc_tf32(K1_M, K1_N);
+            uint32_t stage = 0, phase = 0;
+            uint64_t t = 0;
+            if (total_tiles) {  // the norms of tile 0; tile t+1's are requested when tile t starts (slot (t+1) % 4 was
+                                // last read for tile t-3, which both epilogues finished before releasing tile t-2)
+                tc::mbar_arrive_expect_tx(&nbar[0], K1_N * 4);
+                tc::bulk_load(nrm, p.cent_norm, K1_N * 4, &nbar[0]);
+            }
+            for (uint64_t i = 0; i < my_pairs; ++i) {
+                tc::mbar_wait(aready, (uint32_t)(i & 1));
+                tc::fence_after_thread_sync();
+                for (uint32_t ct = 0; ct < nct; ++ct, ++t) {
+                    const uint32_t buf = (uint32_t)(t & 1), tph = (uint32_t)((t >> 1) & 1);
+                    tc::mbar_wait(&tempty[buf], tph ^ 1);
+                    tc::mbar_wait(&tempty[2 + buf], tph ^ 1);
+                    tc::fence_after_thread_sync();
+                    if (t + 1 < total_tiles) {
+                        const uint32_t slot = (uint32_t)((t + 1) & 3), nct1 = (ct + 1 == nct) ? 0 : ct + 1;
+                        tc::mbar_arrive_expect_tx(&nbar[slot], K1_N * 4);
+                        tc::bulk_load(nrm + slot * K1_N, p.cent_norm + (size_t)nct1 * K1_N, K1_N * 4, &nbar[slot]);
+                    }
+                    tc::mbar_wait(&full[stage], phase);
+                    tc::fence_after_thread_sync();
+                    const uint32_t sb = tc::smem_u32(smem + stage * K1_STAGE_BYTES);
+#pragma unroll
+                    for (uint32_t rb = 0; rb < 2; ++rb) {
+                        const uint32_t d_tmem = tmem_base + K1_ACC_COL0 + (2 * rb + buf) * K1_N;
+                        const uint32_t a_tmem = tmem_base + K1_A_COL0 + rb * 128;
+                        for (uint32_t kc = 0; kc < nk; ++kc) {
+                            const uint64_t db = tc::smem_desc_k_sw128(sb + kc * K1_BOX_BYTES);
+#pragma unroll
+                            for (uint32_t kk = 0; kk < K1_KC / 8; ++kk)
+                                tc::mma_tf32_ts(d_tmem, a_tmem + kc * K1_KC + 8 * kk, db + 2 * kk, idesc, (kc | kk) != 0);
+                        }
+                        tc::mma_commit(&tfull[2 * rb + buf]);
+                    }
+                    tc::mma_commit(&empty[stage]);
+                    if (++stage == K1_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc::mma_commit(afree);
+            }
+        }
+    } else if (warp < K1_EPI_WARP0 + K1_EPI_WARPS) {
+        // epilogue: thread = row.  Five smallest keys (ids of the first four) over all centroid tiles, then the exact
+        // rerank of the four and the certificate.
+        const uint32_t rb = (uint32_t)(warp - K1_EPI_WARP0) >> 2, lane_group = (uint32_t)warp & 3u;
+        const double u = 5.9604644775390625e-08;  // 2^-24
+        const double ncmax = (double)__uint_as_float(*p.ncmax_bits);
+        const float INF = __int_as_float(0x7f800000);
+        uint64_t t = 0;
+        for (uint64_t rbp = blockIdx.x; rbp < nrbp; rbp += gridDim.x) {
+            const uint64_t row = (rbp * 2 + rb) * K1_M + (uint64_t)(lane_group * 32 + lane);
+            float k[5] = {INF, INF, INF, INF, INF};
+            uint32_t id[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+            for (uint32_t ct = 0; ct < nct; ++ct, ++t) {
+                const uint32_t buf = (uint32_t)(t & 1), tph = (uint32_t)((t >> 1) & 1);
+                tc::mbar_wait(&nbar[t & 3], (uint32_t)((t >> 2) & 1));
+                tc::mbar_wait(&tfull[2 * rb + buf], tph);
+                tc::fence_after_thread_sync();
+                const uint32_t tacc = tmem_base + ((lane_group * 32u) << 16) + K1_ACC_COL0 + (2 * rb + buf) * K1_N;
+                uint32_t va[32], vb[32];
+                tc::tmem_ld_32_nowait(tacc, va);
+                tc::tmem_ld_32_nowait(tacc + 32, vb);
+                tc::tmem_ld_wait_32(va);
+                tc::tmem_ld_wait_32(vb);
+                // the accumulator is in registers: hand the buffer back before the selection work
+                tc::fence_before_thread_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&tempty[2 * rb + buf]);
+                const float* nr = nrm + (t & 3) * K1_N;
+                const uint32_t c0 = ct * K1_N;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float key[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 n4 = *reinterpret_cast<const float4*>(nr + 16 * g + j);
+                        const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int col = 16 * g + j + e;
+                            const float acc = __uint_as_float(col < 32 ? va[col] : vb[col - 32]);
+                            key[j + e] = __fmaf_rn(-2.0f, acc, nn[e]);
+                        }
+                    }
+                    float m01 = fminf(fminf(key[0], key[1]), fminf(key[2], key[3]));
+                    float m23 = fminf(fminf(key[4], key[5]), fminf(key[6], key[7]));
+                    float m45 = fminf(fminf(key[8], key[9]), fminf(key[10], key[11]));
+                    float m67 = fminf(fminf(key[12], key[13]), fminf(key[14], key[15]));
+                    const float m = fminf(fminf(m01, m23), fminf(m45, m67));
+                    if (m < k[4]) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e)
+                            if (key[e] < k[4]) k1_insert(k, id, key[e], c0 + 16 * g + e);
+                    }
+                }
+            }
+            if (row < p.n_rows) {
+                // exact-order distances of the (up to) four candidates: sequential over the dimensions like
+                // squared_euclidean (base.rs:119-126), four independent chains per thread
+                const float4* xr = reinterpret_cast<const float4*>(p.rows + row * p.ld);
+                const float4* cr[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    cr[r] = reinterpret_cast<const float4*>(p.cents + (size_t)(id[r] < p.C ? id[r] : 0u) * p.ld);
+                float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                for (uint32_t j = 0; j < (p.ld >> 2); ++j) {
+                    const float4 x = __ldg(xr + j);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float4 c = __ldg(cr[r] + j);
+                        float e0 = __fsub_rn(x.x, c.x), e1 = __fsub_rn(x.y, c.y), e2 = __fsub_rn(x.z, c.z),
+                              e3 = __fsub_rn(x.w, c.w);
+                        d[r] = __fadd_rn(d[r], __fmul_rn(e0, e0));
+                        d[r] = __fadd_rn(d[r], __fmul_rn(e1, e1));
+                        d[r] = __fadd_rn(d[r], __fmul_rn(e2, e2));
+                        d[r] = __fadd_rn(d[r], __fmul_rn(e3, e3));
+                    }
+                }
+                float bd = INF;
+                uint32_t bc = 0xffffffffu;
+                bool any = false, ordered = true;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if (id[r] < p.C) {
+                        // a NaN distance (the reference panics on it) sends the row to the exact path, which reports it
+                        ordered = ordered && (d[r] == d[r]);
+                        if (!any || d[r] < bd || (d[r] == bd && id[r] < bc)) {
+                            bd = d[r];
+                            bc = id[r];
+                            any = true;
+                        }
+                    }
+                }
+                p.assign[row] = bc;
+                // every centroid outside the four has key >= k[4]; |key + ||x||^2 - d_true| <= E and d_ref >=
+                // d_true (1 - rho).  E per unit of (||x||^2 + ||c||^2_max): fp32 norm/key terms, the tf32 rounding of
+                // both operands 2^-10 (1 + 2^-12), the accumulation allowance (n + 8) 2^-22 (same model as above)
+                const double nx = (double)__ldg(p.row_norm + row);
+                const double S = nx + ncmax;
+                const double E = (1.01 * (2.0 * p.ld + 8.0) * u + 1.001 / 1024.0 + (p.ld + 8.0) * 2.384185791015625e-07) * S;
+                const double rho = (p.ld + 3.0) * u;
+                const bool certified = any && ordered && ((double)k[4] + nx - E) * (1.0 - rho) > (double)bd;
+                if (!certified) {
+                    uint32_t at = atomicAdd(p.n_flagged, 1u);
+                    p.flagged[at] = (uint32_t)row;
+                }
+            }
+        }
+    } else {
+        // converters: landed row chunk -> rounded to nearest tf32 -> tensor memory (the A operand of every MMA of the pair)
+        const uint32_t lane_group = (uint32_t)warp & 3u;
+        const uint32_t row = lane_group * 32 + lane;
+        uint32_t chunk = 0;
+        for (uint64_t i = 0; i < my_pairs; ++i) {
+            for (uint32_t rb = 0; rb < 2; ++rb) {
+                for (uint32_t kc = 0; kc < nk; ++kc, ++chunk) {
+                    const uint32_t slot = chunk & 1, ph = (chunk >> 1) & 1;
+                    tc::mbar_wait(&afull[slot], ph);
+                    const uint8_t* arow = smem + K1_OFF_ASLOT + slot * K1_ASLOT_BYTES + row * 128;
+                    uint32_t v[K1_KC];
+#pragma unroll
+                    for (uint32_t c = 0; c < 8; ++c) {
+                        const float4 f = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7u)) << 4));
+                        v[4 * c + 0] = round_tf32_bits(__float_as_uint(f.x));
+                        v[4 * c + 1] = round_tf32_bits(__float_as_uint(f.y));
+                        v[4 * c + 2] = round_tf32_bits(__float_as_uint(f.z));
+                        v[4 * c + 3] = round_tf32_bits(__float_as_uint(f.w));
+                    }
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&aempty[slot]);
+                    if (rb == 0 && kc == 0 && i > 0) {  // the previous pair's MMAs still read the A columns
+                        tc::mbar_wait(afree, (uint32_t)((i - 1) & 1));
+                        tc::fence_after_thread_sync();
+                    }
+                    tc::tmem_st_32(tmem_base + ((lane_group * 32u) << 16) + K1_A_COL0 + rb * 128 + kc * K1_KC, v);
+                }
+            }
+            tc::fence_before_thread_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(aready);
+        }
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, K1_TMEM_COLS);
+}
+
 // squared norms of rows (warp per row, any order) + running max; used for rows and centroids
 __global__ void sqnorm_kernel(const float* __restrict__ rows, uint32_t ld, uint64_t count, float* __restrict__ norm,
                               uint32_t* nmax) {

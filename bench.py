@@ -68,10 +68,13 @@ def parse():
     ap.add_argument("--km-clusters", type=int, default=16384)
     ap.add_argument("--km-mode", type=int, default=0, help="0 tcgen05 candidate argmin + certificate (tf32-first kernel "
                     "for dim <= 128), 1 exact order only, 2 split-precision tcgen05 kernel (3 MMAs per K step)")
-    ap.add_argument("--graph", action="store_true",
-                    help="1 GPU only: time CUDA-graph replays of the step instead of eager launches (measured: 1 %% "
-                         "faster at 1 GPU; capturing the NCCL all-gathers of the N > 1 step hung in this image, so it "
-                         "is not offered there)")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="time eager launches of the step instead of CUDA-graph replays (the default at every N: the "
+                         "step has no NCCL call and no host synchronisation in it)")
+    ap.add_argument("--no-spotcheck", action="store_true", help="skip the oracle parity spot check of 4 queries")
+    ap.add_argument("--no-kmeans", action="store_true",
+                    help="skip the kmeans_c5 sub-record (BASELINE.json configs[4] build seconds) of the default run")
+    ap.add_argument("--km-cpu-rows", type=int, default=50_000, help="rows of the CPU assign sample (kmeans cpu_baseline)")
     ap.add_argument("--trace", type=int, default=0, help="diagnostic: profile this many extra steps with torch.profiler "
                     "(CUPTI) on rank 0 after the timed region and write the kernel timeline to gpurun_out/")
     ap.add_argument("--mode", type=int, default=0, help="candidate pass: 0 tcgen05 split-TF32 (default), 1 exact "
@@ -202,7 +205,7 @@ def config_dict(args, n_gpus):
             "sharding": ("1 GPU" if n_gpus == 1 else
                          (f"inverted lists balanced over {n_gpus} GPUs (rows exchanged once after k-means)"
                           if args.shard_by == "lists" else f"rows/{n_gpus} per GPU (1/{n_gpus} of every list)") +
-                         ", probe split over ranks, all-gather + merge of per-GPU top-k"),
+                         ", probe split over ranks, probe lists + per-GPU top-k exchanged over NVLink peer memory"),
             "kmeans_iters": args.kmeans_iters, "synthetic_natural_clusters": args.n_centers,
             "l2": "per-step scan (>= 3.8 GB per GPU) is far larger than the 126 MB L2; no flush needed"}
 
@@ -222,13 +225,11 @@ def main_reference(args):
     print(json.dumps(line))
 
 
-def main_ours(args):
+def setup_ranks():
+    """torch.distributed is plumbing here: it carries the NCCL unique id of the library's own communicator (vers_comm,
+    csrc/comm.cu) and the object gathers of the parity spot check.  Every collective of the data path is the library's."""
     import torch
     import torch.distributed as dist
-
-    import vers_b200 as vb
-    from vers_b200 import _abi
-    from vers_b200.sharded import ShardedIVFFlat, shard_bounds
 
     rank = int(os.environ.get("RANK", "0"))
     ws = int(os.environ.get("WORLD_SIZE", "1"))
@@ -237,22 +238,82 @@ def main_ours(args):
     if ws > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    return rank, ws, local_rank
+
+
+def parity_spotcheck(args, index, ids_dev, d_dev, rank, ws):
+    """Outside the timed region, at every N: 4 queries of the timed batch are searched by the CPU oracle
+    (ivfflat.rs:153-198 with the nprobe extension) over the rows of the lists it probes — rows REGENERATED from the
+    synthetic-data specification, list membership taken from the ranks that own the lists and itself re-checked by
+    re-assigning a sample of those rows on the CPU — and must give the ids and distance bits of the timed path."""
+    import torch.distributed as dist
+
+    import oracle as vo
+
+    C, dim, k = args.nlist, args.dim, args.k
+    npb = min(args.nprobe, C)
+    qsel = sorted({0, args.nq // 3, (2 * args.nq) // 3, args.nq - 1})
+    q = vo.synth(SEED_QUERY, args.nq, dim, kind=1, n_centers=args.n_centers, center_seed=SEED_CENTERS)[qsel]
+    cents = index.ivf.centroids  # replicated on every rank
+    probed = []
+    for i in range(len(qsel)):
+        dc = np.array([vo.l2sq(q[i], cents[c]) for c in range(C)], np.float32)
+        probed.append(np.lexsort((np.arange(C), dc))[:npb])  # stable sort by distance (ivfflat.rs:155-161)
+    need = sorted(set(int(c) for p in probed for c in p))
+    sizes = index.ivf.list_sizes
+    mine = {c: index.ivf.get_list(c) for c in need if sizes[c] > 0}
+    parts = [mine]
+    if ws > 1:
+        parts = [None] * ws
+        dist.all_gather_object(parts, mine)
+    if rank != 0:
+        return None
+    lists = {c: np.sort(np.concatenate([p[c] for p in parts if c in p] or [np.empty(0, np.uint64)])) for c in need}
+    ok_ids = ok_bits = True
+    for i, qi in enumerate(qsel):
+        sub_ids = np.concatenate([lists[int(c)] for c in probed[i]])
+        sub_assign = np.concatenate([np.full(lists[int(c)].shape[0], int(c), np.uint64) for c in probed[i]])
+        order = np.argsort(sub_ids, kind="stable")
+        sub_ids, sub_assign = sub_ids[order], sub_assign[order]
+        rows = vo.synth_rows(SEED_DATA, sub_ids, dim, kind=1, n_centers=args.n_centers, center_seed=SEED_CENTERS)
+        off, lr = vo.ivf_lists(sub_assign, C)
+        oi, od, _ = vo.ivf_search(rows, cents, off, lr, q[i:i + 1], k, nprobe=npb)
+        got_ids = sub_ids[oi[0].astype(np.int64)]
+        ok_ids = ok_ids and bool(np.array_equal(got_ids, ids_dev[qi]))
+        ok_bits = ok_bits and bool(np.array_equal(od[0].view(np.uint32), d_dev[qi].view(np.uint32)))
+    rng = np.random.default_rng(11)
+    pool_ids = np.concatenate([lists[c] for c in need])
+    pool_lists = np.concatenate([np.full(lists[c].shape[0], c, np.uint64) for c in need])
+    pick = rng.choice(pool_ids.shape[0], min(256, pool_ids.shape[0]), replace=False)
+    prow = vo.synth_rows(SEED_DATA, pool_ids[pick], dim, kind=1, n_centers=args.n_centers, center_seed=SEED_CENTERS)
+    ok_assign = bool(np.array_equal(vo.assign(prow, cents), pool_lists[pick]))
+    return {"queries": len(qsel), "query_rows": [int(x) for x in qsel], "ids_equal_oracle": ok_ids,
+            "distance_bits_equal_oracle": ok_bits, "membership_rows_reassigned_by_oracle": int(pick.shape[0]),
+            "membership_equal_oracle": ok_assign,
+            "how": "oracle search over the probed lists' rows regenerated from include/vers_synth.h; list membership "
+                   "from the owning ranks, re-checked by vo.assign on a sample"}
+
+
+def main_ours(args):
+    import ctypes as C
+
+    import torch
+
+    import vers_b200 as vb
+    from vers_b200 import _abi
+    from vers_b200.sharded import Comm, ShardedIVFFlat, device_view, shard_bounds
+
+    rank, ws, local_rank = setup_ranks()
     dev = torch.device("cuda", local_rank)
-
-    def barrier():
-        if ws > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if ws == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     ctx = vb.Context(local_rank)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    comm = Comm(ctx)  # NCCL communicator + peer-memory exchange buffers of the library (connections made here)
+
+    def barrier():
+        comm.barrier()
+        torch.cuda.synchronize()
+
+    max_over_ranks = comm.max_over_ranks
 
     # ---- data + index build (not in the QPS timed region; build seconds reported separately)
     row0, n_local = shard_bounds(args.rows, rank, ws)
@@ -261,29 +322,26 @@ def main_ours(args):
     init = vb.synth_init_rows(SEED_INIT, 1, args.nlist, args.rows)[0]
     barrier()
     t0 = time.perf_counter()
-    index = ShardedIVFFlat.build(ds, args.nlist, args.kmeans_iters, init, reduce=args.reduce, shard_by=args.shard_by)
+    index = ShardedIVFFlat.build(comm, ds, args.nlist, args.kmeans_iters, init, reduce=args.reduce,
+                                 shard_by=args.shard_by)
     barrier()
     build_s = max_over_ranks(time.perf_counter() - t0)
+    exchange_s = max_over_ranks(comm.last_exchange_s)
 
     index.ivf.set_mode(args.mode)
     qds = vb.Dataset.synth(ctx, SEED_QUERY, args.nq, args.dim, kind=1, n_centers=args.n_centers,
                            center_seed=SEED_CENTERS, row0=0, normalize=True)
-    from vers_b200.sharded import device_view
-
     d_q = device_view(qds.device_ptr, (args.nq, qds.ld))
     h_q = torch.empty((args.nq, qds.ld), dtype=torch.float32).pin_memory()
     h_q.copy_(d_q)
     h_ids = torch.empty((args.nq, args.k), dtype=torch.int64).pin_memory()
     h_d = torch.empty((args.nq, args.k), dtype=torch.float32).pin_memory()
     h_c = torch.empty((args.nq,), dtype=torch.int32).pin_memory()
-    d_q_stage = torch.empty_like(d_q)
 
-    # ---- recall@10 against the exhaustive ground truth (flat scan of every shard + the same merge)
+    # ---- recall@10 against the exhaustive ground truth (flat scan of every row shard + merge by (distance, id))
     nrec = min(args.recall_queries, args.nq)
     recall = None
     if nrec > 0:
-        import ctypes as C
-
         g_ids = torch.empty((nrec, args.k), dtype=torch.int64, device=dev)
         g_d = torch.empty((nrec, args.k), dtype=torch.float32, device=dev)
         g_c = torch.empty((nrec,), dtype=torch.int32, device=dev)
@@ -291,10 +349,14 @@ def main_ours(args):
                                                  C.c_void_p(g_ids.data_ptr()), C.c_void_p(g_d.data_ptr()),
                                                  C.c_void_p(g_c.data_ptr())))
         if ws > 1:
+            import torch.distributed as dist
+
             a_ids = torch.empty((ws, nrec, args.k), dtype=torch.int64, device=dev)
             a_d = torch.empty((ws, nrec, args.k), dtype=torch.float32, device=dev)
+            torch.cuda.synchronize()
             dist.all_gather_into_tensor(a_ids, g_ids)
             dist.all_gather_into_tensor(a_d, g_d)
+            torch.cuda.synchronize()
             _abi.check(vb.lib().vers_topk_merge_dev(ctx.h, C.c_void_p(a_ids.data_ptr()), C.c_void_p(a_d.data_ptr()),
                                                     ws, 0, 0, nrec, args.k, C.c_void_p(g_ids.data_ptr()),
                                                     C.c_void_p(g_d.data_ptr()), C.c_void_p(g_c.data_ptr())))
@@ -303,26 +365,26 @@ def main_ours(args):
         gt = g_ids.cpu().numpy()
         got = ids.cpu().numpy()
         recall = float(np.mean([len(set(got[i]) & set(gt[i])) / args.k for i in range(nrec)]))
+    ds.close()  # the row-major rows are not needed any more (the index holds its list-major copy)
 
-    # ---- device-timed QPS (queries resident in HBM): K eager steps.  With --graph (1 GPU) the step is captured once
-    #      into a CUDA graph and the K timed steps are K replays.  The dominant kernel's duration for the roofline comes
-    #      from K eager steps with per-family CUDA events right after.
+    # ---- device-timed QPS (queries resident in HBM).  The step (probe -> peer all-gather of the probe lists -> list
+    #      scan -> rerank -> peer gather+merge) has no NCCL call and no host synchronisation in it, so at any N it is
+    #      captured once into a CUDA graph and the K timed steps are K replays (--no-graph: eager launches).  The
+    #      dominant kernel's duration for the roofline comes from K eager steps with per-family CUDA events after.
     def eager_step():
         return index.search_dev(d_q, args.k, args.nprobe)
 
     graph = None
-    if args.graph and ws == 1:
+    if not args.no_graph:
         try:
             graph, _ = index.capture_search(d_q, args.k, args.nprobe)
         except Exception as e:  # noqa: BLE001
-            if rank == 0:
-                print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches",
-                      file=sys.stderr)
+            print(f"[bench] rank {rank}: CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches",
+                  file=sys.stderr)
             graph = None
     if ws > 1:  # every rank must take the same path
-        flag = torch.tensor([1 if graph is not None else 0], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
+        ok = -max_over_ranks(-(1.0 if graph is not None else 0.0))
+        if ok < 0.5:
             graph = None
     step = graph.replay if graph is not None else eager_step
 
@@ -364,12 +426,12 @@ def main_ours(args):
     stats = index.ivf.last_search_stats()
     per_rank_cand = None
     if ws > 1:
-        t = torch.tensor([fam["cand_scan"][0] / max(fam["cand_scan"][1], 1), float(stats["distinct_list_rows"])],
-                         dtype=torch.float64, device=dev)
-        allt = torch.empty((ws, 2), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(allt, t)
-        per_rank_cand = {"cand_scan_ms": [round(x, 4) for x in allt[:, 0].cpu().tolist()],
-                         "distinct_list_rows": [int(x) for x in allt[:, 1].cpu().tolist()]}
+        import torch.distributed as dist
+
+        mine = (fam["cand_scan"][0] / max(fam["cand_scan"][1], 1), int(stats["distinct_list_rows"]))
+        allp = [None] * ws
+        dist.all_gather_object(allp, mine)
+        per_rank_cand = {"cand_scan_ms": [round(x[0], 4) for x in allp], "distinct_list_rows": [x[1] for x in allp]}
 
     if args.trace > 0:
         from torch.profiler import ProfilerActivity, profile
@@ -392,19 +454,11 @@ def main_ours(args):
                     prev_end = en if prev_end is None else max(prev_end, en)
         barrier()
 
-    # ---- e2e: host (pinned) queries in, host ids+distances out, every step
+    # ---- e2e: the reference-facing C-ABI call with HOST (pinned) buffers at every N: vers_sharded_ivf_search copies the
+    #      queries in, runs the sharded step, copies ids + distances + counts out and synchronises
     def e2e_step():
-        if ws == 1:
-            # the reference-facing C-ABI call with host buffers
-            _abi.check(vb.lib().vers_ivf_search(index.ivf.h, h_q.data_ptr(), args.nq, qds.ld, args.k, args.nprobe,
-                                                h_ids.data_ptr(), h_d.data_ptr(), h_c.data_ptr()))
-        else:
-            d_q_stage.copy_(h_q, non_blocking=True)
-            ids, d, c = index.search_dev(d_q_stage, args.k, args.nprobe)
-            h_ids.copy_(ids, non_blocking=True)
-            h_d.copy_(d, non_blocking=True)
-            h_c.copy_(c, non_blocking=True)
-            torch.cuda.synchronize()
+        _abi.check(vb.lib().vers_sharded_ivf_search(comm.h, index.ivf.h, h_q.data_ptr(), args.nq, qds.ld, args.k,
+                                                    args.nprobe, h_ids.data_ptr(), h_d.data_ptr(), h_c.data_ptr()))
 
     for _ in range(args.warmup):
         e2e_step()
@@ -416,9 +470,16 @@ def main_ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_qps = args.nq * args.steps / e2e_s
     # the e2e result must equal the device-resident result
-    ids_dev, _, _ = index.search_dev(d_q, args.k, args.nprobe)
+    ids_dev, d_dev, _ = index.search_dev(d_q, args.k, args.nprobe)
     torch.cuda.synchronize()
     e2e_matches = bool(torch.equal(ids_dev.cpu(), h_ids))
+
+    spot = None
+    if not args.no_spotcheck:
+        try:
+            spot = parity_spotcheck(args, index, ids_dev.cpu().numpy().view(np.uint64), d_dev.cpu().numpy(), rank, ws)
+        except Exception as e:  # noqa: BLE001
+            spot = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- roofline of the dominant kernel (list scan)
     peak, peak_src = measured_peaks()
@@ -454,20 +515,38 @@ def main_ours(args):
         cqps, _, info = cpu_arm(args, 1, 1, args.cpu_queries)
         cpu = {"value": cqps, "unit": "queries/s", **info}
 
+    # ---- the metric's second half, in the same record: k-means build seconds (BASELINE.json configs[4])
+    km_rec = None
+    if not args.no_kmeans:
+        index.ivf.close()
+        qds.close()
+        torch.cuda.empty_cache()
+        try:
+            km_rec = kmeans_record(args, comm, ctx, rank, ws, local_rank, iters=20, warm=1,
+                                   cpu=(ws == 1 and not args.no_cpu_baseline), sample_clocks=False)
+        except Exception as e:  # noqa: BLE001
+            km_rec = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         line = {"metric": "IVFFlat QPS@recall10 (10Mx768, batch 1k)", "value": qps, "unit": "queries/s", "n_gpus": ws,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config_dict(args, ws), "recall_at_10": recall,
-                "build_s": build_s, "kmeans_reduce": args.reduce,
+                "build_s": build_s, "build_exchange_s": exchange_s if ws > 1 else None, "kmeans_reduce": args.reduce,
                 "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": args.nq * qds.ld * 4,
-                        "d2h_bytes_per_step": args.nq * args.k * 12 + args.nq * 4, "ids_match_device_path": e2e_matches},
-                "exchange": ("peer-memory gather+merge kernel" if getattr(index, "_want_peer", False) else
-                             ("nccl all-gather + merge kernel" if ws > 1 else None)),
+                        "d2h_bytes_per_step": args.nq * args.k * 12 + args.nq * 4, "ids_match_device_path": e2e_matches,
+                        "call": "vers_sharded_ivf_search (host buffers in and out)"},
+                "exchange": ("probe lists: peer-memory all-gather (remote stores + flags); top-k: ONE fused peer "
+                             "gather+merge kernel; no NCCL call inside a step" if ws > 1 else None),
+                "parity_spotcheck": spot,
                 "gpu_launches": launches, "launch_mode": "cuda_graph_replay" if graph is not None else "eager",
-                "eager_ms_per_step": eager_ms / args.steps, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+                "eager_ms_per_step": eager_ms / args.steps, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "kmeans_c5": km_rec}
         print(json.dumps(line))
+    comm.close()
     if ws > 1:
+        import torch.distributed as dist
+
         dist.destroy_process_group()
 
 
@@ -478,7 +557,7 @@ def kmeans_cpu_sample(args, passes):
         import oracle as vo
 
         use_all_host_threads(vo)
-        n_s = max(1000, min(args.km_rows, 100_000))
+        n_s = max(1000, min(args.km_rows, args.km_cpu_rows))
         rows = vo.synth(SEED_DATA, n_s, args.km_dim, kind=1, n_centers=args.n_centers, center_seed=SEED_CENTERS,
                         normalize=False)
         cents = vo.synth(SEED_INIT, args.km_clusters, args.km_dim, kind=1, n_centers=args.n_centers,
@@ -494,111 +573,116 @@ def kmeans_cpu_sample(args, passes):
         return {"value": None, "unit": "s", "cores": 0, "kind": "port", "sample": f"failed: {type(e).__name__}: {e}"}
 
 
-def main_kmeans(args):
-    """k-means build seconds (BASELINE.json configs[4]): --steps Lloyd iterations (assign + ordered update + bitwise
-    convergence test) + the final assign of build_kmeans (ivfflat.rs:73-100), rows sharded over the GPUs."""
+def kmeans_record(args, comm, ctx, rank, ws, local_rank, iters, warm, cpu, sample_clocks=True):
+    """k-means build seconds (BASELINE.json configs[4]): `iters` Lloyd iterations (assign + ordered update + bitwise
+    convergence test) + the final assign of build_kmeans (ivfflat.rs:73-100), rows sharded over the GPUs, through
+    vers_sharded_kmeans_fit.  Returns the record (rank 0) / None."""
     import torch
-    import torch.distributed as dist
 
     import vers_b200 as vb
     from vers_b200 import _abi
     from vers_b200.sharded import kmeans_fit_sharded, shard_bounds
 
-    rank = int(os.environ.get("RANK", "0"))
-    ws = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if ws > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-    iters = args.steps if args.steps != 10 else 20
-
     def barrier():
-        if ws > 1:
-            dist.barrier()
+        comm.barrier()
         torch.cuda.synchronize()
 
-    ctx = vb.Context(local_rank)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     row0, n_local = shard_bounds(args.km_rows, rank, ws)
     ds = vb.Dataset.synth(ctx, SEED_DATA, n_local, args.km_dim, kind=1, n_centers=args.n_centers,
                           center_seed=SEED_CENTERS, row0=row0, normalize=False)
     init = vb.synth_init_rows(SEED_INIT, 1, args.km_clusters, args.km_rows)[0]
     km = vb.KMeans(ds, args.km_clusters)
     km.set_mode(args.km_mode)
-    kmeans_fit_sharded(km, init, min(args.warmup, 3), reduce=args.reduce)  # warm-up iterations (allocations, clocks)
+    kmeans_fit_sharded(comm, km, init, warm, reduce=args.reduce)  # warm-up iterations (allocations, clocks)
     barrier()
     ctx.enable_timing(True)
+    launches0 = ctx.launch_count
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and sample_clocks:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
     t0 = time.perf_counter()
-    ran = kmeans_fit_sharded(km, init, iters, reduce=args.reduce)
+    ran = kmeans_fit_sharded(comm, km, init, iters, reduce=args.reduce)
     ev1.record()
     barrier()
-    wall = time.perf_counter() - t0
-    dev_s = ev0.elapsed_time(ev1) * 1e-3
-    if ws > 1:
-        t = torch.tensor([dev_s, wall], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_s, wall = float(t[0].item()), float(t[1].item())
-    clocks = sampler.stop() if rank == 0 else None
+    wall = comm.max_over_ranks(time.perf_counter() - t0)
+    dev_s = comm.max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
+    clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
     a_ms, a_n = ctx.kernel_ms(_abi.KF_ASSIGN)
     r_ms, r_n = ctx.kernel_ms(_abi.KF_LIST_SCAN)  # the exact-order redo of uncertified rows is timed in this family
     s_ms, s_n = ctx.kernel_ms(_abi.KF_SUMS)
     ctx.enable_timing(False)
+    launches = ctx.launch_count - launches0
     flagged = km.last_uncertified_rows
-    cpu = None
-    if rank == 0 and ws == 1 and not args.no_cpu_baseline:
-        cpu = kmeans_cpu_sample(args, ran + 1)
+    km.close()
+    ds.close()
+    if rank != 0:
+        return None
+    cpu_rec = kmeans_cpu_sample(args, ran + 1) if cpu else None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    # Roofline of the assign kernel on ALGORITHMIC flops (the GEMM form 2·N·C·D of one pass, SURVEY.md §8d), against
+    # half of the measured cuBLAS bf16 rate (tf32 runs at half the bf16 rate; MEASURED_PEAKS.json has no tf32
+    # figure): the sustained number, because the kernel is timed inside a seconds-long build under the power cap.
+    bf16_sust = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    tf32_peak = bf16_sust / 2
+    peak_src = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained / 2)" if "bf16_tflops_sustained" in peaks else
+                "fallback (B200_PROFILING.md: 1.4 PFLOP/s sustained bf16, / 2)")
+    passes = ran + 1
+    flop_pass = 2.0 * args.km_rows * args.km_clusters * args.km_dim  # the GEMM form of one assign pass
+    mma_per_kstep = {0: 1 if args.km_dim <= 128 else 3, 1: 0, 2: 3}[args.km_mode]
+    avg_assign_ms = a_ms / max(a_n, 1)
+    achieved = flop_pass / ws / (avg_assign_ms * 1e-3) / 1e12 if a_n else None
+    kname = {0: ("tc_assign1_kernel (tcgen05 kind::tf32, 1 MMA per K step, rows resident in TMEM, top-4 + exact "
+                 "rerank + certificate in the epilogue)" if args.km_dim <= 128 else
+                 "tc_assign_kernel (tcgen05 kind::tf32, split hi/lo: 3 MMAs per K step)"),
+             1: "assign_kernel (exact order, fp32 pipe)",
+             2: "tc_assign_kernel (tcgen05 kind::tf32, split hi/lo: 3 MMAs per K step)"}[args.km_mode]
+    return {"metric": "k-means build seconds (50Mx128, 16384 centroids, 20 iterations)", "value": dev_s, "unit": "s",
+            "n_gpus": ws, "steps": ran, "warmup": warm, "ms_per_step": dev_s / max(ran, 1) * 1e3,
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"IVFFlatIndex::build_kmeans: {args.km_rows}x{args.km_dim} fp32 synthetic clustered "
+                                   f"(unnormalized), {args.km_clusters} centroids, {ran} Lloyd iterations + final "
+                                   f"assign (BASELINE.json configs[4])",
+                       "rows": args.km_rows, "dim": args.km_dim, "clusters": args.km_clusters, "iterations": ran,
+                       "reduce": args.reduce, "sharding": f"rows/{ws} per GPU",
+                       "l2": "every assign pass streams the row shard (>= 3 GB) once: far larger than L2"},
+            "wall_s": wall, "assign_passes": passes, "uncertified_rows_last_pass": flagged,
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": tf32_peak,
+                         "unit": "TFLOP/s", "frac": (achieved / tf32_peak) if achieved else None, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_flop_per_launch": flop_pass / ws,
+                         "mma_per_k_step": mma_per_kstep, "avg_launch_ms": avg_assign_ms,
+                         "kernel_share_of_step": a_ms * 1e-3 / dev_s if dev_s else None,
+                         "sums_ms_per_iteration": s_ms / max(s_n, 1),
+                         "exact_redo_ms_per_pass": (r_ms / r_n) if r_n else 0.0},
+            "cpu_baseline": cpu_rec}
+
+
+def main_kmeans(args):
+    import torch
+
+    import vers_b200 as vb
+    from vers_b200.sharded import Comm
+
+    rank, ws, local_rank = setup_ranks()
+    ctx = vb.Context(local_rank)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    comm = Comm(ctx)
+    iters = args.steps if args.steps != 10 else 20
+    rec = kmeans_record(args, comm, ctx, rank, ws, local_rank, iters, min(args.warmup, 3),
+                        cpu=(ws == 1 and not args.no_cpu_baseline))
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        # Roofline of the assign kernel on ALGORITHMIC flops (the GEMM form 2·N·C·D of one pass, SURVEY.md §8d), against
-        # half of the measured cuBLAS bf16 rate (tf32 runs at half the bf16 rate; MEASURED_PEAKS.json has no tf32
-        # figure): the sustained number, because the kernel is timed inside a seconds-long build under the power cap.
-        bf16_sust = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        tf32_peak = bf16_sust / 2
-        peak_src = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained / 2)" if "bf16_tflops_sustained" in peaks else
-                    "fallback (B200_PROFILING.md: 1.4 PFLOP/s sustained bf16, / 2)")
-        passes = ran + 1
-        flop_pass = 2.0 * args.km_rows * args.km_clusters * args.km_dim  # the GEMM form of one assign pass
-        mma_per_kstep = {0: 1 if args.km_dim <= 128 else 3, 1: 0, 2: 3}[args.km_mode]
-        avg_assign_ms = a_ms / max(a_n, 1)
-        achieved = flop_pass / ws / (avg_assign_ms * 1e-3) / 1e12 if a_n else None
-        kname = {0: ("tc_assign1_kernel (tcgen05 kind::tf32, 1 MMA per K step, rows resident in TMEM, top-4 + exact "
-                     "rerank + certificate in the epilogue)" if args.km_dim <= 128 else
-                     "tc_assign_kernel (tcgen05 kind::tf32, split hi/lo: 3 MMAs per K step)"),
-                 1: "assign_kernel (exact order, fp32 pipe)",
-                 2: "tc_assign_kernel (tcgen05 kind::tf32, split hi/lo: 3 MMAs per K step)"}[args.km_mode]
-        line = {"metric": "k-means build seconds (50Mx128, 16384 centroids, 20 iterations)", "value": dev_s, "unit": "s",
-                "n_gpus": ws, "steps": ran, "warmup": min(args.warmup, 3), "ms_per_step": dev_s / max(ran, 1) * 1e3,
-                "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"IVFFlatIndex::build_kmeans: {args.km_rows}x{args.km_dim} fp32 synthetic clustered "
-                                       f"(unnormalized), {args.km_clusters} centroids, {ran} Lloyd iterations + final "
-                                       f"assign (BASELINE.json configs[4])",
-                           "rows": args.km_rows, "dim": args.km_dim, "clusters": args.km_clusters, "iterations": ran,
-                           "reduce": args.reduce, "sharding": f"rows/{ws} per GPU",
-                           "l2": "every assign pass streams the row shard (>= 3 GB) once: far larger than L2"},
-                "wall_s": wall, "assign_passes": passes, "uncertified_rows_last_pass": flagged,
-                "gpu_launches": ctx.launch_count, "clocks": clocks,
-                "roofline": {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": tf32_peak,
-                             "unit": "TFLOP/s", "frac": (achieved / tf32_peak) if achieved else None, "traffic": None,
-                             "peak_source": peak_src, "algorithmic_flop_per_launch": flop_pass / ws,
-                             "mma_per_k_step": mma_per_kstep, "avg_launch_ms": avg_assign_ms,
-                             "kernel_share_of_step": a_ms * 1e-3 / dev_s if dev_s else None,
-                             "sums_ms_per_iteration": s_ms / max(s_n, 1),
-                             "exact_redo_ms_per_pass": (r_ms / r_n) if r_n else 0.0},
-                "cpu_baseline": cpu}
-        print(json.dumps(line))
+        print(json.dumps(rec))
+    comm.close()
     if ws > 1:
+        import torch.distributed as dist
+
         dist.destroy_process_group()
 
 
@@ -742,16 +826,55 @@ def main_lsh(args):
     recall = float(np.mean([len(set(ids[i][: cnt[i]]) & set(gi[i])) / args.k for i in range(nrec)]))
     qps = args.nq * args.steps / dt
     info = idx.info()
+    trees = 16
+    # algorithmic bytes per query: trees x (depth x 4(D+1) plane bytes + leaf rows x 4D) + candidates x 4D
+    # for the rerank.  depth and leaf size are the forest's own averages (a tree of L leaves over n rows).
+    leaves = (info["num_nodes"] / trees + 1) / 2
+    depth = float(np.log2(max(leaves, 1.0)))
+    leaf_rows = n / max(leaves, 1.0)
+    cand = min(trees * args.k, n)
+    bytes_q = trees * (depth * 4 * (dim + 1) + leaf_rows * 4 * dim) + cand * 4 * dim
+    peak, peak_src = measured_peaks()
+    achieved = bytes_q * args.nq / (dt / args.steps) / 1e9
+    cpu = None
+    if not args.no_cpu_baseline:
+        import oracle as vo
+
+        use_all_host_threads(vo)
+        n_s = n // 8
+        t0 = time.perf_counter()
+        o = vo.LSH(rows[:n_s], None, trees, 100, 4)
+        cpu_build = time.perf_counter() - t0
+        o.search(q[:64], args.k)
+        t0 = time.perf_counter()
+        oi, od, oc = o.search(q, args.k)
+        cdt = time.perf_counter() - t0
+        cpu = {"value": args.nq / cdt, "unit": "queries/s", "cores": vo.num_threads(), "kind": "port",
+               "cpu_build_s": round(cpu_build, 2),
+               "sample": f"{args.nq} queries on a forest over rows/8 ({n_s}x{dim}, {trees} trees, max_size 100: 3 levels "
+                         f"shallower than the full forest, same leaf size => ~15 % less work per query than the full "
+                         f"config); OpenMP over queries (the reference parallelises over trees, lsh.rs:268)"}
     line = {"metric": "hyperplane-forest (LSH) search QPS (1Mx300, 16 trees, batch 1k)", "value": qps, "unit": "queries/s",
             "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"ANNIndex build_index + search_approximate batch: {n}x{dim}, 16 trees, max_size 100, "
                                    f"top_k {args.k}, {args.nq}-query batch (BASELINE.json configs[2])",
-                       "rows": n, "dim": dim, "trees": 16, "max_size": 100, "nodes": info["num_nodes"]},
+                       "rows": n, "dim": dim, "trees": trees, "max_size": 100, "nodes": info["num_nodes"],
+                       "l2": "per step the batch touches ~1.7 GB of planes, leaf rows and candidates scattered over the "
+                             "1.2 GB table + 0.6 GB of planes: larger than L2"},
             "build_s": build_s, "recall_at_10": recall,
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": args.nq * dim * 4,
-                    "d2h_bytes_per_step": args.nq * args.k * 12 + args.nq * 4},
-            "gpu_launches": launches, "clocks": clocks, "roofline": None, "cpu_baseline": None}
+                    "d2h_bytes_per_step": args.nq * args.k * 12 + args.nq * 4,
+                    "call": "vers_lsh_search (host buffers in and out): value == e2e for this workload"},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "lsh search step (batched traversal + leaf scan + exact rerank)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_q * args.nq,
+                         "avg_tree_depth": depth, "avg_leaf_rows": leaf_rows,
+                         "note": "whole step incl. H2D/D2H and the host synchronise; the accesses are data-dependent "
+                                 "gathers (one plane per level per tree, one leaf per tree), so the bound is latency "
+                                 "and sector efficiency rather than streaming bandwidth"},
+            "cpu_baseline": cpu}
     print(json.dumps(line))
 
 

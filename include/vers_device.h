@@ -118,7 +118,9 @@ int32_t vers_kmeans_assign_device_ptr(vers_kmeans* km, void** ptr);
 int32_t vers_kmeans_assign_step(vers_kmeans* km);
 /* 0 (default): tensor-core candidate argmin (TMA + tcgen05 kind::tf32, M=128 x N=256 tiles) + a rounding-error
  * certificate on the gap between the two smallest values, uncertified rows re-assigned in exact order;
- * 1: exact order everywhere.  Both give the reference's assignments bit for bit. */
+ * 1: exact order everywhere.  Both give the reference's assignments bit for bit.  For rows of <= 128 floats mode 0
+ * runs the TF32-first kernel (one MMA per K step, rows resident in tensor memory, the four best candidates re-ranked
+ * in exact order inside the kernel, certificate against the fifth key); mode 2 forces the split-precision kernel. */
 int32_t vers_kmeans_set_mode(vers_kmeans* km, int32_t mode);
 /* rows of the most recent assign step whose candidate argmin was not certified (redone in exact order) */
 int32_t vers_kmeans_last_assign_stats(vers_kmeans* km, uint64_t* uncertified_rows);
@@ -217,6 +219,53 @@ int32_t vers_peer_connect(vers_peer* peer, const uint8_t* all_handles /* [world]
 int32_t vers_peer_gather_merge_dev(vers_peer* peer, const uint64_t* d_local_ids, const float* d_local_dists,
                                    uint32_t nq, uint32_t top_k, uint64_t* d_ids, float* d_dists, uint32_t* d_counts);
 int32_t vers_peer_free(vers_peer* peer);
+
+/* ---- multi-GPU: one process per GPU of an NVLink/NVSwitch box ---------------------------------
+ * The reference parallelises with rayon inside one process (ivfflat.rs:31, lsh.rs:146,268); this layer shards the
+ * same work over GPUs.  vers_comm = this process's membership in a group of `world` ranks.  Bootstrap is NCCL's:
+ * rank 0 calls vers_comm_unique_id, the HOST ships those 128 bytes to the other processes (any transport it has),
+ * every rank calls vers_comm_create (collective).  libnccl.so.2 is resolved at that point (dlopen), single-GPU users
+ * never need it.  world == 1 is allowed (unique_id may be NULL) and makes every vers_sharded_* call the plain
+ * single-GPU path.  All collective calls below must be made by every rank, in the same order.
+ * vers_comm_create also establishes every connection the build and search will use (NCCL connects lazily on first
+ * use, which costs seconds at 8 ranks) and maps the peers' exchange buffers (CUDA IPC). */
+#define VERS_REDUCE_CHAINED 0   /* ordered: rank r continues rank r-1's running sums — bit-identical to the reference */
+#define VERS_REDUCE_ALLREDUCE 1 /* ncclAllReduce of per-shard sums: fastest, association differs from the reference's */
+typedef struct vers_comm vers_comm;
+int32_t vers_comm_unique_id(uint8_t id_out[128]);
+int32_t vers_comm_create(vers_ctx* ctx, uint32_t world, uint32_t rank, const uint8_t unique_id[128], vers_comm** out);
+int32_t vers_comm_destroy(vers_comm* comm);
+int32_t vers_comm_info(const vers_comm* comm, uint32_t* world, uint32_t* rank, double* last_exchange_seconds);
+/* rendezvous of all ranks + stream synchronise; max over ranks of a host value (timing: "max over ranks") */
+int32_t vers_comm_barrier(vers_comm* comm);
+int32_t vers_comm_max_f64(vers_comm* comm, double* value_io);
+/* IVFFlatIndex::build_kmeans (ivfflat.rs:73-100) over contiguous row shards (km is over this rank's vers_dataset,
+ * whose id_base is its first GLOBAL row).  init_rows_global: [num_clusters] GLOBAL row numbers (initialize_centroids,
+ * ivfflat.rs:18-27, draws injected); the owner of a row contributes it.  assign is local; update_centroids
+ * (ivfflat.rs:47-71) is reduced per `reduce`; the bitwise convergence test sees identical sums on every rank. */
+int32_t vers_sharded_kmeans_fit(vers_comm* comm, vers_kmeans* km, const uint64_t* init_rows_global,
+                                uint32_t max_iterations, int32_t reduce, uint32_t* iterations_run);
+/* calculate_kmeans_cost (ivfflat.rs:138-149) folded in GLOBAL row order (rank r continues rank r-1's value) */
+int32_t vers_sharded_kmeans_cost(vers_comm* comm, vers_kmeans* km, float* cost);
+/* The index over the fitted k-means state, sharded BY INVERTED LIST: every row (with its global id and cluster) goes
+ * to the rank that owns its list (largest list first onto the least-loaded rank) in one all-to-all over NVLink; a
+ * rank's lists keep ascending-id order like ids[c] (ivfflat.rs:123-127); lists it does not own are empty there,
+ * the centroid table is whole.  The seconds the all-to-all took are reported by vers_comm_info. */
+int32_t vers_sharded_ivf_build(vers_comm* comm, vers_kmeans* km, vers_ivf** out);
+/* the list -> owner rank table that build uses, from the GLOBAL list sizes (host arithmetic, needs no GPU) */
+int32_t vers_sharded_list_owners(const uint64_t* list_sizes, uint32_t num_clusters, uint32_t world,
+                                 uint32_t* owner_out);
+/* Index::search_approximate (ivfflat.rs:153-198, nprobe >= 1 extension) for a batch over the sharded index: every
+ * rank passes the SAME queries and receives the SAME global result.  Per batch: each rank probes 1/world of the
+ * queries, the probe lists are all-gathered, each rank scans the lists it owns, the per-rank top-k are exchanged and
+ * merged by (distance, id).  Both exchanges are stores into the peers' IPC-mapped buffers plus flags (no NCCL call,
+ * no host synchronisation inside a step: the _dev variant is capturable in a CUDA graph); the second one is fused
+ * with the merge in one kernel. */
+int32_t vers_sharded_ivf_search(vers_comm* comm, vers_ivf* ivf, const float* queries, uint32_t nq,
+                                uint32_t q_stride_floats, uint32_t top_k, uint32_t nprobe, uint64_t* ids, float* dists,
+                                uint32_t* counts);
+int32_t vers_sharded_ivf_search_dev(vers_comm* comm, vers_ivf* ivf, const float* d_queries, uint32_t nq, uint32_t top_k,
+                                    uint32_t nprobe, uint64_t* d_ids, float* d_dists, uint32_t* d_counts);
 
 /* ---- "LSH" random-hyperplane forest (indexes/lsh.rs) -------------------------------------------------------- */
 /* Hyperplane::point_is_above (lsh.rs:27-29) for every row x every plane: bits[r*P + p] = dot(plane_p, row_r) +

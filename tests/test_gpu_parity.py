@@ -533,25 +533,44 @@ def test_no_cpu_fallback_symbols(vb):
     assert "oracle" not in out
 
 
-@pytest.mark.parametrize("peer_exchange", ["0", "1"])
-def test_multi_gpu_sharded_parity_when_two_gpus_present(peer_exchange):
-    """runs tests/mgpu_check.py under torchrun on 2 GPUs (skipped on a 1-GPU box); peer_exchange=1: the per-GPU top-k
-    are exchanged and merged by the peer-memory kernel (csrc/peer.cu) instead of NCCL all-gather + merge"""
+@pytest.mark.parametrize("gpus", [2, 4, 8])
+def test_multi_gpu_sharded_parity(gpus):
+    """runs tests/mgpu_check.py under torchrun on `gpus` GPUs (skipped when the box has fewer): chained k-means,
+    list- and row-sharded search through vers_comm / vers_sharded_* against the single-process oracle"""
     import os
     import subprocess
     import sys
 
     import torch
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, VERS_PEER_GATHER=peer_exchange)
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29517" if peer_exchange == "0" else "29518",
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(gpus),
+                        "--master-addr", "127.0.0.1", "--master-port", str(29517 + gpus),
                         os.path.join(root, "tests", "mgpu_check.py")],
-                       capture_output=True, text=True, timeout=600, env=env)
+                       capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "mgpu_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_comm_world1_is_the_single_gpu_path(vb, vo, ctx):
+    """vers_comm with world == 1 (no NCCL needed): the vers_sharded_* calls are the plain single-GPU calls"""
+    from vers_b200.sharded import Comm, ShardedIVFFlat
+
+    n, dim, C, k = 6000, 128, 24, 10
+    rows = data(vo, n, dim)
+    q = data(vo, 40, dim, seed=2)
+    init = vo.init_rows(3, 1, C, n)[0]
+    comm = Comm(ctx, 0, 1)
+    ds = vb.Dataset.upload(ctx, rows)
+    index = ShardedIVFFlat.build(comm, ds, C, 6, init)
+    cents, assign, _ = vo.kmeans_fit(rows, init, 6)
+    assert np.array_equal(index.ivf.assignments, assign) and np.array_equal(bits(index.ivf.centroids), bits(cents))
+    off, lr = vo.ivf_lists(assign, C)
+    ids, d, cnt = index.search(q, k, 4)
+    oi, od, oc = vo.ivf_search(rows, cents, off, lr, q, k, nprobe=4)
+    assert np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od)) and np.array_equal(cnt, oc)
+    comm.close()
 
 
 # ---------------------------------------------------------------------------------------------- LSH forest

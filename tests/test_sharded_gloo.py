@@ -1,7 +1,10 @@
-"""N>1 host logic on CPU: world_size-2 gloo process group (no GPU).  Covers the rank-chained ordered accumulation
-that keeps multi-GPU k-means bit-identical to the single-process reference order, the exact initial-centroid
-exchange, and the shard arithmetic.  The per-shard arithmetic itself is the oracle's here (tests may use it); on
-the GPU box the same driver code calls the CUDA kernels (tests/test_gpu_parity.py::test_kmeans_chained_shards...)."""
+"""N>1 logic on CPU: world_size-2 gloo process group (no GPU).  The multi-GPU data path lives in csrc/comm.cu (NCCL +
+peer memory); what runs here is (a) a torch/gloo MODEL of its protocols (tests/gloo_model.py: rank-chained ordered
+accumulation that keeps multi-GPU k-means bit-identical to the single-process reference order, the exact
+initial-centroid exchange, the all-to-all of a list-sharded build) with the oracle supplying the per-shard
+arithmetic, (b) the host arithmetic the library exposes without a GPU (vers_sharded_list_owners) against that model,
+(c) the bootstrap of vers_b200.sharded.Comm through a gloo group: the NCCL unique id travels, and without a GPU
+vers_comm_create fails loudly on every rank (no CPU fallback)."""
 import os
 import socket
 
@@ -25,7 +28,8 @@ def _worker(rank, ws, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=ws)
     try:
         import oracle as vo
-        from vers_b200.sharded import chained_accumulate, gather_init_centroids, shard_bounds
+        from gloo_model import chained_accumulate, exchange_rows_by_list, gather_init_centroids
+        from vers_b200.sharded import balanced_list_owners, shard_bounds
 
         n, dim, C = 5003, 24, 13
         rows = vo.synth(1, n, dim, normalize=False)
@@ -60,19 +64,44 @@ def _worker(rank, ws, port, out_dir):
         assert not np.array_equal(ar.view(np.uint32), want.view(np.uint32))
 
         # list-sharded index build: the all-to-all hands every rank whole lists, in ascending id order, balanced
-        from vers_b200.sharded import balanced_list_owners, exchange_rows_by_list
-
         a_local = torch.from_numpy(assign[r0:r0 + nl].astype(np.int64))
-        rr, rid, ras, owner = exchange_rows_by_list(local, a_local, r0, C)
+        rr, rid, ras, owner = exchange_rows_by_list(local, a_local, r0, C, balanced_list_owners)
         owner = owner.numpy()
         sizes = np.bincount(assign.astype(np.int64), minlength=C)
-        assert np.array_equal(owner, balanced_list_owners(sizes, ws))
+        # the library's owner table (C++, vers_sharded_list_owners) == the specification: largest list first onto the
+        # least-loaded rank, ties to the lowest rank / lowest list
+        spec_order = np.lexsort((np.arange(C), -sizes))
+        load, spec = np.zeros(ws, np.int64), np.zeros(C, np.int64)
+        for c in spec_order:
+            r = int(np.argmin(load))
+            spec[c] = r
+            load[r] += sizes[c]
+        assert np.array_equal(owner, spec)
         mine = np.flatnonzero(owner[assign.astype(np.int64)] == rank)  # global ids this rank must end up with
         assert np.array_equal(rid.numpy(), mine), "received ids are not the owned lists' rows in ascending order"
         assert np.array_equal(ras.numpy().astype(np.int64), assign[mine].astype(np.int64))
         assert np.array_equal(rr.numpy().view(np.uint32), rows[mine].view(np.uint32))
         loads = np.array([sizes[owner == r].sum() for r in range(ws)])
         assert loads.max() - loads.min() <= sizes.max(), "largest-first placement keeps the ranks within one list"
+
+        # bootstrap of the real Comm over this gloo group: without a CUDA device it must fail loudly, on every rank
+        import vers_b200 as vb
+        from vers_b200.sharded import Comm
+
+        try:
+            vb.Context(0)
+            had_gpu = True
+        except vb.VersError as e:
+            had_gpu = False
+            assert e.code == vb.ERR_CUDA
+        if not had_gpu:
+            class _NoCtx:  # the context handle is only dereferenced after the CUDA check
+                h = None
+            try:
+                Comm(_NoCtx(), rank, ws, unique_id=bytes(128))
+                raise AssertionError("vers_comm_create must fail without a context")
+            except vb.VersError as e:
+                assert e.code in (vb.ERR_ARG, vb.ERR_CUDA)
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

@@ -14,6 +14,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_PANIC, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 METRIC_L2SQ, METRIC_COSINE = 0, 1
 MAX_TOPK = 128
 SYNTH_UNIFORM, SYNTH_CLUSTERED = 0, 1
+REDUCE_CHAINED, REDUCE_ALLREDUCE = 0, 1
 KF_LIST_SCAN, KF_FLAT_SCAN, KF_ASSIGN, KF_SUMS, KF_LSH_HASH, KF_PROBE, KF_CAND_SCAN, KF_RERANK = range(8)
 
 
@@ -93,6 +94,18 @@ SIGNATURES = {
     "vers_peer_connect": [vp, vp],
     "vers_peer_gather_merge_dev": [vp, vp, vp, u32, u32, vp, vp, vp],
     "vers_peer_free": [vp],
+    "vers_comm_unique_id": [vp],
+    "vers_comm_create": [vp, u32, u32, vp, pvp],
+    "vers_comm_destroy": [vp],
+    "vers_comm_info": [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_double)],
+    "vers_comm_barrier": [vp],
+    "vers_comm_max_f64": [vp, C.POINTER(C.c_double)],
+    "vers_sharded_kmeans_fit": [vp, vp, vp, u32, i32, C.POINTER(u32)],
+    "vers_sharded_kmeans_cost": [vp, vp, C.POINTER(f32)],
+    "vers_sharded_ivf_build": [vp, vp, pvp],
+    "vers_sharded_list_owners": [vp, u32, u32, vp],
+    "vers_sharded_ivf_search": [vp, vp, vp, u32, u32, u32, u32, vp, vp, vp],
+    "vers_sharded_ivf_search_dev": [vp, vp, vp, u32, u32, u32, vp, vp, vp],
     "vers_lsh_hash": [vp, vp, u32, u32, vp, vp],
     "vers_lsh_hash_dev": [vp, vp, u32, vp, vp],
     "vers_lsh_build_index": [vp, vp, u64, u32, u32, vp, u32, u32, u64, pvp],

@@ -502,11 +502,17 @@ static int32_t kmeans_assign_tc(vers_kmeans* km) {
         p.assign = km->d_assign;
         p.flagged = km->d_flagged;
         p.n_flagged = km->d_nflagged;
-        VERS_CUDA(cudaFuncSetAttribute(tc_assign1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES));
+        void (*kern)(CUtensorMap, CUtensorMap, TcAssign1Params) = nullptr;
+        switch ((ds->ld + K1_KC - 1) / K1_KC) {
+            case 1: kern = tc_assign1_kernel<1>; break;
+            case 2: kern = tc_assign1_kernel<2>; break;
+            case 3: kern = tc_assign1_kernel<3>; break;
+            default: kern = tc_assign1_kernel<4>; break;
+        }
+        VERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES));
         FamilyTimer ft(ctx, KF_ASSIGN);
         const uint64_t nrbp = ceil_div(ds->n, 2 * K1_M);
-        tc_assign1_kernel<<<(unsigned)std::min<uint64_t>(nrbp, ctx->sm_count), K1_THREADS, K1_SMEM_BYTES, s>>>(tm_rows, tm_c,
-                                                                                                           p);
+        kern<<<(unsigned)std::min<uint64_t>(nrbp, ctx->sm_count), K1_THREADS, K1_SMEM_BYTES, s>>>(tm_rows, tm_c, p);
         VERS_LAUNCH_CHECK(ctx);
     } else {
         split_tf32_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(km->d_cents, (uint64_t)km->C * (ds->ld >> 2), km->d_cent_hi,

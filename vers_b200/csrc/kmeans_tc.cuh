@@ -348,6 +348,22 @@ __device__ __forceinline__ void k1_insert(float (&k)[5], uint32_t (&id)[4], floa
     id[0] = c0 ? idx : id[0];
 }
 
+// one elected lane of a converged warp (the compiler then emits the tcgen05 / TMA instructions straight, without the
+// per-instruction ELECT ... BRA.U.ANY loop it wraps around them under a divergent `if (lane == 0)`: measured ~50
+// clk per tcgen05.mma of issue overhead, more than the 32 clk an M=128 N=64 K=8 MMA runs)
+__device__ __forceinline__ bool k1_elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+template <int NK>  // K chunks of 32 floats: ld <= 32 NK
 __global__ void __launch_bounds__(K1_THREADS, 1)
     tc_assign1_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_c,
                       TcAssign1Params p) {
@@ -366,7 +382,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
     uint64_t* nbar = tempty + 4;           // [4] norm ring
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(nbar + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t nk = (p.ld + K1_KC - 1) / K1_KC;            // <= 4
+    constexpr uint32_t nk = NK;
     const uint32_t nct = (p.C + K1_N - 1) / K1_N;
     const uint64_t nrbp = (p.n_rows + 2 * K1_M - 1) / (2 * K1_M);
     const uint64_t my_pairs = blockIdx.x < nrbp ? (nrbp - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -399,62 +415,72 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0, chunk = 0;
-            for (uint64_t rbp = blockIdx.x; rbp < nrbp; rbp += gridDim.x) {
-                for (uint32_t rb = 0; rb < 2; ++rb) {
-                    for (uint32_t kc = 0; kc < nk; ++kc, ++chunk) {
-                        const uint32_t slot = chunk & 1, ph = (chunk >> 1) & 1;
-                        tc::mbar_wait(&aempty[slot], ph ^ 1);
+        // TMA producer: the whole warp walks the loops (and waits), one elected lane issues
+        uint32_t stage = 0, phase = 0, chunk = 0;
+        for (uint64_t rbp = blockIdx.x; rbp < nrbp; rbp += gridDim.x) {
+            for (uint32_t rb = 0; rb < 2; ++rb) {
+#pragma unroll
+                for (uint32_t kc = 0; kc < nk; ++kc, ++chunk) {
+                    const uint32_t slot = chunk & 1, ph = (chunk >> 1) & 1;
+                    tc::mbar_wait(&aempty[slot], ph ^ 1);
+                    if (k1_elect_one()) {
                         tc::mbar_arrive_expect_tx(&afull[slot], K1_ASLOT_BYTES);
                         tc::tma_load_2d(smem + K1_OFF_ASLOT + slot * K1_ASLOT_BYTES, &tmap_rows, &afull[slot],
                                         (int32_t)(kc * K1_KC), (int32_t)((rbp * 2 + rb) * K1_M));
                     }
+                    __syncwarp();
                 }
-                for (uint32_t ct = 0; ct < nct; ++ct) {
-                    tc::mbar_wait(&empty[stage], phase ^ 1);
+            }
+            for (uint32_t ct = 0; ct < nct; ++ct) {
+                tc::mbar_wait(&empty[stage], phase ^ 1);
+                if (k1_elect_one()) {
                     tc::mbar_arrive_expect_tx(&full[stage], nk * K1_BOX_BYTES);
                     uint8_t* sb = smem + stage * K1_STAGE_BYTES;
+#pragma unroll
                     for (uint32_t kc = 0; kc < nk; ++kc)
                         tc::tma_load_2d(sb + kc * K1_BOX_BYTES, &tmap_c, &full[stage], (int32_t)(kc * K1_KC),
                                         (int32_t)(ct * K1_N));
-                    if (++stage == K1_STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                }
+                __syncwarp();
+                if (++stage == K1_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = tc::idesc_tf32(K1_M, K1_N);
-            uint32_t stage = 0, phase = 0;
-            uint64_t t = 0;
-            if (total_tiles) {  // the norms of tile 0; tile t+1's are requested when tile t starts (slot (t+1) % 4 was
-                                // last read for tile t-3, which both epilogues finished before releasing tile t-2)
-                tc::mbar_arrive_expect_tx(&nbar[0], K1_N * 4);
-                tc::bulk_load(nrm, p.cent_norm, K1_N * 4, &nbar[0]);
-            }
-            for (uint64_t i = 0; i < my_pairs; ++i) {
-                tc::mbar_wait(aready, (uint32_t)(i & 1));
+        // MMA issuer: converged warp, one elected lane issues.  Per tile: 2 row blocks x NK x 4 MMAs (M=128 N=64 K=8)
+        const uint32_t idesc = tc::idesc_tf32(K1_M, K1_N);
+        uint32_t stage = 0, phase = 0;
+        uint64_t t = 0;
+        if (total_tiles && k1_elect_one()) {
+            // the norms of tile 0; tile t+1's are requested when tile t starts (slot (t+1) % 4 was last read for tile
+            // t-3, which both epilogues finished before releasing tile t-2)
+            tc::mbar_arrive_expect_tx(&nbar[0], K1_N * 4);
+            tc::bulk_load(nrm, p.cent_norm, K1_N * 4, &nbar[0]);
+        }
+        __syncwarp();
+        for (uint64_t i = 0; i < my_pairs; ++i) {
+            tc::mbar_wait(aready, (uint32_t)(i & 1));
+            tc::fence_after_thread_sync();
+            for (uint32_t ct = 0; ct < nct; ++ct, ++t) {
+                const uint32_t buf = (uint32_t)(t & 1), tph = (uint32_t)((t >> 1) & 1);
+                tc::mbar_wait(&tempty[buf], tph ^ 1);
+                tc::mbar_wait(&tempty[2 + buf], tph ^ 1);
+                tc::mbar_wait(&full[stage], phase);
                 tc::fence_after_thread_sync();
-                for (uint32_t ct = 0; ct < nct; ++ct, ++t) {
-                    const uint32_t buf = (uint32_t)(t & 1), tph = (uint32_t)((t >> 1) & 1);
-                    tc::mbar_wait(&tempty[buf], tph ^ 1);
-                    tc::mbar_wait(&tempty[2 + buf], tph ^ 1);
-                    tc::fence_after_thread_sync();
+                if (k1_elect_one()) {
                     if (t + 1 < total_tiles) {
                         const uint32_t slot = (uint32_t)((t + 1) & 3), nct1 = (ct + 1 == nct) ? 0 : ct + 1;
                         tc::mbar_arrive_expect_tx(&nbar[slot], K1_N * 4);
                         tc::bulk_load(nrm + slot * K1_N, p.cent_norm + (size_t)nct1 * K1_N, K1_N * 4, &nbar[slot]);
                     }
-                    tc::mbar_wait(&full[stage], phase);
-                    tc::fence_after_thread_sync();
                     const uint32_t sb = tc::smem_u32(smem + stage * K1_STAGE_BYTES);
 #pragma unroll
                     for (uint32_t rb = 0; rb < 2; ++rb) {
                         const uint32_t d_tmem = tmem_base + K1_ACC_COL0 + (2 * rb + buf) * K1_N;
                         const uint32_t a_tmem = tmem_base + K1_A_COL0 + rb * 128;
+#pragma unroll
                         for (uint32_t kc = 0; kc < nk; ++kc) {
                             const uint64_t db = tc::smem_desc_k_sw128(sb + kc * K1_BOX_BYTES);
 #pragma unroll
@@ -464,13 +490,15 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
                         tc::mma_commit(&tfull[2 * rb + buf]);
                     }
                     tc::mma_commit(&empty[stage]);
-                    if (++stage == K1_STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
                 }
-                tc::mma_commit(afree);
+                __syncwarp();
+                if (++stage == K1_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
             }
+            if (k1_elect_one()) tc::mma_commit(afree);
+            __syncwarp();
         }
     } else if (warp < K1_EPI_WARP0 + K1_EPI_WARPS) {
         // epilogue: thread = row.  Five smallest keys (ids of the first four) over all centroid tiles, then the exact
@@ -501,29 +529,42 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
                 if (lane == 0) tc::mbar_arrive(&tempty[2 * rb + buf]);
                 const float* nr = nrm + (t & 3) * K1_N;
                 const uint32_t c0 = ct * K1_N;
+                // phase 1 (straight-line): the 64 keys in place, the min of every quad, of every 16-column group and of
+                // the tile
+                float qm[16];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    float key[16];
+                for (int j = 0; j < 64; j += 4) {
+                    const float4 n4 = *reinterpret_cast<const float4*>(nr + j);
+                    uint32_t* v = j < 32 ? &va[j] : &vb[j - 32];
+                    const float k0 = __fmaf_rn(-2.0f, __uint_as_float(v[0]), n4.x);
+                    const float k1 = __fmaf_rn(-2.0f, __uint_as_float(v[1]), n4.y);
+                    const float k2 = __fmaf_rn(-2.0f, __uint_as_float(v[2]), n4.z);
+                    const float k3 = __fmaf_rn(-2.0f, __uint_as_float(v[3]), n4.w);
+                    v[0] = __float_as_uint(k0), v[1] = __float_as_uint(k1), v[2] = __float_as_uint(k2),
+                    v[3] = __float_as_uint(k3);
+                    qm[j >> 2] = fminf(fminf(k0, k1), fminf(k2, k3));
+                }
+                float gm[4];
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        const float4 n4 = *reinterpret_cast<const float4*>(nr + 16 * g + j);
-                        const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+                for (int g = 0; g < 4; ++g) gm[g] = fminf(fminf(qm[4 * g], qm[4 * g + 1]), fminf(qm[4 * g + 2], qm[4 * g + 3]));
+                const float tm = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
+                // phase 2: descend only where a new top-5 entry can be (tile -> group of 16 -> quad -> element)
+                if (tm < k[4]) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int col = 16 * g + j + e;
-                            const float acc = __uint_as_float(col < 32 ? va[col] : vb[col - 32]);
-                            key[j + e] = __fmaf_rn(-2.0f, acc, nn[e]);
+                    for (int g = 0; g < 4; ++g) {
+                        if (gm[g] < k[4]) {
+#pragma unroll
+                            for (int qd = 0; qd < 4; ++qd) {
+                                if (qm[4 * g + qd] < k[4]) {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const int col = 16 * g + 4 * qd + e;
+                                        const float key = __uint_as_float(col < 32 ? va[col] : vb[col - 32]);
+                                        if (key < k[4]) k1_insert(k, id, key, c0 + col);
+                                    }
+                                }
+                            }
                         }
-                    }
-                    float m01 = fminf(fminf(key[0], key[1]), fminf(key[2], key[3]));
-                    float m23 = fminf(fminf(key[4], key[5]), fminf(key[6], key[7]));
-                    float m45 = fminf(fminf(key[8], key[9]), fminf(key[10], key[11]));
-                    float m67 = fminf(fminf(key[12], key[13]), fminf(key[14], key[15]));
-                    const float m = fminf(fminf(m01, m23), fminf(m45, m67));
-                    if (m < k[4]) {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e)
-                            if (key[e] < k[4]) k1_insert(k, id, key[e], c0 + 16 * g + e);
                     }
                 }
             }

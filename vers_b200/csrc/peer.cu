@@ -14,7 +14,7 @@
 // (all its reads of parity p) has finished: no reader can still be in a slot that is being overwritten.
 #include <algorithm>
 
-#include "engine.cuh"
+#include "peer.cuh"
 
 struct vers_peer {
     vers_ctx* ctx = nullptr;
@@ -23,121 +23,10 @@ struct vers_peer {
     char* d_buf = nullptr;         // this rank's exchange buffer
     char** d_peer_base = nullptr;  // [world] device-visible base pointers (own entry = d_buf)
     std::vector<char*> opened;     // peer mappings to close
-    uint32_t step = 0;
-    size_t flags_off = 0, done_off = 0, total = 0;
+    uint32_t step = 0;             // host-managed step (the vers_comm path keeps it in device memory instead)
+    size_t flags_off = 0, ctl_off = 0, total = 0;
+    unsigned resident = 0;         // blocks of the exchange kernel that fit the GPU at once
 };
-
-namespace vers {
-
-constexpr int PG_WARPS = 4;
-
-__device__ __forceinline__ unsigned long long pg_now_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
-__global__ void __launch_bounds__(PG_WARPS * 32)
-    peer_gather_merge_kernel(char* const* __restrict__ peer_base, uint32_t world, uint32_t rank, uint64_t slot_bytes,
-                             uint64_t flags_off, uint64_t done_off, uint32_t step, const uint64_t* __restrict__ loc_ids,
-                             const float* __restrict__ loc_d, uint32_t nq, uint32_t k, uint64_t* out_ids, float* out_d,
-                             uint32_t* out_cnt) {
-    extern __shared__ __align__(16) unsigned char pgsm[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t q = blockIdx.x * PG_WARPS + warp;
-    const uint32_t parity = step & 1u;
-    const uint64_t nk = (uint64_t)nq * k;
-    const uint64_t my_slot = ((uint64_t)parity * world + rank) * slot_bytes;
-
-    // 1. publish: this query's local top-k into my slot on every rank (ids [nq][k] then distances [nq][k])
-    if (q < nq) {
-        for (uint32_t r = 0; r < world; ++r) {
-            char* base = peer_base[r] + my_slot;
-            uint64_t* pi = reinterpret_cast<uint64_t*>(base) + (uint64_t)q * k;
-            float* pd = reinterpret_cast<float*>(base + nk * 8) + (uint64_t)q * k;
-            for (uint32_t e = lane; e < k; e += 32) {
-                pi[e] = loc_ids[(uint64_t)q * k + e];
-                pd[e] = loc_d[(uint64_t)q * k + e];
-            }
-        }
-    }
-    __threadfence_system();  // my stores are visible system-wide before the block reports in
-    __syncthreads();
-    char* mine = peer_base[rank];
-    if (threadIdx.x == 0) {
-        uint32_t* done = reinterpret_cast<uint32_t*>(mine + done_off);
-        const uint32_t prev = atomicAdd(done, 1u);
-        if (prev == gridDim.x - 1) {  // last block of this rank: everything is published, raise my flag everywhere
-            *done = 0;                // self-cleaning for the next step
-            __threadfence_system();
-            for (uint32_t r = 0; r < world; ++r) {
-                volatile uint32_t* f =
-                    reinterpret_cast<volatile uint32_t*>(peer_base[r] + flags_off) + (uint64_t)parity * world + rank;
-                *f = step;
-            }
-        }
-    }
-    if (q >= nq) return;
-
-    // 2. wait for every rank's flag of this step (bounded: a dead peer traps instead of hanging the GPU)
-    if (lane == 0) {
-        const unsigned long long t0 = pg_now_ns();
-        for (uint32_t r = 0; r < world; ++r) {
-            volatile uint32_t* f = reinterpret_cast<volatile uint32_t*>(mine + flags_off) + (uint64_t)parity * world + r;
-            while ((int32_t)(*f - step) < 0) {
-                if (pg_now_ns() - t0 > 20000000000ull) __trap();  // 20 s
-            }
-        }
-        __threadfence_system();
-    }
-    __syncwarp();
-
-    // 3. merge world x k entries of this query by (distance, id)
-    uint64_t* sp = reinterpret_cast<uint64_t*>(pgsm) + (size_t)warp * k;
-    float* sd = reinterpret_cast<float*>(pgsm + (size_t)PG_WARPS * k * 8) + (size_t)warp * k;
-    for (uint32_t e = lane; e < k; e += 32) {
-        sd[e] = __int_as_float(0x7f800000);
-        sp[e] = 0xffffffffffffffffull;
-    }
-    __syncwarp();
-    const uint32_t total = world * k;
-    for (uint32_t e0 = 0; e0 < total; e0 += 32) {
-        const uint32_t e = e0 + lane;
-        float v = 0.f;
-        uint64_t id = 0xffffffffffffffffull;
-        if (e < total) {
-            const uint32_t r = e / k, j = e % k;
-            const char* base = mine + ((uint64_t)parity * world + r) * slot_bytes;
-            id = __ldcg(reinterpret_cast<const uint64_t*>(base) + (uint64_t)q * k + j);
-            v = __ldcg(reinterpret_cast<const float*>(base + nk * 8) + (uint64_t)q * k + j);
-        }
-        bool live = id != 0xffffffffffffffffull;
-        while (true) {
-            bool pass = live && entry_less<uint64_t>(v, id, sd[k - 1], sp[k - 1]);
-            unsigned m = __ballot_sync(FULL_MASK, pass);
-            if (!m) break;
-            int src = __ffs(m) - 1;
-            float bv = __shfl_sync(FULL_MASK, v, src);
-            uint64_t bid = __shfl_sync(FULL_MASK, id, src);
-            warp_topk_insert<uint64_t>(sd, sp, (int)k, bv, bid, lane);
-            if (lane == src) live = false;
-        }
-    }
-    uint32_t cnt = 0;
-    for (uint32_t e0 = 0; e0 < k; e0 += 32) {
-        const uint32_t e = e0 + lane;
-        bool have = false;
-        if (e < k) {
-            out_ids[(uint64_t)q * k + e] = sp[e];
-            out_d[(uint64_t)q * k + e] = sd[e];
-            have = sp[e] != 0xffffffffffffffffull;
-        }
-        cnt += __popc(__ballot_sync(FULL_MASK, have));
-    }
-    if (out_cnt && lane == 0) out_cnt[q] = cnt;
-}
-
-}  // namespace vers
 
 using namespace vers;
 
@@ -154,8 +43,8 @@ extern "C" int32_t vers_peer_create(vers_ctx* ctx, uint32_t world, uint32_t rank
     p->rank = rank;
     p->slot_bytes = (slot_bytes + 255) & ~uint64_t(255);
     p->flags_off = (size_t)2 * world * p->slot_bytes;
-    p->done_off = p->flags_off + (size_t)2 * world * 4;
-    p->total = p->done_off + 256;
+    p->ctl_off = (p->flags_off + (size_t)2 * world * 4 + 255) & ~size_t(255);
+    p->total = p->ctl_off + 256;
     cudaError_t e = cudaMalloc(&p->d_buf, p->total);
     if (e == cudaSuccess) e = cudaMemset(p->d_buf, 0, p->total);
     if (e == cudaSuccess) e = cudaMalloc(&p->d_peer_base, sizeof(char*) * world);
@@ -205,14 +94,23 @@ extern "C" int32_t vers_peer_gather_merge_dev(vers_peer* p, const uint64_t* d_lo
     vers_ctx* ctx = p->ctx;
     std::lock_guard<std::mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
-    const unsigned grid = (unsigned)ceil_div(nq, PG_WARPS);
-    if (grid > (unsigned)ctx->sm_count * 8)  // every block must be resident while it waits for the peers
-        return fail(VERS_ERR_UNSUPPORTED, "peer_gather_merge: batch of %u queries is too large for one resident grid", nq);
-    p->step += 1;
-    peer_gather_merge_kernel<<<grid, PG_WARPS * 32, (size_t)PG_WARPS * top_k * 12, ctx->stream>>>(
-        p->d_peer_base, p->world, p->rank, p->slot_bytes, p->flags_off, p->done_off, p->step, d_local_ids,
-        d_local_dists, nq, top_k, d_ids, d_dists, d_counts);
+    // every block must be resident while it waits for the peers: the grid is bounded by the occupancy of this kernel
+    // and the warps loop over the queries
+    const size_t smem = (size_t)PG_WARPS * top_k * 12;
+    if (!p->resident) VERS_TRY(peer_resident_blocks(ctx, (size_t)PG_WARPS * VERS_MAX_TOPK * 12, &p->resident));
+    const unsigned grid = std::min<unsigned>((unsigned)ceil_div(nq, PG_WARPS), p->resident);
+    PeerRegion g;
+    g.peer_base = p->d_peer_base;
+    g.data_off = 0;
+    g.slot_bytes = p->slot_bytes;
+    g.flags_off = p->flags_off;
+    g.ctl_off = p->ctl_off;
+    g.world = p->world;
+    g.rank = p->rank;
+    peer_gather_merge_kernel<<<grid, PG_WARPS * 32, smem, ctx->stream>>>(g, p->step + 1, d_local_ids, d_local_dists, nq,
+                                                                        top_k, d_ids, d_dists, d_counts);
     VERS_LAUNCH_CHECK(ctx);
+    p->step += 1;  // only once the launch is known to be queued: a failed launch must not desynchronise the ranks
     return VERS_OK;
 }
 

@@ -61,6 +61,27 @@ def test_flat_search_matches_search_exhaustive(vb, vo, ctx, n, dim, nq, k, metri
     assert np.array_equal(bits(d), bits(od))
 
 
+@pytest.mark.parametrize("n,dim,nq,k", [(40000, 300, 1, 10), (40000, 300, 8, 10), (9999, 768, 1, 10), (9999, 768, 5, 3),
+                                        (30001, 128, 2, 128), (4097, 36, 7, 33), (31, 300, 1, 10), (1000, 7, 4, 1),
+                                        (33, 20, 6, 64)])
+@pytest.mark.parametrize("metric", [0, 1])
+def test_flat_search_small_batch_streaming_kernel(vb, vo, ctx, n, dim, nq, k, metric):
+    """nq <= 8: flat_stream_kernel (bulk-copy staged row tiles, lane = row, one exact-order chain per query): odd and
+    even float4 row strides (staggered lanes), a last partial tile, tables smaller than a tile, k up to 128, both
+    metrics; the exact-order tile engine (flat mode 1) must agree as well"""
+    rows = data(vo, n, dim)
+    rows[n // 2] = rows[3]  # a duplicate row: equal distances, the lower id first
+    q = data(vo, nq, dim, seed=2)
+    q[0] = rows[3]
+    ds = vb.Dataset.upload(ctx, rows, id_base=77)
+    ids, d, cnt = vb.search_exhaustive_batch(ds, q, k, metric)
+    oi, od, oc = vo.exhaustive(rows, q, k, metric, id_base=77)
+    assert np.array_equal(cnt, oc) and np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od))
+    ds.set_flat_mode(1)
+    ids1, d1, cnt1 = vb.search_exhaustive_batch(ds, q, k, metric)
+    assert np.array_equal(ids1, oi) and np.array_equal(bits(d1), bits(od)) and np.array_equal(cnt1, oc)
+
+
 def test_flat_search_ties_broken_by_id(vb, vo, ctx):
     rows = data(vo, 300, 64)
     rows[100:200] = rows[7]  # 101 identical rows -> identical distances

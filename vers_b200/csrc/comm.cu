@@ -346,13 +346,14 @@ static int32_t sharded_search_dev(vers_comm* cm, vers_ivf* ivf, const float* d_q
         peer_publish_kernel<<<grid, 256, 0, ctx->stream>>>(cm->probe_rg, reinterpret_cast<const uint4*>(cm->d_probe_local),
                                                           probe_bytes, 0);
         VERS_LAUNCH_CHECK(ctx);
-        const unsigned grid2 = (unsigned)std::min<uint64_t>(ceil_div((probe_bytes >> 4) * W, 256), (uint64_t)ctx->sm_count);
-        peer_wait_copy_kernel<<<grid2, 256, 0, ctx->stream>>>(cm->probe_rg, reinterpret_cast<uint4*>(cm->d_probe_all),
-                                                             probe_bytes, 0);
+        const uint64_t elems = (uint64_t)per * np;  // u64 probe ids per rank: d_probe_all is the compact [world * per][np]
+        const unsigned grid2 = (unsigned)std::min<uint64_t>(ceil_div(elems * W, 256), (uint64_t)ctx->sm_count);
+        peer_wait_copy_kernel<<<grid2, 256, 0, ctx->stream>>>(cm->probe_rg,
+                                                             reinterpret_cast<unsigned long long*>(cm->d_probe_all), elems, 0);
         VERS_LAUNCH_CHECK(ctx);
     }
-    // (c) scan the lists this rank owns.  d_probe_all is [world][per][np]: query q = r * per + j is row q (the padded
-    // tail of the last rank lies beyond nq * np only when its slot is also the last)
+    // (c) scan the lists this rank owns.  d_probe_all is [world * per][np]: query q = r * per + j is row q (rows past nq
+    // are the unused tail of the last ranks)
     VERS_TRY(vers_ivf_search_probed_dev(ivf, d_queries, nq, top_k, np, cm->d_probe_all, cm->d_loc_ids, cm->d_loc_d,
                                         cm->d_loc_cnt));
     {   // (d) exchange + merge of the per-rank top-k, one kernel

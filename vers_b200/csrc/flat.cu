@@ -40,6 +40,291 @@ __global__ void __launch_bounds__(Cfg::NT, 2) flat_scan_kernel(FlatScanParams p)
     }
 }
 
+// =====================================================================================================================
+// flat_stream_kernel — the single-query / small-batch scan (nq <= 8): the reference's own API shape (one query per
+// call, utils.rs:68-82; ivfflat.rs:153).  The tile engine above pads one query to 8 columns and stages 32-float
+// k-chunks with cp.async; here the table is STREAMED: one producer warp issues ONE bulk copy (cp.async.bulk, SASS
+// UBLKCP) per row tile — rows are contiguous, so a tile is a single linear rows x ld x 4-byte transfer — into a ring
+// of six shared-memory stages (mbarrier full/empty).  Three consumer GROUPS own two stages each (one being computed,
+// one in flight), lane = row, and every lane walks ITS row's dimensions in order with one exact-order chain per query
+// (rounded sub/mul/add, no FMA: base.rs:91-93, :119-126) — independent chains per lane, no padding columns, queries
+// read from shared memory.  For 4 and 8 queries a group is two warps that split the queries (the fp32 pipe, not HBM,
+// is the bound there: 3 instructions per row, query and dimension).
+// A stage is always consumed by the same group, so every waiter observes every phase of its barriers in order (a
+// parity wait cannot tell "not yet" from "two phases ago").
+// Bank conflicts: a lane reads its row with LDS.128 at stride ld/4 float4s; when that stride is even the 8 lanes of a
+// phase would collide, so lane i runs i mod 8 float4s BEHIND (its chain is still strictly sequential; the loop runs 7
+// extra iterations) — then the 8 lanes of a phase always hit 8 distinct 16-byte bank groups, for the row AND for the
+// query.  Selection: per (consumer warp, query) sorted top-k list in shared memory, ballot + insertion like the merge
+// kernels; the lists of a query are folded per CTA at the end, the per-CTA lists go through merge_topk_kernel.
+constexpr int FS_GROUPS = 3, FS_STAGES = 2 * FS_GROUPS, FS_MAX_ROWS = 32;
+
+struct FlatStreamParams {
+    const float* rows;     // [n][ld]
+    uint64_t n;
+    uint32_t ld;
+    const float* queries;  // [nq][ld]
+    uint32_t k, kpad, tile_rows;
+    float* part_d;         // [nq][gridDim.x][k]
+    uint32_t* part_p;
+};
+
+__device__ __forceinline__ bool fs_elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t fs_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fs_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fs_smem(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fs_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(fs_smem(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+// one float4 of the row against the same float4 of NQW queries
+template <int NQW, int OP>
+__device__ __forceinline__ void fs_step(float (&acc)[NQW], const float4* __restrict__ x4, const float4* __restrict__ q4,
+                                        uint32_t nf4, uint32_t j) {
+    const float4 x = x4[j];
+#pragma unroll
+    for (int q = 0; q < NQW; ++q) {
+        const float4 b = q4[(uint32_t)q * nf4 + j];
+        pair_step<OP>(acc[q], x.x, b.x);
+        pair_step<OP>(acc[q], x.y, b.y);
+        pair_step<OP>(acc[q], x.z, b.z);
+        pair_step<OP>(acc[q], x.w, b.w);
+    }
+}
+
+// fold (v, pp) of the live lanes into the sorted list (sd, sp) of k entries
+__device__ __forceinline__ void fs_fold(float* sd, uint32_t* sp, uint32_t k, float v, uint32_t pp, bool live, int lane) {
+    while (true) {
+        const bool pass = live && entry_less<uint32_t>(v, pp, sd[k - 1], sp[k - 1]);
+        const unsigned m = __ballot_sync(FULL_MASK, pass);
+        if (!m) break;
+        const int src = __ffs(m) - 1;
+        const float bv = __shfl_sync(FULL_MASK, v, src);
+        const uint32_t bp = __shfl_sync(FULL_MASK, pp, src);
+        warp_topk_insert<uint32_t>(sd, sp, (int)k, bv, bp, lane);
+        if (lane == src) live = false;
+    }
+}
+
+template <int NQW, int NH, int OP>  // NQW queries per consumer warp, NH warps per group: NQW * NH queries
+__global__ void __launch_bounds__((FS_GROUPS * NH + 1) * 32, 1) flat_stream_kernel(FlatStreamParams p) {
+    constexpr int NQ = NQW * NH, CONS = FS_GROUPS * NH, THREADS = (CONS + 1) * 32;
+    extern __shared__ __align__(128) unsigned char fs_raw[];
+    const uint32_t nf4 = p.ld >> 2;
+    const uint32_t tile_bytes = p.tile_rows * p.ld * 4;
+    unsigned char* tiles = fs_raw;
+    float* qs = reinterpret_cast<float*>(fs_raw + (size_t)FS_STAGES * tile_bytes);
+    float* list_d = qs + NQ * p.ld;
+    uint32_t* list_p = reinterpret_cast<uint32_t*>(list_d + CONS * NQW * p.kpad);
+    uint64_t* full = reinterpret_cast<uint64_t*>(list_p + CONS * NQW * p.kpad);
+    uint64_t* empty = full + FS_STAGES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t ntiles = (p.n + p.tile_rows - 1) / p.tile_rows;
+    const uint64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < FS_STAGES; ++s) {
+            fs_mbar_init(&full[s], 1);
+            fs_mbar_init(&empty[s], NH);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (uint32_t i = threadIdx.x; i < NQ * p.ld; i += THREADS) qs[i] = p.queries[i];
+    for (uint32_t i = threadIdx.x; i < CONS * NQW * p.kpad; i += THREADS) {
+        list_d[i] = __int_as_float(0x7f800000);
+        list_p[i] = 0xffffffffu;
+    }
+    __syncthreads();
+
+    if (warp == CONS) {
+        // producer: one linear bulk copy per tile
+        for (uint64_t i = 0; i < my_tiles; ++i) {
+            const uint32_t stage = (uint32_t)(i % FS_STAGES), use = (uint32_t)(i / FS_STAGES);
+            fs_mbar_wait(&empty[stage], (use & 1u) ^ 1u);
+            if (fs_elect_one()) {
+                const uint64_t r0 = (blockIdx.x + i * gridDim.x) * p.tile_rows;
+                const uint32_t bytes = (uint32_t)(min((uint64_t)p.tile_rows, p.n - r0) * p.ld * 4);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fs_smem(&full[stage])), "r"(bytes)
+                             : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 fs_smem(tiles + (size_t)stage * tile_bytes)),
+                             "l"(p.rows + r0 * p.ld), "r"(bytes), "r"(fs_smem(&full[stage]))
+                             : "memory");
+            }
+            __syncwarp();
+        }
+    } else {
+        const int group = warp % FS_GROUPS, half = warp / FS_GROUPS;
+        const uint32_t sg = (nf4 & 1u) ? 0u : (uint32_t)(lane & 7);  // stagger (float4s) when the row stride is even
+        const float4* q4 = reinterpret_cast<const float4*>(qs) + (size_t)half * NQW * nf4;
+        float* my_d = list_d + (size_t)warp * NQW * p.kpad;
+        uint32_t* my_p = list_p + (size_t)warp * NQW * p.kpad;
+        for (uint64_t i = group; i < my_tiles; i += FS_GROUPS) {  // tile i lives in stage i % 6: stages g and g + 3
+            const uint32_t stage = (uint32_t)(i % FS_STAGES), use = (uint32_t)(i / FS_STAGES);
+            const uint64_t r0 = (blockIdx.x + i * gridDim.x) * p.tile_rows;
+            fs_mbar_wait(&full[stage], use & 1u);
+            const bool has_row = (uint32_t)lane < p.tile_rows;
+            const float4* x4 = reinterpret_cast<const float4*>(tiles + (size_t)stage * tile_bytes) +
+                               (size_t)(has_row ? lane : 0) * nf4;
+            float acc[NQW];
+#pragma unroll
+            for (int q = 0; q < NQW; ++q) acc[q] = 0.0f;
+            if (nf4 & 1u) {  // odd stride, no stagger: every lane walks j = 0 .. nf4-1 together
+#pragma unroll 4
+                for (uint32_t j = 0; j < nf4; ++j) fs_step<NQW, OP>(acc, x4, q4, nf4, j);
+            } else {
+                // staggered: lane runs sg float4s behind; head and tail iterations are predicated, the body is not
+                const uint32_t head = min(7u, nf4);
+                for (uint32_t t = 0; t < head; ++t)
+                    if (t >= sg) fs_step<NQW, OP>(acc, x4, q4, nf4, t - sg);
+#pragma unroll 4
+                for (uint32_t t = head; t < nf4; ++t) fs_step<NQW, OP>(acc, x4, q4, nf4, t - sg);  // t >= 7 >= sg
+                for (uint32_t t = nf4; t < nf4 + 7; ++t)
+                    if (t >= sg && t - sg < nf4) fs_step<NQW, OP>(acc, x4, q4, nf4, t - sg);
+            }
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fs_smem(&empty[stage])) : "memory");
+            const uint64_t row = r0 + (uint64_t)lane;
+#pragma unroll
+            for (int q = 0; q < NQW; ++q) {
+                float v = acc[q];
+                if (OP == OP_DOT) v = __fsub_rn(1.0f, v);  // cosine distance 1 - dot (base.rs:155)
+                fs_fold(my_d + (size_t)q * p.kpad, my_p + (size_t)q * p.kpad, p.k, v, (uint32_t)row, has_row && row < p.n, lane);
+            }
+        }
+    }
+    __syncthreads();
+    // fold the groups' lists of every query into group 0's, write the CTA's partial result
+    if (warp < CONS && warp % FS_GROUPS == 0) {
+        const int half = warp / FS_GROUPS;
+        for (int ql = 0; ql < NQW; ++ql) {
+            float* sd = list_d + ((size_t)warp * NQW + ql) * p.kpad;
+            uint32_t* sp = list_p + ((size_t)warp * NQW + ql) * p.kpad;
+            for (int g = 1; g < FS_GROUPS; ++g) {
+                const float* od = list_d + ((size_t)(warp + g) * NQW + ql) * p.kpad;
+                const uint32_t* op = list_p + ((size_t)(warp + g) * NQW + ql) * p.kpad;
+                for (uint32_t e0 = 0; e0 < p.k; e0 += 32) {
+                    const uint32_t e = e0 + lane;
+                    const float v = e < p.k ? od[e] : 0.f;
+                    const uint32_t pp = e < p.k ? op[e] : 0xffffffffu;
+                    fs_fold(sd, sp, p.k, v, pp, pp != 0xffffffffu, lane);
+                }
+            }
+            __syncwarp();
+            const uint64_t base = ((uint64_t)(half * NQW + ql) * gridDim.x + blockIdx.x) * p.k;
+            for (uint32_t e = lane; e < p.k; e += 32) {
+                p.part_d[base + e] = sd[e];
+                p.part_p[base + e] = sp[e];
+            }
+        }
+    }
+}
+
+template <int NQW, int NH>
+static int32_t launch_flat_stream(vers_ctx* ctx, const FlatStreamParams& p, uint32_t metric, unsigned grid, size_t smem) {
+    constexpr int THREADS = (FS_GROUPS * NH + 1) * 32;
+    if (metric == VERS_METRIC_L2SQ) {
+        auto kern = flat_stream_kernel<NQW, NH, OP_L2SQ>;
+        VERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, THREADS, smem, ctx->stream>>>(p);
+    } else {
+        auto kern = flat_stream_kernel<NQW, NH, OP_DOT>;
+        VERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, THREADS, smem, ctx->stream>>>(p);
+    }
+    VERS_LAUNCH_CHECK(ctx);
+    return VERS_OK;
+}
+
+// small-batch exhaustive scan of a contiguous row table; returns VERS_ERR_UNSUPPORTED when the shape does not fit
+// (the caller then runs the tile engine).  Caller holds ctx->mu.
+int32_t flat_stream_search(vers_ctx* ctx, const float* rows, uint64_t n, uint32_t ld, const float* d_queries, uint32_t nq,
+                           uint32_t k, uint32_t metric, uint64_t id_base, uint64_t* d_ids, float* d_d, uint32_t* d_cnt,
+                           int family) {
+    if (nq == 0 || nq > 8 || k == 0 || k > VERS_MAX_TOPK || n == 0 || n >= 0xffffffffull) return VERS_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(rows) & 15) != 0) return VERS_ERR_UNSUPPORTED;  // bulk copies need 16-byte alignment
+    const uint32_t NQ = nq == 1 ? 1 : nq == 2 ? 2 : nq <= 4 ? 4 : 8;
+    const uint32_t NH = NQ >= 4 ? 2 : 1, NQW = NQ / NH, CONS = FS_GROUPS * NH;
+    const uint32_t kpad = round_up(k, 32);
+    const size_t fixed = (size_t)NQ * ld * 4 + (size_t)CONS * NQW * kpad * 8 + 2 * FS_STAGES * 8 + 128;
+    const size_t budget = 227 * 1024;
+    if (fixed + (size_t)FS_STAGES * 4 * ld * 4 > budget) return VERS_ERR_UNSUPPORTED;  // not even 4-row tiles fit
+    const uint32_t tile_rows = (uint32_t)std::min<size_t>(FS_MAX_ROWS, (budget - fixed) / ((size_t)FS_STAGES * ld * 4));
+    const size_t smem = (size_t)FS_STAGES * tile_rows * ld * 4 + fixed;
+    const uint64_t ntiles = ceil_div(n, tile_rows);
+    const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count);
+    // queries padded to NQ rows (zero rows: their results are not merged), partial lists [NQ][grid][k]
+    ScratchCarver plan(nullptr);
+    plan.plan<float>((size_t)NQ * ld);
+    plan.plan<float>((size_t)NQ * grid * k);
+    plan.plan<uint32_t>((size_t)NQ * grid * k);
+    VERS_TRY(scratch_reserve(ctx, plan.off + 256));
+    ScratchCarver sc(ctx->scratch);
+    float* qpad = sc.take<float>((size_t)NQ * ld);
+    FlatStreamParams p;
+    p.rows = rows;
+    p.n = n;
+    p.ld = ld;
+    p.k = k;
+    p.kpad = kpad;
+    p.tile_rows = tile_rows;
+    p.part_d = sc.take<float>((size_t)NQ * grid * k);
+    p.part_p = sc.take<uint32_t>((size_t)NQ * grid * k);
+    p.queries = d_queries;
+    if (NQ != nq) {
+        VERS_CUDA(cudaMemsetAsync(qpad, 0, (size_t)NQ * ld * 4, ctx->stream));
+        VERS_CUDA(cudaMemcpyAsync(qpad, d_queries, (size_t)nq * ld * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        p.queries = qpad;
+    }
+    {
+        FamilyTimer ft(ctx, family);
+        switch (NQ) {
+            case 1: VERS_TRY((launch_flat_stream<1, 1>(ctx, p, metric, grid, smem))); break;
+            case 2: VERS_TRY((launch_flat_stream<2, 1>(ctx, p, metric, grid, smem))); break;
+            case 4: VERS_TRY((launch_flat_stream<2, 2>(ctx, p, metric, grid, smem))); break;
+            default: VERS_TRY((launch_flat_stream<4, 2>(ctx, p, metric, grid, smem))); break;
+        }
+    }
+    MergeParams mp;
+    mp.part_d = p.part_d;
+    mp.part_p = p.part_p;
+    mp.seg = nullptr;
+    mp.seg_scale = 1;
+    mp.seg_stride = 1;
+    mp.per_query = (uint64_t)grid * k;
+    mp.map = nullptr;
+    mp.id_base = id_base;
+    mp.nq = nq;
+    mp.k = k;
+    mp.out_ids = d_ids;
+    mp.out_d = d_d;
+    mp.out_cnt = d_cnt;
+    mp.qmask = nullptr;
+    return launch_merge(ctx, mp);
+}
+
 constexpr int MERGE_WARPS = 4;
 
 __global__ void __launch_bounds__(MERGE_WARPS * 32) merge_topk_kernel(MergeParams p) {
@@ -430,6 +715,11 @@ static int32_t flat_search_dev_locked(vers_dataset* ds, const float* d_queries, 
         if (used || rc != VERS_ERR_UNSUPPORTED) return rc;
     }
     if (ds->d_stats) VERS_CUDA(cudaMemsetAsync(ds->d_stats, 0, 64, ctx->stream));  // the exact-order engine ran
+    if (nq <= 8 && ds->flat_mode == 0) {  // single query / small batch: the streaming kernel (exact order as well)
+        int32_t rc = flat_stream_search(ctx, ds->d_rows, ds->n, ds->ld, d_queries, nq, top_k, metric, ds->id_base, d_ids,
+                                        d_dists, d_counts, KF_FLAT_SCAN);
+        if (rc != VERS_ERR_UNSUPPORTED) return rc;
+    }
     RowSrc A{ds->d_rows, nullptr, ds->ld, ds->n};
     RowSrc B{d_queries, nullptr, ds->ld, nq};
     return scan_topk_dev(ctx, A, B, nq, ds->ld, top_k, metric, nullptr, ds->id_base, d_ids, d_dists, d_counts,

@@ -105,19 +105,19 @@ static __global__ void __launch_bounds__(256) peer_publish_kernel(PeerRegion g, 
     peer_block_published(g, step);
 }
 
-// ---- all-gather, part 2: wait for every rank's flag, copy the world slots to dst [world][bytes]
-static __global__ void __launch_bounds__(256) peer_wait_copy_kernel(PeerRegion g, uint4* __restrict__ dst, uint64_t bytes,
-                                                             uint32_t host_step) {
+// ---- all-gather, part 2: wait for every rank's flag, copy the first `elems` 8-byte words of each of the world slots
+// to dst [world][elems] (compact: the slots themselves are padded to 16 bytes)
+static __global__ void __launch_bounds__(256) peer_wait_copy_kernel(PeerRegion g, unsigned long long* __restrict__ dst,
+                                                                    uint64_t elems, uint32_t host_step) {
     const uint32_t step = peer_step(g, host_step);
     if (threadIdx.x == 0) peer_wait_flags(g, step);
     __syncthreads();
     const char* mine = g.peer_base[g.rank] + g.data_off + (uint64_t)(step & 1u) * g.world * g.slot_bytes;
-    const uint64_t n16 = bytes >> 4;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16 * g.world;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < elems * g.world;
          i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t r = (uint32_t)(i / n16);
-        const uint64_t j = i - (uint64_t)r * n16;
-        dst[i] = __ldcg(reinterpret_cast<const uint4*>(mine + (uint64_t)r * g.slot_bytes) + j);
+        const uint32_t r = (uint32_t)(i / elems);
+        const uint64_t j = i - (uint64_t)r * elems;
+        dst[i] = __ldcg(reinterpret_cast<const unsigned long long*>(mine + (uint64_t)r * g.slot_bytes) + j);
     }
     if (!host_step) peer_block_consumed(g);
 }

@@ -251,11 +251,54 @@ def test_flat_search_tensor_core_path_bit_exact(vb, vo, ctx, n, dim, nq, k):
     st = ds.last_flat_search_stats()
     oi, od, oc = vo.exhaustive(rows, q, k, 0, id_base=77)
     assert np.array_equal(cnt, oc) and np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od))
-    assert st["reranked"] > 0 and st["uncertified_queries"] <= nq // 4 and st["max_candidate_error"] < 2e-5
+    # batches of >= 96 queries over rows of <= 320 floats with k <= 16 run tc_flat_kernel (ONE tf32 MMA per K step:
+    # candidate values carry the tf32 rounding of both operands); the others the split-precision list-scan kernel
+    single_tf32 = nq >= 96 and dim <= 320 and k <= 16 and n >= 4096
+    assert st["reranked"] > 0 and st["uncertified_queries"] <= nq // 4
+    assert st["max_candidate_error"] < (2e-3 if single_tf32 else 2e-5)
+    ds.set_flat_mode(2)  # the list-scan style kernel for every eligible batch
+    ids2, d2, cnt2 = vb.search_exhaustive_batch(ds, q, k, 0)
+    assert np.array_equal(ids2, oi) and np.array_equal(bits(d2), bits(od))
+    assert ds.last_flat_search_stats()["max_candidate_error"] < 2e-5
     ds.set_flat_mode(1)
     ids1, d1, cnt1 = vb.search_exhaustive_batch(ds, q, k, 0)
     assert np.array_equal(ids1, oi) and np.array_equal(bits(d1), bits(od))
     assert ds.last_flat_search_stats()["reranked"] == 0
+
+
+@pytest.mark.parametrize("n,dim,nq,k,normalize", [(100000, 300, 1000, 10, True), (40000, 128, 130, 16, True),
+                                                  (5000, 64, 96, 5, False), (9000, 36, 200, 1, True),
+                                                  (4100, 320, 128, 10, False), (33333, 100, 257, 10, True)])
+def test_flat_search_query_block_kernel_bit_exact(vb, vo, ctx, n, dim, nq, k, normalize):
+    """tc_flat_kernel: 128 queries resident in tensor memory, the table streamed in 64-row tiles once per query block;
+    last query block partly empty, last slice / last tile ragged, K chunks 2..10, unnormalised rows"""
+    rows = data(vo, n, dim, n_centers=50, normalize=normalize)
+    q = data(vo, nq, dim, seed=2, n_centers=50, normalize=normalize)
+    q[3] = rows[n - 1]  # the very last row of the table is its own nearest neighbour
+    ds = vb.Dataset.upload(ctx, rows, id_base=5)
+    ids, d, cnt = vb.search_exhaustive_batch(ds, q, k, 0)
+    st = ds.last_flat_search_stats()
+    oi, od, oc = vo.exhaustive(rows, q, k, 0, id_base=5)
+    assert np.array_equal(cnt, oc) and np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od))
+    assert ids[3][0] == n - 1 + 5 and d[3][0] == 0.0
+    assert st["reranked"] == 32 * nq and st["uncertified_queries"] <= max(2, nq // 8)
+    ids_b, d_b, _ = vb.search_exhaustive_batch(ds, q, k, 0)  # run-to-run: the shared bounds must not change anything
+    assert np.array_equal(ids_b, ids) and np.array_equal(bits(d_b), bits(d))
+
+
+def test_flat_search_query_block_kernel_ties_fall_back(vb, vo, ctx):
+    """200 copies of one row: more ties than the 32 candidates, the certificate must fail and the exact redo order
+    them by id (the other queries stay certified)"""
+    rows = data(vo, 30000, 96, n_centers=32)
+    rows[5000:5200] = rows[11]
+    q = data(vo, 128, 96, seed=2, n_centers=32)
+    q[0] = rows[11]
+    ds = vb.Dataset.upload(ctx, rows)
+    ids, d, cnt = vb.search_exhaustive_batch(ds, q, 10, 0)
+    oi, od, oc = vo.exhaustive(rows, q, 10, 0)
+    assert np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od))
+    assert list(ids[0]) == [11] + list(range(5000, 5009))
+    assert 1 <= ds.last_flat_search_stats()["uncertified_queries"] <= 16
 
 
 def test_flat_search_tensor_core_path_ties_fall_back(vb, vo, ctx):

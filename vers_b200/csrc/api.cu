@@ -313,6 +313,8 @@ extern "C" int32_t vers_dataset_normalize(vers_dataset* ds) {
         cudaFree(ds->d_norm);
         cudaFree(ds->d_nmax);
         cudaFree(ds->d_stats);
+        cudaFree(ds->d_tiles);
+        ds->d_tiles = nullptr;
         ds->d_norm = nullptr;
         ds->d_nmax = nullptr;
         ds->d_stats = nullptr;
@@ -374,6 +376,7 @@ extern "C" int32_t vers_dataset_free(vers_dataset* ds) {
     cudaFree(ds->d_norm);
     cudaFree(ds->d_nmax);
     cudaFree(ds->d_stats);
+    cudaFree(ds->d_tiles);
     delete ds;
     return VERS_OK;
 }

@@ -77,7 +77,9 @@ struct vers_dataset {
     float* d_norm = nullptr;
     uint32_t* d_nmax = nullptr;
     unsigned long long* d_stats = nullptr;
-    int flat_mode = 0;  // 0: tensor-core candidate path for eligible batches, 1: exact-order engine only
+    float* d_tiles = nullptr;  // tile-major tf32 image of the rows (tc_flat_kernel's B operand), built on first use
+    int flat_mode = 0;  // 0: tensor-core candidate paths for eligible batches, 1: exact-order engine only, 2: like 0
+                        // without the query-block kernel (the list-scan style kernel for every eligible batch)
 };
 
 namespace vers {

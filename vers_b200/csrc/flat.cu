@@ -701,21 +701,37 @@ using namespace vers;
 static int32_t flat_search_dev_locked(vers_dataset* ds, const float* d_queries, uint32_t nq, uint32_t top_k,
                                       uint32_t metric, uint64_t* d_ids, float* d_dists, uint32_t* d_counts) {
     vers_ctx* ctx = ds->ctx;
-    if (metric == VERS_METRIC_L2SQ && ds->flat_mode == 0 && nq >= 32 && top_k >= 1 && top_k <= 64) {
+    if (metric == VERS_METRIC_L2SQ && ds->flat_mode != 1 && nq >= 32 && top_k >= 1 && top_k <= 64) {
         // large batches: tensor-core candidate keys -> exact-order rerank -> certificate -> exact redo (ivf.cu)
         if (!ds->d_norm) {
-            VERS_CUDA(cudaMalloc(&ds->d_norm, (ds->n ? ds->n : 1) * 4));
-            VERS_CUDA(cudaMalloc(&ds->d_nmax, 4));
-            VERS_CUDA(cudaMalloc(&ds->d_stats, 128));
+            // all or nothing; ||row||^2 padded with +inf up to a multiple of 64 rows (tc_flat_kernel reads whole tiles)
+            float* norm = nullptr;
+            uint32_t* nmax = nullptr;
+            unsigned long long* stats = nullptr;
+            cudaError_t e = cudaMalloc(&norm, ((size_t)ds->n + 64) * 4);
+            if (e == cudaSuccess) e = cudaMalloc(&nmax, 4);
+            if (e == cudaSuccess) e = cudaMalloc(&stats, 128);
+            if (e == cudaSuccess) {
+                std::vector<float> inf(64, __builtin_inff());
+                e = cudaMemcpyAsync(norm + ds->n, inf.data(), 64 * 4, cudaMemcpyHostToDevice, ctx->stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            }
+            if (e != cudaSuccess) {
+                cudaFree(norm), cudaFree(nmax), cudaFree(stats);
+                return fail(e == cudaErrorMemoryAllocation ? VERS_ERR_NOMEM : VERS_ERR_CUDA, "flat search buffers: %s",
+                            cudaGetErrorString(e));
+            }
+            ds->d_norm = norm, ds->d_nmax = nmax, ds->d_stats = stats;
             VERS_TRY(launch_rownorm(ctx, ds->d_rows, ds->ld, ds->n, ds->d_norm, ds->d_nmax));
         }
         bool used = false;
         int32_t rc = flat_search_tc_plan_and_run(ctx, ds->d_rows, ds->n, ds->ld, ds->d_norm, ds->d_nmax, ds->id_base,
-                                                 ds->d_stats, d_queries, nq, top_k, d_ids, d_dists, d_counts, &used);
+                                                 ds->d_stats, d_queries, nq, top_k, d_ids, d_dists, d_counts, &used, ds->flat_mode,
+                                                 &ds->d_tiles);
         if (used || rc != VERS_ERR_UNSUPPORTED) return rc;
     }
     if (ds->d_stats) VERS_CUDA(cudaMemsetAsync(ds->d_stats, 0, 64, ctx->stream));  // the exact-order engine ran
-    if (nq <= 8 && ds->flat_mode == 0) {  // single query / small batch: the streaming kernel (exact order as well)
+    if (nq <= 8 && ds->flat_mode != 1) {  // single query / small batch: the streaming kernel (exact order as well)
         int32_t rc = flat_stream_search(ctx, ds->d_rows, ds->n, ds->ld, d_queries, nq, top_k, metric, ds->id_base, d_ids,
                                         d_dists, d_counts, KF_FLAT_SCAN);
         if (rc != VERS_ERR_UNSUPPORTED) return rc;
@@ -737,7 +753,7 @@ extern "C" int32_t vers_flat_search_dev(vers_dataset* ds, const float* d_queries
 
 extern "C" int32_t vers_flat_set_mode(vers_dataset* ds, int32_t mode) {
     if (!ds) return fail(VERS_ERR_ARG, "flat_set_mode: null");
-    if (mode < 0 || mode > 1) return fail(VERS_ERR_ARG, "flat_set_mode: mode %d", mode);
+    if (mode < 0 || mode > 2) return fail(VERS_ERR_ARG, "flat_set_mode: mode %d", mode);
     ds->flat_mode = mode;
     return VERS_OK;
 }

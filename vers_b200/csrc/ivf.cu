@@ -337,6 +337,7 @@ __global__ void __launch_bounds__(Cfg::NT, (Cfg::TILE_FLOATS * 4 > 110 * 1024) ?
 
 }  // namespace vers
 #include "ivf_tc.cuh"
+#include "flat_tc.cuh"
 namespace vers {
 
 // ---------------------------------------------------------------- reference spill semantics (nprobe == 0)
@@ -866,6 +867,8 @@ __global__ void __launch_bounds__(128)
             // split precision (hi.hi + lo.hi + hi.lo): dropped lo.lo and the truncation of lo are <= 3 * 2^-20 per
             // product; accumulation allowance (n + 8) 2^-22 per unit of sum |x_i q_i|
             if (tf32_pass == 2) E += (3.003 / 1048576.0 + (ld + 8.0) * 2.384185791015625e-07) * (nxmax + (double)nq2);
+            // both operands ROUNDED to nearest tf32 (tc_flat_kernel): 2^-11 per operand => 2^-10 (1 + 2^-12) per product
+            if (tf32_pass == 3) E += (1.001 / 1024.0 + (ld + 8.0) * 4.76837158203125e-07) * (nxmax + (double)nq2);
             const double lower = ((double)bound + (double)nq2 - E) * (1.0 - (ld + 3.0) * u);
             certified = lower > (double)sd[k - 1];
         }
@@ -1318,12 +1321,117 @@ static int32_t probe_run(vers_ctx* ctx, const RankTable& tb, const ProbePlan& pp
     return VERS_OK;
 }
 
+// ---- exhaustive search of a large batch, table streamed once per 128 queries (flat_tc.cuh): tc_flat_kernel ->
+// cand_merge (top-32 by key) -> exact-order rerank + certificate (TF32 error model) -> exact redo of uncertified queries
+struct QblockPlan {
+    bool ok = false;
+    ScanPlan exact;
+    uint32_t nk = 0, nqb = 0, nslices = 0, slice_rows = 0, stages = 0;
+    size_t smem = 0, bytes = 0;
+};
+struct QblockBufs {
+    uint32_t *qtau, *part_p, *cand_pos, *fail, *fail_idx, *n_fail;
+    float *part_d, *cand_key, *bound, *tmp_d;
+    uint64_t *pair_chunk_off, *tmp_ids;
+};
+static void qblock_carve(ScratchCarver& sc, const QblockPlan& qp, uint32_t nq, uint32_t k, QblockBufs& b) {
+    b.qtau = sc.take<uint32_t>(nq);
+    b.n_fail = sc.take<uint32_t>(1);
+    b.pair_chunk_off = sc.take<uint64_t>((size_t)nq + 1);
+    b.part_d = sc.take<float>((size_t)nq * qp.nslices * FT_LIST);
+    b.part_p = sc.take<uint32_t>((size_t)nq * qp.nslices * FT_LIST);
+    b.cand_pos = sc.take<uint32_t>((size_t)nq * 32);
+    b.cand_key = sc.take<float>((size_t)nq * 32);
+    b.bound = sc.take<float>(nq);
+    b.fail = sc.take<uint32_t>(nq);
+    b.fail_idx = sc.take<uint32_t>(nq);
+    b.tmp_ids = sc.take<uint64_t>((size_t)nq * k);
+    b.tmp_d = sc.take<float>((size_t)nq * k);
+}
+static QblockPlan qblock_plan(const vers_ctx* ctx, uint64_t n, uint32_t ld, uint32_t nq, uint32_t k) {
+    QblockPlan qp;
+    qp.nk = (ld + FT_KC - 1) / FT_KC;
+    // eligible: enough queries to fill 128-wide blocks, rows that fit tensor memory, a top-k the 32 candidates cover
+    if (nq < 96 || qp.nk > FT_MAX_KCH || ld < FT_KC || k > 16 || n < 4096 || n >= 0x7fffffffull) return qp;
+    qp.nqb = (nq + FT_M - 1) / FT_M;
+    const uint32_t want_items = (uint32_t)ctx->sm_count * 4;
+    uint64_t nsl = std::max<uint64_t>(1, (want_items + qp.nqb - 1) / qp.nqb);
+    nsl = std::min<uint64_t>(nsl, (n + 4 * FT_N - 1) / (4 * FT_N));  // at least 4 tiles per slice
+    qp.slice_rows = round_up((uint32_t)((n + nsl - 1) / nsl), (uint32_t)FT_N);
+    qp.nslices = (uint32_t)((n + qp.slice_rows - 1) / qp.slice_rows);
+    const size_t budget = 227 * 1024;
+    uint32_t st = 4;
+    while (st > 2 && ft_smem_bytes(qp.nk, st) > budget) --st;
+    if (ft_smem_bytes(qp.nk, st) > budget) return qp;
+    qp.stages = st;
+    qp.smem = ft_smem_bytes(qp.nk, st);
+    qp.exact = scan_topk_plan(ctx, n, nq, k);
+    ScratchCarver sc(nullptr);
+    sc.off = (qp.exact.bytes + 255) & ~size_t(255);
+    QblockBufs b;
+    qblock_carve(sc, qp, nq, k, b);
+    qp.bytes = (sc.off + 255) & ~size_t(255);
+    qp.ok = true;
+    return qp;
+}
+
+__global__ void qblock_tables_kernel(uint32_t nq, uint32_t nslices, uint64_t* pair_chunk_off, uint32_t* qtau) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= nq) pair_chunk_off[i] = (uint64_t)i * nslices;
+    if (i < nq) qtau[i] = TAU_INF;
+}
+
+static int32_t qblock_run(vers_ctx* ctx, const RankTable& tb, const QblockPlan& qp, const float* row_tiles,
+                          const float* d_queries, uint32_t nq, uint32_t k, uint64_t* out_ids, float* out_d,
+                          uint32_t* out_cnt, int family) {
+    ScratchCarver sc(ctx->scratch);
+    sc.off = (qp.exact.bytes + 255) & ~size_t(255);
+    QblockBufs b;
+    qblock_carve(sc, qp, nq, k, b);
+    FamilyTimer ft(ctx, family);
+    VERS_CUDA(cudaMemsetAsync(b.n_fail, 0, 4, ctx->stream));
+    qblock_tables_kernel<<<(unsigned)ceil_div((uint64_t)nq + 1, 256), 256, 0, ctx->stream>>>(nq, qp.nslices, b.pair_chunk_off,
+                                                                                           b.qtau);
+    VERS_LAUNCH_CHECK(ctx);
+    CUtensorMap tm_q;
+    VERS_TRY(make_tmap_2d_f32(&tm_q, d_queries, nq, tb.ld, tb.ld, FT_M, FT_KC));
+    TcFlatParams p;
+    p.n_rows = tb.n;
+    p.nq = nq;
+    p.ld = tb.ld;
+    p.nk = qp.nk;
+    p.nqb = qp.nqb;
+    p.nslices = qp.nslices;
+    p.slice_rows = qp.slice_rows;
+    p.stages = qp.stages;
+    p.row_tiles = row_tiles;
+    p.row_norm = tb.norm;
+    p.part_d = b.part_d;
+    p.part_p = b.part_p;
+    p.qtau = b.qtau;
+    VERS_CUDA(cudaFuncSetAttribute(tc_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qp.smem));
+    const uint64_t nitems = (uint64_t)qp.nslices * qp.nqb;
+    tc_flat_kernel<<<(unsigned)std::min<uint64_t>(nitems, ctx->sm_count), FT_THREADS, qp.smem, ctx->stream>>>(tm_q, p);
+    VERS_LAUNCH_CHECK(ctx);
+    VERS_TRY(launch_cand_merge(ctx, 32, b.part_d, b.part_p, b.pair_chunk_off, nq, 1, 1, b.cand_pos, b.cand_key, b.bound));
+    VERS_TRY(launch_rerank(ctx, 32, tb.rows, nullptr, tb.id_base, tb.ld, d_queries, nq, k, b.cand_pos, b.bound,
+                           tb.nmax_bits, b.cand_key, 3, out_ids, out_d, out_cnt, b.fail, tb.stats, b.fail_idx, b.n_fail));
+    // exact redo of the uncertified queries: the launch is sized for nq, the blocks read n_fail
+    RowSrc CA{tb.rows, nullptr, tb.ld, tb.n};
+    RowSrc QF{d_queries, b.fail_idx, tb.ld, nq};
+    VERS_TRY(scan_topk_run(ctx, qp.exact, ctx->scratch, CA, QF, nq, tb.ld, k, VERS_METRIC_L2SQ, nullptr, tb.id_base,
+                           b.tmp_ids, b.tmp_d, nullptr, -1, b.n_fail));
+    probe_scatter_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(b.fail_idx, b.n_fail, b.tmp_ids, b.tmp_d, k, out_ids, out_d);
+    VERS_LAUNCH_CHECK(ctx);
+    return VERS_OK;
+}
+
 // exhaustive search (utils.rs:68-82) of a query batch through the same tensor-core candidate path: the dataset is the
 // table.  Declared in scan.cuh, called by vers_flat_search_dev (caller holds ctx->mu).
 int32_t flat_search_tc_plan_and_run(vers_ctx* ctx, const float* rows, uint64_t n, uint32_t ld, const float* norm,
                                     const uint32_t* nmax_bits, uint64_t id_base, unsigned long long* stats,
                                     const float* d_queries, uint32_t nq, uint32_t k, uint64_t* d_ids, float* d_d,
-                                    uint32_t* d_cnt, bool* used_tc) {
+                                    uint32_t* d_cnt, bool* used_tc, int flat_path, float** row_tiles_io) {
     RankTable tb;
     tb.rows = rows;
     tb.n = n;
@@ -1333,6 +1441,27 @@ int32_t flat_search_tc_plan_and_run(vers_ctx* ctx, const float* rows, uint64_t n
     tb.id_base = id_base;
     tb.allow_tc = true;
     tb.stats = stats;
+    if (flat_path != 2) {  // large batches: queries resident in tensor memory, the table streamed once per 128 queries
+        const QblockPlan qp = qblock_plan(ctx, n, ld, nq, k);
+        if (qp.ok && row_tiles_io) {
+            if (used_tc) *used_tc = true;
+            if (!*row_tiles_io) {  // the tile-major tf32 image of the table, built once per dataset
+                float* img = nullptr;
+                VERS_CUDA(cudaMalloc(&img, (size_t)ceil_div(n, FT_N) * qp.nk * FT_BOX_BYTES));
+                tile_image_tf32_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(rows, n, ld, qp.nk, img);
+                ctx->launches += 1;
+                const cudaError_t e = cudaGetLastError();
+                if (e != cudaSuccess) {
+                    cudaFree(img);
+                    return fail(VERS_ERR_CUDA, "tile image: %s", cudaGetErrorString(e));
+                }
+                *row_tiles_io = img;
+            }
+            VERS_TRY(scratch_reserve(ctx, qp.bytes));
+            VERS_CUDA(cudaMemsetAsync(stats, 0, 64, ctx->stream));
+            return qblock_run(ctx, tb, qp, *row_tiles_io, d_queries, nq, k, d_ids, d_d, d_cnt, KF_FLAT_SCAN);
+        }
+    }
     const ProbePlan pp = probe_plan(ctx, tb, nq, k);
     if (used_tc) *used_tc = pp.tc;
     if (!pp.tc) return VERS_ERR_UNSUPPORTED;  // the caller runs the exact-order engine

@@ -301,6 +301,7 @@ extern "C" int32_t vers_kmeans_free(vers_kmeans* km) {
     cudaFree(km->d_cent_norm);
     cudaFree(km->d_cent_hi);
     cudaFree(km->d_cent_lo);
+    cudaFree(km->d_cent_tiles);
     cudaFree(km->d_ncmax);
     cudaFree(km->d_flagged);
     cudaFree(km->d_nflagged);
@@ -437,7 +438,7 @@ static int32_t kmeans_tc_buffers(vers_kmeans* km) {
     if (km->d_row_norm && km->norm_epoch == ds->epoch) return VERS_OK;
     if (!km->d_row_norm) {
         // all or nothing: a failed allocation must not leave a half-initialised state behind
-        float *row_norm = nullptr, *cent_norm = nullptr, *cent_hi = nullptr, *cent_lo = nullptr;
+        float *row_norm = nullptr, *cent_norm = nullptr, *cent_hi = nullptr, *cent_lo = nullptr, *cent_tiles = nullptr;
         uint32_t *ncmax = nullptr, *flagged = nullptr, *nflagged = nullptr, *exact = nullptr;
         cudaError_t e = cudaSuccess;
         auto A = [&](void** p, size_t bytes) {
@@ -447,6 +448,8 @@ static int32_t kmeans_tc_buffers(vers_kmeans* km) {
         A((void**)&cent_norm, ((size_t)km->C + KA_N) * 4);
         A((void**)&cent_hi, (size_t)km->C * ds->ld * 4);
         A((void**)&cent_lo, (size_t)km->C * ds->ld * 4);
+        if (ds->ld <= K1_MAX_KCH * K1_KC)  // image of the centroid tiles for tc_assign1_kernel
+            A((void**)&cent_tiles, (size_t)ceil_div(km->C, K1_N) * ((ds->ld + K1_KC - 1) / K1_KC) * K1_BOX_BYTES);
         A((void**)&ncmax, 4);
         A((void**)&flagged, ds->n * 4);
         A((void**)&nflagged, 4);
@@ -457,12 +460,13 @@ static int32_t kmeans_tc_buffers(vers_kmeans* km) {
             if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         }
         if (e != cudaSuccess) {
-            cudaFree(row_norm), cudaFree(cent_norm), cudaFree(cent_hi), cudaFree(cent_lo);
+            cudaFree(row_norm), cudaFree(cent_norm), cudaFree(cent_hi), cudaFree(cent_lo), cudaFree(cent_tiles);
             cudaFree(ncmax), cudaFree(flagged), cudaFree(nflagged), cudaFree(exact);
             return fail(e == cudaErrorMemoryAllocation ? VERS_ERR_NOMEM : VERS_ERR_CUDA, "kmeans assign buffers: %s",
                         cudaGetErrorString(e));
         }
         km->d_row_norm = row_norm, km->d_cent_norm = cent_norm, km->d_cent_hi = cent_hi, km->d_cent_lo = cent_lo;
+        km->d_cent_tiles = cent_tiles;
         km->d_ncmax = ncmax, km->d_flagged = flagged, km->d_nflagged = nflagged, km->d_exact = exact;
     }
     // (re)computed whenever the rows changed since (vers_dataset_normalize bumps ds->epoch)
@@ -485,24 +489,25 @@ static int32_t kmeans_assign_tc(vers_kmeans* km) {
                                                                                km->d_cent_norm, km->d_ncmax);
     VERS_LAUNCH_CHECK(ctx);
     if (tf32_first) {
-        round_tf32_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(km->d_cents, (uint64_t)km->C * (ds->ld >> 2), km->d_cent_hi);
+        const uint32_t nk1 = (ds->ld + K1_KC - 1) / K1_KC;
+        tile_image_tf32_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(km->d_cents, km->C, ds->ld, nk1, km->d_cent_tiles);
         VERS_LAUNCH_CHECK(ctx);
-        CUtensorMap tm_rows, tm_c;
+        CUtensorMap tm_rows;
         VERS_TRY(make_tmap_2d_f32(&tm_rows, ds->d_rows, ds->n, ds->ld, ds->ld, K1_M, K1_KC));
-        VERS_TRY(make_tmap_2d_f32(&tm_c, km->d_cent_hi, km->C, ds->ld, ds->ld, K1_N, K1_KC));
         TcAssign1Params p;
         p.n_rows = ds->n;
         p.C = km->C;
         p.ld = ds->ld;
         p.rows = ds->d_rows;
         p.cents = km->d_cents;
+        p.cent_tiles = km->d_cent_tiles;
         p.row_norm = km->d_row_norm;
         p.cent_norm = km->d_cent_norm;
         p.ncmax_bits = km->d_ncmax;
         p.assign = km->d_assign;
         p.flagged = km->d_flagged;
         p.n_flagged = km->d_nflagged;
-        void (*kern)(CUtensorMap, CUtensorMap, TcAssign1Params) = nullptr;
+        void (*kern)(CUtensorMap, TcAssign1Params) = nullptr;
         switch ((ds->ld + K1_KC - 1) / K1_KC) {
             case 1: kern = tc_assign1_kernel<1>; break;
             case 2: kern = tc_assign1_kernel<2>; break;
@@ -512,7 +517,7 @@ static int32_t kmeans_assign_tc(vers_kmeans* km) {
         VERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES));
         FamilyTimer ft(ctx, KF_ASSIGN);
         const uint64_t nrbp = ceil_div(ds->n, 2 * K1_M);
-        kern<<<(unsigned)std::min<uint64_t>(nrbp, ctx->sm_count), K1_THREADS, K1_SMEM_BYTES, s>>>(tm_rows, tm_c, p);
+        kern<<<(unsigned)std::min<uint64_t>(nrbp, ctx->sm_count), K1_THREADS, K1_SMEM_BYTES, s>>>(tm_rows, p);
         VERS_LAUNCH_CHECK(ctx);
     } else {
         split_tf32_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(km->d_cents, (uint64_t)km->C * (ds->ld >> 2), km->d_cent_hi,

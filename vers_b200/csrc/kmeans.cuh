@@ -29,6 +29,7 @@ struct vers_kmeans {
     float* d_cent_norm = nullptr;    // [C]
     float* d_cent_hi = nullptr;      // [C][ld] tf32 hi part of the centroids
     float* d_cent_lo = nullptr;      // [C][ld] tf32 lo part
+    float* d_cent_tiles = nullptr;   // shared-memory image of the rounded centroid tiles (tc_assign1_kernel's B operand)
     uint32_t* d_ncmax = nullptr;     // [1] bits of max ||c||^2
     uint32_t* d_flagged = nullptr;   // [n] rows whose candidate argmin was not certified
     uint32_t* d_nflagged = nullptr;  // [1]

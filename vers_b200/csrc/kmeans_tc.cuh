@@ -310,6 +310,7 @@ struct TcAssign1Params {
     uint32_t C, ld;
     const float* rows;       // [n][ld] the rows themselves (exact rerank)
     const float* cents;      // [C][ld] the centroids themselves (exact rerank)
+    const float* cent_tiles; // tile_image_tf32_kernel's image of the centroids: [ceil(C/64)][nk][64][32] swizzled
     const float* row_norm;   // [n] ||x||^2 (any order)
     const float* cent_norm;  // [round_up(C, 128)] ||c||^2 (any order), +inf past C
     const uint32_t* ncmax_bits;
@@ -317,22 +318,6 @@ struct TcAssign1Params {
     uint32_t* flagged;
     uint32_t* n_flagged;
 };
-
-__device__ __forceinline__ uint32_t round_tf32_bits(uint32_t u) {  // round to nearest even at bit 13
-    return (u + 0xFFFu + ((u >> 13) & 1u)) & 0xFFFFE000u;
-}
-
-// centroids rounded to nearest tf32 (the tensor core would truncate; rounding halves the error term)
-__global__ void round_tf32_kernel(const float* __restrict__ in, uint64_t n4, float* __restrict__ out) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
-        float4 v = reinterpret_cast<const float4*>(in)[i];
-        v.x = __uint_as_float(round_tf32_bits(__float_as_uint(v.x)));
-        v.y = __uint_as_float(round_tf32_bits(__float_as_uint(v.y)));
-        v.z = __uint_as_float(round_tf32_bits(__float_as_uint(v.z)));
-        v.w = __uint_as_float(round_tf32_bits(__float_as_uint(v.w)));
-        reinterpret_cast<float4*>(out)[i] = v;
-    }
-}
 
 // sorted insertion into the five smallest keys (ids for the first four); strict `<`: an equal key stays behind
 __device__ __forceinline__ void k1_insert(float (&k)[5], uint32_t (&id)[4], float key, uint32_t idx) {
@@ -365,8 +350,7 @@ __device__ __forceinline__ bool k1_elect_one() {
 
 template <int NK>  // K chunks of 32 floats: ld <= 32 NK
 __global__ void __launch_bounds__(K1_THREADS, 1)
-    tc_assign1_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_c,
-                      TcAssign1Params p) {
+    tc_assign1_kernel(const __grid_constant__ CUtensorMap tmap_rows, TcAssign1Params p) {
     extern __shared__ uint8_t k1_smem_raw[];
     const uint32_t raw = tc::smem_u32(k1_smem_raw);
     uint8_t* smem = k1_smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -406,7 +390,6 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
         }
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&tmap_rows);
-        tc::tma_prefetch_desc(&tmap_c);
     }
     if (warp == 1) tc::tmem_alloc(tmem_slot, K1_TMEM_COLS);
     tc::fence_before_thread_sync();
@@ -433,13 +416,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
             }
             for (uint32_t ct = 0; ct < nct; ++ct) {
                 tc::mbar_wait(&empty[stage], phase ^ 1);
-                if (k1_elect_one()) {
+                if (k1_elect_one()) {  // the whole 64-centroid tile (all K chunks) is one linear copy of its image
                     tc::mbar_arrive_expect_tx(&full[stage], nk * K1_BOX_BYTES);
-                    uint8_t* sb = smem + stage * K1_STAGE_BYTES;
-#pragma unroll
-                    for (uint32_t kc = 0; kc < nk; ++kc)
-                        tc::tma_load_2d(sb + kc * K1_BOX_BYTES, &tmap_c, &full[stage], (int32_t)(kc * K1_KC),
-                                        (int32_t)(ct * K1_N));
+                    tc::bulk_load(smem + stage * K1_STAGE_BYTES, p.cent_tiles + (size_t)ct * nk * (K1_BOX_BYTES / 4),
+                                  nk * K1_BOX_BYTES, &full[stage]);
                 }
                 __syncwarp();
                 if (++stage == K1_STAGES) {

@@ -60,11 +60,14 @@ int32_t launch_merge(vers_ctx* ctx, const MergeParams& mp);
 
 // ivf.cu: exhaustive L2 search of a batch through the tensor-core candidate path (top-M keys -> exact-order rerank ->
 // certificate -> exact redo of uncertified queries).  Returns VERS_ERR_UNSUPPORTED (and *used_tc = false) when the
-// batch is not eligible; the caller then runs the exact-order engine.  stats: >= 8 device counters.
+// batch is not eligible; the caller then runs the exact-order engine.  stats: >= 8 device counters.  norm must be
+// padded with +inf up to a multiple of 64 rows.  flat_path 2 forces the list-scan style kernel (rows on the M side, the
+// table re-streamed per 32 queries); otherwise eligible batches take tc_flat_kernel (queries resident in TMEM), which
+// streams a tile-major tf32 image of the table: *row_tiles_io caches it (allocated on first use, owned by the caller).
 int32_t flat_search_tc_plan_and_run(vers_ctx* ctx, const float* rows, uint64_t n, uint32_t ld, const float* norm,
                                     const uint32_t* nmax_bits, uint64_t id_base, unsigned long long* stats,
                                     const float* d_queries, uint32_t nq, uint32_t k, uint64_t* d_ids, float* d_d,
-                                    uint32_t* d_cnt, bool* used_tc);
+                                    uint32_t* d_cnt, bool* used_tc, int flat_path = 0, float** row_tiles_io = nullptr);
 int32_t launch_rownorm(vers_ctx* ctx, const float* rows, uint32_t ld, uint64_t n, float* norm, uint32_t* nmax_bits);
 
 // exclusive scan of n uint32 -> uint64 out[n+1] (single block; n up to a few million is fine)

@@ -178,4 +178,37 @@ __device__ __forceinline__ void tmem_st_32(uint32_t taddr, const uint32_t (&r)[3
 
 }  // namespace tc
 
+__device__ __forceinline__ uint32_t round_tf32_bits(uint32_t u) {  // round to nearest even at bit 13
+    return (u + 0xFFFu + ((u >> 13) & 1u)) & 0xFFFFE000u;
+}
+
+// A row table [n][ld] fp32 rounded to nearest tf32 (the tensor core would truncate; rounding halves the error term),
+// written as the SHARED-MEMORY IMAGE of 64-row B tiles: per tile and K chunk one [64 rows x 32 floats] box in the
+// 128-byte swizzle the UMMA descriptor expects (16-byte chunk c of row r at chunk position c ^ (r & 7)), the boxes of
+// a tile back to back, rows past n and columns past ld zero.  A tile is then ONE linear cp.async.bulk of nk x 8 KB
+// instead of nk TMA boxes of 64 separate 128-byte rows: the TMA row-request rate (~1 per 6-8 clk per SM), not L2 or HBM
+// bandwidth, is what bounds a kernel that streams such boxes (measured: 52 % tensor-pipe activity in tc_assign1_kernel,
+// 11 % in tc_flat_kernel with 2D TMA loads).
+static __global__ void tile_image_tf32_kernel(const float* __restrict__ in, uint64_t n, uint32_t ld, uint32_t nk,
+                                              float* __restrict__ out) {
+    const uint64_t n4 = ((n + 63) / 64) * nk * 64 * 8;  // float4s of the image
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c4 = (uint32_t)(i & 7u);        // chunk position inside the 128-byte row of the image
+        const uint32_t r = (uint32_t)((i >> 3) & 63u);  // row of the box
+        const uint64_t box = i >> 9;                   // (tile, K chunk)
+        const uint32_t kc = (uint32_t)(box % nk);
+        const uint64_t tile = box / nk;
+        const uint32_t src_c4 = c4 ^ (r & 7u);         // the logical chunk stored at this position
+        const uint64_t row = tile * 64 + r;
+        const uint32_t col = kc * 32 + src_c4 * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < n && col < ld) v = *reinterpret_cast<const float4*>(in + row * ld + col);  // ld % 4 == 0
+        v.x = __uint_as_float(round_tf32_bits(__float_as_uint(v.x)));
+        v.y = __uint_as_float(round_tf32_bits(__float_as_uint(v.y)));
+        v.z = __uint_as_float(round_tf32_bits(__float_as_uint(v.z)));
+        v.w = __uint_as_float(round_tf32_bits(__float_as_uint(v.w)));
+        reinterpret_cast<float4*>(out)[i] = v;
+    }
+}
+
 }  // namespace vers

@@ -2,6 +2,8 @@
 // Built and run by tests/test_gpu_parity.py::test_cpp_host_mirror (prints "host_check ok").
 #include <cstdio>
 #include <cstdlib>
+#include <iterator>
+#include <string>
 
 #include "vers_index.hpp"
 #include "../include/vers_synth.h"
@@ -49,6 +51,29 @@ int main(int argc, char** argv) {
     if (l.empty() || l[0].first != 42) {
         std::printf("lsh: nearest of a member is not itself\n");
         return 1;
+    }
+    // ANNIndex: add, save_index, load_index (the reference's run_test order) — same neighbours, byte-identical re-save
+    Vector<N> extra2 = rows[9];
+    extra2[1] += 0.25f;
+    ann->add(extra2, n);
+    const std::string apath = std::string(path) + ".ann";
+    ann->save_index(apath);
+    auto ann2 = ANNIndex<N>::load_index(ctx, apath, 4);
+    auto l2 = ann2->search_approximate(rows[42], k);
+    auto l1 = ann->search_approximate(rows[42], k);
+    if (l1 != l2 || ann2->search_approximate(extra2, 1)[0].first != n) {
+        std::printf("lsh: save/load changed the result\n");
+        return 1;
+    }
+    ann2->save_index(apath + "2");
+    {
+        std::ifstream a(apath, std::ios::binary), b(apath + "2", std::ios::binary);
+        std::string sa((std::istreambuf_iterator<char>(a)), std::istreambuf_iterator<char>());
+        std::string sb((std::istreambuf_iterator<char>(b)), std::istreambuf_iterator<char>());
+        if (sa.empty() || sa != sb) {
+            std::printf("lsh: re-saved index differs\n");
+            return 1;
+        }
     }
     bool threw = false;
     try {

@@ -8,7 +8,8 @@
 //   vers::ANNIndex<N>::build_index          indexes/lsh.rs:132-161
 //   vers::search_exhaustive                 utils.rs:68-82
 // Error behaviour: the reference panics; here every non-zero ABI status throws vers::Panic (std::runtime_error).
-// save_index / load_index write/read the reference's bincode 1.3 layout of IVFFlatIndex (ivfflat.rs:9-15).
+// save_index / load_index write/read the reference's bincode 1.3 layouts of IVFFlatIndex (ivfflat.rs:9-15) and
+// ANNIndex (lsh.rs:13-55, the recursive Node enum included).
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -200,6 +201,7 @@ class ANNIndex : public Index<N> {
         std::unique_ptr<ANNIndex> ix(new ANNIndex());
         check(vers_lsh_build_index(ctx.h, &vectors[0].v[0], vectors.size(), N, vector_stride<N>(), vector_ids.data(),
                                    (uint32_t)num_trees, (uint32_t)max_size, seed, &ix->lsh_));
+        ix->max_node_size_ = max_size;
         return ix;
     }
     ~ANNIndex() override { vers_lsh_free(lsh_); }
@@ -213,13 +215,162 @@ class ANNIndex : public Index<N> {
         for (uint32_t i = 0; i < cnt; ++i) out.emplace_back((size_t)ids[i], d[i]);
         return out;
     }
-    void save_index(const std::string&) const override {
-        throw std::runtime_error("ANNIndex::save_index: the recursive Node enum layout is not mirrored yet (SURVEY §8f)");
+    // Index::save_index (base.rs:31-43): bincode 1.3 layout of ANNIndex (lsh.rs:13-55):
+    //   max_node_size u64 | trees: u64 len, every tree as the recursive enum Node { Inner(Box<InnerNode>) = variant 0:
+    //   coefficients N f32, constant f32, left_node, right_node | Leaf(Box<LeafNode(Vec<usize>)>) = variant 1: u64 len,
+    //   len u64 } | values: u64 len, len * N f32 | ids: u64 len, len u64
+    void save_index(const std::string& file_path) const override {
+        uint64_t nv = 0, nn_all = 0;
+        uint32_t nt = 0;
+        check(vers_lsh_info(lsh_, &nv, &nt, &nn_all));
+        std::ofstream f(file_path, std::ios::binary);
+        if (!f) throw std::runtime_error("save_index: cannot open " + file_path);
+        auto put64 = [&](uint64_t v) { f.write(reinterpret_cast<const char*>(&v), 8); };
+        auto put32 = [&](uint32_t v) { f.write(reinterpret_cast<const char*>(&v), 4); };
+        put64(max_node_size_);
+        put64(nt);
+        for (uint32_t t = 0; t < nt; ++t) {
+            uint32_t nn = 0, ni = 0;
+            uint64_t nit = 0;
+            check(vers_lsh_flatten(lsh_, t, nullptr, nullptr, nullptr, nullptr, nullptr, &nn, &ni, &nit));
+            std::vector<uint8_t> kind(nn);
+            std::vector<uint32_t> leaf_len(nn), items(nit ? nit : 1);
+            std::vector<float> planes((size_t)ni * N + 1), consts(ni + 1);
+            check(vers_lsh_flatten(lsh_, t, kind.data(), leaf_len.data(), planes.data(), consts.data(), items.data(), &nn,
+                                   &ni, &nit));
+            // the flattened preorder is (node, ABOVE subtree, BELOW subtree); the file wants (node, left = below, right =
+            // above): per node its plane / item offset and the end of its subtree, then an explicit-stack emit
+            std::vector<uint32_t> plane_of(nn, 0), end(nn, 0);
+            std::vector<uint64_t> item_off(nn, 0);
+            uint32_t pi = 0;
+            uint64_t io = 0;
+            for (uint32_t i = 0; i < nn; ++i) {
+                if (kind[i] == 0) plane_of[i] = pi++;
+                else { item_off[i] = io; io += leaf_len[i]; }
+            }
+            std::vector<std::pair<uint32_t, int>> open_nodes;
+            for (uint32_t i = 0; i < nn; ++i) {
+                if (kind[i] == 0) { open_nodes.emplace_back(i, 2); continue; }
+                end[i] = i + 1;
+                while (!open_nodes.empty() && --open_nodes.back().second == 0) {
+                    end[open_nodes.back().first] = i + 1;
+                    open_nodes.pop_back();
+                }
+            }
+            std::vector<uint32_t> todo{0};
+            while (!todo.empty()) {
+                const uint32_t i = todo.back();
+                todo.pop_back();
+                if (kind[i] == 1) {
+                    put32(1);
+                    put64(leaf_len[i]);
+                    for (uint32_t e = 0; e < leaf_len[i]; ++e) put64(items[item_off[i] + e]);
+                } else {
+                    put32(0);
+                    f.write(reinterpret_cast<const char*>(&planes[(size_t)plane_of[i] * N]), N * 4);
+                    f.write(reinterpret_cast<const char*>(&consts[plane_of[i]]), 4);
+                    todo.push_back(i + 1);       // above = right_node: emitted second
+                    todo.push_back(end[i + 1]);  // below = left_node: emitted first
+                }
+            }
+        }
+        std::vector<float> values((size_t)nv * N + 1);
+        std::vector<uint64_t> ids(nv + 1);
+        check(vers_lsh_get_values(lsh_, values.data(), N, ids.data()));
+        put64(nv);
+        f.write(reinterpret_cast<const char*>(values.data()), (std::streamsize)((size_t)nv * N * 4));
+        put64(nv);
+        f.write(reinterpret_cast<const char*>(ids.data()), (std::streamsize)(nv * 8));
+        if (!f) throw std::runtime_error("save_index: write failed");
+    }
+    // Index::load_index (base.rs:45-58) + the device forest (vers_lsh_from_parts); seed feeds later leaf splits
+    static std::unique_ptr<ANNIndex> load_index(Context& ctx, const std::string& file_path, uint64_t seed = 4) {
+        std::ifstream f(file_path, std::ios::binary);
+        if (!f) throw std::runtime_error("load_index: cannot open " + file_path);
+        auto get64 = [&]() { uint64_t v = 0; f.read(reinterpret_cast<char*>(&v), 8); return v; };
+        auto get32 = [&]() { uint32_t v = 0; f.read(reinterpret_cast<char*>(&v), 4); return v; };
+        std::unique_ptr<ANNIndex> ix(new ANNIndex());
+        ix->max_node_size_ = get64();
+        const uint64_t nt = get64();
+        std::vector<uint32_t> tree_nodes, leaf_len, items;
+        std::vector<uint8_t> kind;
+        std::vector<float> planes, consts;
+        // the file is (node, left = below, right = above); vers_lsh_from_parts wants (node, above, below): parse each
+        // tree into node records first, then walk it in the other order
+        struct Rec { uint8_t kind; uint32_t left, right; size_t plane, item0; uint32_t len; };
+        for (uint64_t t = 0; t < nt; ++t) {
+            std::vector<Rec> recs;
+            std::vector<float> tp, tc;
+            std::vector<uint32_t> ti;
+            std::vector<std::pair<uint32_t, int>> open_nodes;  // (inner node, children attached so far)
+            auto attach = [&](uint32_t child) {
+                while (true) {
+                    if (open_nodes.empty()) return;
+                    auto& top = open_nodes.back();
+                    if (top.second == 0) { recs[top.first].left = child; top.second = 1; return; }
+                    recs[top.first].right = child;
+                    open_nodes.pop_back();
+                    return;
+                }
+            };
+            do {
+                const uint32_t variant = get32();
+                if (!f) throw std::runtime_error("load_index: truncated tree");
+                const uint32_t me = (uint32_t)recs.size();
+                if (variant == 1) {
+                    const uint64_t len = get64();
+                    recs.push_back(Rec{1, 0, 0, 0, ti.size(), (uint32_t)len});
+                    for (uint64_t e = 0; e < len; ++e) ti.push_back((uint32_t)get64());
+                    if (me) attach(me);
+                } else if (variant == 0) {
+                    recs.push_back(Rec{0, 0, 0, tc.size(), 0, 0});
+                    tp.resize(tp.size() + N);
+                    f.read(reinterpret_cast<char*>(&tp[tp.size() - N]), N * 4);
+                    float c = 0.f;
+                    f.read(reinterpret_cast<char*>(&c), 4);
+                    tc.push_back(c);
+                    if (me) attach(me);
+                    open_nodes.emplace_back(me, 0);
+                } else {
+                    throw std::runtime_error("load_index: bad Node variant (wrong N or not an ANNIndex file)");
+                }
+            } while (!open_nodes.empty());
+            const size_t n0 = kind.size();
+            std::vector<uint32_t> todo{0};
+            while (!todo.empty()) {
+                const Rec& r = recs[todo.back()];
+                todo.pop_back();
+                kind.push_back(r.kind);
+                leaf_len.push_back(r.len);
+                if (r.kind == 1) {
+                    items.insert(items.end(), ti.begin() + (long)r.item0, ti.begin() + (long)(r.item0 + r.len));
+                } else {
+                    planes.insert(planes.end(), tp.begin() + (long)(r.plane * N), tp.begin() + (long)((r.plane + 1) * N));
+                    consts.push_back(tc[r.plane]);
+                    todo.push_back(r.left);   // below: visited second
+                    todo.push_back(r.right);  // above: visited first
+                }
+            }
+            tree_nodes.push_back((uint32_t)(kind.size() - n0));
+        }
+        const uint64_t nv = get64();
+        std::vector<float> values((size_t)nv * N + 1);
+        f.read(reinterpret_cast<char*>(values.data()), (std::streamsize)((size_t)nv * N * 4));
+        const uint64_t ni = get64();
+        std::vector<uint64_t> ids(ni + 1);
+        f.read(reinterpret_cast<char*>(ids.data()), (std::streamsize)(ni * 8));
+        if (!f || ni != nv) throw std::runtime_error("load_index: truncated file");
+        planes.push_back(0.f), consts.push_back(0.f), items.push_back(0), kind.push_back(0), leaf_len.push_back(0);
+        check(vers_lsh_from_parts(ctx.h, values.data(), nv, N, N, ids.data(), (uint32_t)nt, (uint32_t)ix->max_node_size_, seed,
+                                  tree_nodes.data(), kind.data(), leaf_len.data(), planes.data(), consts.data(),
+                                  items.data(), &ix->lsh_));
+        return ix;
     }
 
   private:
     ANNIndex() = default;
     vers_lsh* lsh_ = nullptr;
+    uint64_t max_node_size_ = 0;
 };
 
 }  // namespace vers

@@ -199,6 +199,11 @@ int32_t vers_ivf_search_probed_dev(vers_ivf* ivf, const float* d_queries, uint32
  * (the id is assignments.len()); *assigned_id / *cluster report what was stored. */
 int32_t vers_ivf_add(vers_ivf* ivf, const float* embedding, uint64_t vec_id, uint64_t* assigned_id,
                      uint32_t* cluster);
+/* Index::add for a batch, in order (exactly n sequential adds: the centroids do not move on add): embedding i gets id
+ * assignments.len() + i; one exact-order assign launch, at most one re-layout of the lists, one scatter.  A NaN
+ * distance returns VERS_ERR_PANIC with nothing modified.  assigned_ids / clusters may be NULL. */
+int32_t vers_ivf_add_batch(vers_ivf* ivf, const float* embeddings, uint64_t n, uint32_t stride_floats,
+                           uint64_t* assigned_ids, uint32_t* clusters);
 
 /* merge `parts` per-shard result lists per query into the global top_k by (distance, id): the step after the
  * NCCL all-gather of per-GPU top-k.  Part p's [nq][top_k] block starts at d_ids_all + p*part_stride_ids (u64
@@ -266,6 +271,13 @@ int32_t vers_sharded_ivf_search(vers_comm* comm, vers_ivf* ivf, const float* que
                                 uint32_t* counts);
 int32_t vers_sharded_ivf_search_dev(vers_comm* comm, vers_ivf* ivf, const float* d_queries, uint32_t nq, uint32_t top_k,
                                     uint32_t nprobe, uint64_t* d_ids, float* d_dists, uint32_t* d_counts);
+/* ANNIndex::search_approximate (lsh.rs:264-282) for a batch with the forest REPLICATED on every rank (tree construction
+ * is a data-dependent recursion and does not shard; the reference parallelises the search over trees and queries,
+ * lsh.rs:146,268): every rank passes the SAME queries, searches its 1/world slice of them on its replica, and the
+ * slices are all-gathered (ncclAllGather of ids + distances + counts), so every rank returns the full result.
+ * Hashing a row shard (vers_lsh_hash) needs no collective at all: rows are independent. */
+int32_t vers_sharded_lsh_search(vers_comm* comm, vers_lsh* lsh, const float* queries, uint32_t nq,
+                                uint32_t q_stride_floats, uint32_t top_k, uint64_t* ids, float* dists, uint32_t* counts);
 
 /* ---- "LSH" random-hyperplane forest (indexes/lsh.rs) -------------------------------------------------------- */
 /* Hyperplane::point_is_above (lsh.rs:27-29) for every row x every plane: bits[r*P + p] = dot(plane_p, row_r) +
@@ -287,8 +299,20 @@ int32_t vers_lsh_flatten(const vers_lsh* lsh, uint32_t tree, uint8_t* kind, uint
 /* Index::search_approximate (lsh.rs:264-282) for a batch; ties by deduplicated row index */
 int32_t vers_lsh_search(vers_lsh* lsh, const float* queries, uint32_t nq, uint32_t q_stride_floats, uint32_t top_k,
                         uint64_t* ids, float* dists, uint32_t* counts);
-/* Index::add (lsh.rs:255-263) */
+/* Index::add (lsh.rs:255-263).  vec_id is stored in the leaves as a ROW INDEX like the reference does (lsh.rs:247): an id
+ * that is not one returns VERS_ERR_PANIC before anything is modified. */
 int32_t vers_lsh_add(vers_lsh* lsh, const float* embedding, uint64_t vec_id);
+/* `values` and `ids` of the struct (lsh.rs:47-55): the deduplicated rows in stored order, rows added later included —
+ * what Index::save_index serialises.  Either pointer may be NULL; sizes from vers_lsh_info. */
+int32_t vers_lsh_get_values(const vers_lsh* lsh, float* values, uint32_t stride_floats, uint64_t* ids);
+/* The device forest from deserialised parts (Index::load_index, base.rs:45-58; struct layout lsh.rs:13-55).  values:
+ * the stored (already deduplicated) rows; the trees arrive concatenated, each in the preorder of vers_lsh_flatten
+ * (node, ABOVE subtree, BELOW subtree): tree_nodes[t] nodes for tree t, kind / leaf_len per node, planes [dim] and
+ * consts per inner node, items per leaf.  seed only feeds the sample pairs of later leaf splits (Index::add). */
+int32_t vers_lsh_from_parts(vers_ctx* ctx, const float* values, uint64_t n, uint32_t dim, uint32_t stride_floats,
+                            const uint64_t* ids, uint32_t num_trees, uint32_t max_size, uint64_t seed,
+                            const uint32_t* tree_nodes, const uint8_t* kind, const uint32_t* leaf_len,
+                            const float* planes, const float* consts, const uint32_t* items, vers_lsh** out);
 
 #ifdef __cplusplus
 }

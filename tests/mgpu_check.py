@@ -94,6 +94,22 @@ def main():
         assert np.array_equal(ids.cpu().numpy().view(np.uint64), oi)
         del g
 
+    # --- hyperplane forest: replicated on every rank (tree construction does not shard), queries sharded, slices
+    #     all-gathered (vers_sharded_lsh_search): the oracle's ids and distance bits on every rank
+    import ctypes as C
+    frows = rows[:6000]
+    g = vb.ANNIndex.build_index(6, 40, frows, None, seed=4, ctx=ctx)
+    o = vo.LSH(frows, None, 6, 40, 4)
+    fq = np.ascontiguousarray(q[:51])
+    fi = np.empty((51, 7), np.uint64)
+    fd = np.empty((51, 7), np.float32)
+    fc = np.empty(51, np.uint32)
+    vb._abi.check(vb.lib().vers_sharded_lsh_search(comm.h, g.h, fq.ctypes.data_as(C.c_void_p), 51, dim, 7,
+                                                   fi.ctypes.data_as(C.c_void_p), fd.ctypes.data_as(C.c_void_p),
+                                                   fc.ctypes.data_as(C.c_void_p)))
+    oi, od, oc = o.search(fq, 7)
+    assert np.array_equal(fi, oi) and np.array_equal(bits(fd), bits(od)) and np.array_equal(fc, oc), "sharded LSH search"
+
     # --- all-reduce mode: same counts, centroids within tolerance of the oracle's sharded-order mode
     km2 = vb.KMeans(ds, C)
     kmeans_fit_sharded(comm, km2, init, 1, reduce="allreduce")

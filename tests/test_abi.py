@@ -166,3 +166,22 @@ def test_bincode_ann_index_layout(tmp_path, vo):
         ls = leaves(trees[t])
         assert all(l.shape[0] < max_size for l in ls)
         assert np.array_equal(np.sort(np.concatenate(ls)), np.arange(keep.shape[0], dtype=np.uint64))
+
+
+def test_rust_sys_crate_declares_the_whole_header():
+    """rust/vers-cuda-sys/src/lib.rs is generated from include/vers_device.h (tools/gen_rust_sys.py): it must be up to
+    date and declare every entry point the header (and the ctypes table) does"""
+    import re
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert subprocess.run([sys.executable, os.path.join(root, "tools", "gen_rust_sys.py"), "--check"]).returncode == 0, \
+        "rust/vers-cuda-sys/src/lib.rs is stale: run tools/gen_rust_sys.py"
+    rs = open(os.path.join(root, "rust", "vers-cuda-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (vers_\w+)\(", rs))
+    from vers_b200 import _abi
+
+    assert declared == set(_abi.SIGNATURES), sorted(declared ^ set(_abi.SIGNATURES))
+    used = set(re.findall(r"sys::(vers_\w+)\(", open(os.path.join(root, "rust", "vers-gpu", "src", "lib.rs")).read()))
+    assert used <= declared, sorted(used - declared)

@@ -520,6 +520,43 @@ def test_ivf_add_then_search(vb, vo, ctx):
         assert np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od)) and np.array_equal(cnt, oc)
 
 
+def test_ivf_add_batch_equals_sequential_adds(vb, vo, ctx):
+    """vers_ivf_add_batch == the same embeddings added one by one (ivfflat.rs:200-213): ids, clusters, list contents and
+    every later search; large enough to overflow the lists' slack (one re-layout); a NaN row panics and changes nothing"""
+    n, dim, C = 3000, 64, 12
+    rows = data(vo, n, dim)
+    extra = data(vo, 700, dim, seed=5)
+    init = vo.init_rows(3, 1, C, n)
+    a = vb.IVFFlatIndex.build_index(C, 1, 6, rows, init_rows=init, ctx=ctx)
+    b = vb.IVFFlatIndex.build_index(C, 1, 6, rows, init_rows=init, ctx=ctx)
+    ids, cl = a.add_batch(extra)
+    seq = [b.add(extra[i], 12345) for i in range(extra.shape[0])]
+    assert np.array_equal(ids, np.arange(n, n + 700, dtype=np.uint64)) and [int(x) for x in ids] == [s[0] for s in seq]
+    assert [int(x) for x in cl] == [s[1] for s in seq]
+    cents = a.centroids
+    assert np.array_equal(cl.astype(np.uint64), vo.assign(extra, cents))  # nearest centroid, first minimum
+    assert np.array_equal(a.assignments, b.assignments) and np.array_equal(a.list_sizes, b.list_sizes)
+    for c in range(C):
+        ia, ra = a.get_list(c, with_rows=True)
+        ib, rb = b.get_list(c, with_rows=True)
+        assert np.array_equal(ia, ib) and np.array_equal(bits(ra), bits(rb))
+    q = np.vstack([extra[:40], data(vo, 40, dim, seed=2)])
+    allrows = np.vstack([rows, extra])
+    off, lr = vo.ivf_lists(a.assignments, C)
+    for nprobe in (0, 3):
+        ga = a.search_batch(q, 5, nprobe=nprobe)
+        gb = b.search_batch(q, 5, nprobe=nprobe)
+        oi, od, oc = vo.ivf_search(allrows, cents, off, lr, q, 5, nprobe=nprobe)
+        assert np.array_equal(ga[0], gb[0]) and np.array_equal(bits(ga[1]), bits(gb[1]))
+        assert np.array_equal(ga[0], oi) and np.array_equal(bits(ga[1]), bits(od)) and np.array_equal(ga[2], oc)
+    bad = extra[:5].copy()
+    bad[2, 7] = np.nan
+    sizes = a.list_sizes.copy()
+    with pytest.raises(vb.VersPanic):
+        a.add_batch(bad)
+    assert np.array_equal(a.list_sizes, sizes) and len(a) == n + 700
+
+
 def test_ivf_from_parts_and_save_load_roundtrip(vb, vo, ctx, tmp_path, ivf_c1):
     s = ivf_c1
     p = str(tmp_path / "ivf.bin")
@@ -754,3 +791,45 @@ def test_lsh_save_index_writes_the_reference_layout(vb, vo, ctx, tmp_path):
     assert open(pg, "rb").read() == open(po, "rb").read()
     mns, trees, values, rid = read_ann(pg, dim)
     assert mns == max_size and len(trees) == T and values.shape == (n - 1, dim) and np.array_equal(rid, ids[keep])
+
+
+def test_lsh_load_index_roundtrip_after_adds(vb, vo, ctx, tmp_path):
+    """the reference's run_test order: build_index, add, save_index, load_index (base.rs:31-58): the loaded forest is
+    the same forest (structure, plane bits, leaf members), searches identically, still equals the oracle that went
+    through the same adds, and keeps accepting adds (leaf splits draw their sample pairs from the node path hash)"""
+    n, dim, T, max_size = 900, 40, 3, 10
+    rows = data(vo, n, dim, n_centers=8)
+    extra = data(vo, 120, dim, seed=5, n_centers=8)
+    g = vb.ANNIndex.build_index(T, max_size, rows, None, seed=4, ctx=ctx)
+    o = vo.LSH(rows, None, T, max_size, 4)
+    for i in range(60):
+        g.add(extra[i], n + i)
+        o.add(extra[i], n + i)
+    path = str(tmp_path / "ann.bin")
+    g.save_index(path)
+    h = vb.ANNIndex.load_index(path, dim, seed=4, ctx=ctx)
+    assert h.info() == g.info() and h.max_node_size == max_size
+    _same_forest(h, o, T)
+    v, ids = h.values_and_ids()
+    assert np.array_equal(bits(v), bits(np.vstack([rows, extra[:60]]))) and np.array_equal(ids, np.arange(n + 60))
+    q = np.vstack([extra[:10], data(vo, 30, dim, seed=2, n_centers=8)])
+    hi, hd, hc = h.search_batch(q, 7)
+    gi, gd, gc = g.search_batch(q, 7)
+    oi, od, oc = o.search(q, 7)
+    assert np.array_equal(hi, gi) and np.array_equal(bits(hd), bits(gd)) and np.array_equal(hc, gc)
+    assert np.array_equal(hi, oi) and np.array_equal(bits(hd), bits(od)) and np.array_equal(hc, oc)
+    for i in range(60, 120):  # the loaded index and the original keep evolving identically
+        g.add(extra[i], n + i)
+        h.add(extra[i], n + i)
+        o.add(extra[i], n + i)
+    _same_forest(h, o, T)
+    _same_forest(g, o, T)
+    # a rejected add leaves the index untouched (vec_id is used as a row index, lsh.rs:247)
+    before = h.info()
+    with pytest.raises(vb.VersPanic):
+        h.add(extra[0], 10**6)
+    assert h.info() == before
+    path2 = str(tmp_path / "ann2.bin")
+    h.save_index(path2)
+    g.save_index(path)
+    assert open(path, "rb").read() == open(path2, "rb").read()

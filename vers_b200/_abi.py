@@ -89,6 +89,7 @@ SIGNATURES = {
     "vers_ivf_probe_dev": [vp, vp, u32, u32, vp],
     "vers_ivf_search_probed_dev": [vp, vp, u32, u32, u32, vp, vp, vp, vp],
     "vers_ivf_add": [vp, vp, u64, C.POINTER(u64), C.POINTER(u32)],
+    "vers_ivf_add_batch": [vp, vp, u64, u32, vp, vp],
     "vers_topk_merge_dev": [vp, vp, vp, u32, u64, u64, u32, u32, vp, vp, vp],
     "vers_peer_create": [vp, u32, u32, u64, pvp, vp],
     "vers_peer_connect": [vp, vp],
@@ -106,6 +107,7 @@ SIGNATURES = {
     "vers_sharded_list_owners": [vp, u32, u32, vp],
     "vers_sharded_ivf_search": [vp, vp, vp, u32, u32, u32, u32, vp, vp, vp],
     "vers_sharded_ivf_search_dev": [vp, vp, vp, u32, u32, u32, vp, vp, vp],
+    "vers_sharded_lsh_search": [vp, vp, vp, u32, u32, u32, vp, vp, vp],
     "vers_lsh_hash": [vp, vp, u32, u32, vp, vp],
     "vers_lsh_hash_dev": [vp, vp, u32, vp, vp],
     "vers_lsh_build_index": [vp, vp, u64, u32, u32, vp, u32, u32, u64, pvp],
@@ -114,6 +116,8 @@ SIGNATURES = {
     "vers_lsh_flatten": [vp, u32, vp, vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)],
     "vers_lsh_search": [vp, vp, u32, u32, u32, vp, vp, vp],
     "vers_lsh_add": [vp, vp, u64],
+    "vers_lsh_get_values": [vp, vp, u32, vp],
+    "vers_lsh_from_parts": [vp, vp, u64, u32, u32, vp, u32, u32, u64, vp, vp, vp, vp, vp, vp, pvp],
 }
 _RESTYPES = {"vers_last_error": C.c_char_p}
 

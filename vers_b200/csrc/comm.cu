@@ -810,3 +810,49 @@ extern "C" int32_t vers_sharded_ivf_search(vers_comm* cm, vers_ivf* ivf, const f
     VERS_CUDA(cudaStreamSynchronize(ctx->stream));
     return VERS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------- forest search, queries sharded
+extern "C" int32_t vers_sharded_lsh_search(vers_comm* cm, vers_lsh* lsh, const float* queries, uint32_t nq,
+                                           uint32_t q_stride_floats, uint32_t top_k, uint64_t* ids, float* dists,
+                                           uint32_t* counts) {
+    if (!cm || !lsh || (!queries && nq) || (!ids && nq && top_k) || (!dists && nq && top_k))
+        return fail(VERS_ERR_ARG, "sharded_lsh_search: null argument");
+    if (cm->world == 1) return vers_lsh_search(lsh, queries, nq, q_stride_floats, top_k, ids, dists, counts);
+    if (nq == 0) return VERS_OK;
+    if (top_k == 0) {
+        if (counts) memset(counts, 0, sizeof(uint32_t) * nq);
+        return VERS_OK;
+    }
+    vers_ctx* ctx = cm->ctx;
+    VERS_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t W = cm->world, per = (nq + W - 1) / W;
+    const uint32_t q0 = std::min(nq, cm->rank * per), nql = std::min(nq, q0 + per) - q0;
+    // my slice on my replica (host buffers in and out), packed as [per*k ids | per*k dists | per counts]
+    const size_t nk = (size_t)per * top_k, slot = (nk * 12 + (size_t)per * 4 + 15) & ~size_t(15);
+    std::vector<unsigned char> mine(slot, 0), all((size_t)slot * W);
+    uint64_t* m_ids = reinterpret_cast<uint64_t*>(mine.data());
+    float* m_d = reinterpret_cast<float*>(mine.data() + nk * 8);
+    uint32_t* m_c = reinterpret_cast<uint32_t*>(mine.data() + nk * 12);
+    if (nql) VERS_TRY(vers_lsh_search(lsh, queries + (size_t)q0 * q_stride_floats, nql, q_stride_floats, top_k, m_ids, m_d, m_c));
+    unsigned char* d_buf = nullptr;
+    VERS_CUDA(cudaMalloc(&d_buf, slot * (W + 1)));
+    int32_t rc = VERS_OK;
+    cudaError_t e = cudaMemcpyAsync(d_buf + slot * W, mine.data(), slot, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        ncclResult_t r = g_nccl.AllGather(d_buf + slot * W, d_buf, slot, ncclChar, cm->nccl, ctx->stream);
+        if (r != ncclSuccess) rc = fail(VERS_ERR_CUDA, "ncclAllGather(lsh results): %s", g_nccl.GetErrorString(r));
+    }
+    if (rc == VERS_OK && e == cudaSuccess) e = cudaMemcpyAsync(all.data(), d_buf, slot * W, cudaMemcpyDeviceToHost, ctx->stream);
+    if (rc == VERS_OK && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_buf);
+    if (rc == VERS_OK && e != cudaSuccess) rc = fail(VERS_ERR_CUDA, "sharded_lsh_search: %s", cudaGetErrorString(e));
+    VERS_TRY(rc);
+    for (uint32_t r = 0; r < W; ++r) {
+        const uint32_t r0 = std::min(nq, r * per), rn = std::min(nq, r0 + per) - r0;
+        const unsigned char* blk = all.data() + (size_t)slot * r;
+        memcpy(ids + (size_t)r0 * top_k, blk, (size_t)rn * top_k * 8);
+        memcpy(dists + (size_t)r0 * top_k, blk + nk * 8, (size_t)rn * top_k * 4);
+        if (counts) memcpy(counts + r0, blk + nk * 12, (size_t)rn * 4);
+    }
+    return VERS_OK;
+}

@@ -502,14 +502,16 @@ static int32_t ivf_from_state(vers_kmeans* km, float cost, uint32_t attempt, ver
 }
 
 // give every list slack capacity and move the rows (rare: only when an add hits a full list)
-static int32_t ivf_relayout(vers_ivf* ivf) {
+// (extra: optional per-list number of rows about to be appended; the slack is computed on top of it)
+static int32_t ivf_relayout(vers_ivf* ivf, const uint32_t* extra = nullptr) {
     vers_ctx* ctx = ivf->ctx;
     std::vector<uint64_t> noff(ivf->C);
     std::vector<uint32_t> ncap(ivf->C);
     uint64_t total = 0;
     for (uint32_t c = 0; c < ivf->C; ++c) {
         uint32_t len = ivf->seg_len[c];
-        uint32_t cap = len + std::max<uint32_t>(32u, len / 8);
+        const uint32_t want = len + (extra ? extra[c] : 0u);
+        uint32_t cap = want + std::max<uint32_t>(32u, want / 8);
         noff[c] = total;
         ncap[c] = cap;
         total += cap;
@@ -1995,5 +1997,123 @@ extern "C" int32_t vers_ivf_add(vers_ivf* ivf, const float* embedding, uint64_t 
     cudaFree(d_row);
     cudaFree(d_best);
     cudaFree(d_bd);
+    return rc;
+}
+
+namespace vers {
+// appended rows -> their list slots: row, global id, ||row||^2 (any order) and the running maximum
+__global__ void add_scatter_kernel(const float* __restrict__ rows, uint32_t ld, const uint64_t* __restrict__ pos,
+                                   uint64_t n, uint64_t first_id, float* __restrict__ lm, uint64_t* __restrict__ lm_ids,
+                                   float* __restrict__ lm_norm, uint32_t* nxmax) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    float mx = 0.0f;
+    for (uint64_t j = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); j < n; j += warps) {
+        const float4* src = reinterpret_cast<const float4*>(rows + j * ld);
+        float4* dst = reinterpret_cast<float4*>(lm + pos[j] * ld);
+        float s = 0.0f;
+        for (uint32_t c = lane; c < (ld >> 2); c += 32) {
+            const float4 v = src[c];
+            dst[c] = v;
+            s = __fmaf_rn(v.x, v.x, s);
+            s = __fmaf_rn(v.y, v.y, s);
+            s = __fmaf_rn(v.z, v.z, s);
+            s = __fmaf_rn(v.w, v.w, s);
+        }
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL_MASK, s, o);
+        if (lane == 0) {
+            lm_norm[pos[j]] = s;
+            lm_ids[pos[j]] = first_id + j;
+        }
+        mx = fmaxf(mx, s);
+    }
+    if (lane == 0 && mx > 0.0f) atomicMax(nxmax, __float_as_uint(mx));
+}
+}  // namespace vers
+
+// Index::add (ivfflat.rs:200-213) for a batch, in order: embedding i gets id assignments.len() + i and goes to its
+// nearest centroid (first minimum).  The centroids do not move on add, so this is exactly n sequential adds: one
+// exact-order assign launch over the batch, one relayout at most, one scatter into the list slots.
+extern "C" int32_t vers_ivf_add_batch(vers_ivf* ivf, const float* embeddings, uint64_t n, uint32_t stride_floats,
+                                      uint64_t* assigned_ids, uint32_t* clusters) {
+    if (!ivf || (!embeddings && n)) return fail(VERS_ERR_ARG, "ivf_add_batch: null argument");
+    if (stride_floats < ivf->dim) return fail(VERS_ERR_ARG, "ivf_add_batch: stride < dim");
+    if (n == 0) return VERS_OK;
+    if (n >= 0x7fffffffull || ivf->n + n >= 0xffffffffull) return fail(VERS_ERR_UNSUPPORTED, "ivf_add_batch: too many rows");
+    vers_ctx* ctx = ivf->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    VERS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    float* d_rows = nullptr;
+    uint32_t *d_assign = nullptr, *d_bad = nullptr;
+    uint64_t* d_pos = nullptr;
+    auto cleanup = [&]() { cudaFree(d_rows), cudaFree(d_assign), cudaFree(d_bad), cudaFree(d_pos); };
+    cudaError_t e = cudaMalloc(&d_rows, n * ivf->ld * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_assign, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_bad, 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_pos, n * 8);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, 4, s);
+    if (e == cudaSuccess && ivf->ld != ivf->dim) e = cudaMemsetAsync(d_rows, 0, n * ivf->ld * 4, s);
+    if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(d_rows, (size_t)ivf->ld * 4, embeddings, (size_t)stride_floats * 4, (size_t)ivf->dim * 4, n,
+                              cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(e == cudaErrorMemoryAllocation ? VERS_ERR_NOMEM : VERS_ERR_CUDA, "ivf_add_batch: %s", cudaGetErrorString(e));
+    }
+    // nearest centroid of every new row, first minimum on ties (min_by, ivfflat.rs:201-207)
+    RowSrc A{d_rows, nullptr, ivf->ld, n};
+    int32_t rc = kmeans_assign_rows(ctx, A, ivf->d_cents, ivf->C, ivf->ld, d_assign, KF_ASSIGN, d_bad);
+    std::vector<uint32_t> assign(n);
+    uint32_t bad = 0;
+    if (rc == VERS_OK) {
+        e = cudaMemcpyAsync(assign.data(), d_assign, n * 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = fail(VERS_ERR_CUDA, "ivf_add_batch: %s", cudaGetErrorString(e));
+    }
+    if (rc == VERS_OK && bad)
+        rc = fail(VERS_ERR_PANIC, "ivf_add: a distance is NaN (partial_cmp(..).unwrap() panics, ivfflat.rs:207)");
+    if (rc != VERS_OK) {
+        cleanup();
+        return rc;  // nothing was modified
+    }
+    std::vector<uint32_t> extra(ivf->C, 0);
+    for (uint64_t i = 0; i < n; ++i) extra[assign[i]] += 1;
+    bool grow = false;
+    for (uint32_t c = 0; c < ivf->C; ++c) grow = grow || ivf->seg_len[c] + extra[c] > ivf->seg_cap[c];
+    if (grow) rc = ivf_relayout(ivf, extra.data());
+    if (rc != VERS_OK) {
+        cleanup();
+        return rc;
+    }
+    std::vector<uint64_t> pos(n);
+    std::vector<uint32_t> fill(ivf->C, 0);
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t c = assign[i];
+        pos[i] = ivf->seg_off[c] + ivf->seg_len[c] + fill[c]++;
+    }
+    e = cudaMemcpyAsync(d_pos, pos.data(), n * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        add_scatter_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(d_rows, ivf->ld, d_pos, n, ivf->id_base + ivf->n, ivf->d_lm,
+                                                            ivf->d_lm_ids, ivf->d_lm_norm, ivf->d_nxmax);
+        ctx->launches += 1;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(VERS_ERR_CUDA, "ivf_add_batch: %s", cudaGetErrorString(e));
+    }
+    for (uint32_t c = 0; c < ivf->C; ++c) ivf->seg_len[c] += extra[c];
+    ivf->seg_epoch += 1;
+    rc = ivf_upload_segments(ivf);
+    for (uint64_t i = 0; i < n; ++i) {
+        ivf->assign_tail.push_back(assign[i]);
+        if (assigned_ids) assigned_ids[i] = ivf->id_base + ivf->n + i;
+        if (clusters) clusters[i] = assign[i];
+    }
+    ivf->n += n;
+    cleanup();
     return rc;
 }

@@ -1,6 +1,7 @@
 // lsh_forest.cu — ANNIndex (indexes/lsh.rs:47-283): the random-hyperplane forest, built and searched on the GPU.
 //
-// build_index (lsh.rs:132-161)  dedup by bit pattern on the host (hash set, lsh.rs:113-130), then a LEVEL-SYNCHRONOUS
+// build_index (lsh.rs:132-161)  dedup by bit pattern on the device (64-bit row hash + stable sort + bit compare inside
+//   equal-hash runs, lsh.rs:113-130), then a LEVEL-SYNCHRONOUS
 //   build of all trees at once: every node still to be split gets its plane from two sampled members
 //   (vers_lsh_pick_pair stands in for choose_multiple(thread_rng, 2), lsh.rs:63-65), every member of every such node
 //   is hashed in one launch with the exact-order dot engine (Hyperplane::point_is_above, lsh.rs:27-29), and a stable
@@ -12,6 +13,7 @@
 //   trees' candidates (the DashSet), re-computes exact distances and takes the top-k by (distance, row index).
 // add (lsh.rs:255-263, insert :218-251)  descend every tree on the device, append to the leaf or split it with the
 //   same level-synchronous builder.
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -159,6 +161,53 @@ __global__ void emit_leaves_kernel(const uint32_t* __restrict__ members, const L
     const LeafItem it = items[blockIdx.x];
     for (uint32_t r = threadIdx.x; r < it.len; r += blockDim.x)
         leaf_items[(uint64_t)it.slot * slot_cap + r] = members[it.start + r];
+}
+
+// ---- deduplicate (lsh.rs:113-130) on the device
+// 64-bit hash of a row's bit pattern (one warp per row: per-lane chains over its columns, combined with the lane index)
+__global__ void dedup_hash_kernel(const float* __restrict__ rows, uint64_t n, uint32_t dim, uint32_t ld,
+                                  unsigned long long* __restrict__ hash, uint32_t* __restrict__ row_id) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < n; r += warps) {
+        const uint32_t* x = reinterpret_cast<const uint32_t*>(rows + r * ld);
+        uint64_t h = 0x243F6A8885A308D3ull + (uint64_t)lane;
+        for (uint32_t c = lane; c < dim; c += 32) h = vers_splitmix64(h ^ x[c]);
+        for (int o = 16; o; o >>= 1) h = vers_splitmix64(h + 31 * __shfl_xor_sync(FULL_MASK, h, o));
+        if (lane == 0) {
+            hash[r] = h;
+            row_id[r] = (uint32_t)r;
+        }
+    }
+}
+// sorted position p: keep[row] = 1 unless an earlier row of the same hash run has identical bits (one warp per position)
+__global__ void dedup_flag_kernel(const float* __restrict__ rows, uint64_t n, uint32_t dim, uint32_t ld,
+                                  const unsigned long long* __restrict__ hs, const uint32_t* __restrict__ rs,
+                                  uint32_t* __restrict__ keep) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t p = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); p < n; p += warps) {
+        const uint32_t row = rs[p];
+        const uint32_t* x = reinterpret_cast<const uint32_t*>(rows + (uint64_t)row * ld);
+        bool dup = false;
+        for (uint64_t q = p; q > 0 && hs[q - 1] == hs[p] && !dup; --q) {
+            const uint32_t* y = reinterpret_cast<const uint32_t*>(rows + (uint64_t)rs[q - 1] * ld);
+            bool same = true;
+            for (uint32_t c = lane; c < dim; c += 32) same = same && x[c] == y[c];
+            dup = __all_sync(FULL_MASK, same);  // the stable sort put the earlier rows of the run first
+        }
+        if (lane == 0) keep[row] = dup ? 0u : 1u;
+    }
+}
+__global__ void dedup_gather_kernel(const float* __restrict__ rows, uint64_t n, uint32_t ld,
+                                    const uint32_t* __restrict__ keep, const uint32_t* __restrict__ at,
+                                    float* __restrict__ out) {
+    const uint32_t ld4 = ld >> 2;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * ld4; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / ld4;
+        const uint32_t c = (uint32_t)(i - r * ld4);
+        if (keep[r]) reinterpret_cast<float4*>(out)[(uint64_t)at[r] * ld4 + c] = reinterpret_cast<const float4*>(rows)[i];
+    }
 }
 
 __global__ void iota_trees_kernel(uint32_t* p, uint64_t n, uint32_t trees) {
@@ -721,37 +770,10 @@ extern "C" int32_t vers_lsh_build_index(vers_ctx* ctx, const float* rows, uint64
     L->num_trees = num_trees;
     L->slot_cap = max_size + 1;
     L->seed = seed;
-    // deduplicate (lsh.rs:113-130): keep the first row of every distinct bit pattern
-    std::vector<float> dedup;
-    dedup.reserve((size_t)n * L->ld);
-    {
-        std::unordered_multimap<uint64_t, uint32_t> seen;
-        seen.reserve((size_t)n * 2);
-        for (uint64_t r = 0; r < n; ++r) {
-            const float* x = rows + r * (uint64_t)stride_floats;
-            uint64_t h = 0x243F6A8885A308D3ull;
-            for (uint32_t i = 0; i < dim; ++i) {
-                uint32_t b;
-                memcpy(&b, x + i, 4);
-                h = vers_splitmix64(h ^ b);
-            }
-            bool dup = false;
-            auto range = seen.equal_range(h);
-            for (auto it = range.first; it != range.second; ++it)
-                if (memcmp(dedup.data() + (size_t)it->second * L->ld, x, (size_t)dim * 4) == 0) {
-                    dup = true;
-                    break;
-                }
-            if (dup) continue;
-            seen.emplace(h, (uint32_t)L->ids.size());
-            size_t at = dedup.size();
-            dedup.resize(at + L->ld, 0.0f);
-            memcpy(dedup.data() + at, x, (size_t)dim * 4);
-            L->ids.push_back(vector_ids ? vector_ids[r] : r);
-        }
-    }
-    L->n = L->ids.size();
-    L->cap = L->n + L->n / 8 + 64;
+    // deduplicate (lsh.rs:113-130) ON THE DEVICE: keep the first row of every distinct bit pattern, in row order.
+    // 64-bit hash of every row's bit pattern -> stable radix sort of (hash, row) -> a row is a duplicate iff an
+    // EARLIER row of its equal-hash run has the same bits (runs are one row long unless rows repeat or hashes collide;
+    // the backward walk stops at the first bit-identical row) -> exclusive scan of the keep flags -> gather.
     int32_t rc = VERS_OK;
     uint32_t* d_mem_a = nullptr;
     uint32_t* d_mem_b = nullptr;
@@ -761,12 +783,73 @@ extern "C" int32_t vers_lsh_build_index(vers_ctx* ctx, const float* rows, uint64
         vers_lsh_free(L);
         return code;
     };
-    if (cudaMalloc(&L->d_values, (size_t)L->cap * L->ld * 4) != cudaSuccess)
-        return bail(fail(VERS_ERR_NOMEM, "lsh_build_index: cudaMalloc values"));
-    if (L->n) {
-        cudaError_t e = cudaMemcpyAsync(L->d_values, dedup.data(), (size_t)L->n * L->ld * 4, cudaMemcpyHostToDevice,
-                                        ctx->stream);
-        if (e != cudaSuccess) return bail(fail(VERS_ERR_CUDA, "lsh_build_index: %s", cudaGetErrorString(e)));
+    {
+        cudaStream_t s = ctx->stream;
+        float* d_all = nullptr;
+        unsigned long long *d_h = nullptr, *d_hs = nullptr;
+        uint32_t *d_r = nullptr, *d_rs = nullptr, *d_keep = nullptr, *d_at = nullptr;
+        void* d_cub = nullptr;
+        std::vector<uint32_t> keep(n);
+        auto drop = [&]() {
+            cudaFree(d_all), cudaFree(d_h), cudaFree(d_hs), cudaFree(d_r), cudaFree(d_rs), cudaFree(d_keep), cudaFree(d_at);
+            cudaFree(d_cub);
+        };
+        const size_t n1 = n ? n : 1;
+        cudaError_t e = cudaMalloc(&d_all, n1 * L->ld * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&d_h, n1 * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&d_hs, n1 * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&d_r, n1 * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&d_rs, n1 * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&d_keep, (n1 + 1) * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&d_at, (n1 + 1) * 4);
+        uint64_t kept = 0;
+        if (e == cudaSuccess && n) {
+            if (L->ld != dim) e = cudaMemsetAsync(d_all, 0, n * L->ld * 4, s);
+            if (e == cudaSuccess)
+                e = cudaMemcpy2DAsync(d_all, (size_t)L->ld * 4, rows, (size_t)stride_floats * 4, (size_t)dim * 4, n,
+                                      cudaMemcpyHostToDevice, s);
+            if (e == cudaSuccess) {
+                dedup_hash_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(d_all, n, dim, L->ld, d_h, d_r);
+                size_t need = 0, need2 = 0;
+                cub::DeviceRadixSort::SortPairs(nullptr, need, d_h, d_hs, d_r, d_rs, (int64_t)n, 0, 64, s);
+                cub::DeviceScan::ExclusiveSum(nullptr, need2, d_keep, d_at, (int64_t)(n + 1), s);
+                e = cudaMalloc(&d_cub, std::max(need, need2));
+                if (e == cudaSuccess) {
+                    size_t nb = std::max(need, need2);
+                    e = cub::DeviceRadixSort::SortPairs(d_cub, nb, d_h, d_hs, d_r, d_rs, (int64_t)n, 0, 64, s);
+                    if (e == cudaSuccess) e = cudaMemsetAsync(d_keep, 0, (n + 1) * 4, s);
+                    if (e == cudaSuccess) {
+                        dedup_flag_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(d_all, n, dim, L->ld, d_hs, d_rs, d_keep);
+                        nb = std::max(need, need2);
+                        e = cub::DeviceScan::ExclusiveSum(d_cub, nb, d_keep, d_at, (int64_t)(n + 1), s);
+                    }
+                    ctx->launches += 4;
+                }
+            }
+            uint32_t total_kept = 0;
+            if (e == cudaSuccess) e = cudaMemcpyAsync(keep.data(), d_keep, n * 4, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&total_kept, d_at + n, 4, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            kept = total_kept;
+        }
+        if (e == cudaSuccess) {
+            L->n = kept;
+            L->cap = L->n + L->n / 8 + 64;
+            e = cudaMalloc(&L->d_values, (size_t)L->cap * L->ld * 4);
+            if (e == cudaSuccess && n) {
+                dedup_gather_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(d_all, n, L->ld, d_keep, d_at, L->d_values);
+                ctx->launches += 1;
+                e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            }
+        }
+        drop();
+        if (e != cudaSuccess)
+            return bail(fail(e == cudaErrorMemoryAllocation ? VERS_ERR_NOMEM : VERS_ERR_CUDA, "lsh_build_index: %s",
+                             cudaGetErrorString(e)));
+        L->ids.reserve(kept);
+        for (uint64_t r = 0; r < n; ++r)
+            if (keep[r]) L->ids.push_back(vector_ids ? vector_ids[r] : r);
     }
     L->trees.resize(num_trees);
     const uint64_t total = (uint64_t)L->n * num_trees;
@@ -925,6 +1008,12 @@ extern "C" int32_t vers_lsh_add(vers_lsh* L, const float* embedding, uint64_t ve
     std::lock_guard<std::mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
+    // insert (lsh.rs:218-251) stores vec_id ITSELF in the leaf as a row index (quirk kept).  The reference would only
+    // panic later (values[vec_id] out of bounds during a split or a search); we refuse up front — BEFORE anything is
+    // mutated — rather than store an index that a kernel would dereference out of bounds.
+    if (L->num_trees && (vec_id >= 0xffffffffull || vec_id >= L->n + 1))
+        return fail(VERS_ERR_PANIC, "lsh_add: vec_id %llu is not a row index (lsh.rs:247 stores it as one)",
+                    (unsigned long long)vec_id);
     // values.push(embedding); ids.push(vec_id)  (lsh.rs:257-258)
     if (L->n + 1 > L->cap) {
         uint64_t capw = L->cap * L->ld;
@@ -940,13 +1029,7 @@ extern "C" int32_t vers_lsh_add(vers_lsh* L, const float* embedding, uint64_t ve
     L->ids_dirty = true;
     if (L->num_trees == 0) return VERS_OK;
     VERS_TRY(sync_device_mirror(L));
-    // insert (lsh.rs:218-251): the reference stores vec_id ITSELF in the leaf as a row index (quirk kept)
-    if (vec_id >= 0xffffffffull) return fail(VERS_ERR_PANIC, "lsh_add: vec_id used as a row index is out of range");
     const uint32_t member = (uint32_t)vec_id;
-    // the reference would only panic later (values[vec_id] out of bounds during a split or a search); we refuse now
-    // rather than store an index that a kernel would dereference out of bounds
-    if (member >= L->n) return fail(VERS_ERR_PANIC, "lsh_add: vec_id %llu is not a row index (lsh.rs:247 stores it as one)",
-                                    (unsigned long long)vec_id);
     uint32_t* d_leaf = nullptr;
     VERS_CUDA(cudaMalloc(&d_leaf, (size_t)L->num_trees * 4));
     ForestDev f = forest_dev(L);
@@ -996,5 +1079,140 @@ extern "C" int32_t vers_lsh_add(vers_lsh* L, const float* embedding, uint64_t ve
         cudaFree(d_b);
         if (rc != VERS_OK) return rc;
     }
+    return VERS_OK;
+}
+
+// values / ids of the index (the deduplicated rows in their stored order: what Index::save_index serialises,
+// lsh.rs:47-55), including rows added after build_index
+extern "C" int32_t vers_lsh_get_values(const vers_lsh* L, float* values, uint32_t stride_floats, uint64_t* ids) {
+    if (!L) return fail(VERS_ERR_ARG, "lsh_get_values: null");
+    if (values && stride_floats < L->dim) return fail(VERS_ERR_ARG, "lsh_get_values: stride < dim");
+    VERS_CUDA(cudaSetDevice(L->ctx->device));
+    if (values && L->n) {
+        VERS_CUDA(cudaMemcpy2DAsync(values, (size_t)stride_floats * 4, L->d_values, (size_t)L->ld * 4, (size_t)L->dim * 4,
+                                    L->n, cudaMemcpyDeviceToHost, L->ctx->stream));
+        VERS_CUDA(cudaStreamSynchronize(L->ctx->stream));
+    }
+    if (ids) memcpy(ids, L->ids.data(), L->ids.size() * 8);
+    return VERS_OK;
+}
+
+// The forest from deserialised parts (after Index::load_index, base.rs:45-58): `values` are the stored (already
+// deduplicated) rows, every tree arrives in the preorder of vers_lsh_flatten (node, ABOVE subtree, BELOW subtree), the
+// trees concatenated: kind / leaf_len per node, planes / consts per inner node, items per leaf.
+extern "C" int32_t vers_lsh_from_parts(vers_ctx* ctx, const float* values, uint64_t n, uint32_t dim,
+                                       uint32_t stride_floats, const uint64_t* ids, uint32_t num_trees, uint32_t max_size,
+                                       uint64_t seed, const uint32_t* tree_nodes, const uint8_t* kind,
+                                       const uint32_t* leaf_len, const float* planes, const float* consts,
+                                       const uint32_t* items, vers_lsh** out) {
+    if (!ctx || !out || (!values && n) || (num_trees && (!tree_nodes || !kind || !leaf_len)))
+        return fail(VERS_ERR_ARG, "lsh_from_parts: null argument");
+    *out = nullptr;
+    if (dim == 0 || stride_floats < dim) return fail(VERS_ERR_ARG, "lsh_from_parts: bad dim/stride");
+    if (n >= 0xffffffffull) return fail(VERS_ERR_UNSUPPORTED, "lsh_from_parts: more than 2^32-2 rows");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    VERS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    vers_lsh* L = new vers_lsh();
+    L->ctx = ctx;
+    L->dim = dim;
+    L->ld = round_up(dim, 4);
+    L->max_size = max_size;
+    L->num_trees = num_trees;
+    L->slot_cap = max_size + 1;
+    L->seed = seed;
+    L->n = n;
+    L->cap = n + n / 8 + 64;
+    L->ids.resize(n);
+    for (uint64_t r = 0; r < n; ++r) L->ids[r] = ids ? ids[r] : r;
+    L->trees.resize(num_trees);
+    // host: node arrays, planes and leaf slots from the preorder walk
+    std::vector<float> h_planes, h_consts;
+    std::vector<uint32_t> h_items;
+    uint64_t node_at = 0, plane_at = 0, item_at = 0;
+    auto bail = [&](int32_t code) {
+        vers_lsh_free(L);
+        return code;
+    };
+    for (uint32_t t = 0; t < num_trees; ++t) {
+        HostTree& T = L->trees[t];
+        const uint64_t node_end = node_at + tree_nodes[t];
+        struct Todo {
+            uint32_t node;
+            uint64_t hash;
+        };
+        std::vector<Todo> stack;
+        stack.push_back(Todo{T.add_node(), vers_lsh_root_hash(seed, t)});
+        while (!stack.empty()) {
+            const Todo cur = stack.back();
+            stack.pop_back();
+            if (node_at >= node_end) return bail(fail(VERS_ERR_ARG, "lsh_from_parts: tree %u is truncated", t));
+            const uint64_t i = node_at++;
+            T.hash[cur.node] = cur.hash;
+            if (kind[i] == 1) {
+                const uint32_t len = leaf_len[i];
+                if (len > L->slot_cap)
+                    return bail(fail(VERS_ERR_UNSUPPORTED, "lsh_from_parts: a leaf of %u rows exceeds max_size + 1 = %u", len,
+                                     L->slot_cap));
+                if (len && !items) return bail(fail(VERS_ERR_ARG, "lsh_from_parts: null items"));
+                T.kind[cur.node] = 1;
+                T.leaf_len[cur.node] = len;
+                T.slot[cur.node] = L->n_slots++;
+                const size_t at = h_items.size();
+                h_items.resize(at + L->slot_cap, 0u);
+                for (uint32_t e = 0; e < len; ++e) {
+                    if (items[item_at + e] >= n)
+                        return bail(fail(VERS_ERR_PANIC, "lsh_from_parts: leaf member %u is not a row (index out of bounds)",
+                                         items[item_at + e]));
+                    h_items[at + e] = items[item_at + e];
+                }
+                item_at += len;
+            } else if (kind[i] == 0) {
+                if (!planes || !consts) return bail(fail(VERS_ERR_ARG, "lsh_from_parts: null planes"));
+                T.kind[cur.node] = 0;
+                T.plane[cur.node] = L->n_planes++;
+                const size_t at = h_planes.size();
+                h_planes.resize(at + L->ld, 0.0f);
+                memcpy(h_planes.data() + at, planes + plane_at * dim, (size_t)dim * 4);
+                h_consts.push_back(consts[plane_at]);
+                ++plane_at;
+                const uint32_t nr = T.add_node();  // above -> right_node (lsh.rs:108)
+                const uint32_t nl = T.add_node();  // below -> left_node  (lsh.rs:107)
+                T.right[cur.node] = nr;
+                T.left[cur.node] = nl;
+                stack.push_back(Todo{nl, vers_lsh_child_hash(cur.hash, 0)});  // popped second: the below subtree
+                stack.push_back(Todo{nr, vers_lsh_child_hash(cur.hash, 1)});  // popped first: the above subtree
+            } else {
+                return bail(fail(VERS_ERR_ARG, "lsh_from_parts: bad node kind %u", (unsigned)kind[i]));
+            }
+        }
+        if (node_at != node_end) return bail(fail(VERS_ERR_ARG, "lsh_from_parts: tree %u has trailing nodes", t));
+    }
+    // device: rows, planes, leaf slots (with the same slack build_index leaves for later adds)
+    L->cap_planes = L->n_planes + L->n_planes / 2 + 64;
+    L->cap_slots = L->n_slots + L->n_slots / 2 + 64;
+    cudaError_t e = cudaMalloc(&L->d_values, (size_t)L->cap * L->ld * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&L->d_planes, (size_t)L->cap_planes * L->ld * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&L->d_consts, (size_t)L->cap_planes * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&L->d_leaf_items, (size_t)L->cap_slots * L->slot_cap * 4);
+    if (e == cudaSuccess && n) {
+        e = cudaMemsetAsync(L->d_values, 0, (size_t)n * L->ld * 4, s);
+        if (e == cudaSuccess)
+            e = cudaMemcpy2DAsync(L->d_values, (size_t)L->ld * 4, values, (size_t)stride_floats * 4, (size_t)dim * 4, n,
+                                  cudaMemcpyHostToDevice, s);
+    }
+    if (e == cudaSuccess && L->n_planes) {
+        e = cudaMemcpyAsync(L->d_planes, h_planes.data(), h_planes.size() * 4, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(L->d_consts, h_consts.data(), h_consts.size() * 4, cudaMemcpyHostToDevice, s);
+    }
+    if (e == cudaSuccess && L->n_slots)
+        e = cudaMemcpyAsync(L->d_leaf_items, h_items.data(), h_items.size() * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess)
+        return bail(fail(e == cudaErrorMemoryAllocation ? VERS_ERR_NOMEM : VERS_ERR_CUDA, "lsh_from_parts: %s",
+                         cudaGetErrorString(e)));
+    L->nodes_dirty = true;
+    L->ids_dirty = true;
+    *out = L;
     return VERS_OK;
 }

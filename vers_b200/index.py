@@ -411,6 +411,17 @@ class IVFFlatIndex:
             self.values = np.vstack([self.values, e[None, :]])
         return aid.value, cl.value
 
+    def add_batch(self, embeddings) -> Tuple[np.ndarray, np.ndarray]:
+        """Index::add (ivfflat.rs:200-213) for a batch, in order: exactly len(embeddings) sequential adds (the centroids
+        do not move on add).  Returns (stored ids, clusters)."""
+        e = _rows(embeddings)
+        ids = np.empty(e.shape[0], np.uint64)
+        cl = np.empty(e.shape[0], np.uint32)
+        check(lib().vers_ivf_add_batch(self.h, ptr(e), e.shape[0], e.shape[1], ptr(ids), ptr(cl)))
+        if self.values is not None:
+            self.values = np.vstack([self.values, e])
+        return ids, cl
+
     def search_approximate(self, query, top_k: int) -> List[Tuple[int, float]]:
         """Index::search_approximate(query, top_k) -> Vec<(usize, f32)> (ivfflat.rs:153-198), squared L2."""
         ids, d, cnt = self.search_batch(query, top_k, nprobe=0)
@@ -493,7 +504,7 @@ class ANNIndex:
         check(lib().vers_lsh_build_index(ctx.h, ptr(v), v.shape[0], v.shape[1], v.shape[1],
                                          None if ids is None else ptr(ids), num_trees, max_size, seed, C.byref(h)))
         self = cls(ctx, h, v.shape[1])
-        self.max_node_size, self._src, self._src_ids = max_size, v, ids
+        self.max_node_size = max_size
         return self
 
     def close(self):
@@ -521,21 +532,66 @@ class ANNIndex:
                                      C.byref(nn), C.byref(ni), C.byref(nit)))
         return dict(kind=kind, leaf_len=leaf_len, planes=planes, consts=consts, items=items)
 
+    def values_and_ids(self):
+        """`values` / `ids` of the struct (lsh.rs:47-55): the deduplicated rows in stored order (lsh.rs:113-130: first
+        occurrence of every bit pattern), rows added later included"""
+        n = self.info()["num_values"]
+        values = np.empty((n, self.dim), np.float32)
+        ids = np.empty(n, np.uint64)
+        check(lib().vers_lsh_get_values(self.h, ptr(values), self.dim, ptr(ids)))
+        return values, ids
+
     def save_index(self, file_path: str):
-        """Index::save_index (base.rs:31-43): the reference's bincode layout of ANNIndex (lsh.rs:47-55).  `values` /
-        `ids` are the deduplicated rows (lsh.rs:113-130: first occurrence of every bit pattern, original order).
-        Only valid for an index that has not been modified by add() since build_index."""
+        """Index::save_index (base.rs:31-43): the reference's bincode layout of ANNIndex (lsh.rs:47-55), from the
+        device state (valid after add() as well)"""
         from . import bincode
 
-        v = self._src
-        _, first = np.unique(np.ascontiguousarray(v).view(np.uint32).reshape(v.shape[0], -1), axis=0, return_index=True)
-        keep = np.sort(first)
-        ids = np.arange(v.shape[0], dtype=np.uint64) if self._src_ids is None else self._src_ids
-        info = self.info()
-        if info["num_values"] != keep.shape[0]:
-            raise ValueError("save_index: the index was modified after build_index")
-        bincode.write_ann(file_path, self.max_node_size, [self.flatten(t) for t in range(info["num_trees"])], v[keep],
-                          ids[keep])
+        values, ids = self.values_and_ids()
+        bincode.write_ann(file_path, self.max_node_size, [self.flatten(t) for t in range(self.info()["num_trees"])],
+                          values, ids)
+
+    @classmethod
+    def load_index(cls, file_path: str, dim: int, *, seed: int = 4, ctx: Optional[Context] = None) -> "ANNIndex":
+        """Index::load_index (base.rs:45-58) + the device forest (vers_lsh_from_parts).  N is a const generic in the
+        reference, not stored in the file: the caller supplies ``dim``.  ``seed`` only feeds the sample pairs of leaf
+        splits caused by later add() calls (the reference draws them from thread_rng)."""
+        from . import bincode
+
+        ctx = ctx or default_context()
+        max_node_size, trees, values, ids = bincode.read_ann(file_path, dim)
+        kind, leaf_len, planes, consts, items, tree_nodes = [], [], [], [], [], []
+        for root in trees:  # preorder (node, ABOVE = right_node, BELOW = left_node), like vers_lsh_flatten
+            n0 = len(kind)
+            stack = [root]
+            while stack:
+                node = stack.pop()
+                if node[0] == "leaf":
+                    kind.append(1)
+                    leaf_len.append(node[1].shape[0])
+                    items.append(node[1])
+                else:
+                    kind.append(0)
+                    leaf_len.append(0)
+                    planes.append(node[1])
+                    consts.append(node[2])
+                    stack.append(node[3])  # left (below): popped second
+                    stack.append(node[4])  # right (above): popped first
+            tree_nodes.append(len(kind) - n0)
+        kind = np.asarray(kind, np.uint8)
+        leaf_len = np.asarray(leaf_len, np.uint32)
+        planes = np.ascontiguousarray(np.asarray(planes, np.float32).reshape(-1, dim))
+        consts = np.asarray(consts, np.float32)
+        items = np.concatenate(items).astype(np.uint32) if items else np.empty(0, np.uint32)
+        tree_nodes = np.asarray(tree_nodes, np.uint32)
+        values = np.ascontiguousarray(values, np.float32)
+        ids = np.ascontiguousarray(ids, np.uint64)
+        h = C.c_void_p()
+        check(lib().vers_lsh_from_parts(ctx.h, ptr(values), values.shape[0], dim, dim, ptr(ids), len(trees),
+                                        max_node_size, seed, ptr(tree_nodes), ptr(kind), ptr(leaf_len), ptr(planes),
+                                        ptr(consts), ptr(items), C.byref(h)))
+        self = cls(ctx, h, dim)
+        self.max_node_size = max_node_size
+        return self
 
     def add(self, embedding, vec_id: int):
         """Index::add (lsh.rs:255-263)"""

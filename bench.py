@@ -77,8 +77,10 @@ def parse():
     ap.add_argument("--km-cpu-rows", type=int, default=50_000, help="rows of the CPU assign sample (kmeans cpu_baseline)")
     ap.add_argument("--trace", type=int, default=0, help="diagnostic: profile this many extra steps with torch.profiler "
                     "(CUPTI) on rank 0 after the timed region and write the kernel timeline to gpurun_out/")
-    ap.add_argument("--mode", type=int, default=0, help="candidate pass: 0 tcgen05 split-TF32 (default), 1 exact "
-                    "order only, 2 fp32 FMA SIMT, 3 tcgen05 plain TF32")
+    ap.add_argument("--mode", type=int, default=4, help="candidate pass: 4 fp16 candidate copy (tcgen05 kind::f16) + "
+                    "exact fp32 rerank + certificate (default: BASELINE.json configs[3] '16-bit candidate / fp32 "
+                    "rerank'), 0 tcgen05 split-TF32 over the fp32 rows, 1 exact order only, 2 fp32 FMA SIMT, "
+                    "3 tcgen05 plain TF32")
     return ap.parse_args()
 
 
@@ -207,7 +209,12 @@ def config_dict(args, n_gpus):
                           if args.shard_by == "lists" else f"rows/{n_gpus} per GPU (1/{n_gpus} of every list)") +
                          ", probe split over ranks, probe lists + per-GPU top-k exchanged over NVLink peer memory"),
             "kmeans_iters": args.kmeans_iters, "synthetic_natural_clusters": args.n_centers,
-            "l2": "per-step scan (>= 3.8 GB per GPU) is far larger than the 126 MB L2; no flush needed"}
+            "candidate_pass": {4: "fp16 candidate copy of the lists (tcgen05 kind::f16), exact fp32 rerank, certificate, "
+                                  "exact redo (results bit-identical to the fp32 reference arithmetic)",
+                               0: "fp32 rows, split-precision tf32 (tcgen05), exact fp32 rerank, certificate",
+                               1: "exact order only", 2: "fp32 FMA SIMT candidates", 3: "plain tf32 candidates"}[args.mode],
+            "l2": "per-step scan (>= 1.7 GB per GPU at 8 GPUs, 13.8 GB at 1) is far larger than the 126 MB L2; no flush "
+                  "needed"}
 
 
 def main_reference(args):
@@ -483,16 +490,19 @@ def main_ours(args):
 
     # ---- roofline of the dominant kernel (list scan)
     peak, peak_src = measured_peaks()
-    alg_bytes = stats["distinct_list_rows"] * args.dim * 4
+    # bytes the candidate pass must stream: the distinct probed rows once, fp32 or (mode 4) the fp16 candidate copy
+    alg_bytes = stats["distinct_list_rows"] * (((args.dim + 7) // 8 * 8) * 2 if args.mode == 4 else args.dim * 4)
     roof = None
     dom = "cand_scan" if fam["cand_scan"][1] else "list_scan"
     dom_ms, dom_n = fam[dom]
     if dom_n:
         avg_ms = dom_ms / dom_n
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
-        cand_names = {0: "tc_list_scan_kernel<true> (candidate pass: TMA + tcgen05 kind::tf32 split hi/lo, fp32 rows "
+        cand_names = {0: "tc_list_scan_kernel<1> (candidate pass: TMA + tcgen05 kind::tf32 split hi/lo, fp32 rows "
                          "streamed once)",
-                      3: "tc_list_scan_kernel<false> (candidate pass: TMA + tcgen05 kind::tf32)",
+                      3: "tc_list_scan_kernel<0> (candidate pass: TMA + tcgen05 kind::tf32)",
+                      4: "tc_list_scan_kernel<2> (candidate pass: TMA + tcgen05 kind::f16 over the fp16 candidate copy "
+                         "of the lists x [q_hi; q_lo], streamed once; exact fp32 rerank + Cauchy-Schwarz certificate)",
                       2: "list_scan_kernel<StreamCfg,1> (candidate pass: fp32 FMA SIMT)"}
         kname = {"cand_scan": cand_names.get(args.mode, "candidate pass"),
                  "list_scan": "list_scan_kernel<NarrowCfg,0> (exact-order scan)"}[dom]

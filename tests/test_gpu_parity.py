@@ -336,12 +336,13 @@ def test_ivf_build_index_bit_exact(ivf_c1):
     assert np.array_equal(s["idx"].list_sizes, np.bincount(s["assign"].astype(np.int64), minlength=s["C"]))
 
 
-@pytest.mark.parametrize("exact_mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("exact_mode", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("k", [1, 10, 37, 100])
 @pytest.mark.parametrize("nprobe", [0, 1, 4, 16])
 def test_ivf_search_bit_exact(vo, ivf_c1, k, nprobe, exact_mode):
     """mode 0: tensor-core (TMA + tcgen05 TF32) candidate pass + exact-order rerank + certificate (+ exact redo when
-    uncertified); mode 2: the same with an fp32 FMA candidate pass; mode 1: exact order everywhere.
+    uncertified); mode 2: the same with an fp32 FMA candidate pass; mode 1: exact order everywhere; mode 4: candidates
+    from the fp16 copy of the lists (kind::f16 MMA), exact fp32 rerank, Cauchy-Schwarz certificate.
     Every mode must return the oracle's ids AND distance bits."""
     s = ivf_c1
     q = data(vo, 100, 300, seed=2)
@@ -358,8 +359,9 @@ def test_ivf_search_bit_exact(vo, ivf_c1, k, nprobe, exact_mode):
     assert np.array_equal(bits(d), bits(od))
     if exact_mode != 1 and nprobe > 0 and k <= 16:
         assert st["reranked"] > 0  # the candidate path really ran
-        assert st["uncertified_queries"] <= (10 if exact_mode in (0, 2) else 100)  # plain TF32 (3) certifies less often
-        assert st["max_candidate_error"] < (3e-3 if exact_mode == 3 else 2e-5)
+        # plain TF32 (3) and the 16-bit copy (4) certify less often on this small, dense set
+        assert st["uncertified_queries"] <= (10 if exact_mode in (0, 2) else 100)
+        assert st["max_candidate_error"] < {3: 3e-3, 4: 5e-4}.get(exact_mode, 2e-5)
 
 
 @pytest.fixture(scope="module")
@@ -454,6 +456,74 @@ def test_ivf_candidate_path_falls_back_on_ties(vb, vo, ctx):
     assert np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od)) and np.array_equal(cnt, oc)
     assert list(ids[0]) == [17] + list(range(1000, 1009))
     assert st["uncertified_queries"] >= 2  # the duplicate-heavy queries took the exact redo
+
+
+@pytest.mark.parametrize("dim", [96, 300, 768])
+def test_ivf_h16_candidate_copy_bit_exact(vb, vo, ctx, dim):
+    """mode 4 (BASELINE configs[3] "16-bit candidate / fp32 rerank"): the scan streams an fp16 copy of the lists; ids and
+    distance bits must still be the oracle's, most queries must certify (the copy's error bound is ~2e-4 on unit rows),
+    and the copy must follow add (in place), a row too large for the copy's scale (rebuild) and add_batch (rebuild)."""
+    n, C, k = 40000, 64, 10
+    rows = data(vo, n, dim, n_centers=300)
+    init = vo.init_rows(3, 1, C, n)
+    idx = vb.IVFFlatIndex.build_index(C, 1, 4, rows, init_rows=init, ctx=ctx)
+    cents, assign, _, _ = vo.ivf_build_index(rows, C, 1, 4, init)
+    assert np.array_equal(idx.assignments, assign)
+    idx.set_mode(4)
+    q = data(vo, 200, dim, seed=2, n_centers=300)
+    off, lr = vo.ivf_lists(assign, C)
+    for nprobe in (1, 8, 32):
+        ids, d, cnt = idx.search_batch(q, k, nprobe=nprobe)
+        st = idx.last_search_stats()
+        oi, od, oc = vo.ivf_search(rows, cents, off, lr, q, k, nprobe=nprobe)
+        assert np.array_equal(cnt, oc) and np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od))
+        assert st["reranked"] > 0
+        assert st["uncertified_queries"] <= 60
+        assert st["max_candidate_error"] < 5e-4
+    # single adds keep the copy current in place; the last one is 50x larger than anything the copy's scale admits
+    extra = data(vo, 40, dim, seed=5, n_centers=300)
+    extra[-1] *= np.float32(50.0)
+    all_rows, all_assign = np.vstack([rows, extra]), list(assign)
+    for i in range(extra.shape[0]):
+        if i == extra.shape[0] - 1:  # search once more before the oversized row: the in-place rows must be visible
+            o2, l2 = vo.ivf_lists(np.array(all_assign, np.uint64), C)
+            ids, d, cnt = idx.search_batch(extra[:8], k, nprobe=8)
+            oi, od, oc = vo.ivf_search(all_rows[: n + i], cents, o2, l2, extra[:8], k, nprobe=8)
+            assert np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od))
+            assert all(ids[j][0] == n + j for j in range(8))  # each added row finds itself
+        _, cl = idx.add(extra[i], 0)
+        all_assign.append(cl)
+    batch = data(vo, 500, dim, seed=6, n_centers=300)
+    _, cl = idx.add_batch(batch)
+    all_rows = np.vstack([all_rows, batch])
+    all_assign = np.array(all_assign + [int(c) for c in cl], np.uint64)
+    off, lr = vo.ivf_lists(all_assign, C)
+    q2 = np.vstack([q[:60], extra[-4:], batch[:20]])
+    ids, d, cnt = idx.search_batch(q2, k, nprobe=8)
+    oi, od, oc = vo.ivf_search(all_rows, cents, off, lr, q2, k, nprobe=8)
+    assert np.array_equal(cnt, oc) and np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od))
+
+
+def test_ivf_h16_candidate_copy_falls_back_on_ties(vb, vo, ctx):
+    """duplicates beyond the candidate list and unnormalised rows of very different norms: the fp16 pass must flag
+    what it cannot prove and the exact redo must return the reference's order"""
+    n, dim, C, k = 6000, 96, 8, 10
+    rows = data(vo, n, dim, normalize=False)
+    rows[::7] *= np.float32(37.0)
+    rows[1000:1100] = rows[17]
+    init = vo.init_rows(3, 1, C, n)
+    idx = vb.IVFFlatIndex.build_index(C, 1, 6, rows, init_rows=init, ctx=ctx)
+    cents, assign, _, _ = vo.ivf_build_index(rows, C, 1, 6, init)
+    off, lr = vo.ivf_lists(assign, C)
+    q = data(vo, 40, dim, seed=2, normalize=False)
+    q[0] = rows[17]
+    idx.set_mode(4)
+    ids, d, cnt = idx.search_batch(q, k, nprobe=4)
+    st = idx.last_search_stats()
+    oi, od, oc = vo.ivf_search(rows, cents, off, lr, q, k, nprobe=4)
+    assert np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od)) and np.array_equal(cnt, oc)
+    assert list(ids[0]) == [17] + list(range(1000, 1009))
+    assert st["uncertified_queries"] >= 1
 
 
 def test_ivf_search_approximate_single_query_trait_call(vo, ivf_c1):

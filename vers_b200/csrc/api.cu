@@ -64,8 +64,8 @@ int32_t upload_queries(vers_ctx* ctx, const float* q, uint32_t nq, uint32_t stri
 }
 
 // cuTensorMapEncodeTiled is a driver-API entry point; resolve it through the runtime so the library only links cudart
-int32_t make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t row_stride_floats,
-                         uint32_t box_rows, uint32_t box_cols) {
+static int32_t make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dtype, uint32_t elem_bytes, const void* base,
+                            uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols) {
     static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -76,14 +76,21 @@ int32_t make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uin
         encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
     }
     cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstride[1] = {row_stride_floats * sizeof(float)};
+    cuuint64_t gstride[1] = {row_stride_elems * elem_bytes};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = encode(out, dtype, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(VERS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return VERS_OK;
+}
+int32_t make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t row_stride_floats,
+                         uint32_t box_rows, uint32_t box_cols) {
+    return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, rows, cols, row_stride_floats, box_rows, box_cols);
+}
+int32_t make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_halfs,
+                         uint32_t box_rows, uint32_t box_cols) {
+    return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, rows, cols, row_stride_halfs, box_rows, box_cols);
 }
 
 // ---------------------------------------------------------------- kernels

@@ -90,6 +90,9 @@ inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 // host: 2D fp32 TMA tensor map {inner = cols, outer = rows}, box {box_cols, box_rows}, 128-byte swizzle, zero fill
 int32_t make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t row_stride_floats,
                          uint32_t box_rows, uint32_t box_cols);
+// the same over fp16 elements (box_cols = 64 halfs = one 128-byte swizzle row)
+int32_t make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_halfs,
+                         uint32_t box_rows, uint32_t box_cols);
 
 // grow-only scratch; caller holds ctx->mu
 int32_t scratch_reserve(vers_ctx* ctx, size_t bytes);

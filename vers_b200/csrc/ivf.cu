@@ -14,7 +14,11 @@
 //   merge      : nprobe >= 1: per query global top-k by (d, id) over its partial lists
 //                nprobe == 0: the reference's spill semantics (ivfflat.rs:163-197): lists are consumed in probe
 //                order; every list but the last contributes all its rows (sorted), the last one the remainder.
+#include <cuda_fp16.h>
+
 #include <algorithm>
+#include <cmath>
+#include <cstring>
 
 #include "kmeans.cuh"
 #include "scan.cuh"
@@ -44,6 +48,15 @@ struct vers_ivf {
     float* d_cent_norm = nullptr;           // [C] ||centroid||^2 (any order; tensor-core probe only)
     uint32_t* d_ncmax = nullptr;            // [1] bit pattern of max ||centroid||^2
     int mode = 0;                           // 0 = candidate pass + exact rerank + certificate, 1 = exact-order everywhere
+    // 16-bit candidate copy (mode 4): fp16(row * h16_scale), list-major like d_lm, ld16 = round_up(dim, 8) halfs per row;
+    // rebuilt lazily by ivf_ensure_h16 when a bulk change invalidated it, updated in place by a single Index::add
+    __half* d_lm16 = nullptr;
+    uint64_t h16_cap = 0;                   // rows d_lm16 was allocated for
+    uint32_t ld16 = 0;
+    bool h16_valid = false;
+    float h16_scale = 1.0f;                 // power of two: no element of a row with ||row||^2 <= h16_norm2_limit overflows
+    double h16_norm2_limit = 0.0;
+    uint32_t* d_h16_stat = nullptr;         // [0] bits of max ||x - x~||^2 over the live rows, [1] elements that did not fit
     // cache of ivf_max_chunks_per_query (host loop over the lists): valid while seg_epoch == mc_epoch
     uint64_t seg_epoch = 1, mc_epoch = 0;
     uint32_t mc_np = 0;
@@ -556,7 +569,47 @@ static int32_t ivf_relayout(vers_ivf* ivf, const uint32_t* extra = nullptr) {
     ivf->cap_total = total;
     ivf->seg_off = noff;
     ivf->seg_cap = ncap;
+    ivf->h16_valid = false;  // positions moved: the 16-bit copy is rebuilt by the next search that wants it
     return ivf_upload_segments(ivf);
+}
+
+// (re)builds the fp16 candidate copy when it is missing or stale.  One pass over the live rows (10M x 768: ~8 ms).
+// Caller holds ctx->mu; never called under stream capture with a stale copy (the first eager search builds it).
+static int32_t ivf_ensure_h16(vers_ivf* ivf) {
+    if (ivf->h16_valid) return VERS_OK;
+    vers_ctx* ctx = ivf->ctx;
+    ivf->ld16 = round_up(ivf->dim, 8);
+    const uint64_t cap = std::max<uint64_t>(ivf->cap_total, 1);
+    if (!ivf->d_h16_stat) VERS_CUDA(cudaMalloc(&ivf->d_h16_stat, 8));
+    if (!ivf->d_lm16 || ivf->h16_cap < cap) {
+        VERS_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ivf->d_lm16);
+        ivf->d_lm16 = nullptr;
+        ivf->h16_cap = 0;
+        VERS_CUDA(cudaMalloc(&ivf->d_lm16, (size_t)cap * ivf->ld16 * 2));
+        ivf->h16_cap = cap;
+    }
+    uint32_t nxbits = 0;
+    VERS_CUDA(cudaMemcpyAsync(&nxbits, ivf->d_nxmax, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    VERS_CUDA(cudaStreamSynchronize(ctx->stream));
+    float nxmax;
+    memcpy(&nxmax, &nxbits, 4);
+    // |x_i| <= ||x|| < 2^ex  =>  |x_i| * 2^(14 - ex) < 2^14: a row may grow to 3x the current largest norm (later adds)
+    // before an element could pass fp16's 65504
+    int ex = 0;
+    if (nxmax > 0.0f && std::isfinite(nxmax)) (void)std::frexp(std::sqrt((double)nxmax) * 1.0001, &ex);
+    int e2 = std::max(-100, std::min(100, 14 - ex));
+    ivf->h16_scale = std::ldexp(1.0f, e2);
+    const double lim = 65504.0 / (double)ivf->h16_scale * 0.999;
+    ivf->h16_norm2_limit = lim * lim;
+    VERS_CUDA(cudaMemsetAsync(ivf->d_h16_stat, 0, 8, ctx->stream));
+    // pad columns of the copy are written by the kernel (zeros), gap rows between the lists are never read as results
+    rows_to_h16_kernel<<<std::min<uint32_t>(ivf->C, (uint32_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(
+        ivf->d_lm, ivf->ld, ivf->ld16, ivf->d_seg_off, ivf->d_seg_len, 0, ivf->C, 0, ivf->h16_scale, 1.0f / ivf->h16_scale,
+        ivf->d_lm16, ivf->d_h16_stat, ivf->d_h16_stat + 1);
+    VERS_LAUNCH_CHECK(ctx);
+    ivf->h16_valid = true;
+    return VERS_OK;
 }
 
 // upper bound on the number of (pair, chunk) partial lists one query can produce when it opens np lists
@@ -745,7 +798,8 @@ __global__ void __launch_bounds__(128)
                           const uint32_t* __restrict__ cand_pos, const float* __restrict__ cand_bound,
                           const uint32_t* __restrict__ nxmax_bits, const float* __restrict__ cand_key, int tf32_pass,
                           uint64_t* out_ids, float* out_d, uint32_t* out_cnt, uint32_t* fail_flag,
-                          unsigned long long* stats, uint32_t* fail_list, uint32_t* n_fail) {
+                          unsigned long long* stats, uint32_t* fail_list, uint32_t* n_fail,
+                          const uint32_t* __restrict__ h16_stat) {
     constexpr uint32_t M = 32 * R;
     constexpr int QPB = 4 / R;  // queries per block
     __shared__ __align__(16) float tile[4][32][RR_LDS];
@@ -772,7 +826,7 @@ __global__ void __launch_bounds__(128)
                          : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
-    float s = 0.0f, nq2 = 0.0f;
+    float s = 0.0f, nq2 = 0.0f, qres2 = 0.0f;  // qres2: ||q - (q_hi + q_lo)||^2 of the fp16 pass's query split
     fetch(0);
     for (uint32_t k0 = 0; k0 < ld; k0 += RR_KCH) {
         const uint32_t kn = min((uint32_t)RR_KCH, ld - k0);  // multiple of 4
@@ -786,6 +840,15 @@ __global__ void __launch_bounds__(128)
             *reinterpret_cast<float2*>(&qs[warp][lane * 2]) = v;
             nq2 = __fmaf_rn(v.x, v.x, nq2);
             nq2 = __fmaf_rn(v.y, v.y, nq2);
+            if (tf32_pass == 4) {
+                __half h, l;
+                h16_split(v.x, h, l);
+                float r = __fsub_rn(__fsub_rn(v.x, __half2float(h)), __fmul_rn(__half2float(l), H16_LO_INV));
+                qres2 = __fmaf_rn(r, r, qres2);
+                h16_split(v.y, h, l);
+                r = __fsub_rn(__fsub_rn(v.y, __half2float(h)), __fmul_rn(__half2float(l), H16_LO_INV));
+                qres2 = __fmaf_rn(r, r, qres2);
+            }
         }
         __syncwarp();
         if (k0 + RR_KCH < ld) fetch(k0 + RR_KCH);
@@ -801,7 +864,10 @@ __global__ void __launch_bounds__(128)
             }
         }
     }
-    for (int o = 16; o; o >>= 1) nq2 += __shfl_xor_sync(FULL_MASK, nq2, o);
+    for (int o = 16; o; o >>= 1) {
+        nq2 += __shfl_xor_sync(FULL_MASK, nq2, o);
+        qres2 += __shfl_xor_sync(FULL_MASK, qres2, o);
+    }
     sdist[warp][lane] = s;
     skey[warp][lane] = live ? cand_key[(uint64_t)q * M + wr * 32 + lane] : 0.f;
     sid[warp][lane] = live ? (lm_ids ? lm_ids[pos] : id_base + pos) : 0xffffffffffffffffull;
@@ -871,8 +937,19 @@ __global__ void __launch_bounds__(128)
             if (tf32_pass == 2) E += (3.003 / 1048576.0 + (ld + 8.0) * 2.384185791015625e-07) * (nxmax + (double)nq2);
             // both operands ROUNDED to nearest tf32 (tc_flat_kernel): 2^-11 per operand => 2^-10 (1 + 2^-12) per product
             if (tf32_pass == 3) E += (1.001 / 1024.0 + (ld + 8.0) * 4.76837158203125e-07) * (nxmax + (double)nq2);
+            // fp16 candidate copy: key error 2 |x.q - x~.q~| <= 2 (||x - x~|| ||q|| + ||x~|| ||q - q~||) (Cauchy-Schwarz;
+            // max ||x - x~||^2 over the index measured when the copy was written, ||q - q~||^2 computed above,
+            // ||x~|| <= ||x|| + ||x - x~||), fp16 products are exact in the fp32 accumulator: allowance (n + 8) 2^-22 per
+            // unit of sum |x_i q_i|.  A copy with elements that did not fit certifies nothing.
+            bool h16_ok = true;
+            if (tf32_pass == 4) {
+                const double xlo2 = (double)__uint_as_float(h16_stat[0]);
+                h16_ok = h16_stat[1] == 0u;
+                E += 2.002 * (sqrt(xlo2 * (double)nq2) + (sqrt(nxmax) + sqrt(xlo2)) * sqrt((double)qres2)) +
+                     (ld + 8.0) * 2.384185791015625e-07 * (nxmax + (double)nq2);
+            }
             const double lower = ((double)bound + (double)nq2 - E) * (1.0 - (ld + 3.0) * u);
-            certified = lower > (double)sd[k - 1];
+            certified = h16_ok && lower > (double)sd[k - 1];
         }
         fail_flag[q] = certified ? 0u : 1u;
         if (!certified && fail_list) fail_list[atomicAdd(n_fail, 1u)] = q;
@@ -886,12 +963,13 @@ static int32_t launch_rerank(vers_ctx* ctx, uint32_t M, const float* lm, const u
                              uint32_t ld, const float* queries, uint32_t nq, uint32_t k, const uint32_t* cand_pos,
                              const float* cand_bound, const uint32_t* nxmax_bits, const float* cand_key, int tf32_pass,
                              uint64_t* out_ids, float* out_d, uint32_t* out_cnt, uint32_t* fail_flag,
-                             unsigned long long* stats, uint32_t* fail_list, uint32_t* n_fail) {
+                             unsigned long long* stats, uint32_t* fail_list, uint32_t* n_fail,
+                             const uint32_t* h16_stat = nullptr) {
     if (k > M) return fail(VERS_ERR_ARG, "rerank: k %u > %u candidates", k, M);
 #define VERS_RR(R)                                                                                                  \
     rerank_certify_kernel<R><<<(unsigned)ceil_div(nq, 4 / R), 128, (size_t)(4 / R) * k * 12, ctx->stream>>>(       \
         lm, lm_ids, id_base, ld, queries, nq, k, cand_pos, cand_bound, nxmax_bits, cand_key, tf32_pass, out_ids, out_d, \
-        out_cnt, fail_flag, stats, fail_list, n_fail)
+        out_cnt, fail_flag, stats, fail_list, n_fail, h16_stat)
     if (M == 32) VERS_RR(1);
     else if (M == 64) VERS_RR(2);
     else if (M == 128) VERS_RR(4);
@@ -994,20 +1072,33 @@ static int32_t run_list_scan(vers_ivf* ivf, const SearchBufs& b, const float* d_
 }
 
 // launches the tensor-core scan over `rows` ([n_rows][ld], norms in tp.lm_norm) with the grouped queries gq / gq_lo
-// ([gq_rows][ld]); tp carries the work-item tables
-template <bool SPLIT3>
-static int32_t launch_tc_scan(vers_ctx* ctx, const float* rows, uint64_t n_rows, uint32_t ld, const float* gq,
-                              const float* gq_lo, uint64_t gq_rows, const TcScanParams& tp, int family) {
-    using Cfg = TcCfg<SPLIT3>;
+// ([gq_rows][ld]); tp carries the work-item tables.  PREC 2: rows / gq / gq_lo are fp16 tables of ld halfs per row.
+template <int PREC>
+static int32_t launch_tc_scan(vers_ctx* ctx, const void* rows, uint64_t n_rows, uint32_t ld, const void* gq,
+                              const void* gq_lo, uint64_t gq_rows, const TcScanParams& tp, int family) {
+    using Cfg = TcCfg<PREC>;
     CUtensorMap tm_rows, tm_rows32, tm_q16, tm_ql16, tm_q32, tm_ql32;
-    const float* lo_src = SPLIT3 ? gq_lo : gq;
-    VERS_TRY(make_tmap_2d_f32(&tm_rows, rows, n_rows ? n_rows : 1, ld, ld, TC_M, TC_KC));
-    VERS_TRY(make_tmap_2d_f32(&tm_rows32, rows, n_rows ? n_rows : 1, ld, ld, 32, TC_KC));
-    VERS_TRY(make_tmap_2d_f32(&tm_q16, gq, gq_rows, ld, ld, 16, TC_KC));
-    VERS_TRY(make_tmap_2d_f32(&tm_ql16, lo_src, gq_rows, ld, ld, 16, TC_KC));
-    VERS_TRY(make_tmap_2d_f32(&tm_q32, gq, gq_rows, ld, ld, 32, TC_KC));
-    VERS_TRY(make_tmap_2d_f32(&tm_ql32, lo_src, gq_rows, ld, ld, 32, TC_KC));
-    auto kern = tc_list_scan_kernel<SPLIT3>;
+    const void* lo_src = (Cfg::SPLIT3 || Cfg::H16) ? gq_lo : gq;
+    const uint64_t nr = n_rows ? n_rows : 1;
+    if (Cfg::H16) {
+        VERS_TRY(make_tmap_2d_f16(&tm_rows, rows, nr, ld, ld, TC_M, Cfg::KC_ELEMS));
+        VERS_TRY(make_tmap_2d_f16(&tm_rows32, rows, nr, ld, ld, 32, Cfg::KC_ELEMS));
+        VERS_TRY(make_tmap_2d_f16(&tm_q16, gq, gq_rows, ld, ld, 16, Cfg::KC_ELEMS));
+        VERS_TRY(make_tmap_2d_f16(&tm_ql16, lo_src, gq_rows, ld, ld, 16, Cfg::KC_ELEMS));
+        VERS_TRY(make_tmap_2d_f16(&tm_q32, gq, gq_rows, ld, ld, 32, Cfg::KC_ELEMS));
+        VERS_TRY(make_tmap_2d_f16(&tm_ql32, lo_src, gq_rows, ld, ld, 32, Cfg::KC_ELEMS));
+    } else {
+        const float* frows = static_cast<const float*>(rows);
+        const float* fq = static_cast<const float*>(gq);
+        const float* fl = static_cast<const float*>(lo_src);
+        VERS_TRY(make_tmap_2d_f32(&tm_rows, frows, nr, ld, ld, TC_M, TC_KC));
+        VERS_TRY(make_tmap_2d_f32(&tm_rows32, frows, nr, ld, ld, 32, TC_KC));
+        VERS_TRY(make_tmap_2d_f32(&tm_q16, fq, gq_rows, ld, ld, 16, TC_KC));
+        VERS_TRY(make_tmap_2d_f32(&tm_ql16, fl, gq_rows, ld, ld, 16, TC_KC));
+        VERS_TRY(make_tmap_2d_f32(&tm_q32, fq, gq_rows, ld, ld, 32, TC_KC));
+        VERS_TRY(make_tmap_2d_f32(&tm_ql32, fl, gq_rows, ld, ld, 32, TC_KC));
+    }
+    auto kern = tc_list_scan_kernel<PREC>;
     VERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     FamilyTimer ft(ctx, family);
     kern<<<ctx->sm_count, Cfg::THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(tm_rows, tm_rows32, tm_q16, tm_ql16, tm_q32,
@@ -1016,16 +1107,22 @@ static int32_t launch_tc_scan(vers_ctx* ctx, const float* rows, uint64_t n_rows,
     return VERS_OK;
 }
 
-template <bool SPLIT3>
+template <int PREC>
 static int32_t run_list_scan_tc(vers_ivf* ivf, const SearchBufs& b, const float* d_queries, uint32_t nq, uint32_t np,
                                 uint32_t chunk_rows) {
     vers_ctx* ctx = ivf->ctx;
+    constexpr bool H16 = PREC == 2;
     const uint64_t npairs = (uint64_t)nq * np;
-    gather_queries_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_queries, b.lq_query, b.lq_off, ivf->C, ivf->ld,
-                                                                     b.gq, b.gq_lo, SPLIT3 ? 1 : 0);
+    if (H16)
+        gather_queries_h16_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(
+            d_queries, b.lq_query, b.lq_off, ivf->C, ivf->ld, ivf->ld16, reinterpret_cast<__half*>(b.gq),
+            reinterpret_cast<__half*>(b.gq_lo));
+    else
+        gather_queries_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_queries, b.lq_query, b.lq_off, ivf->C, ivf->ld,
+                                                                         b.gq, b.gq_lo, PREC == 1 ? 1 : 0);
     VERS_LAUNCH_CHECK(ctx);
     TcScanParams tp;
-    tp.ld = ivf->ld;
+    tp.ld = H16 ? ivf->ld16 : ivf->ld;
     tp.C = ivf->C;
     tp.chunk_rows = chunk_rows;
     tp.chunk_rows_tail = TC_TAIL_CHUNK_ROWS;
@@ -1044,8 +1141,9 @@ static int32_t run_list_scan_tc(vers_ivf* ivf, const SearchBufs& b, const float*
     tp.lq_query = b.lq_query;
     tp.dense_out = nullptr;
     tp.dense_ld = 0;
-    return launch_tc_scan<SPLIT3>(ctx, ivf->d_lm, ivf->cap_total, ivf->ld, b.gq, b.gq_lo, npairs + TC_NQ, tp,
-                                  KF_CAND_SCAN);
+    tp.key_scale = H16 ? -2.0f / ivf->h16_scale : -2.0f;
+    const void* rows = H16 ? static_cast<const void*>(ivf->d_lm16) : static_cast<const void*>(ivf->d_lm);
+    return launch_tc_scan<PREC>(ctx, rows, ivf->cap_total, tp.ld, b.gq, b.gq_lo, npairs + TC_NQ, tp, KF_CAND_SCAN);
 }
 
 // ---------------------------------------------------------------- centroid probe
@@ -1145,7 +1243,7 @@ static RankTable centroid_table(const vers_ivf* ivf) {
     tb.norm = ivf->d_cent_norm;
     tb.nmax_bits = ivf->d_ncmax;
     tb.id_base = 0;
-    tb.allow_tc = ivf->mode == 0;
+    tb.allow_tc = ivf->mode == 0 || ivf->mode == 4;  // the probe itself always runs split-precision tf32
     tb.stats = ivf->d_stats + 3;  // stats[7] = uncertified probe queries, [8] = re-ranked centroids
     return tb;
 }
@@ -1302,7 +1400,8 @@ static int32_t probe_run(vers_ctx* ctx, const RankTable& tb, const ProbePlan& pp
     tp.lq_query = nullptr;
     tp.dense_out = pp.dense ? b.dense : nullptr;
     tp.dense_ld = tb.n;
-    VERS_TRY(launch_tc_scan<true>(ctx, tb.rows, tb.n, tb.ld, b.gq, b.gq_lo, (uint64_t)nq + TC_NQ, tp, -1));
+    tp.key_scale = -2.0f;
+    VERS_TRY(launch_tc_scan<1>(ctx, tb.rows, tb.n, tb.ld, b.gq, b.gq_lo, (uint64_t)nq + TC_NQ, tp, -1));
     if (pp.dense) {
         probe_select_kernel<<<nq, 256, (size_t)tb.n * 4, ctx->stream>>>(b.dense, (uint32_t)tb.n, pp.M, b.cand_pos,
                                                                        b.cand_key, b.bound);
@@ -1490,8 +1589,11 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
     // candidate list length of the approximate pass: the private lists are one register per lane
     const uint32_t M = 32;
     const bool approx = !ref_mode && ivf->mode != 1 && k <= 16;
-    const bool use_tc = approx && (ivf->mode == 0 || ivf->mode == 3) && ivf->ld >= TC_KC && ivf->cap_total < 0x7fffffffull;
+    const bool use_tc = approx && (ivf->mode == 0 || ivf->mode == 3 || ivf->mode == 4) && ivf->ld >= TC_KC &&
+                        ivf->cap_total < 0x7fffffffull;
     const bool split3 = use_tc && ivf->mode == 0;
+    const bool h16 = use_tc && ivf->mode == 4;  // 16-bit candidate copy
+    if (h16) VERS_TRY(ivf_ensure_h16(ivf));
     const uint64_t npairs = (uint64_t)nq * np;
     uint64_t mc[2];
     ivf_max_chunks(ivf, np, mc);
@@ -1526,7 +1628,7 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
         b.part_d = sc.take<float>(entries);
         b.part_p = sc.take<uint32_t>(entries);
         b.gq = sc.take<float>(use_tc ? (size_t)(npairs + TC_NQ) * ivf->ld : 4);
-        b.gq_lo = sc.take<float>(split3 ? (size_t)(npairs + TC_NQ) * ivf->ld : 4);
+        b.gq_lo = sc.take<float>((split3 || h16) ? (size_t)(npairs + TC_NQ) * ivf->ld : 4);
         b.cand_key = sc.take<float>((size_t)nq * M);
         b.qtau = sc.take<uint32_t>(nq);
     };
@@ -1579,10 +1681,12 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
             const uint32_t cr = tc_chunk_rows(ivf, nq, np);
             VERS_TRY(run_group(ivf, b, nq, np, nullptr, nullptr, true, TC_NQ, cr, TC_TAIL_CHUNK_ROWS,
                                tc_tail_list0(ivf->C), b.qtau));
-            if (split3)
-                VERS_TRY(run_list_scan_tc<true>(ivf, b, d_queries, nq, np, cr));
+            if (h16)
+                VERS_TRY(run_list_scan_tc<2>(ivf, b, d_queries, nq, np, cr));
+            else if (split3)
+                VERS_TRY(run_list_scan_tc<1>(ivf, b, d_queries, nq, np, cr));
             else
-                VERS_TRY(run_list_scan_tc<false>(ivf, b, d_queries, nq, np, cr));
+                VERS_TRY(run_list_scan_tc<0>(ivf, b, d_queries, nq, np, cr));
             nsplit = TC_PARTS;
         } else {
             VERS_TRY(run_group(ivf, b, nq, np, nullptr, nullptr, true));
@@ -1594,8 +1698,8 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
         {
             FamilyTimer ftr(ctx, KF_RERANK);
             VERS_TRY(launch_rerank(ctx, M, ivf->d_lm, ivf->d_lm_ids, 0, ivf->ld, d_queries, nq, k, b.cand_pos, b.cand_bound,
-                                   ivf->d_nxmax, b.cand_key, use_tc ? (split3 ? 2 : 1) : 0, d_ids, d_d, d_cnt,
-                                   b.fail_flag, ivf->d_stats, nullptr, nullptr));
+                                   ivf->d_nxmax, b.cand_key, use_tc ? (h16 ? 4 : split3 ? 2 : 1) : 0, d_ids, d_d, d_cnt,
+                                   b.fail_flag, ivf->d_stats, nullptr, nullptr, h16 ? ivf->d_h16_stat : nullptr));
         }
         qmask = b.fail_flag;  // 2b. exact-order redo of the (rare) uncertified queries, no host round trip
     }
@@ -1640,6 +1744,8 @@ extern "C" int32_t vers_ivf_free(vers_ivf* ivf) {
     cudaFree(ivf->d_assign);
     cudaFree(ivf->d_stats);
     cudaFree(ivf->d_lm_norm);
+    cudaFree(ivf->d_lm16);
+    cudaFree(ivf->d_h16_stat);
     cudaFree(ivf->d_nxmax);
     cudaFree(ivf->d_cent_norm);
     cudaFree(ivf->d_ncmax);
@@ -1921,7 +2027,7 @@ extern "C" int32_t vers_ivf_get_list(const vers_ivf* ivf, uint32_t list, uint64_
 }
 
 extern "C" int32_t vers_ivf_set_mode(vers_ivf* ivf, int32_t mode) {
-    if (!ivf || mode < 0 || mode > 3) return fail(VERS_ERR_ARG, "ivf_set_mode: bad argument");
+    if (!ivf || mode < 0 || mode > 4) return fail(VERS_ERR_ARG, "ivf_set_mode: bad argument");
     ivf->mode = mode;
     return VERS_OK;
 }
@@ -1979,6 +2085,20 @@ extern "C" int32_t vers_ivf_add(vers_ivf* ivf, const float* embedding, uint64_t 
                 rownorm_kernel<<<1, 32, 0, ctx->stream>>>(ivf->d_lm, ivf->ld, pos, 1, ivf->d_lm_norm, ivf->d_nxmax);
                 ctx->launches += 1;
                 e = cudaGetLastError();
+            }
+            if (e == cudaSuccess && ivf->h16_valid) {
+                // keep the 16-bit candidate copy current: convert the one row in place when it fits the copy's scale
+                double n2 = 0.0;
+                for (uint32_t i = 0; i < ivf->dim; ++i) n2 += (double)embedding[i] * (double)embedding[i];
+                if (n2 <= ivf->h16_norm2_limit && pos < ivf->h16_cap) {
+                    rows_to_h16_kernel<<<1, 32, 0, ctx->stream>>>(ivf->d_lm, ivf->ld, ivf->ld16, nullptr, nullptr, 0, 1, pos,
+                                                                 ivf->h16_scale, 1.0f / ivf->h16_scale, ivf->d_lm16,
+                                                                 ivf->d_h16_stat, ivf->d_h16_stat + 1);
+                    ctx->launches += 1;
+                    e = cudaGetLastError();
+                } else {
+                    ivf->h16_valid = false;  // rebuilt with a new scale by the next search
+                }
             }
             ivf->seg_len[c] += 1;
             ivf->seg_epoch += 1;
@@ -2107,6 +2227,7 @@ extern "C" int32_t vers_ivf_add_batch(vers_ivf* ivf, const float* embeddings, ui
     }
     for (uint32_t c = 0; c < ivf->C; ++c) ivf->seg_len[c] += extra[c];
     ivf->seg_epoch += 1;
+    ivf->h16_valid = false;  // bulk change: the 16-bit candidate copy is rebuilt by the next search that wants it
     rc = ivf_upload_segments(ivf);
     for (uint64_t i = 0; i < n; ++i) {
         ivf->assign_tail.push_back(assign[i]);

@@ -21,6 +21,11 @@
 //     appended to a 32-entry shared-memory queue with one ballot; a full queue is sorted across the lanes (bitonic
 //     network) and merged into the sorted list, which tightens the threshold.  Selection cost is per batch of 32
 //     survivors, not per survivor, so the epilogue stays far below the HBM time of a tile.
+//   * PREC 2 (16-bit candidate copy, BASELINE configs[3] "16-bit candidate / fp32 rerank"): the rows come from an fp16
+//     copy of the list-major table (x~ = fp16(x * 2^e), half the HBM bytes per row), 128-row x 64-half boxes, one
+//     kind::f16 MMA per 16 dimensions against [q_hi; q_lo] (q_hi = fp16(q), q_lo = fp16((q - q_hi) * 2^11): the query is
+//     represented to ~2^-22, so the only real error is (x - x~).q, bounded through max ||x - x~|| by Cauchy-Schwarz in
+//     the certificate).  No converter warps, no second issuer; the epilogue reads 8 accumulator columns per load.
 // What leaves the kernel is the same (key, position) partial lists as the SIMT candidate pass, so the merge ->
 // exact-order rerank -> certificate -> exact redo chain behind it is unchanged.  The kernel does no fp32 SIMT math
 // per (row, query, dim): it is an HBM stream.
@@ -42,16 +47,20 @@ constexpr int TC_QPW = TC_NQ / 2;  // query columns per epilogue warp (at most)
 constexpr int TC_QCAP = 32;       // queue entries per (epilogue warp, query)
 constexpr int TC_A_BYTES = TC_M * TC_KC * 4;
 
-template <bool SPLIT3>
+// PREC: 0 = tf32 operands as loaded, 1 = split-precision tf32 (hi/lo, three products), 2 = fp16 row copy x [q_hi; q_lo]
+template <int PREC>
 struct TcCfg {
+    static constexpr bool SPLIT3 = PREC == 1, H16 = PREC == 2;
     static constexpr int STAGES = 7;
     static constexpr int THREADS = SPLIT3 ? 512 : 384;
-    static constexpr int B_ROWS = SPLIT3 ? 2 * TC_NQ : TC_NQ;      // B rows per stage at most: [q_hi; q_lo] or q
-    static constexpr int ACC_COLS = SPLIT3 ? 3 * TC_NQ : TC_NQ;    // per buffer: [hi.hi | hi.lo | lo.hi] or [x.q]
-    static constexpr int STAGE_BYTES = TC_A_BYTES + B_ROWS * TC_KC * 4;
+    static constexpr int KC_ELEMS = H16 ? 64 : TC_KC;              // K elements per stage: one 128-byte swizzle row
+    static constexpr int B_ROWS = (SPLIT3 || H16) ? 2 * TC_NQ : TC_NQ;  // B rows per stage at most: [q_hi; q_lo] or q
+    // per buffer: [hi.hi | hi.lo | lo.hi], [x~.q_hi | x~.q_lo] or [x.q]
+    static constexpr int ACC_COLS = SPLIT3 ? 3 * TC_NQ : (H16 ? 2 * TC_NQ : TC_NQ);
+    static constexpr int STAGE_BYTES = TC_A_BYTES + B_ROWS * 128;
     static constexpr int OFF_B = TC_A_BYTES;
     static constexpr int ALO_COL0 = 2 * ACC_COLS;                  // x_lo tiles live in TMEM after the accumulators
-    static constexpr uint32_t TMEM_COLS = SPLIT3 ? 512 : 64;       // 192 + 7*32 = 416 -> 512 / 2*32 = 64
+    static constexpr uint32_t TMEM_COLS = SPLIT3 ? 512 : (H16 ? 128 : 64);  // 192 + 7*32 = 416 -> 512 / 2*64 / 2*32
     // per epilogue warp: sorted list + queue, keys (fp32) and row offsets (u16), for TC_QPW queries
     static constexpr int SEL_WARP_BYTES = TC_QPW * (32 + TC_QCAP) * 6;
     static constexpr int OFF_SEL = STAGES * STAGE_BYTES;
@@ -86,8 +95,83 @@ __global__ void gather_queries_kernel(const float* __restrict__ queries, const u
 }
 
 
+// PREC 2: the grouped queries as fp16 [q_hi; q_lo] rows of ld16 halfs (ld16 % 8 == 0, columns past ld zero):
+// q_hi = fp16(q), q_lo = fp16((q - q_hi) * 2^11) (the scaling keeps q_lo in the normal fp16 range whenever q_hi is)
+constexpr float H16_LO_SCALE = 2048.0f, H16_LO_INV = 1.0f / 2048.0f;
+__device__ __forceinline__ void h16_split(float v, __half& hi, __half& lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(__fmul_rn(__fsub_rn(v, __half2float(hi)), H16_LO_SCALE));
+}
+__global__ void gather_queries_h16_kernel(const float* __restrict__ queries, const uint32_t* __restrict__ lq_query,
+                                          const uint64_t* __restrict__ lq_off, uint32_t C, uint32_t ld, uint32_t ld16,
+                                          __half* __restrict__ gq_hi, __half* __restrict__ gq_lo) {
+    const uint64_t n = lq_off[C];
+    const uint32_t ld8 = ld16 >> 3;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * ld8;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / ld8;
+        const uint32_t c = (uint32_t)(i - r * ld8) * 8;
+        const float* q = queries + (uint64_t)(lq_query ? lq_query[r] : (uint32_t)r) * ld + c;
+        const float4 a = *reinterpret_cast<const float4*>(q);  // ld % 4 == 0 and c < ld
+        const float4 b = c + 4 < ld ? *reinterpret_cast<const float4*>(q + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        __align__(16) __half h[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) h16_split(v[e], h[e], l[e]);
+        reinterpret_cast<uint4*>(gq_hi)[i] = *reinterpret_cast<const uint4*>(h);
+        reinterpret_cast<uint4*>(gq_lo)[i] = *reinterpret_cast<const uint4*>(l);
+    }
+}
+
+// the fp16 candidate copy of the list-major rows: lm16[pos][c] = fp16(lm[pos][c] * scale) (scale = 2^e chosen by the
+// host so that no element can overflow), one block per list (grid-stride), one warp per row.  Also the maximum over the
+// live rows of ||x - x~||^2 (x~ = the value the copy represents) for the certificate, and a count of elements that
+// did not fit (must stay 0: the host's scale guarantees it; the certificate refuses everything otherwise).
+__global__ void __launch_bounds__(256) rows_to_h16_kernel(const float* __restrict__ lm, uint32_t ld, uint32_t ld16,
+                                                          const uint64_t* __restrict__ seg_off,
+                                                          const uint32_t* __restrict__ seg_len, uint32_t list0,
+                                                          uint32_t nlists, uint64_t pos_override, float scale,
+                                                          float inv_scale, __half* __restrict__ lm16,
+                                                          uint32_t* __restrict__ xlo2max, uint32_t* __restrict__ bad) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t ld8 = ld16 >> 3;
+    float mx = 0.0f;
+    uint32_t nbad = 0;
+    for (uint32_t l = list0 + blockIdx.x; l < list0 + nlists; l += gridDim.x) {
+        // seg_off == null: one explicit row at pos_override (in-place update after Index::add)
+        const uint64_t off = seg_off ? seg_off[l] : pos_override;
+        const uint32_t len = seg_len ? seg_len[l] : 1u;
+        for (uint32_t j = warp; j < len; j += nwarps) {
+            const float* x = lm + (off + j) * ld;
+            __half* y = lm16 + (off + j) * ld16;
+            float s = 0.0f;
+            for (uint32_t c8 = lane; c8 < ld8; c8 += 32) {
+                const uint32_t c = c8 * 8;
+                const float4 a = *reinterpret_cast<const float4*>(x + c);
+                const float4 b = c + 4 < ld ? *reinterpret_cast<const float4*>(x + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                __align__(16) __half h[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    h[e] = __float2half_rn(__fmul_rn(v[e], scale));
+                    const float back = __fmul_rn(__half2float(h[e]), inv_scale);
+                    const float r = __fsub_rn(v[e], back);
+                    s = __fmaf_rn(r, r, s);
+                    if (!(fabsf(back) <= 3.0e38f)) ++nbad;  // inf or nan
+                }
+                reinterpret_cast<uint4*>(y)[c8] = *reinterpret_cast<const uint4*>(h);
+            }
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL_MASK, s, o);
+            mx = fmaxf(mx, s);
+        }
+    }
+    if (lane == 0 && mx > 0.0f) atomicMax(xlo2max, __float_as_uint(mx));
+    if (nbad) atomicAdd(bad, nbad);
+}
+
+
 struct TcScanParams {
-    uint32_t ld, C;
+    uint32_t ld, C;            // ld: K elements of a row (PREC 2: halfs of the fp16 copy)
     uint32_t chunk_rows;       // rows per work item (multiple of 128, <= 65535)
     uint32_t chunk_rows_tail;  // ... for the lists >= tail_list0: the items handed out last are small, so the
     uint32_t tail_list0;       //     persistent CTAs finish within a fraction of a full item of each other
@@ -112,6 +196,7 @@ struct TcScanParams {
     // (the centroid probe of small tables: C keys per query, selected afterwards by probe_select_kernel)
     float* dense_out;
     uint64_t dense_ld;
+    float key_scale;  // PREC 2: key = ||x||^2 + key_scale * acc, key_scale = -2 / (row scale 2^e); else unused (-2)
 };
 
 __device__ __forceinline__ uint32_t tau_encode(float f) {
@@ -200,13 +285,15 @@ __device__ __noinline__ float sel_flush(float* lk, uint16_t* lr, const float* qk
     return __shfl_sync(FULL_MASK, ld_, 31);
 }
 
-template <bool SPLIT3>
-__global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
+template <int PREC>
+__global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
     tc_list_scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_rows32,
                         const __grid_constant__ CUtensorMap tmap_qhi16,
                         const __grid_constant__ CUtensorMap tmap_qlo16, const __grid_constant__ CUtensorMap tmap_qhi32,
                         const __grid_constant__ CUtensorMap tmap_qlo32, TcScanParams p) {
-    using Cfg = TcCfg<SPLIT3>;
+    using Cfg = TcCfg<PREC>;
+    constexpr bool SPLIT3 = Cfg::SPLIT3, H16 = Cfg::H16;
+    constexpr bool TWO_B = SPLIT3 || H16;  // the B stage holds [q_hi; q_lo]
     constexpr int S = Cfg::STAGES;
     extern __shared__ uint8_t tc_smem_raw[];
     const uint32_t raw = tc::smem_u32(tc_smem_raw);
@@ -223,7 +310,7 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t total_items = p.item_off[p.C];
-    const uint32_t nk = (p.ld + TC_KC - 1) / TC_KC;
+    const uint32_t nk = (p.ld + Cfg::KC_ELEMS - 1) / Cfg::KC_ELEMS;
     // consumers of a scheduled item besides the producer: MMA thread + epilogue warps (+ lo MMA thread + converters)
     constexpr uint32_t SCHED_CONSUMERS = 1 + TC_EPI_WARPS + (SPLIT3 ? 1 + TC_CONV_WARPS : 0);
 
@@ -246,7 +333,7 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
         tc::tma_prefetch_desc(&tmap_rows32);
         tc::tma_prefetch_desc(&tmap_qhi16);
         tc::tma_prefetch_desc(&tmap_qhi32);
-        if (SPLIT3) {
+        if (TWO_B) {
             tc::tma_prefetch_desc(&tmap_qlo16);
             tc::tma_prefetch_desc(&tmap_qlo32);
         }
@@ -297,21 +384,21 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
                     // finite row data whose products land in accumulator rows nobody reads
                     const uint32_t rem = (uint32_t)min((uint64_t)TC_M, t.r1 - a0);
                     const uint32_t nbox = rem > 96 ? 0u : (rem + 31) / 32;  // 0: one full 128-row box
-                    const uint32_t tx = (nbox ? nbox * (TC_A_BYTES / 4) : TC_A_BYTES) + (SPLIT3 ? 2 : 1) * b_bytes;
+                    const uint32_t tx = (nbox ? nbox * (TC_A_BYTES / 4) : TC_A_BYTES) + (TWO_B ? 2 : 1) * b_bytes;
                     for (uint32_t kc = 0; kc < nk; ++kc) {
                         tc::mbar_wait(&empty[stage], phase ^ 1);
                         tc::mbar_arrive_expect_tx(&full[stage], tx);
                         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                         if (nbox == 0) {
-                            tc::tma_load_2d(sa, &tmap_rows, &full[stage], (int32_t)(kc * TC_KC), (int32_t)(t.base_pos + a0));
+                            tc::tma_load_2d(sa, &tmap_rows, &full[stage], (int32_t)(kc * Cfg::KC_ELEMS), (int32_t)(t.base_pos + a0));
                         } else {
                             for (uint32_t bx = 0; bx < nbox; ++bx)
                                 tc::tma_load_2d(sa + bx * (TC_A_BYTES / 4), &tmap_rows32, &full[stage],
-                                                (int32_t)(kc * TC_KC), (int32_t)(t.base_pos + a0 + bx * 32));
+                                                (int32_t)(kc * Cfg::KC_ELEMS), (int32_t)(t.base_pos + a0 + bx * 32));
                         }
-                        tc::tma_load_2d(sa + Cfg::OFF_B, mhi, &full[stage], (int32_t)(kc * TC_KC), (int32_t)t.q0);
-                        if (SPLIT3)
-                            tc::tma_load_2d(sa + Cfg::OFF_B + b_bytes, mlo, &full[stage], (int32_t)(kc * TC_KC),
+                        tc::tma_load_2d(sa + Cfg::OFF_B, mhi, &full[stage], (int32_t)(kc * Cfg::KC_ELEMS), (int32_t)t.q0);
+                        if (TWO_B)
+                            tc::tma_load_2d(sa + Cfg::OFF_B + b_bytes, mlo, &full[stage], (int32_t)(kc * Cfg::KC_ELEMS),
                                             (int32_t)t.q0);
                         if (++stage == S) {
                             stage = 0;
@@ -330,7 +417,8 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
                 if (it < 0) break;
                 const TcItem t = tc_decode_item(p, (uint64_t)it);
                 // x_hi . [q_hi; q_lo]  (or x . q unsplit)
-                const uint32_t idesc_main = tc::idesc_tf32(TC_M, SPLIT3 ? 2 * t.nq : t.nq);
+                const uint32_t idesc_main =
+                    H16 ? tc::idesc_f16(TC_M, 2 * t.nq) : tc::idesc_tf32(TC_M, SPLIT3 ? 2 * t.nq : t.nq);
                 for (uint64_t a0 = t.r0; a0 < t.r1; a0 += TC_M) {
                     const uint32_t buf = tile_ctr & 1, tphase = (tile_ctr >> 1) & 1;
                     tc::mbar_wait(&tempty[buf], tphase ^ 1);  // epilogue has drained this accumulator buffer
@@ -342,8 +430,12 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
                         const uint32_t sa = tc::smem_u32(smem + stage * Cfg::STAGE_BYTES);
                         const uint64_t da = tc::smem_desc_k_sw128(sa), db = tc::smem_desc_k_sw128(sa + Cfg::OFF_B);
 #pragma unroll
-                        for (uint32_t kk = 0; kk < TC_KC / 8; ++kk)
-                            tc::mma_tf32(d_tmem, da + 2 * kk, db + 2 * kk, idesc_main, (kc | kk) != 0);
+                        for (uint32_t kk = 0; kk < 4; ++kk) {  // 4 x (8 tf32 | 16 fp16) = one 128-byte row, 32 B per step
+                            if (H16)
+                                tc::mma_f16(d_tmem, da + 2 * kk, db + 2 * kk, idesc_main, (kc | kk) != 0);
+                            else
+                                tc::mma_tf32(d_tmem, da + 2 * kk, db + 2 * kk, idesc_main, (kc | kk) != 0);
+                        }
                         tc::mma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
                         if (++stage == S) {
                             stage = 0;
@@ -419,14 +511,14 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
                     for (uint32_t j = 0; j < nlive; ++j) {
                         float dot = tc::tmem_ld_1_nowait(tacc + col0 + j);
                         float w = 0.0f, z = 0.0f;
-                        if (SPLIT3) {
-                            w = tc::tmem_ld_1_nowait(tacc + t.nq + col0 + j);
-                            z = tc::tmem_ld_1_nowait(tacc + 2 * t.nq + col0 + j);
-                        }
+                        if (TWO_B) w = tc::tmem_ld_1_nowait(tacc + t.nq + col0 + j);
+                        if (SPLIT3) z = tc::tmem_ld_1_nowait(tacc + 2 * t.nq + col0 + j);
                         tc::tmem_ld_wait3(dot, w, z);
                         if (SPLIT3) dot = __fadd_rn(dot, __fadd_rn(w, z));
+                        if (H16) dot = __fmaf_rn(w, H16_LO_INV, dot);
                         if (rowlive)
-                            p.dense_out[(t.q0 + col0 + j) * p.dense_ld + t.base_pos + row] = __fmaf_rn(-2.0f, dot, nx);
+                            p.dense_out[(t.q0 + col0 + j) * p.dense_ld + t.base_pos + row] =
+                                __fmaf_rn(H16 ? p.key_scale : -2.0f, dot, nx);
                     }
                     tc::fence_before_thread_sync();
                     __syncwarp();
@@ -459,16 +551,8 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
                 const float nx = rowlive ? __ldg(p.lm_norm + t.base_pos + row) : 0.0f;
                 if (p.qtau && (uint32_t)lane < nlive && a0 != t.r0)  // bounds published by other CTAs meanwhile
                     my_tau = fminf(my_tau, tau_decode(__ldcg(p.qtau + my_q)));
-                for (uint32_t j = 0; j < nlive; ++j) {
-                    float dot = tc::tmem_ld_1_nowait(tacc + c_hh + j);
-                    float w = 0.0f, z = 0.0f;
-                    if (SPLIT3) {
-                        w = tc::tmem_ld_1_nowait(tacc + c_hl + j);  // x_hi . q_lo
-                        z = tc::tmem_ld_1_nowait(tacc + c_lh + j);  // x_lo . q_hi
-                    }
-                    tc::tmem_ld_wait3(dot, w, z);
-                    if (SPLIT3) dot = __fadd_rn(dot, __fadd_rn(w, z));
-                    const float key = __fmaf_rn(-2.0f, dot, nx);
+                // one (row, query j) key: rows that beat the query's threshold are appended to its queue
+                auto consider = [&](uint32_t j, float key) {
                     float tau = __shfl_sync(FULL_MASK, my_tau, j);
                     bool pass = rowlive && key <= tau;
                     unsigned m = __ballot_sync(FULL_MASK, pass);
@@ -492,6 +576,34 @@ __global__ void __launch_bounds__(TcCfg<SPLIT3>::THREADS, 1)
                             qr[j * TC_QCAP + o] = (uint16_t)roff;
                         }
                         if ((uint32_t)lane == j) my_cnt = c + n;
+                    }
+                };
+                if (H16) {
+                    // 8 accumulator columns of both blocks per load: one TMEM round trip per 8 queries
+                    for (uint32_t c8 = 0; c8 < nlive; c8 += 8) {
+                        uint32_t hh[8], hl[8];
+                        tc::tmem_ld_8_nowait(tacc + c_hh + c8, hh);
+                        tc::tmem_ld_8_nowait(tacc + c_hl + c8, hl);
+                        tc::tmem_ld_wait_16(hh, hl);
+#pragma unroll
+                        for (uint32_t jj = 0; jj < 8; ++jj) {
+                            if (c8 + jj < nlive) {  // warp-uniform
+                                const float dot = __fmaf_rn(__uint_as_float(hl[jj]), H16_LO_INV, __uint_as_float(hh[jj]));
+                                consider(c8 + jj, __fmaf_rn(p.key_scale, dot, nx));
+                            }
+                        }
+                    }
+                } else {
+                    for (uint32_t j = 0; j < nlive; ++j) {
+                        float dot = tc::tmem_ld_1_nowait(tacc + c_hh + j);
+                        float w = 0.0f, z = 0.0f;
+                        if (SPLIT3) {
+                            w = tc::tmem_ld_1_nowait(tacc + c_hl + j);  // x_hi . q_lo
+                            z = tc::tmem_ld_1_nowait(tacc + c_lh + j);  // x_lo . q_hi
+                        }
+                        tc::tmem_ld_wait3(dot, w, z);
+                        if (SPLIT3) dot = __fadd_rn(dot, __fadd_rn(w, z));
+                        consider(j, __fmaf_rn(-2.0f, dot, nx));
                     }
                 }
                 tc::fence_before_thread_sync();

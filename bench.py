@@ -57,7 +57,8 @@ def parse():
     ap.add_argument("--recall-queries", type=int, default=100)
     ap.add_argument("--cpu-queries", type=int, default=256, help="queries in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="ivf", choices=["ivf", "kmeans", "flat", "lsh"],
+    ap.add_argument("--pairs", type=int, default=1 << 22, help="--workload hnswdist: (query, neighbour) pairs per step")
+    ap.add_argument("--workload", default="ivf", choices=["ivf", "kmeans", "flat", "lsh", "hnswdist"],
                     help="ivf (default): the QPS line; kmeans: BASELINE.json configs[4], k-means build seconds on "
                          "50M x 128, 16384 centroids, --steps Lloyd iterations (default 20), rows sharded over the GPUs")
     ap.add_argument("--flat-rows", type=int, default=1_000_000, help="--workload flat: BASELINE.json configs[1]")
@@ -809,6 +810,112 @@ def main_flat(args):
     print(json.dumps(line))
 
 
+def main_hnswdist(args):
+    """HNSW distance offload.  One step = --pairs (query, neighbour id) pairs evaluated with
+    Vector::cosine_similarity_simd's association (base.rs:158-223) over the 1M x 300 table of BASELINE.json configs[1];
+    neighbour ids are uniform random (a graph frontier gathers rows from all over the table), 1000 queries."""
+    import ctypes as C
+
+    import torch
+
+    import vers_b200 as vb
+    from vers_b200 import _abi
+    from vers_b200.sharded import device_view
+
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    ctx = vb.Context(0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    n, dim, npairs = args.flat_rows, args.flat_dim, args.pairs
+    ds = vb.Dataset.synth(ctx, SEED_DATA, n, dim, kind=1, n_centers=args.n_centers, center_seed=SEED_CENTERS, row0=0,
+                          normalize=True)
+    qds = vb.Dataset.synth(ctx, SEED_QUERY, args.nq, dim, kind=1, n_centers=args.n_centers, center_seed=SEED_CENTERS,
+                           row0=0, normalize=True)
+    d_q = device_view(qds.device_ptr, (args.nq, qds.ld))
+    rng = np.random.default_rng(5)
+    pr = rng.integers(0, n, npairs).astype(np.int64)
+    pq = (np.arange(npairs) % args.nq).astype(np.int32)
+    h_pr, h_pq = torch.from_numpy(pr).pin_memory(), torch.from_numpy(pq).pin_memory()
+    d_pr, d_pq = h_pr.to(dev), h_pq.to(dev)
+    d_out = torch.empty((npairs,), dtype=torch.float32, device=dev)
+    d_bad = torch.zeros((1,), dtype=torch.int32, device=dev)
+
+    def step():
+        _abi.check(vb.lib().vers_pair_distances_simd_dev(ds.h, C.c_void_p(d_q.data_ptr()), args.nq, qds.ld,
+                                                         C.c_void_p(d_pq.data_ptr()), C.c_void_p(d_pr.data_ptr()), npairs,
+                                                         1, C.c_void_p(d_out.data_ptr()), C.c_void_p(d_bad.data_ptr())))
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(0)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    dev_ms = ev0.elapsed_time(ev1) / args.steps
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    assert int(d_bad.item()) == 0
+    # e2e through the host-buffer call: queries, pair lists in; distances out
+    h_q = torch.empty((args.nq, qds.ld), dtype=torch.float32).pin_memory()
+    h_q.copy_(d_q)
+    h_out = torch.empty((npairs,), dtype=torch.float32).pin_memory()
+
+    def e2e():
+        _abi.check(vb.lib().vers_pair_distances_simd(ds.h, h_q.data_ptr(), args.nq, qds.ld, h_pq.data_ptr(),
+                                                     h_pr.data_ptr(), npairs, 1, h_out.data_ptr()))
+
+    for _ in range(args.warmup):
+        e2e()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    match = bool(torch.equal(d_out.cpu().view(torch.int32), h_out.view(torch.int32)))
+    # parity spot check + CPU leg: the oracle on a bounded sample of the same pairs
+    import oracle as vo
+
+    use_all_host_threads(vo)
+    rows = ds.download()
+    q = qds.download()
+    ns = min(npairs, 1 << 20)
+    vo.pair_distances_simd(rows, q, pr[:4096].astype(np.uint64), pq[:4096].astype(np.uint32), 1)
+    t0 = time.perf_counter()
+    want = vo.pair_distances_simd(rows, q, pr[:ns].astype(np.uint64), pq[:ns].astype(np.uint32), 1)
+    cdt = time.perf_counter() - t0
+    bits_equal = bool(np.array_equal(want.view(np.uint32), h_out.numpy()[:ns].view(np.uint32)))
+    peak, peak_src = measured_peaks()
+    alg = npairs * dim * 4
+    line = {"metric": "HNSW distance offload: cosine_similarity_simd pairs/s (1Mx300 table, random neighbour ids)",
+            "value": npairs / (dev_ms * 1e-3), "unit": "pairs/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"Vector::cosine_similarity_simd over {npairs} (query, neighbour) pairs per step, "
+                                   f"{n}x{dim} table, {args.nq} queries (SURVEY.md §8f HNSW distance offload)",
+                       "rows": n, "dim": dim, "pairs": npairs,
+                       "l2": f"the pairs gather {alg / 1e9:.1f} GB of rows per step from a 1.2 GB table: every step re-reads "
+                             f"the table ~{alg / (n * dim * 4):.1f}x in random order, far beyond the 126 MB L2"},
+            "e2e": {"value": npairs / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": npairs * 12 + args.nq * qds.ld * 4,
+                    "d2h_bytes_per_step": npairs * 4, "bits_match_device_path": match,
+                    "call": "vers_pair_distances_simd (host buffers in and out)"},
+            "parity_spotcheck": {"pairs": ns, "distance_bits_equal_oracle": bits_equal},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "pair_distances_simd_kernel (one warp per pair, lane = SIMD chunk)",
+                         "achieved": alg / (dev_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (dev_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg, "avg_launch_ms": dev_ms,
+                         "note": "row gathers of dim*4 = 1200 B at random positions; the query rows stay in L2"},
+            "cpu_baseline": {"value": ns / cdt, "unit": "pairs/s", "cores": vo.num_threads(), "kind": "port",
+                             "sample": f"the first {ns} pairs of the step, OpenMP over pairs (the reference evaluates them "
+                                       f"one at a time inside the traversal, hnsw.rs:258-273)"}}
+    print(json.dumps(line))
+
+
 def main_lsh(args):
     """BASELINE.json configs[2]: the hyperplane forest ("LSH", indexes/lsh.rs) on 1M x 300, 16 trees, max_size 100,
     1000-query batches, 1 GPU.  build = level-synchronous split of every tree on the device; search = batched
@@ -903,6 +1010,8 @@ if __name__ == "__main__":
         main_kmeans(a)
     elif a.workload == "flat":
         main_flat(a)
+    elif a.workload == "hnswdist":
+        main_hnswdist(a)
     elif a.workload == "lsh":
         main_lsh(a)
     else:

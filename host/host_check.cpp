@@ -75,6 +75,33 @@ int main(int argc, char** argv) {
             return 1;
         }
     }
+    {   // HNSW distance offload == the SIMD-order cosine distance of base.rs:158-223, bit for bit
+        DeviceVectors<N> dv(ctx, rows);
+        std::vector<uint64_t> nb = {7, 42, 0, n - 1, 13};
+        auto got = dv.cosine_similarity_simd(rows[5], nb);
+        for (size_t j = 0; j < nb.size(); ++j) {
+            const float* u = rows[5].v;
+            const float* v = rows[nb[j]].v;
+            volatile float res = 0.0f;  // volatile: keep every add separately rounded, in this order
+            size_t i = 0;
+            for (; i + 64 <= N; i += 64) {
+                volatile float s = 0.0f;
+                for (size_t e = 0; e < 64; ++e) { volatile float p = u[i + e] * v[i + e]; s = s + p; }
+                res = res + s;
+            }
+            for (; i + 4 <= N; i += 4) {
+                volatile float s = 0.0f;
+                for (size_t e = 0; e < 4; ++e) { volatile float p = u[i + e] * v[i + e]; s = s + p; }
+                res = res + s;
+            }
+            for (; i < N; ++i) { volatile float p = u[i] * v[i]; res = res + p; }
+            const float want = 1.0f - res;
+            if (std::memcmp(&want, &got[j], 4) != 0) {
+                std::printf("hnsw distance %zu: %a vs %a\n", j, (double)got[j], (double)want);
+                return 1;
+            }
+        }
+    }
     bool threw = false;
     try {
         ix->search_approximate(rows[0], 200);  // > VERS_MAX_TOPK

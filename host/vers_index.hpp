@@ -7,6 +7,7 @@
 //   vers::IVFFlatIndex<N>::build_index      indexes/ivfflat.rs:102-136
 //   vers::ANNIndex<N>::build_index          indexes/lsh.rs:132-161
 //   vers::search_exhaustive                 utils.rs:68-82
+//   vers::DeviceVectors<N>::cosine_similarity_simd   indexes/base.rs:158-223 (HNSW's distance, batched: hnsw.rs:146,258,273)
 // Error behaviour: the reference panics; here every non-zero ABI status throws vers::Panic (std::runtime_error).
 // save_index / load_index write/read the reference's bincode 1.3 layouts of IVFFlatIndex (ivfflat.rs:9-15) and
 // ANNIndex (lsh.rs:13-55, the recursive Node enum included).
@@ -75,6 +76,35 @@ std::vector<std::pair<size_t, float>> search_exhaustive(Context& ctx, const std:
     for (uint32_t i = 0; i < cnt; ++i) out.emplace_back((size_t)ids[i], d[i]);
     return out;
 }
+
+// HNSW distance offload: the id -> vector map of hnsw.rs (id_to_vec) resident on the device; the CPU traversal hands it
+// the neighbour ids of a step and gets Vector::cosine_similarity_simd(query, neighbour, true) for each, bit for bit
+// (base.rs:158-223: 64-wide chunks, 4-wide chunks, scalar tail).  A missing id throws like id_to_vec.get(..).unwrap().
+template <size_t N>
+class DeviceVectors {
+  public:
+    DeviceVectors(Context& ctx, const std::vector<Vector<N>>& vectors, uint64_t first_id = 0) {
+        check(vers_dataset_upload(ctx.h, &vectors[0].v[0], vectors.size(), N, vector_stride<N>(), first_id, &ds_));
+    }
+    ~DeviceVectors() { vers_dataset_free(ds_); }
+    DeviceVectors(const DeviceVectors&) = delete;
+    DeviceVectors& operator=(const DeviceVectors&) = delete;
+    std::vector<float> cosine_similarity_simd(const Vector<N>& query, const std::vector<uint64_t>& neighbour_ids) const {
+        std::vector<float> out(neighbour_ids.size());
+        check(vers_pair_distances_simd(ds_, query.v, 1, N, nullptr, neighbour_ids.data(), neighbour_ids.size(),
+                                       VERS_METRIC_COSINE, out.data()));
+        return out;
+    }
+    std::vector<float> squared_euclidean_simd(const Vector<N>& query, const std::vector<uint64_t>& neighbour_ids) const {
+        std::vector<float> out(neighbour_ids.size());
+        check(vers_pair_distances_simd(ds_, query.v, 1, N, nullptr, neighbour_ids.data(), neighbour_ids.size(),
+                                       VERS_METRIC_L2SQ, out.data()));
+        return out;
+    }
+
+  private:
+    vers_dataset* ds_ = nullptr;
+};
 
 template <size_t N>
 class IVFFlatIndex : public Index<N> {

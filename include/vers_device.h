@@ -101,6 +101,22 @@ int32_t vers_flat_search_dev(vers_dataset* ds, const float* d_queries, uint32_t 
 int32_t vers_flat_set_mode(vers_dataset* ds, int32_t mode);
 int32_t vers_flat_last_search_stats(const vers_dataset* ds, uint64_t out[8]);
 
+/* ---- HNSW distance offload: Vector::cosine_similarity_simd (indexes/base.rs:158-223, the only
+ *      distance hnsw.rs evaluates: hnsw.rs:146, :258, :273) and squared_euclidean_simd (base.rs:225-294) for a batch of
+ *      (query, row) pairs.  out[i] = distance(queries[pair_query[i]], row with global id pair_row[i]) in the reference's
+ *      SIMD association: 64-wide chunks summed by the ordered reduce_sum, then 4-wide chunks, then the scalar tail,
+ *      chunk sums added in order; metric VERS_METRIC_COSINE returns 1 - dot like the reference.  The graph traversal
+ *      stays on the host; it hands the neighbour ids of a step (or of many queries' steps) to this call.
+ *      pair_query == NULL: every pair uses query 0.  A pair naming a row outside the dataset or a query >= nq returns
+ *      VERS_ERR_PANIC (id_to_vec.get(..).unwrap(), hnsw.rs:133, :270); the _dev variant writes NaN for such pairs and
+ *      counts them in *d_bad_count (which the caller zeroes). */
+int32_t vers_pair_distances_simd(vers_dataset* ds, const float* queries, uint32_t nq, uint32_t q_stride_floats,
+                                 const uint32_t* pair_query, const uint64_t* pair_row, uint64_t n_pairs, uint32_t metric,
+                                 float* out);
+int32_t vers_pair_distances_simd_dev(vers_dataset* ds, const float* d_queries, uint32_t nq, uint32_t q_stride_floats,
+                                     const uint32_t* d_pair_query, const uint64_t* d_pair_row, uint64_t n_pairs,
+                                     uint32_t metric, float* d_out, uint32_t* d_bad_count);
+
 /* ---- k-means: IVFFlatIndex::{assign_to_clusters, update_centroids, build_kmeans, calculate_kmeans_cost}
  *      (indexes/ivfflat.rs:29-46, :47-71, :73-100, :138-149) ------------------------------------------------ */
 int32_t vers_kmeans_create(vers_dataset* ds, uint32_t num_clusters, vers_kmeans** out);
@@ -179,8 +195,11 @@ int32_t vers_ivf_last_search_stats(const vers_ivf* ivf, uint64_t out[8]);
 /* nprobe >= 1 searches: 0 (default) = tensor-core candidate pass (TMA + tcgen05 kind::tf32 on the fp32 rows) +
  * exact-order rerank of the candidates + a rounding-error certificate, uncertified queries redone in exact order;
  * (the default splits every operand into tf32 hi + lo parts: 3 MMAs per K step, fp32-grade candidate values);
- * 1 = exact order everywhere; 2 = like 0 with an fp32 FMA (SIMT) candidate pass; 3 = like 0 with plain TF32.
- * Every mode returns the reference's ids and distance bits; the knob exists for tests and for timing. */
+ * 1 = exact order everywhere; 2 = like 0 with an fp32 FMA (SIMT) candidate pass; 3 = like 0 with plain TF32;
+ * 4 = candidates from an fp16 copy of the inverted lists (tcgen05 kind::f16, half the HBM bytes per scanned row; the
+ * copy is built by the first search that wants it: +dim*2 bytes per row of device memory, kept current by vers_ivf_add),
+ * same exact fp32 rerank, certificate extended by the copy's measured rounding error (Cauchy-Schwarz).
+ * Every mode returns the reference's ids and distance bits; the knob selects speed and memory, never results. */
 int32_t vers_ivf_set_mode(vers_ivf* ivf, int32_t mode);
 /* Index::search_approximate (ivfflat.rs:153-198) for a batch.  nprobe == 0: the reference's semantics (nearest
  * list, spill to the next list while fewer than top_k found, output = concatenated per-list prefixes).

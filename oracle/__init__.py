@@ -71,6 +71,8 @@ def lib():
         ),
         "vo_nearest_centroid": (i32, [_f32p, u32, u32, u32, _f32p, C.POINTER(u32)]),
         "vo_exhaustive_batch": (i32, [_f32p, u64, u32, u32, _f32p, u32, u32, u32, u32, u64, _u64p, _f32p, _u32p]),
+        "vo_simd_distance": (f32, [_f32p, _f32p, u32, u32]),
+        "vo_pair_distances_simd": (i32, [_f32p, u64, u32, u32, _f32p, u32, u32, C.c_void_p, _u64p, u64, u32, _f32p]),
         "vo_lsh_hash": (None, [_f32p, u64, u32, u32, _f32p, u32, u32, _f32p, _u8p]),
         "vo_lsh_make_plane": (None, [_f32p, _f32p, u32, _f32p, C.POINTER(f32)]),
         "vo_lsh_build": (C.c_void_p, [_f32p, u64, u32, u32, C.c_void_p, u32, u32, u64]),
@@ -273,6 +275,19 @@ def exhaustive(rows, queries, k, metric=0, id_base=0):
     _chk(lib().vo_exhaustive_batch(rows, rows.shape[0], rows.shape[1], rows.shape[1], queries, nq, queries.shape[1], k,
                                    metric, id_base, ids, d, cnt), "exhaustive")
     return ids[:, :k], d[:, :k], cnt
+
+
+def pair_distances_simd(rows, queries, pair_row, pair_query=None, metric=1) -> np.ndarray:
+    """HNSW's distances (base.rs:158-294, SIMD association) for a batch of (query, row) pairs; metric 1 = cosine
+    distance (what hnsw.rs calls), 0 = squared euclidean"""
+    rows, queries = _rows(rows), _rows(queries)
+    pair_row = np.ascontiguousarray(pair_row, np.uint64)
+    pq = None if pair_query is None else np.ascontiguousarray(pair_query, np.uint32)
+    out = np.empty(pair_row.shape[0], np.float32)
+    _chk(lib().vo_pair_distances_simd(rows, rows.shape[0], rows.shape[1], rows.shape[1], queries, queries.shape[0],
+                                      queries.shape[1], None if pq is None else pq.ctypes.data, pair_row,
+                                      pair_row.shape[0], metric, out), "pair_distances_simd")
+    return out
 
 
 # ---------------------------------------------------------------- LSH

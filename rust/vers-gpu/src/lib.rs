@@ -228,3 +228,51 @@ impl<const N: usize> Index<N> for GpuANNIndex<N> {
         self.trees = (0..self.trees.len() as u32).map(|t| Self::read_tree(lsh, t)).collect();
     }
 }
+
+/// HNSW distance offload (hnsw.rs:146, 258, 273 call `Vector::cosine_similarity_simd`, base.rs:158-223): the
+/// `id_to_vec` map of `HNSWIndex` resident on the device.  The graph build and traversal stay in `hnsw.rs`; where it
+/// evaluates a node against a list of neighbours it can hand the ids of the whole list (or of many queries' lists) to
+/// `cosine_similarity_simd_batch` and gets the reference's values bit for bit (same 64-wide / 4-wide / scalar chunking).
+pub struct DeviceVectors<const N: usize> { ctx: *mut sys::vers_ctx, ds: *mut sys::vers_dataset }
+unsafe impl<const N: usize> Send for DeviceVectors<N> {}
+unsafe impl<const N: usize> Sync for DeviceVectors<N> {}
+impl<const N: usize> Drop for DeviceVectors<N> {
+    fn drop(&mut self) { unsafe { sys::vers_dataset_free(self.ds); sys::vers_ctx_destroy(self.ctx); } }
+}
+
+impl<const N: usize> DeviceVectors<N> {
+    /// `vectors[i]` has id `first_id + i` (HNSWIndex::build_index numbers its nodes 0..n, hnsw.rs:447-452)
+    pub fn new(vectors: &Vec<Vector<N>>, first_id: usize) -> Self {
+        let mut d = DeviceVectors { ctx: null_mut(), ds: null_mut() };
+        unsafe {
+            check(sys::vers_ctx_create(0, &mut d.ctx));
+            check(sys::vers_dataset_upload(d.ctx, vectors.as_ptr() as *const f32, vectors.len() as u64, N as u32,
+                                           (std::mem::size_of::<Vector<N>>() / 4) as u32, first_id as u64, &mut d.ds));
+        }
+        d
+    }
+
+    /// `query.cosine_similarity_simd(&id_to_vec[id], true)` for every id; panics on a missing id like `.unwrap()`
+    pub fn cosine_similarity_simd_batch(&self, query: &Vector<N>, neighbour_ids: &[usize]) -> Vec<f32> {
+        let ids: Vec<u64> = neighbour_ids.iter().map(|&i| i as u64).collect();
+        let mut out = vec![0f32; ids.len()];
+        unsafe {
+            check(sys::vers_pair_distances_simd(self.ds, query.0.as_ptr(), 1, N as u32, std::ptr::null(), ids.as_ptr(),
+                                                ids.len() as u64, sys::VERS_METRIC_COSINE, out.as_mut_ptr()));
+        }
+        out
+    }
+
+    /// many (query, neighbour) pairs in one call: `pairs[i] = (index into queries, neighbour id)`
+    pub fn cosine_similarity_simd_pairs(&self, queries: &[Vector<N>], pairs: &[(u32, usize)]) -> Vec<f32> {
+        let pq: Vec<u32> = pairs.iter().map(|p| p.0).collect();
+        let pr: Vec<u64> = pairs.iter().map(|p| p.1 as u64).collect();
+        let mut out = vec![0f32; pairs.len()];
+        unsafe {
+            check(sys::vers_pair_distances_simd(self.ds, queries.as_ptr() as *const f32, queries.len() as u32,
+                                                (std::mem::size_of::<Vector<N>>() / 4) as u32, pq.as_ptr(), pr.as_ptr(),
+                                                pairs.len() as u64, sys::VERS_METRIC_COSINE, out.as_mut_ptr()));
+        }
+        out
+    }
+}

@@ -1,6 +1,8 @@
 """GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
 Bar: bit-exact ids / assignments / hash bits AND bit-exact distances / centroids (the device computes in the
 reference's own summation order, so the 1e-5 tolerance of the north star is met with zero slack)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -313,6 +315,37 @@ def test_flat_search_tensor_core_path_ties_fall_back(vb, vo, ctx):
     assert np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od))
     assert list(ids[0]) == [11] + list(range(5000, 5009))
     assert ds.last_flat_search_stats()["uncertified_queries"] >= 1
+
+
+# ---------------------------------------------------------------------------------------------- HNSW distance offload
+@pytest.mark.parametrize("dim", [3, 64, 67, 128, 300, 768, 2100])
+def test_pair_distances_simd_bit_exact(vb, vo, ctx, dim):
+    """vers_pair_distances_simd == Vector::cosine_similarity_simd / squared_euclidean_simd (base.rs:158-294) for a batch
+    of (query, row id) pairs: 64-wide chunks, 4-wide chunks, scalar tail, ordered chunk sums; global ids with an id
+    base; a missing row panics like id_to_vec.get(..).unwrap() (hnsw.rs:133)"""
+    n, nq, npairs = 3000, 7, 5000
+    rows = data(vo, n, dim)
+    q = data(vo, nq, dim, seed=2)
+    rng = np.random.default_rng(dim)
+    pr = rng.integers(0, n, npairs).astype(np.uint64)
+    pq = rng.integers(0, nq, npairs).astype(np.uint32)
+    ds = vb.Dataset.upload(ctx, rows, id_base=1000)
+    golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "simd_small.npz"))
+    for metric in (0, 1):
+        got = vb.pair_distances_simd(ds, q, pr + 1000, pq, metric)
+        assert np.array_equal(bits(got), bits(vo.pair_distances_simd(rows, q, pr, pq, metric)))
+        one = vb.pair_distances_simd(ds, q[3], pr[:100] + 1000, None, metric)  # one node against its neighbours
+        assert np.array_equal(bits(one), bits(vo.pair_distances_simd(rows, q[3:4], pr[:100], None, metric)))
+        if dim in (300, 67):  # the committed golden vectors, straight through the C ABI
+            grows = vo.synth(1, 500, dim, kind=1, n_centers=8, center_seed=7, normalize=True)
+            gq = vo.synth(2, 6, dim, kind=1, n_centers=8, center_seed=7, normalize=True)
+            gds = vb.Dataset.upload(ctx, grows)
+            d = vb.pair_distances_simd(gds, gq, golden[f"pair_row_{dim}"], golden[f"pair_query_{dim}"], metric)
+            assert np.array_equal(bits(d), golden[f"d_{dim}_m{metric}_bits"])
+    assert vb.pair_distances_simd(ds, q, np.zeros(0, np.uint64), None, 1).shape == (0,)
+    for bad_row, bad_q in ((999, 0), (1000 + n, 0), (1000, nq)):
+        with pytest.raises(vb.VersPanic):
+            vb.pair_distances_simd(ds, q, np.array([bad_row], np.uint64), np.array([bad_q], np.uint32), 1)
 
 
 # ---------------------------------------------------------------------------------------------- IVFFlat

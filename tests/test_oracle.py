@@ -350,6 +350,61 @@ def test_lsh_add_splits_full_leaf(vo):
     assert [int(ids[i][0]) for i in range(5)] == [n + i for i in range(5)] and np.all(d[:, 0] == 0)
 
 
+def np_simd_distance(u, v, metric):
+    """independent restatement of base.rs:158-294: numpy float32 scalars, chunk sums by an explicit left-to-right loop
+    (std::simd reduce_sum is the ordered reduction), chunk sums added in order"""
+    dim = u.shape[0]
+    p = ((u - v) * (u - v)).astype(np.float32) if metric == 0 else (u * v).astype(np.float32)
+    res = np.float32(0.0)
+
+    def chunk(lo, hi):
+        s = np.float32(0.0)
+        for i in range(lo, hi):
+            s = np.float32(s + p[i])
+        return s
+
+    n64 = dim // 64
+    for c in range(n64):
+        res = np.float32(res + chunk(c * 64, c * 64 + 64))
+    n4 = (dim - n64 * 64) // 4
+    for c in range(n4):
+        res = np.float32(res + chunk(n64 * 64 + c * 4, n64 * 64 + c * 4 + 4))
+    for i in range(n64 * 64 + n4 * 4, dim):
+        res = np.float32(res + p[i])
+    return res if metric == 0 else np.float32(np.float32(1.0) - res)
+
+
+@pytest.mark.parametrize("dim", [1, 3, 4, 63, 64, 67, 128, 300, 768])
+def test_hnsw_simd_distances_vs_numpy(vo, dim):
+    """the HNSW distance (SIMD association) differs from the scalar left-to-right one in the low bits and must match the
+    numpy restatement exactly; panics on a missing row like id_to_vec.get(..).unwrap()"""
+    rows = vo.synth(1, 40, dim, kind=1, n_centers=4, center_seed=7, normalize=True)
+    q = vo.synth(2, 3, dim, kind=1, n_centers=4, center_seed=7, normalize=True)
+    pr = np.arange(40, dtype=np.uint64)
+    for metric in (0, 1):
+        for qi in range(3):
+            got = vo.pair_distances_simd(rows, q, pr, np.full(40, qi, np.uint32), metric)
+            want = np.array([np_simd_distance(q[qi], rows[r], metric) for r in range(40)], np.float32)
+            assert np.array_equal(bits(got), bits(want))
+        assert np.array_equal(bits(vo.pair_distances_simd(rows, q, pr, None, metric)),
+                              bits(vo.pair_distances_simd(rows, q, pr, np.zeros(40, np.uint32), metric)))
+    if dim >= 128:  # a different association than the scalar path: some low bits must differ
+        scalar = np.array([vo.l2sq(rows[r], q[0]) for r in range(40)], np.float32)
+        assert not np.array_equal(bits(scalar), bits(vo.pair_distances_simd(rows, q, pr, None, 0)))
+    with pytest.raises(Exception):
+        vo.pair_distances_simd(rows, q, np.array([40], np.uint64), None, 1)
+
+
+def test_golden_simd_vectors_reproduce(vo):
+    g = np.load(os.path.join(GOLD, "simd_small.npz"))
+    for dim in (300, 67):
+        rows = vo.synth(1, 500, dim, kind=1, n_centers=8, center_seed=7, normalize=True)
+        q = vo.synth(2, 6, dim, kind=1, n_centers=8, center_seed=7, normalize=True)
+        for metric in (0, 1):
+            d = vo.pair_distances_simd(rows, q, g[f"pair_row_{dim}"], g[f"pair_query_{dim}"], metric)
+            assert np.array_equal(bits(d), g[f"d_{dim}_m{metric}_bits"])
+
+
 def test_golden_vectors_reproduce(vo):
     g = np.load(os.path.join(GOLD, "c1_small.npz"))
     rows = vo.synth(int(g["seed_data"]), int(g["n"]), int(g["dim"]), kind=1, n_centers=int(g["n_centers"]),

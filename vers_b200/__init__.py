@@ -7,10 +7,10 @@ fallback: importing works without a GPU (so the CPU test tier can check the ABI)
 from ._abi import (ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_PANIC, ERR_UNSUPPORTED, LIB_PATH, MAX_TOPK, METRIC_COSINE,  # noqa: F401
                    METRIC_L2SQ, SYNTH_CLUSTERED, SYNTH_UNIFORM, VersError, VersPanic, lib)
 from .index import (ANNIndex, Context, Dataset, IVFFlatIndex, KMeans, assign_to_clusters, default_context,  # noqa: F401
-                    lsh_hash, search_exhaustive, search_exhaustive_batch, synth_init_rows, update_centroids)
+                    lsh_hash, pair_distances_simd, search_exhaustive, search_exhaustive_batch, synth_init_rows, update_centroids)
 
 __all__ = [
     "ANNIndex", "Context", "Dataset", "IVFFlatIndex", "KMeans", "VersError", "VersPanic", "assign_to_clusters",
-    "default_context", "lib", "lsh_hash", "search_exhaustive", "search_exhaustive_batch", "synth_init_rows",
+    "default_context", "lib", "lsh_hash", "pair_distances_simd", "search_exhaustive", "search_exhaustive_batch", "synth_init_rows",
     "update_centroids",
 ]

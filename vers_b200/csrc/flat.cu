@@ -147,7 +147,7 @@ __global__ void __launch_bounds__((FS_GROUPS * NH + 1) * 32, 1) flat_stream_kern
     if (threadIdx.x == 0) {
         for (int s = 0; s < FS_STAGES; ++s) {
             fs_mbar_init(&full[s], 1);
-            fs_mbar_init(&empty[s], NH);
+            fs_mbar_init(&empty[s], NH * 32);  // every consumer lane arrives itself (its own reads ordered by its own arrive)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -204,8 +204,7 @@ __global__ void __launch_bounds__((FS_GROUPS * NH + 1) * 32, 1) flat_stream_kern
                 for (uint32_t t = nf4; t < nf4 + 7; ++t)
                     if (t >= sg && t - sg < nf4) fs_step<NQW, OP>(acc, x4, q4, nf4, t - sg);
             }
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fs_smem(&empty[stage])) : "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fs_smem(&empty[stage])) : "memory");
             const uint64_t row = r0 + (uint64_t)lane;
 #pragma unroll
             for (int q = 0; q < NQW; ++q) {

@@ -181,6 +181,21 @@ def search_exhaustive(ds: Dataset, query, top_k: int) -> List[Tuple[int, float]]
     return _to_pairs(ids[0], d[0], int(cnt[0]))
 
 
+def pair_distances_simd(ds: Dataset, queries, pair_row, pair_query=None, metric: int = _abi.METRIC_COSINE) -> np.ndarray:
+    """HNSW distance offload: ``Vector::cosine_similarity_simd`` (base.rs:158-223; metric 1, what hnsw.rs:146/258/273
+    call) or ``squared_euclidean_simd`` (base.rs:225-294; metric 0) for a batch of (query, row id) pairs, in the
+    reference's SIMD summation order.  ``pair_query`` None: every pair uses query 0 (one node against its neighbours)."""
+    q = _rows(queries)
+    rows = np.ascontiguousarray(pair_row, np.uint64)
+    pq = None if pair_query is None else np.ascontiguousarray(pair_query, np.uint32)
+    if pq is not None and pq.shape[0] != rows.shape[0]:
+        raise ValueError("pair_query and pair_row differ in length")
+    out = np.empty(rows.shape[0], np.float32)
+    check(lib().vers_pair_distances_simd(ds.h, ptr(q), q.shape[0], q.shape[1], None if pq is None else ptr(pq), ptr(rows),
+                                         rows.shape[0], metric, ptr(out)))
+    return out
+
+
 # --------------------------------------------------------------------------------------------- k-means steps
 class KMeans:
     """Device k-means state on one GPU's row shard (vers_kmeans); the single-GPU driver is ``fit``; the

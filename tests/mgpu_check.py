@@ -63,13 +63,15 @@ def main():
             c0 = int(np.flatnonzero(owner == rank)[0])  # ids of an owned list: ascending global ids (ivfflat.rs:123-127)
             lids = ivf.get_list(c0)
             assert np.array_equal(lids, np.flatnonzero(assign == c0).astype(np.uint64))
-        for nprobe in (1, 8, C):
+        for mode, nprobe in [(m, p) for m in (0, 4) for p in (1, 8, C)]:
+            # mode 0: candidates from the fp32 rows (split tf32); mode 4: from the fp16 candidate copy of this rank's lists
+            ivf.set_mode(mode)
             oi, od, oc = vo.ivf_search(rows, cents, off, lrw, q, k, nprobe=nprobe)
             for rep in range(3):  # repeated steps: the double-buffered slots and flags of the peer protocol
                 ids, d, cnt = index.search_dev(d_q, k, nprobe)
             torch.cuda.synchronize()
-            assert np.array_equal(ids.cpu().numpy().view(np.uint64), oi), f"ids differ nprobe={nprobe} {shard_by}"
-            assert np.array_equal(bits(d.cpu().numpy()), bits(od)), f"distances differ nprobe={nprobe} {shard_by}"
+            assert np.array_equal(ids.cpu().numpy().view(np.uint64), oi), f"ids differ nprobe={nprobe} {shard_by} {mode}"
+            assert np.array_equal(bits(d.cpu().numpy()), bits(od)), f"distances differ nprobe={nprobe} {shard_by} {mode}"
             assert np.array_equal(cnt.cpu().numpy().astype(np.uint32), oc)
             # host buffers through vers_sharded_ivf_search, an odd batch size (ranks get unequal probe shares)
             hi, hd, hc = index.search(q[:37], k, nprobe)
@@ -96,7 +98,7 @@ def main():
 
     # --- hyperplane forest: replicated on every rank (tree construction does not shard), queries sharded, slices
     #     all-gathered (vers_sharded_lsh_search): the oracle's ids and distance bits on every rank
-    import ctypes as C
+    import ctypes
     frows = rows[:6000]
     g = vb.ANNIndex.build_index(6, 40, frows, None, seed=4, ctx=ctx)
     o = vo.LSH(frows, None, 6, 40, 4)
@@ -104,9 +106,9 @@ def main():
     fi = np.empty((51, 7), np.uint64)
     fd = np.empty((51, 7), np.float32)
     fc = np.empty(51, np.uint32)
-    vb._abi.check(vb.lib().vers_sharded_lsh_search(comm.h, g.h, fq.ctypes.data_as(C.c_void_p), 51, dim, 7,
-                                                   fi.ctypes.data_as(C.c_void_p), fd.ctypes.data_as(C.c_void_p),
-                                                   fc.ctypes.data_as(C.c_void_p)))
+    vp = ctypes.c_void_p
+    vb._abi.check(vb.lib().vers_sharded_lsh_search(comm.h, g.h, fq.ctypes.data_as(vp), 51, dim, 7, fi.ctypes.data_as(vp),
+                                                   fd.ctypes.data_as(vp), fc.ctypes.data_as(vp)))
     oi, od, oc = o.search(fq, 7)
     assert np.array_equal(fi, oi) and np.array_equal(bits(fd), bits(od)) and np.array_equal(fc, oc), "sharded LSH search"
 
@@ -120,8 +122,8 @@ def main():
     comm.barrier()
     if rank == 0:
         print(f"mgpu_check ok: world={ws}, chained k-means bit-identical to the single-process oracle "
-              f"({iters} iterations), sharded search (row shards and list shards; device, host and graph-replay "
-              f"paths) ids+distances identical")
+              f"({iters} iterations), sharded search (row shards and list shards; fp32-row and fp16-copy candidate "
+              f"passes; device, host and graph-replay paths) ids+distances identical, sharded LSH search identical")
     comm.close()
     dist.destroy_process_group()
 

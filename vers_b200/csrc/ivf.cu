@@ -74,6 +74,8 @@ inline uint32_t tc_tail_list0(uint32_t C) { return C - C / 6; }
 // ... and when this GPU's share of the batch is small (many GPUs, few queries) every item shrinks so that each SM
 // still gets >= ~8 of them: rows the batch will stream ~ min(rows held, nq * nprobe * mean list length)
 inline uint32_t tc_chunk_rows(const vers_ivf* ivf, uint32_t nq, uint32_t np) {
+    static const int forced = getenv("VERS_TC_CHUNK_ROWS") ? atoi(getenv("VERS_TC_CHUNK_ROWS")) : 0;  // tuning knob
+    if (forced >= (int)TC_TAIL_CHUNK_ROWS) return (uint32_t)forced / 128u * 128u;
     const double mean_len = ivf->C ? (double)ivf->n / ivf->C : 0.0;
     const double est_rows = std::min((double)ivf->n, (double)nq * np * mean_len);
     const double per_sm = est_rows / std::max(ivf->ctx->sm_count, 1);

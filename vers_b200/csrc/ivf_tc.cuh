@@ -30,8 +30,10 @@
 // exact-order rerank -> certificate -> exact redo chain behind it is unchanged.  The kernel does no fp32 SIMT math
 // per (row, query, dim): it is an HBM stream.
 //
-// Warp roles (16 warps): 0 = scheduler + TMA producer, 1 = TMEM allocator + main MMA issuer, 2 = x_lo MMA issuer,
-// 3 = idle, 4..11 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31 = tile rows; warps 4..7 take the first half of
+// Warp roles (16 warps): 0 = TMA producer, 1 = TMEM allocator + main MMA issuer, 2 = x_lo MMA issuer,
+// 3 = scheduler (claims work items from the atomic counter one item ahead of the producer, decodes them with a
+// warp-wide 32-ary search and publishes them DECODED through a shared-memory ring, so no role pays the chain of
+// dependent global loads of a decode on its critical path), 4..11 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31 = tile rows; warps 4..7 take the first half of
 // the group's query columns, 8..11 the second), 12..15 = hi/lo converters (SPLIT3 only).  mbarriers: full / conv /
 // empty per smem stage, tmem_full / tmem_empty per accumulator buffer, sched_full / sched_empty for the work-item
 // ring (work items = (list, query group, 4096-row chunk), handed out dynamically through an atomic counter).
@@ -214,25 +216,34 @@ struct TcItem {
     uint64_t q0, base_pos, r0, r1;
 };
 
-__device__ __forceinline__ TcItem tc_decode_item(const TcScanParams& p, uint64_t it) {
-    uint32_t lo = 0, hi = p.C;
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (p.item_off[mid] <= it) lo = mid; else hi = mid;
+constexpr uint32_t TC_ITEM_END = 0xffffffffu;  // TcItem::list of the ring entry that ends the launch
+
+// item number -> (list, query group, row chunk) by a whole converged warp: 32-ary search over item_off (3 rounds for
+// C <= 32768 instead of 15 dependent loads), then the item's table entries in one round of independent loads
+__device__ __forceinline__ TcItem tc_decode_item_warp(const TcScanParams& p, uint64_t it, int lane) {
+    uint32_t lo = 0, n = p.C;  // invariant: item_off[lo] <= it, the answer lies in [lo, lo + n)
+    while (n > 1) {
+        const uint32_t step = (n + 31) / 32, idx = lo + (uint32_t)lane * step;
+        const bool ok = idx < lo + n && p.item_off[idx] <= it;  // monotone in the lane; lane 0 always holds
+        const unsigned m = __ballot_sync(FULL_MASK, ok);
+        const uint32_t j = 31u - (uint32_t)__clz((int)m);
+        const uint32_t hi = lo + n;
+        lo += j * step;
+        n = min(step, hi - lo);
     }
     TcItem t;
     t.list = lo;
-    const uint64_t local = it - p.item_off[lo];
+    const uint64_t io = p.item_off[lo], l0 = p.lq_off[lo], l1 = p.lq_off[lo + 1], so = p.seg_off[lo];
     const uint32_t len = p.seg_len[lo];
+    const uint64_t local = it - io;
     const uint32_t cr = lo >= p.tail_list0 ? p.chunk_rows_tail : p.chunk_rows;
     const uint32_t nch = (len + cr - 1) / cr;
     const uint32_t group = (uint32_t)(local / nch);
     t.chunk = (uint32_t)(local % nch);
-    t.q0 = p.lq_off[lo] + (uint64_t)group * TC_NQ;
-    const uint64_t m_l = p.lq_off[lo + 1] - p.lq_off[lo];
-    t.nB = (uint32_t)min((uint64_t)TC_NQ, m_l - (uint64_t)group * TC_NQ);
+    t.q0 = l0 + (uint64_t)group * TC_NQ;
+    t.nB = (uint32_t)min((uint64_t)TC_NQ, (l1 - l0) - (uint64_t)group * TC_NQ);
     t.nq = t.nB <= 16 ? 16u : 32u;
-    t.base_pos = p.seg_off[lo];
+    t.base_pos = so;
     t.r0 = (uint64_t)t.chunk * cr;
     t.r1 = min((uint64_t)len, t.r0 + cr);
     return t;
@@ -305,14 +316,15 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
     uint64_t* tempty = tfull + 2;
     uint64_t* sfull = tempty + 2;
     uint64_t* sempty = sfull + TC_SCHED;
-    long long* sched = reinterpret_cast<long long*>(sempty + TC_SCHED);
+    uint64_t* pgo = sempty + TC_SCHED;  // the producer has started the item it last received
+    TcItem* sched = reinterpret_cast<TcItem*>(pgo + 1);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched + TC_SCHED);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t total_items = p.item_off[p.C];
     const uint32_t nk = (p.ld + Cfg::KC_ELEMS - 1) / Cfg::KC_ELEMS;
-    // consumers of a scheduled item besides the producer: MMA thread + epilogue warps (+ lo MMA thread + converters)
-    constexpr uint32_t SCHED_CONSUMERS = 1 + TC_EPI_WARPS + (SPLIT3 ? 1 + TC_CONV_WARPS : 0);
+    // consumers of a scheduled item: producer + MMA thread + epilogue warps (+ lo MMA thread + converters)
+    constexpr uint32_t SCHED_CONSUMERS = 2 + TC_EPI_WARPS + (SPLIT3 ? 1 + TC_CONV_WARPS : 0);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -328,6 +340,7 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
             tc::mbar_init(&sfull[i], 1);
             tc::mbar_init(&sempty[i], SCHED_CONSUMERS);
         }
+        tc::mbar_init(pgo, 1);
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&tmap_rows);
         tc::tma_prefetch_desc(&tmap_rows32);
@@ -346,9 +359,9 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
 
     // every consumer role walks the same ring of scheduled items
     uint32_t sslot = 0, sphase = 0;
-    auto next_item = [&](bool leader, bool whole_warp) -> long long {
+    auto next_item = [&](bool leader, bool whole_warp) -> TcItem {
         tc::mbar_wait(&sfull[sslot], sphase);
-        long long it = sched[sslot];
+        const TcItem it = sched[sslot];
         if (whole_warp) __syncwarp();  // every lane has read the slot before the leader releases it
         if (leader) tc::mbar_arrive(&sempty[sslot]);
         if (++sslot == TC_SCHED) {
@@ -359,21 +372,13 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
     };
 
     if (warp == 0) {
-        // ===================== scheduler + TMA producer =====================
+        // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             while (true) {
-                tc::mbar_wait(&sempty[sslot], sphase ^ 1);
-                unsigned long long itu = atomicAdd(p.counter, 1ull);
-                const long long it = itu < total_items ? (long long)itu : -1;
-                sched[sslot] = it;
-                tc::mbar_arrive(&sfull[sslot]);  // release: the slot value is visible to the waiters
-                if (++sslot == TC_SCHED) {
-                    sslot = 0;
-                    sphase ^= 1;
-                }
-                if (it < 0) break;
-                const TcItem t = tc_decode_item(p, (uint64_t)it);
+                const TcItem t = next_item(true, false);
+                if (t.list == TC_ITEM_END) break;
+                tc::mbar_arrive(pgo);  // the scheduler may claim (and decode) the next item while this one streams
                 const bool wide = t.nq == 32;
                 const CUtensorMap* mhi = wide ? &tmap_qhi32 : &tmap_qhi16;
                 const CUtensorMap* mlo = wide ? &tmap_qlo32 : &tmap_qlo16;
@@ -413,9 +418,8 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, tile_ctr = 0;
             while (true) {
-                const long long it = next_item(true, false);
-                if (it < 0) break;
-                const TcItem t = tc_decode_item(p, (uint64_t)it);
+                const TcItem t = next_item(true, false);
+                if (t.list == TC_ITEM_END) break;
                 // x_hi . [q_hi; q_lo]  (or x . q unsplit)
                 const uint32_t idesc_main =
                     H16 ? tc::idesc_f16(TC_M, 2 * t.nq) : tc::idesc_tf32(TC_M, SPLIT3 ? 2 * t.nq : t.nq);
@@ -453,9 +457,8 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
         if (SPLIT3 && lane == 0) {
             uint32_t stage = 0, phase = 0, tile_ctr = 0;
             while (true) {
-                const long long it = next_item(true, false);
-                if (it < 0) break;
-                const TcItem t = tc_decode_item(p, (uint64_t)it);
+                const TcItem t = next_item(true, false);
+                if (t.list == TC_ITEM_END) break;
                 const uint32_t idesc_lo = tc::idesc_tf32(TC_M, t.nq);
                 for (uint64_t a0 = t.r0; a0 < t.r1; a0 += TC_M) {
                     const uint32_t buf = tile_ctr & 1, tphase = (tile_ctr >> 1) & 1;
@@ -481,6 +484,35 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
                 }
             }
         }
+    } else if (warp == 3) {
+        // ===================== scheduler: claim -> decode -> publish, one item ahead of the producer =============
+        uint32_t k = 0;
+        while (true) {
+            tc::mbar_wait(&sempty[sslot], sphase ^ 1);
+            if (k > 0) tc::mbar_wait(pgo, (k - 1) & 1u);  // item k-1 is streaming: claiming further ahead would only
+                                                          // hoard work the other CTAs could take at the end
+            unsigned long long itu = 0;
+            if (lane == 0) itu = atomicAdd(p.counter, 1ull);
+            itu = __shfl_sync(FULL_MASK, itu, 0);
+            const bool end = itu >= total_items;
+            TcItem t;
+            if (end) {
+                t.list = TC_ITEM_END, t.chunk = 0, t.nB = 0, t.nq = 16, t.q0 = 0, t.base_pos = 0, t.r0 = 0, t.r1 = 0;
+            } else {
+                t = tc_decode_item_warp(p, itu, lane);
+            }
+            if (lane == 0) {
+                sched[sslot] = t;
+                tc::mbar_arrive(&sfull[sslot]);  // release: the slot is visible to the waiters
+            }
+            __syncwarp();
+            if (++sslot == TC_SCHED) {
+                sslot = 0;
+                sphase ^= 1;
+            }
+            if (end) break;
+            ++k;
+        }
     } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_EPI_WARPS) {
         // ===================== epilogue: TMEM -> keys -> 32 smallest (key, row) per (lane group, query) ==========
         const int lane_group = warp & 3;                   // TMEM lanes this warp may touch
@@ -493,11 +525,12 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
         const uint32_t lt_mask = (1u << lane) - 1u;
         uint32_t tile_ctr = 0;
         while (true) {
-            const long long it = next_item(lane == 0, true);
-            if (it < 0) break;
-            const TcItem t = tc_decode_item(p, (uint64_t)it);
-            const uint32_t ncol = t.nq >> 1, col0 = half * ncol;
-            const uint32_t nlive = t.nB > col0 ? min(ncol, t.nB - col0) : 0u;  // this warp's live queries
+            const TcItem t = next_item(lane == 0, true);
+            if (t.list == TC_ITEM_END) break;
+            // the group's live queries are split evenly between the two warps of a lane group (a list probed by 8
+            // queries costs each of them 4 columns per tile, not 8 and 0)
+            const uint32_t first = (t.nB + 1) >> 1;
+            const uint32_t col0 = half ? first : 0u, nlive = half ? t.nB - first : first;  // this warp's live queries
             if (p.dense_out) {
                 // dense mode: keys straight to global memory, lanes = consecutive rows => coalesced
                 for (uint64_t a0 = t.r0; a0 < t.r1; a0 += TC_M) {
@@ -530,9 +563,15 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
             // lane j keeps query j's threshold (its list's 32nd key, or the query's shared bound) and queue fill
             float my_tau = __int_as_float(0x7f800000);
             uint32_t my_cnt = 0, my_q = 0;
-            if (p.qtau && (uint32_t)lane < nlive) {
-                my_q = p.lq_query[t.q0 + col0 + lane];
-                my_tau = tau_decode(__ldcg(p.qtau + my_q));
+            uint64_t my_base = 0;  // where query `lane`'s partial list of this (item, lane group) goes: fetched now, so
+                                   // the two dependent loads are long done when the item ends
+            if ((uint32_t)lane < nlive) {
+                const uint32_t pair = p.lq_pair[t.q0 + col0 + lane];
+                my_base = ((p.pair_chunk_off[pair] + t.chunk) * TC_PARTS + lane_group) * 32;
+                if (p.qtau) {
+                    my_q = p.lq_query[t.q0 + col0 + lane];
+                    my_tau = tau_decode(__ldcg(p.qtau + my_q));
+                }
             }
             for (uint32_t j = 0; j < nlive; ++j) {
                 lk[j * 32 + lane] = __int_as_float(0x7f800000);
@@ -540,17 +579,24 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
             }
             __syncwarp();
             const uint32_t c_hh = col0, c_hl = t.nq + col0, c_lh = 2 * t.nq + col0;
+            // ||x||^2 of the tile's row is fetched one tile ahead, the query's shared bound before the wait for the
+            // accumulator: neither global load sits on the epilogue's critical path
+            const uint64_t row_first = t.r0 + (uint64_t)(lane_group * 32 + lane);
+            float nx_next = row_first < t.r1 ? __ldg(p.lm_norm + t.base_pos + row_first) : 0.0f;
             for (uint64_t a0 = t.r0; a0 < t.r1; a0 += TC_M) {
                 const uint32_t buf = tile_ctr & 1, tphase = (tile_ctr >> 1) & 1;
+                uint32_t tau_bits = TAU_INF;
+                if (p.qtau && (uint32_t)lane < nlive && a0 != t.r0)  // bounds published by other CTAs meanwhile
+                    tau_bits = __ldcg(p.qtau + my_q);
                 tc::mbar_wait(&tfull[buf], tphase);
                 tc::fence_after_thread_sync();
                 const uint32_t tacc = tmem_base + ((uint32_t)(lane_group * 32) << 16) + buf * Cfg::ACC_COLS;
                 const uint64_t row = a0 + (uint64_t)(lane_group * 32 + lane);
                 const bool rowlive = row < t.r1;
                 const uint32_t roff = (uint32_t)(row - t.r0);
-                const float nx = rowlive ? __ldg(p.lm_norm + t.base_pos + row) : 0.0f;
-                if (p.qtau && (uint32_t)lane < nlive && a0 != t.r0)  // bounds published by other CTAs meanwhile
-                    my_tau = fminf(my_tau, tau_decode(__ldcg(p.qtau + my_q)));
+                const float nx = nx_next;
+                if (row + TC_M < t.r1) nx_next = __ldg(p.lm_norm + t.base_pos + row + TC_M);
+                my_tau = fminf(my_tau, tau_decode(tau_bits));
                 // one (row, query j) key: rows that beat the query's threshold are appended to its queue
                 auto consider = [&](uint32_t j, float key) {
                     float tau = __shfl_sync(FULL_MASK, my_tau, j);
@@ -618,8 +664,7 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
                     const float tau = sel_flush(lk + j * 32, lr + j * 32, qk + j * TC_QCAP, qr + j * TC_QCAP, c, lane);
                     if (p.qtau && (uint32_t)lane == j && tau < my_tau) atomicMin(p.qtau + my_q, tau_encode(tau));
                 }
-                const uint32_t pair = p.lq_pair[t.q0 + col0 + j];
-                const uint64_t base = ((p.pair_chunk_off[pair] + t.chunk) * TC_PARTS + lane_group) * 32;
+                const uint64_t base = __shfl_sync(FULL_MASK, my_base, j);
                 const uint32_t r = lr[j * 32 + lane];
                 p.part_d[base + lane] = lk[j * 32 + lane];
                 p.part_p[base + lane] = r == 0xffffu ? 0xffffffffu : pos0 + r;
@@ -632,9 +677,8 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
         const uint32_t row = (uint32_t)(lane_group * 32 + lane);  // tile row == TMEM lane of this thread
         uint32_t stage = 0, phase = 0;
         while (true) {
-            const long long it = next_item(lane == 0, true);
-            if (it < 0) break;
-            const TcItem t = tc_decode_item(p, (uint64_t)it);
+            const TcItem t = next_item(lane == 0, true);
+            if (t.list == TC_ITEM_END) break;
             for (uint64_t a0 = t.r0; a0 < t.r1; a0 += TC_M) {
                 for (uint32_t kc = 0; kc < nk; ++kc) {
                     tc::mbar_wait(&full[stage], phase);

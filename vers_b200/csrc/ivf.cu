@@ -72,14 +72,15 @@ constexpr uint32_t LIST_CHUNK_ROWS = 4096;  // rows per work item; multiple of N
 constexpr uint32_t TC_TAIL_CHUNK_ROWS = 512;
 inline uint32_t tc_tail_list0(uint32_t C) { return C - C / 6; }
 // ... and when this GPU's share of the batch is small (many GPUs, few queries) every item shrinks so that each SM
-// still gets >= ~8 of them: rows the batch will stream ~ min(rows held, nq * nprobe * mean list length)
+// still gets >= ~4 of them (measured on the per-rank share of an 8-GPU step: 2048-row items 0.329 ms, 1024 0.343,
+// 512 0.402, whole lists 0.346): rows the batch will stream ~ min(rows held, nq * nprobe * mean list length)
 inline uint32_t tc_chunk_rows(const vers_ivf* ivf, uint32_t nq, uint32_t np) {
     static const int forced = getenv("VERS_TC_CHUNK_ROWS") ? atoi(getenv("VERS_TC_CHUNK_ROWS")) : 0;  // tuning knob
     if (forced >= (int)TC_TAIL_CHUNK_ROWS) return (uint32_t)forced / 128u * 128u;
     const double mean_len = ivf->C ? (double)ivf->n / ivf->C : 0.0;
     const double est_rows = std::min((double)ivf->n, (double)nq * np * mean_len);
     const double per_sm = est_rows / std::max(ivf->ctx->sm_count, 1);
-    uint32_t cr = (uint32_t)(per_sm / 8.0) / 128u * 128u;
+    uint32_t cr = (uint32_t)(per_sm / 4.0) / 128u * 128u;  // >= ~4 full items per SM + the small tail items
     return std::min<uint32_t>(LIST_CHUNK_ROWS, std::max<uint32_t>(TC_TAIL_CHUNK_ROWS, cr));
 }
 using ScanCfg = NarrowCfg;
@@ -199,6 +200,150 @@ __global__ void group_fill_kernel(GroupParams g) {
     uint64_t at = g.lq_off[l] + slot;
     g.lq_query[at] = pi / g.np;
     g.lq_pair[at] = pi;
+}
+
+// The whole grouping (the memset and the six launches above) as ONE block when the per-list counters fit shared
+// memory.  Used for the exact redo pass of the candidate path: that pass almost always has no query to redo, and one
+// launch that returns at once replaces seven.  Same tables, same (arbitrary) order of the queries inside a list.
+constexpr uint32_t GROUP_FUSED_MAX_C = 8192, GROUP_FUSED_MAX_PAIRS = 1u << 19;
+
+// exclusive prefix of x over the block's 1024 threads (thread order) and the block total; two barriers
+__device__ __forceinline__ uint64_t group_block_scan(uint64_t x, uint64_t* warp_tot, uint64_t& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t inc = x;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t y = __shfl_up_sync(FULL_MASK, inc, o);
+        if (lane >= o) inc += y;
+    }
+    __syncthreads();  // warp_tot may still be read from the previous call
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    uint64_t w = warp_tot[lane];  // every warp scans the 32 warp totals itself
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t y = __shfl_up_sync(FULL_MASK, w, o);
+        if (lane >= o) w += y;
+    }
+    total = __shfl_sync(FULL_MASK, w, 31);
+    const uint64_t before = __shfl_sync(FULL_MASK, w, warp ? warp - 1 : 0);
+    return (warp ? before : 0ull) + inc - x;
+}
+
+__global__ void __launch_bounds__(1024) group_fused_kernel(GroupParams g, uint64_t* __restrict__ lq_off,
+                                                           uint64_t* __restrict__ item_off,
+                                                           uint64_t* __restrict__ pair_chunk_off,
+                                                           unsigned long long* __restrict__ work_counter) {
+    if (g.skip_if_zero && *g.skip_if_zero == 0) return;
+    extern __shared__ uint32_t gf_sm[];
+    uint32_t* s_cnt = gf_sm;          // [C] queries per list, then the fill cursor (counts down)
+    uint32_t* s_off = gf_sm + g.C;    // [C] start of the list's group in lq_query / lq_pair
+    __shared__ uint64_t warp_tot[32];
+    const uint32_t tid = threadIdx.x, npairs = g.nq * g.np;
+    for (uint32_t l = tid; l < g.C; l += 1024) s_cnt[l] = 0;
+    if (g.qtau)
+        for (uint32_t q = tid; q < g.nq; q += 1024) g.qtau[q] = 0xff800000u;  // TAU_INF (ivf_tc.cuh)
+    if (tid == 0) *work_counter = 0ull;
+    __syncthreads();
+    // 1. chunks of every active pair's list, queries per list (unrolled: the loads of 8 pairs are in flight together)
+#pragma unroll 8
+    for (uint32_t pi = tid; pi < npairs; pi += 1024) {
+        const uint32_t q = pi / g.np, sl = pi % g.np;
+        uint32_t nch = 0;
+        if ((!g.used || sl < g.used[q]) && (!g.qmask || g.qmask[q] != 0)) {
+            const uint32_t l = (uint32_t)g.probe_ids[pi];
+            const uint32_t len = g.seg_len[l];
+            const uint32_t cr = l >= g.tail_list0 ? g.chunk_rows_tail : g.chunk_rows;
+            nch = (len + cr - 1) / cr;
+            if (nch) atomicAdd(&s_cnt[l], 1u);
+        }
+        g.pair_nch[pi] = nch;
+    }
+    __syncthreads();
+    // 2. per list: work items; exclusive scans of both over the lists (8 consecutive lists per thread)
+    {
+        constexpr int IT = GROUP_FUSED_MAX_C / 1024;
+        uint32_t m[IT], items[IT];
+        uint64_t msum = 0, isum = 0;
+        unsigned long long v0 = 0, v1 = 0, v3 = 0;
+#pragma unroll
+        for (int k = 0; k < IT; ++k) {
+            const uint32_t l = tid * IT + k;
+            m[k] = 0, items[k] = 0;
+            if (l < g.C) {
+                m[k] = s_cnt[l];
+                const uint32_t len = g.seg_len[l];
+                const uint32_t cr = l >= g.tail_list0 ? g.chunk_rows_tail : g.chunk_rows;
+                items[k] = ((m[k] + g.tb - 1) / g.tb) * ((len + cr - 1) / cr);
+                if (m[k]) v0 += len, v1 += (unsigned long long)len * m[k], v3 += 1;
+            }
+            msum += m[k];
+            isum += items[k];
+        }
+        uint64_t mtot, itot;
+        uint64_t mrun = group_block_scan(msum, warp_tot, mtot);
+        uint64_t irun = group_block_scan(isum, warp_tot, itot);
+#pragma unroll
+        for (int k = 0; k < IT; ++k) {
+            const uint32_t l = tid * IT + k;
+            if (l < g.C) {
+                lq_off[l] = mrun;
+                item_off[l] = irun;
+                s_off[l] = (uint32_t)mrun;
+            }
+            mrun += m[k];
+            irun += items[k];
+        }
+        if (tid == 0) {
+            lq_off[g.C] = mtot;
+            item_off[g.C] = itot;
+        }
+        if (g.stats) {  // rows of the distinct lists, (row, query) pairs, work items, lists touched
+            for (int o = 16; o; o >>= 1) {
+                v0 += __shfl_xor_sync(FULL_MASK, v0, o);
+                v1 += __shfl_xor_sync(FULL_MASK, v1, o);
+                v3 += __shfl_xor_sync(FULL_MASK, v3, o);
+            }
+            if ((tid & 31) == 0 && v3) {
+                atomicAdd(&g.stats[0], v0);
+                atomicAdd(&g.stats[1], v1);
+                atomicAdd(&g.stats[3], v3);
+            }
+            if (tid == 0) atomicAdd(&g.stats[2], (unsigned long long)itot);
+        }
+    }
+    // 3. exclusive scan of the pairs' chunk counts (tiles of 8192 with a running carry)
+    {
+        uint64_t carry = 0;
+        for (uint32_t base = 0; base < npairs; base += 8192) {
+            const uint32_t i0 = base + tid * 8;
+            uint32_t v[8];
+            uint64_t tsum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                v[k] = i0 + k < npairs ? g.pair_nch[i0 + k] : 0u;
+                tsum += v[k];
+            }
+            uint64_t tot;
+            uint64_t run = carry + group_block_scan(tsum, warp_tot, tot);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (i0 + k < npairs) pair_chunk_off[i0 + k] = run;
+                run += v[k];
+            }
+            carry += tot;
+        }
+        if (tid == 0) pair_chunk_off[npairs] = carry;
+    }
+    __syncthreads();  // s_off complete (and every read of s_cnt as a count is over)
+    // 4. the pairs grouped by list
+#pragma unroll 8
+    for (uint32_t pi = tid; pi < npairs; pi += 1024) {
+        if (g.pair_nch[pi] == 0) continue;
+        const uint32_t l = (uint32_t)g.probe_ids[pi];
+        const uint32_t slot = atomicSub(&s_cnt[l], 1u) - 1u;
+        const uint64_t at = (uint64_t)s_off[l] + slot;
+        g.lq_query[at] = pi / g.np;
+        g.lq_pair[at] = pi;
+    }
 }
 
 // ---------------------------------------------------------------- list scan (the dominant kernel)
@@ -720,22 +865,35 @@ __global__ void __launch_bounds__(128)
     const uint64_t beg = pair_chunk_off[(uint64_t)q * np] * nsplit * 32;  // partial lists hold 32 entries each
     const uint64_t end = pair_chunk_off[(uint64_t)(q + 1) * np] * nsplit * 32;
     float tfull = INF;
-    for (uint64_t e0 = beg + (uint64_t)warp * 32 * PF; e0 < end; e0 += 4 * 32 * PF) {
-        float fd[PF];
-        uint32_t fp[PF];
+    // the next group of runs is requested before the current one is folded: the fold of mostly-skipped runs is far
+    // shorter than a trip to the partial lists (46 % of this kernel's stall samples sat on the first use of a load)
+    float fd[PF], nd[PF];
+    uint32_t fp[PF], npp[PF];
+    auto load = [&](uint64_t e0, float (&d)[PF], uint32_t (&pp)[PF]) {
 #pragma unroll
         for (int f = 0; f < PF; ++f) {
             const uint64_t e = e0 + (uint64_t)f * 32 + lane;
             const bool in = e < end;
-            fd[f] = in ? part_d[e] : INF;
-            fp[f] = in ? part_p[e] : 0xffffffffu;
+            d[f] = in ? __ldcg(part_d + e) : INF;
+            pp[f] = in ? __ldcg(part_p + e) : 0xffffffffu;
         }
+    };
+    uint64_t e0 = beg + (uint64_t)warp * 32 * PF;
+    if (e0 < end) load(e0, fd, fp);
+    for (; e0 < end; e0 += 4 * 32 * PF) {
+        const uint64_t e1 = e0 + 4 * 32 * PF;
+        if (e1 < end) load(e1, nd, npp);
 #pragma unroll
         for (int f = 0; f < PF; ++f) {
             const float last_d = __shfl_sync(FULL_MASK, fd[f], 31);
             const uint32_t last_p = __shfl_sync(FULL_MASK, fp[f], 31);
             if (last_p != 0xffffffffu) tfull = fminf(tfull, last_d);  // a full run: its dropped rows are >= last_d
             fold(fd[f], fp[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < PF; ++f) {
+            fd[f] = nd[f];
+            fp[f] = npp[f];
         }
     }
     if (warp > 0) {
@@ -789,10 +947,16 @@ static int32_t launch_cand_merge(vers_ctx* ctx, uint32_t M, const float* part_d,
 // Exact-order l2sq of the M = 32 R candidates of every query (lane = candidate, strictly sequential over the
 // dimensions like base.rs:119-126), top-k by (distance, id), certificate.  R warps per query, 4 warps per block.
 // The candidate rows are scattered over the index, so each warp stages them chunk by chunk: 16 coalesced 16-byte
-// loads per lane (two candidates' 64-float chunks per instruction, all in flight together, the next chunk fetched
-// while the current one is consumed) into a padded shared-memory tile that lane c then walks sequentially.
-constexpr int RR_KCH = 64;          // dimensions per staged chunk
-constexpr int RR_LDS = RR_KCH + 4;  // padded tile row (floats): lanes walking their own rows stay conflict-free
+// asynchronous copies per lane (cp.async; two candidates' 64-float chunks per instruction) into one of two padded
+// shared-memory tiles, chunk c + 1 in flight while lane i walks row i of chunk c sequentially.
+// Dimensions per staged chunk: 64 with one warp per query (72 KB of staging per block, the 250 blocks of a 1000-query
+// batch are all resident); 32 when R warps share a query (37 KB: the 500+ blocks still fit one wave)
+template <int R>
+struct RrCfg {
+    static constexpr int KCH = R == 1 ? 64 : 32;
+    static constexpr int LDS = KCH + 4;  // padded tile row (floats): lanes walking their own rows stay conflict-free
+    static constexpr size_t STAGE_BYTES = (size_t)(2 * 4 * 32 * LDS + 2 * 4 * KCH) * 4;
+};
 template <int R>
 __global__ void __launch_bounds__(128)
     rerank_certify_kernel(const float* __restrict__ lm, const uint64_t* __restrict__ lm_ids, uint64_t id_base,
@@ -804,11 +968,16 @@ __global__ void __launch_bounds__(128)
                           const uint32_t* __restrict__ h16_stat) {
     constexpr uint32_t M = 32 * R;
     constexpr int QPB = 4 / R;  // queries per block
-    __shared__ __align__(16) float tile[4][32][RR_LDS];
-    __shared__ __align__(16) float qs[4][RR_KCH];
+    constexpr int RR_KCH = RrCfg<R>::KCH, RR_LDS = RrCfg<R>::LDS;
+    constexpr int LPR = RR_KCH / 4, RPI = 32 / LPR;  // lanes per row chunk, rows per copy instruction
     __shared__ float sdist[4][32], skey[4][32];
     __shared__ uint64_t sid[4][32];
-    extern __shared__ __align__(16) unsigned char rsm2[];  // per query of the block: k ids (u64) then k distances
+    // dynamic: two staging buffers (row tiles [2][4 warps][32][RR_LDS], query chunks [2][4][RR_KCH]), then per query of
+    // the block k ids (u64) and k distances
+    extern __shared__ __align__(16) unsigned char rr_dyn[];
+    float* tile_base = reinterpret_cast<float*>(rr_dyn);
+    float* qs_base = tile_base + 2 * 4 * 32 * RR_LDS;
+    unsigned char* rsm2 = reinterpret_cast<unsigned char*>(qs_base + 2 * 4 * RR_KCH);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wq = warp / R, wr = warp % R;
     const uint32_t q = blockIdx.x * QPB + wq;
@@ -816,48 +985,56 @@ __global__ void __launch_bounds__(128)
     const uint32_t pos = active ? cand_pos[(uint64_t)q * M + wr * 32 + lane] : 0xffffffffu;
     const bool live = pos != 0xffffffffu;
     const float* qrow = queries + (uint64_t)(active ? q : 0) * ld;
-    const int half = lane >> 4, sub = lane & 15;
-    float4 nxt[16];
-    auto fetch = [&](uint32_t k0) {
-        const uint32_t col = k0 + sub * 4;
+    const int half = lane / LPR, sub = lane % LPR;
+    // chunk c of the warp's 32 candidate rows and of its query -> staging buffer c & 1, asynchronously (cp.async, 16 B
+    // per lane and copy: RPI candidates' chunks per instruction): the copies of chunk c + 1 are in flight
+    // while chunk c is consumed, so the scattered-row latency is paid once, not once per chunk
+    auto issue = [&](uint32_t c) {
+        const uint32_t k0 = c * RR_KCH, col = k0 + sub * 4;
+        float* tb = tile_base + ((size_t)(c & 1u) * 4 + warp) * 32 * RR_LDS;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const uint32_t cpos = __shfl_sync(FULL_MASK, pos, 2 * i + half);
-            nxt[i] = (cpos != 0xffffffffu && col < ld)
-                         ? __ldg(reinterpret_cast<const float4*>(lm + (uint64_t)cpos * ld + col))
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 32 / RPI; ++i) {
+            const uint32_t cpos = __shfl_sync(FULL_MASK, pos, RPI * i + half);
+            const bool ok = cpos != 0xffffffffu && col < ld;
+            cp_async16(tb + (RPI * i + half) * RR_LDS + sub * 4, ok ? (const void*)(lm + (uint64_t)cpos * ld + col) : (const void*)lm, ok);
         }
+        if (lane < LPR) {
+            const uint32_t qc = k0 + lane * 4;
+            const bool ok = active && qc < ld;
+            cp_async16(qs_base + ((size_t)(c & 1u) * 4 + warp) * RR_KCH + lane * 4, ok ? (const void*)(qrow + qc) : (const void*)queries, ok);
+        }
+        cp_async_commit();
     };
     float s = 0.0f, nq2 = 0.0f, qres2 = 0.0f;  // qres2: ||q - (q_hi + q_lo)||^2 of the fp16 pass's query split
-    fetch(0);
-    for (uint32_t k0 = 0; k0 < ld; k0 += RR_KCH) {
-        const uint32_t kn = min((uint32_t)RR_KCH, ld - k0);  // multiple of 4
-        __syncwarp();
+    const uint32_t nch = (ld + RR_KCH - 1) / RR_KCH;
+    issue(0);
+    for (uint32_t c = 0; c < nch; ++c) {
+        const uint32_t k0 = c * RR_KCH, kn = min((uint32_t)RR_KCH, ld - k0);  // multiple of 4
+        if (c + 1 < nch) {
+            issue(c + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();  // every lane's copies of chunk c have landed
+        const float* tl = tile_base + (((size_t)(c & 1u) * 4 + warp) * 32 + lane) * RR_LDS;
+        const float* qc = qs_base + ((size_t)(c & 1u) * 4 + warp) * RR_KCH;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) *reinterpret_cast<float4*>(&tile[warp][2 * i + half][sub * 4]) = nxt[i];
-        {
-            const uint32_t c = k0 + lane * 2;
-            float2 v = make_float2(0.f, 0.f);
-            if (active && c < ld) v = *reinterpret_cast<const float2*>(qrow + c);  // ld % 4 == 0: the pair is in range
-            *reinterpret_cast<float2*>(&qs[warp][lane * 2]) = v;
-            nq2 = __fmaf_rn(v.x, v.x, nq2);
-            nq2 = __fmaf_rn(v.y, v.y, nq2);
+        for (int e = 0; e < RR_KCH / 32; ++e) {
+            const float v = qc[lane + 32 * e];  // zero past ld
+            nq2 = __fmaf_rn(v, v, nq2);
             if (tf32_pass == 4) {
                 __half h, l;
-                h16_split(v.x, h, l);
-                float r = __fsub_rn(__fsub_rn(v.x, __half2float(h)), __fmul_rn(__half2float(l), H16_LO_INV));
-                qres2 = __fmaf_rn(r, r, qres2);
-                h16_split(v.y, h, l);
-                r = __fsub_rn(__fsub_rn(v.y, __half2float(h)), __fmul_rn(__half2float(l), H16_LO_INV));
+                h16_split(v, h, l);
+                const float r = __fsub_rn(__fsub_rn(v, __half2float(h)), __fmul_rn(__half2float(l), H16_LO_INV));
                 qres2 = __fmaf_rn(r, r, qres2);
             }
         }
-        __syncwarp();
-        if (k0 + RR_KCH < ld) fetch(k0 + RR_KCH);
         if (live) {
+#pragma unroll 4
             for (uint32_t i = 0; i < kn; i += 4) {
-                const float4 a = *reinterpret_cast<const float4*>(&tile[warp][lane][i]);
-                const float4 b = *reinterpret_cast<const float4*>(&qs[warp][i]);
+                const float4 a = *reinterpret_cast<const float4*>(tl + i);
+                const float4 b = *reinterpret_cast<const float4*>(qc + i);
                 float t;
                 t = __fsub_rn(a.x, b.x); s = __fadd_rn(s, __fmul_rn(t, t));
                 t = __fsub_rn(a.y, b.y); s = __fadd_rn(s, __fmul_rn(t, t));
@@ -865,6 +1042,7 @@ __global__ void __launch_bounds__(128)
                 t = __fsub_rn(a.w, b.w); s = __fadd_rn(s, __fmul_rn(t, t));
             }
         }
+        __syncwarp();  // the buffer is rewritten by the copies of chunk c + 2
     }
     for (int o = 16; o; o >>= 1) {
         nq2 += __shfl_xor_sync(FULL_MASK, nq2, o);
@@ -961,6 +1139,26 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+template <int R>
+static int32_t launch_rerank_r(vers_ctx* ctx, const float* lm, const uint64_t* lm_ids, uint64_t id_base, uint32_t ld,
+                               const float* queries, uint32_t nq, uint32_t k, const uint32_t* cand_pos,
+                               const float* cand_bound, const uint32_t* nxmax_bits, const float* cand_key, int tf32_pass,
+                               uint64_t* out_ids, float* out_d, uint32_t* out_cnt, uint32_t* fail_flag,
+                               unsigned long long* stats, uint32_t* fail_list, uint32_t* n_fail, const uint32_t* h16_stat) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        VERS_CUDA(cudaFuncSetAttribute(rerank_certify_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(RrCfg<R>::STAGE_BYTES + 4 * VERS_MAX_TOPK * 12)));
+        attr_set = true;
+    }
+    const size_t smem = RrCfg<R>::STAGE_BYTES + (size_t)(4 / R) * k * 12;
+    rerank_certify_kernel<R><<<(unsigned)ceil_div(nq, 4 / R), 128, smem, ctx->stream>>>(
+        lm, lm_ids, id_base, ld, queries, nq, k, cand_pos, cand_bound, nxmax_bits, cand_key, tf32_pass, out_ids, out_d,
+        out_cnt, fail_flag, stats, fail_list, n_fail, h16_stat);
+    VERS_LAUNCH_CHECK(ctx);
+    return VERS_OK;
+}
+
 static int32_t launch_rerank(vers_ctx* ctx, uint32_t M, const float* lm, const uint64_t* lm_ids, uint64_t id_base,
                              uint32_t ld, const float* queries, uint32_t nq, uint32_t k, const uint32_t* cand_pos,
                              const float* cand_bound, const uint32_t* nxmax_bits, const float* cand_key, int tf32_pass,
@@ -968,17 +1166,14 @@ static int32_t launch_rerank(vers_ctx* ctx, uint32_t M, const float* lm, const u
                              unsigned long long* stats, uint32_t* fail_list, uint32_t* n_fail,
                              const uint32_t* h16_stat = nullptr) {
     if (k > M) return fail(VERS_ERR_ARG, "rerank: k %u > %u candidates", k, M);
-#define VERS_RR(R)                                                                                                  \
-    rerank_certify_kernel<R><<<(unsigned)ceil_div(nq, 4 / R), 128, (size_t)(4 / R) * k * 12, ctx->stream>>>(       \
-        lm, lm_ids, id_base, ld, queries, nq, k, cand_pos, cand_bound, nxmax_bits, cand_key, tf32_pass, out_ids, out_d, \
-        out_cnt, fail_flag, stats, fail_list, n_fail, h16_stat)
-    if (M == 32) VERS_RR(1);
-    else if (M == 64) VERS_RR(2);
-    else if (M == 128) VERS_RR(4);
-    else return fail(VERS_ERR_ARG, "rerank: unsupported candidate count %u", M);
-#undef VERS_RR
-    VERS_LAUNCH_CHECK(ctx);
-    return VERS_OK;
+#define VERS_RR_ARGS                                                                                                   \
+    ctx, lm, lm_ids, id_base, ld, queries, nq, k, cand_pos, cand_bound, nxmax_bits, cand_key, tf32_pass, out_ids, out_d, \
+        out_cnt, fail_flag, stats, fail_list, n_fail, h16_stat
+    if (M == 32) return launch_rerank_r<1>(VERS_RR_ARGS);
+    if (M == 64) return launch_rerank_r<2>(VERS_RR_ARGS);
+    if (M == 128) return launch_rerank_r<4>(VERS_RR_ARGS);
+#undef VERS_RR_ARGS
+    return fail(VERS_ERR_ARG, "rerank: unsupported candidate count %u", M);
 }
 
 // ---------------------------------------------------------------- host: one batched search
@@ -1004,8 +1199,12 @@ static int32_t run_group(vers_ivf* ivf, const SearchBufs& b, uint32_t nq, uint32
                          uint32_t* qtau = nullptr, const uint32_t* skip_if_zero = nullptr) {
     vers_ctx* ctx = ivf->ctx;
     const uint64_t npairs = (uint64_t)nq * np;
+    // the fused single-block kernel only for the exact redo pass, which almost always has nothing to do: ONE launch
+    // that returns at once instead of seven (measured with work to do: 85 us for 32000 pairs in one block against 31 us
+    // for the multi-block path, so the main grouping keeps the latter)
+    const bool fused = skip_if_zero != nullptr && ivf->C <= GROUP_FUSED_MAX_C && npairs <= GROUP_FUSED_MAX_PAIRS;
     // lq_cnt, cursor and the work counter are carved back to back: one memset (counter[1], the short flag, survives)
-    VERS_CUDA(cudaMemsetAsync(b.lq_cnt, 0, (size_t)((char*)b.counter - (char*)b.lq_cnt) + 8, ctx->stream));
+    if (!fused) VERS_CUDA(cudaMemsetAsync(b.lq_cnt, 0, (size_t)((char*)b.counter - (char*)b.lq_cnt) + 8, ctx->stream));
     GroupParams g;
     g.probe_ids = b.probe_ids;
     g.seg_len = ivf->d_seg_len;
@@ -1028,6 +1227,18 @@ static int32_t run_group(vers_ivf* ivf, const SearchBufs& b, uint32_t nq, uint32
     g.stats = record_stats ? ivf->d_stats : nullptr;
     g.lq_query = b.lq_query;
     g.lq_pair = b.lq_pair;
+    if (fused) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            VERS_CUDA(cudaFuncSetAttribute(group_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(2 * GROUP_FUSED_MAX_C * 4)));
+            attr_set = true;
+        }
+        group_fused_kernel<<<1, 1024, (size_t)2 * ivf->C * 4, ctx->stream>>>(g, b.lq_off, b.item_off, b.pair_chunk_off,
+                                                                            b.counter);
+        VERS_LAUNCH_CHECK(ctx);
+        return VERS_OK;
+    }
     group_count_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, ctx->stream>>>(g);
     VERS_LAUNCH_CHECK(ctx);
     group_items_kernel<<<(unsigned)ceil_div(ivf->C, 256), 256, 0, ctx->stream>>>(g);

@@ -67,7 +67,7 @@ def parse():
     ap.add_argument("--km-rows", type=int, default=50_000_000)
     ap.add_argument("--km-dim", type=int, default=128)
     ap.add_argument("--km-clusters", type=int, default=16384)
-    ap.add_argument("--km-mode", type=int, default=0, help="0 tcgen05 candidate argmin + certificate (tf32-first kernel "
+    ap.add_argument("--km-mode", type=int, default=0, help="0 tcgen05 candidate argmin + certificate (single-MMA fp16 kernel "
                     "for dim <= 128), 1 exact order only, 2 split-precision tcgen05 kernel (3 MMAs per K step)")
     ap.add_argument("--no-graph", action="store_true",
                     help="time eager launches of the step instead of CUDA-graph replays (the default at every N: the "
@@ -413,6 +413,13 @@ def main_ours(args):
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.stop() if rank == 0 else None
     qps = args.nq * args.steps / (dev_ms * 1e-3)
+    peer_us = None
+    if ws > 1:  # where the fused top-k exchange of the LAST timed step spent its time on this rank (device timestamps)
+        t = (C.c_uint64 * 4)()
+        _abi.check(vb.lib().vers_debug_peer_times(comm.h, t))
+        mine = [(t[1] - t[0]) / 1e3, (t[2] - t[1]) / 1e3, (t[3] - t[2]) / 1e3]
+        peer_us = {"publish": max_over_ranks(mine[0]), "wait_for_peers_max": max_over_ranks(mine[1]),
+                   "wait_for_peers_min": -max_over_ranks(-mine[1]), "merge": max_over_ranks(mine[2])}
 
     # eager steps with per-family events: kernel durations for the roofline, launch count
     for _ in range(2):
@@ -549,6 +556,7 @@ def main_ours(args):
                         "call": "vers_sharded_ivf_search (host buffers in and out)"},
                 "exchange": ("probe lists: peer-memory all-gather (remote stores + flags); top-k: ONE fused peer "
                              "gather+merge kernel; no NCCL call inside a step" if ws > 1 else None),
+                "peer_exchange_us": peer_us,
                 "parity_spotcheck": spot,
                 "gpu_launches": launches, "launch_mode": "cuda_graph_replay" if graph is not None else "eager",
                 "eager_ms_per_step": eager_ms / args.steps, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
@@ -641,16 +649,22 @@ def kmeans_record(args, comm, ctx, rank, ws, local_rank, iters, warm, cpu, sampl
     # half of the measured cuBLAS bf16 rate (tf32 runs at half the bf16 rate; MEASURED_PEAKS.json has no tf32
     # figure): the sustained number, because the kernel is timed inside a seconds-long build under the power cap.
     bf16_sust = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    tf32_peak = bf16_sust / 2
-    peak_src = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained / 2)" if "bf16_tflops_sustained" in peaks else
-                "fallback (B200_PROFILING.md: 1.4 PFLOP/s sustained bf16, / 2)")
+    # the default kernel for dim <= 128 issues kind::f16 MMAs (fp16 operands, the bf16 rate); every other path kind::tf32
+    f16_mma = args.km_mode == 0 and args.km_dim <= 128
+    tf32_peak = bf16_sust if f16_mma else bf16_sust / 2
+    peak_src = (("measured (MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else
+                 "fallback (B200_PROFILING.md: 1.4 PFLOP/s sustained bf16") +
+                (": the kernel issues kind::f16 MMAs)" if f16_mma else " / 2: the kernel issues kind::tf32 MMAs)"))
     passes = ran + 1
     flop_pass = 2.0 * args.km_rows * args.km_clusters * args.km_dim  # the GEMM form of one assign pass
-    mma_per_kstep = {0: 1 if args.km_dim <= 128 else 3, 1: 0, 2: 3}[args.km_mode]
+    mma_per_kstep = {0: 1 if args.km_dim <= 128 else 3, 1: 0, 2: 3, 3: 1 if args.km_dim <= 128 else 3}[args.km_mode]
     avg_assign_ms = a_ms / max(a_n, 1)
     achieved = flop_pass / ws / (avg_assign_ms * 1e-3) / 1e12 if a_n else None
-    kname = {0: ("tc_assign1_kernel (tcgen05 kind::tf32, 1 MMA per K step, rows resident in TMEM, top-4 + exact "
+    kname = {3: ("tc_assign1_kernel (tcgen05 kind::tf32, 1 MMA per K step, rows resident in TMEM, top-4 + exact "
                  "rerank + certificate in the epilogue)" if args.km_dim <= 128 else
+                 "tc_assign_kernel (tcgen05 kind::tf32, split hi/lo: 3 MMAs per K step)"),
+             0: ("tc_assign1_kernel<F16> (tcgen05 kind::f16, 1 MMA per 16 dims, rows resident in TMEM as packed fp16, "
+                 "top-4 + exact rerank + certificate in the epilogue)" if args.km_dim <= 128 else
                  "tc_assign_kernel (tcgen05 kind::tf32, split hi/lo: 3 MMAs per K step)"),
              1: "assign_kernel (exact order, fp32 pipe)",
              2: "tc_assign_kernel (tcgen05 kind::tf32, split hi/lo: 3 MMAs per K step)"}[args.km_mode]

@@ -135,8 +135,10 @@ int32_t vers_kmeans_assign_step(vers_kmeans* km);
 /* 0 (default): tensor-core candidate argmin (TMA + tcgen05 kind::tf32, M=128 x N=256 tiles) + a rounding-error
  * certificate on the gap between the two smallest values, uncertified rows re-assigned in exact order;
  * 1: exact order everywhere.  Both give the reference's assignments bit for bit.  For rows of <= 128 floats mode 0
- * runs the TF32-first kernel (one MMA per K step, rows resident in tensor memory, the four best candidates re-ranked
- * in exact order inside the kernel, certificate against the fifth key); mode 2 forces the split-precision kernel. */
+ * runs the single-MMA kernel (one MMA per K step, rows resident in tensor memory, the four best candidates re-ranked
+ * in exact order inside the kernel, certificate against the fifth key) with fp16 operands (kind::f16: the same 11-bit
+ * significand as tf32 at twice the MMA rate; both operands scaled by one power of two so nothing overflows); mode 3 runs
+ * the same kernel with kind::tf32; mode 2 forces the split-precision kernel. */
 int32_t vers_kmeans_set_mode(vers_kmeans* km, int32_t mode);
 /* rows of the most recent assign step whose candidate argmin was not certified (redone in exact order) */
 int32_t vers_kmeans_last_assign_stats(vers_kmeans* km, uint64_t* uncertified_rows);
@@ -262,6 +264,9 @@ int32_t vers_comm_destroy(vers_comm* comm);
 int32_t vers_comm_info(const vers_comm* comm, uint32_t* world, uint32_t* rank, double* last_exchange_seconds);
 /* rendezvous of all ranks + stream synchronise; max over ranks of a host value (timing: "max over ranks") */
 int32_t vers_comm_barrier(vers_comm* comm);
+/* diagnostic: GPU globaltimer stamps (ns) of the most recent fused top-k exchange of a sharded search step on this rank:
+ * [0] kernel entry, [1] own slice stored on every peer and flag raised, [2] every rank's flag seen, [3] merged */
+int32_t vers_debug_peer_times(vers_comm* comm, uint64_t out_ns[4]);
 int32_t vers_comm_max_f64(vers_comm* comm, double* value_io);
 /* IVFFlatIndex::build_kmeans (ivfflat.rs:73-100) over contiguous row shards (km is over this rank's vers_dataset,
  * whose id_base is its first GLOBAL row).  init_rows_global: [num_clusters] GLOBAL row numbers (initialize_centroids,

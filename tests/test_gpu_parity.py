@@ -130,7 +130,7 @@ def test_assign_first_minimum_on_duplicate_centroids(vb, vo, ctx):
     # every row whose nearest centroid has a twin must fail its certificate and be redone in exact order.  The
     # tf32-first pass (mode 0, ld <= 128) re-ranks its four best candidates in exact order inside the kernel: twins and
     # triplets are resolved there (first minimum wins) without a redo.
-    for mode in (0, 2):
+    for mode in (0, 2, 3):
         km = vb.KMeans(ds, 6)
         km.set_mode(mode)
         km.set_centroids(cents)
@@ -143,9 +143,11 @@ def test_assign_first_minimum_on_duplicate_centroids(vb, vo, ctx):
 
 @pytest.mark.parametrize("n,dim,C,normalize", [(5000, 128, 1000, False), (3001, 100, 65, True), (777, 36, 3, True),
                                                (2048, 64, 1, True), (1500, 128, 5, False), (513, 32, 200, True)])
-def test_assign_tf32_first_kernel_bit_exact(vb, vo, ctx, n, dim, C, normalize):
-    """tc_assign1_kernel (ld <= 128): one tf32 MMA per K step, top-4 + exact rerank + certificate; tile edges (C not a
-    multiple of 64, fewer than five centroids, a last row-block pair that is half empty), duplicated centroids"""
+@pytest.mark.parametrize("km_mode", [0, 3])
+def test_assign_tf32_first_kernel_bit_exact(vb, vo, ctx, n, dim, C, normalize, km_mode):
+    """tc_assign1_kernel (ld <= 128): one MMA per K step (mode 0: kind::f16 with both operands scaled into fp16's range,
+    mode 3: kind::tf32), top-4 + exact rerank + certificate; tile edges (C not a multiple of 64, fewer than five
+    centroids, a last row-block pair that is half empty, an odd number of 32-float chunks), duplicated centroids"""
     rows = data(vo, n, dim, normalize=normalize)
     pick = vo.init_rows(5, 1, C, n)[0].astype(np.int64)
     cents = rows[pick].copy()
@@ -154,10 +156,37 @@ def test_assign_tf32_first_kernel_bit_exact(vb, vo, ctx, n, dim, C, normalize):
         cents[1] = 0.5 * (cents[2] + cents[3])  # and a centroid that is not a data row
     ds = vb.Dataset.upload(ctx, rows)
     km = vb.KMeans(ds, C)
+    km.set_mode(km_mode)
     km.set_centroids(cents)
     km.assign_step()
     assert np.array_equal(km.assignments(), vo.assign(rows, cents))
     assert km.last_uncertified_rows <= n // 4
+    km.close()
+
+
+def test_assign_f16_kernel_scaling_and_overflow(vb, vo, ctx):
+    """kind::f16 assign (mode 0, ld <= 128): rows of very different magnitudes (1e-4 .. 3e4, far outside fp16's own range: the
+    kernel scales by a power of two chosen from max ||row||), and centroids set far beyond any row (their fp16 image
+    overflows): the assignments must still be the oracle's — the second case through the exact redo of every row"""
+    n, dim, C = 3000, 96, 40
+    rows = data(vo, n, dim, normalize=False)
+    rows *= np.float32(3.0e4)
+    rows[::5] *= np.float32(1.0e-8)
+    pick = vo.init_rows(5, 1, C, n)[0].astype(np.int64)
+    cents = rows[pick].copy()
+    ds = vb.Dataset.upload(ctx, rows)
+    km = vb.KMeans(ds, C)
+    km.set_mode(0)
+    km.set_centroids(cents)
+    km.assign_step()
+    assert np.array_equal(km.assignments(), vo.assign(rows, cents))
+    assert km.last_uncertified_rows <= n // 2
+    far = cents.copy()
+    far[3] *= np.float32(1.0e6)  # not a mean of rows: does not fit the rows' scale
+    km.set_centroids(far)
+    km.assign_step()
+    assert np.array_equal(km.assignments(), vo.assign(rows, far))
+    assert km.last_uncertified_rows == n
     km.close()
 
 
@@ -168,7 +197,7 @@ def test_assign_nan_row_panics_like_the_reference(vb, vo, ctx):
     rows[123, 7] = np.nan
     cents = rows[[1, 2, 3, 4, 5, 6, 7, 8]].copy()
     ds = vb.Dataset.upload(ctx, rows)
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         km = vb.KMeans(ds, 8)
         km.set_mode(mode)
         km.set_centroids(cents)
@@ -191,7 +220,7 @@ def test_update_centroids_bit_exact(vb, vo, ctx, n, dim, C):
     assert counts[3] == 0 and not cents[3].any()
 
 
-@pytest.mark.parametrize("km_mode", [0, 1, 2])
+@pytest.mark.parametrize("km_mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("n,dim,C", [(10000, 300, 16), (6000, 128, 300), (4097, 36, 129)])
 def test_kmeans_fit_and_cost_bit_exact(vb, vo, ctx, km_mode, n, dim, C):
     """km_mode 0: tensor-core candidate argmin + certificate + exact redo of uncertified rows (tf32-first kernel for

@@ -54,6 +54,7 @@ SIGNATURES = {
     "vers_flat_search": [vp, vp, u32, u32, u32, u32, vp, vp, vp],
     "vers_flat_search_dev": [vp, vp, u32, u32, u32, vp, vp, vp],
     "vers_flat_set_mode": [vp, i32],
+    "vers_debug_peer_times": [vp, vp],
     "vers_pair_distances_simd": [vp, vp, u32, u32, vp, vp, u64, u32, vp],
     "vers_pair_distances_simd_dev": [vp, vp, u32, u32, vp, vp, u64, u32, vp, vp],
     "vers_flat_last_search_stats": [vp, vp],

@@ -459,6 +459,14 @@ extern "C" int32_t vers_comm_info(const vers_comm* cm, uint32_t* world, uint32_t
     return VERS_OK;
 }
 
+extern "C" int32_t vers_debug_peer_times(vers_comm* cm, uint64_t out_ns[4]) {
+    if (!cm || !out_ns) return fail(VERS_ERR_ARG, "debug_peer_times: null");
+    VERS_CUDA(cudaSetDevice(cm->ctx->device));
+    VERS_CUDA(cudaStreamSynchronize(cm->ctx->stream));
+    VERS_CUDA(cudaMemcpyFromSymbol(out_ns, g_peer_dbg, 32));
+    return VERS_OK;
+}
+
 extern "C" int32_t vers_comm_barrier(vers_comm* cm) {
     if (!cm) return fail(VERS_ERR_ARG, "comm_barrier: null");
     VERS_CUDA(cudaSetDevice(cm->ctx->device));

@@ -303,6 +303,7 @@ extern "C" int32_t vers_kmeans_free(vers_kmeans* km) {
     cudaFree(km->d_cent_lo);
     cudaFree(km->d_cent_tiles);
     cudaFree(km->d_ncmax);
+    cudaFree(km->d_nxmax);
     cudaFree(km->d_flagged);
     cudaFree(km->d_nflagged);
     cudaFree(km->d_exact);
@@ -429,8 +430,9 @@ extern "C" int32_t vers_kmeans_assign_device_ptr(vers_kmeans* km, void** ptr) {
 }
 
 // tensor-core candidate argmin + certificate; uncertified rows redone by the exact-order kernel.
-// ld <= 128 (mode 0): tc_assign1_kernel (one tf32 MMA per K step, rows resident in tensor memory, top-4 + exact rerank
-// inside the kernel); otherwise / mode 2: tc_assign_kernel (split precision, three MMAs per K step, top-2 gap).
+// ld <= 128 (mode 0 / 3): tc_assign1_kernel (one MMA per K step — kind::f16 by default, kind::tf32 in mode 3 — rows
+// resident in tensor memory, top-4 + exact rerank inside the kernel); otherwise / mode 2: tc_assign_kernel (split
+// precision, three MMAs per K step, top-2 gap).
 static int32_t kmeans_tc_buffers(vers_kmeans* km) {
     vers_dataset* ds = km->ds;
     vers_ctx* ctx = ds->ctx;
@@ -439,7 +441,7 @@ static int32_t kmeans_tc_buffers(vers_kmeans* km) {
     if (!km->d_row_norm) {
         // all or nothing: a failed allocation must not leave a half-initialised state behind
         float *row_norm = nullptr, *cent_norm = nullptr, *cent_hi = nullptr, *cent_lo = nullptr, *cent_tiles = nullptr;
-        uint32_t *ncmax = nullptr, *flagged = nullptr, *nflagged = nullptr, *exact = nullptr;
+        uint32_t *ncmax = nullptr, *nxmax = nullptr, *flagged = nullptr, *nflagged = nullptr, *exact = nullptr;
         cudaError_t e = cudaSuccess;
         auto A = [&](void** p, size_t bytes) {
             if (e == cudaSuccess) e = cudaMalloc(p, bytes);
@@ -451,6 +453,7 @@ static int32_t kmeans_tc_buffers(vers_kmeans* km) {
         if (ds->ld <= K1_MAX_KCH * K1_KC)  // image of the centroid tiles for tc_assign1_kernel
             A((void**)&cent_tiles, (size_t)ceil_div(km->C, K1_N) * ((ds->ld + K1_KC - 1) / K1_KC) * K1_BOX_BYTES);
         A((void**)&ncmax, 4);
+        A((void**)&nxmax, 8);
         A((void**)&flagged, ds->n * 4);
         A((void**)&nflagged, 4);
         A((void**)&exact, ds->n * 4);
@@ -461,17 +464,28 @@ static int32_t kmeans_tc_buffers(vers_kmeans* km) {
         }
         if (e != cudaSuccess) {
             cudaFree(row_norm), cudaFree(cent_norm), cudaFree(cent_hi), cudaFree(cent_lo), cudaFree(cent_tiles);
-            cudaFree(ncmax), cudaFree(flagged), cudaFree(nflagged), cudaFree(exact);
+            cudaFree(ncmax), cudaFree(nxmax), cudaFree(flagged), cudaFree(nflagged), cudaFree(exact);
             return fail(e == cudaErrorMemoryAllocation ? VERS_ERR_NOMEM : VERS_ERR_CUDA, "kmeans assign buffers: %s",
                         cudaGetErrorString(e));
         }
         km->d_row_norm = row_norm, km->d_cent_norm = cent_norm, km->d_cent_hi = cent_hi, km->d_cent_lo = cent_lo;
         km->d_cent_tiles = cent_tiles;
-        km->d_ncmax = ncmax, km->d_flagged = flagged, km->d_nflagged = nflagged, km->d_exact = exact;
+        km->d_ncmax = ncmax, km->d_nxmax = nxmax, km->d_flagged = flagged, km->d_nflagged = nflagged, km->d_exact = exact;
     }
     // (re)computed whenever the rows changed since (vers_dataset_normalize bumps ds->epoch)
-    sqnorm_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(ds->d_rows, ds->ld, ds->n, km->d_row_norm, nullptr);
+    VERS_CUDA(cudaMemsetAsync(km->d_nxmax, 0, 8, s));
+    sqnorm_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(ds->d_rows, ds->ld, ds->n, km->d_row_norm, km->d_nxmax);
     VERS_LAUNCH_CHECK(ctx);
+    // the fp16 kernel's scale: |x_i| <= ||x|| < 2^ex  =>  |x_i| 2^(14 - ex) < 2^14 for every row, and for every centroid
+    // that is a mean of rows (user-set centroids beyond that are caught by the image's overflow count)
+    uint32_t nxbits = 0;
+    VERS_CUDA(cudaMemcpyAsync(&nxbits, km->d_nxmax, 4, cudaMemcpyDeviceToHost, s));
+    VERS_CUDA(cudaStreamSynchronize(s));
+    float nxmax;
+    memcpy(&nxmax, &nxbits, 4);
+    int ex = 0;
+    if (nxmax > 0.0f && std::isfinite(nxmax)) (void)std::frexp(std::sqrt((double)nxmax) * 1.0001, &ex);
+    km->f16_scale = std::ldexp(1.0f, std::max(-60, std::min(60, 14 - ex)));
     km->norm_epoch = ds->epoch;
     return VERS_OK;
 }
@@ -481,7 +495,8 @@ static int32_t kmeans_assign_tc(vers_kmeans* km) {
     vers_ctx* ctx = ds->ctx;
     cudaStream_t s = ctx->stream;
     VERS_TRY(kmeans_tc_buffers(km));
-    const bool tf32_first = km->mode == 0 && ds->ld <= K1_MAX_KCH * K1_KC;
+    const bool tf32_first = (km->mode == 0 || km->mode == 3) && ds->ld <= K1_MAX_KCH * K1_KC;
+    const bool f16 = tf32_first && km->mode == 0;  // default: the same kernel on kind::f16 (mode 3 keeps kind::tf32)
     VERS_CUDA(cudaMemsetAsync(km->d_ncmax, 0, 4, s));
     VERS_CUDA(cudaMemsetAsync(km->d_nflagged, 0, 4, s));
     VERS_CUDA(cudaMemsetAsync(km->d_bad, 0, 4, s));
@@ -490,7 +505,14 @@ static int32_t kmeans_assign_tc(vers_kmeans* km) {
     VERS_LAUNCH_CHECK(ctx);
     if (tf32_first) {
         const uint32_t nk1 = (ds->ld + K1_KC - 1) / K1_KC;
-        tile_image_tf32_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(km->d_cents, km->C, ds->ld, nk1, km->d_cent_tiles);
+        if (f16) {
+            VERS_CUDA(cudaMemsetAsync(km->d_nxmax + 1, 0, 4, s));
+            tile_image_f16_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(km->d_cents, km->C, ds->ld, (nk1 + 1) / 2, km->f16_scale,
+                                                                   reinterpret_cast<uint4*>(km->d_cent_tiles),
+                                                                   km->d_nxmax + 1);
+        } else {
+            tile_image_tf32_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(km->d_cents, km->C, ds->ld, nk1, km->d_cent_tiles);
+        }
         VERS_LAUNCH_CHECK(ctx);
         CUtensorMap tm_rows;
         VERS_TRY(make_tmap_2d_f32(&tm_rows, ds->d_rows, ds->n, ds->ld, ds->ld, K1_M, K1_KC));
@@ -507,12 +529,15 @@ static int32_t kmeans_assign_tc(vers_kmeans* km) {
         p.assign = km->d_assign;
         p.flagged = km->d_flagged;
         p.n_flagged = km->d_nflagged;
+        p.scale = km->f16_scale;
+        p.key_scale = -2.0f / (km->f16_scale * km->f16_scale);
+        p.f16_bad = km->d_nxmax + 1;
         void (*kern)(CUtensorMap, TcAssign1Params) = nullptr;
         switch ((ds->ld + K1_KC - 1) / K1_KC) {
-            case 1: kern = tc_assign1_kernel<1>; break;
-            case 2: kern = tc_assign1_kernel<2>; break;
-            case 3: kern = tc_assign1_kernel<3>; break;
-            default: kern = tc_assign1_kernel<4>; break;
+            case 1: kern = f16 ? tc_assign1_kernel<1, true> : tc_assign1_kernel<1, false>; break;
+            case 2: kern = f16 ? tc_assign1_kernel<2, true> : tc_assign1_kernel<2, false>; break;
+            case 3: kern = f16 ? tc_assign1_kernel<3, true> : tc_assign1_kernel<3, false>; break;
+            default: kern = f16 ? tc_assign1_kernel<4, true> : tc_assign1_kernel<4, false>; break;
         }
         VERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES));
         FamilyTimer ft(ctx, KF_ASSIGN);
@@ -573,7 +598,7 @@ extern "C" int32_t vers_kmeans_assign_step(vers_kmeans* km) {
 }
 
 extern "C" int32_t vers_kmeans_set_mode(vers_kmeans* km, int32_t mode) {
-    if (!km || mode < 0 || mode > 2) return fail(VERS_ERR_ARG, "kmeans_set_mode: bad argument");
+    if (!km || mode < 0 || mode > 3) return fail(VERS_ERR_ARG, "kmeans_set_mode: bad argument");
     km->mode = mode;
     return VERS_OK;
 }

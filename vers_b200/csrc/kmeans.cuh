@@ -31,6 +31,9 @@ struct vers_kmeans {
     float* d_cent_lo = nullptr;      // [C][ld] tf32 lo part
     float* d_cent_tiles = nullptr;   // shared-memory image of the rounded centroid tiles (tc_assign1_kernel's B operand)
     uint32_t* d_ncmax = nullptr;     // [1] bits of max ||c||^2
+    uint32_t* d_nxmax = nullptr;     // [2] bits of max ||row||^2 (the fp16 kernel's scale) | elements of the fp16
+                                     //     centroid image that did not fit
+    float f16_scale = 1.0f;          // power of two: fp16(x * scale) cannot overflow for any row (nor for any mean of rows)
     uint32_t* d_flagged = nullptr;   // [n] rows whose candidate argmin was not certified
     uint32_t* d_nflagged = nullptr;  // [1]
     uint32_t* d_exact = nullptr;     // [n] exact re-assignments of the flagged rows

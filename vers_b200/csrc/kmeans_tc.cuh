@@ -290,7 +290,9 @@ __global__ void __launch_bounds__(KA_THREADS, 1)
 //   * epilogue: key = ||c||^2 - 2 acc per element (one FFMA), a min-tree per 16 columns and ONE compare against the
 //     row's current fifth key; the insertion code runs only for groups that contain a new top-5 entry.
 // Warp roles (14 warps): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = epilogue (warps 2..5 row block 0,
-// 6..9 row block 1; warp w reads TMEM lanes 32*(w%4)..+31), 10..13 = converters.
+// 6..9 row block 1; warp w reads TMEM lanes 32*(w%4)..+31), 10..13 = converters.  (Measured: splitting a row's columns
+// over two epilogue threads — 16 epilogue warps — is SLOWER, 323 -> 368 ms per C5 pass with kind::f16: the extra
+// warps compete with the single MMA-issuing thread for issue slots and with the MMA's A operand for TMEM reads.)
 constexpr int K1_M = 128, K1_N = 64, K1_KC = 32, K1_STAGES = 5, K1_MAX_KCH = 4;
 constexpr int K1_EPI_WARP0 = 2, K1_EPI_WARPS = 8, K1_CONV_WARP0 = 10, K1_CONV_WARPS = 4;
 constexpr int K1_THREADS = (2 + K1_EPI_WARPS + K1_CONV_WARPS) * 32;
@@ -311,6 +313,10 @@ struct TcAssign1Params {
     const float* rows;       // [n][ld] the rows themselves (exact rerank)
     const float* cents;      // [C][ld] the centroids themselves (exact rerank)
     const float* cent_tiles; // tile_image_tf32_kernel's image of the centroids: [ceil(C/64)][nk][64][32] swizzled
+                             // (F16: tile_image_f16_kernel's, [ceil(C/64)][nk16][64 rows][64 halfs], values * scale)
+    float scale;             // F16: the power of two both operands are multiplied with before the fp16 rounding
+    float key_scale;         // F16: -2 / scale^2 (key = ||c||^2 + key_scale * acc); tf32: -2
+    const uint32_t* f16_bad; // F16: elements of the centroid image that did not fit fp16 (nothing is certified then)
     const float* row_norm;   // [n] ||x||^2 (any order)
     const float* cent_norm;  // [round_up(C, 128)] ||c||^2 (any order), +inf past C
     const uint32_t* ncmax_bits;
@@ -348,7 +354,12 @@ __device__ __forceinline__ bool k1_elect_one() {
     return pred != 0;
 }
 
-template <int NK>  // K chunks of 32 floats: ld <= 32 NK
+// F16: the same kernel with fp16 operands (kind::f16, K = 16 per MMA): fp16 rounds to the same 11-bit significand as
+// tf32, so the certificate's error model is unchanged, while the tensor pipe runs at twice the rate and the centroid
+// tiles are half the bytes.  Both operands are scaled by one power of two (host: from max ||row||^2; centroids are means
+// of rows, so they fit as well — an image with elements that do not fit certifies nothing, f16_bad).  The rows are
+// packed two per 32-bit tensor-memory column (even dimension in the low half).
+template <int NK, bool F16>  // K chunks of 32 floats: ld <= 32 NK
 __global__ void __launch_bounds__(K1_THREADS, 1)
     tc_assign1_kernel(const __grid_constant__ CUtensorMap tmap_rows, TcAssign1Params p) {
     extern __shared__ uint8_t k1_smem_raw[];
@@ -367,6 +378,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(nbar + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t nk = NK;
+    constexpr uint32_t nk16 = (NK + 1) / 2;                          // F16: B boxes / MMA groups of 64 dimensions
+    constexpr uint32_t tile_bytes = F16 ? nk16 * K1_BOX_BYTES : nk * K1_BOX_BYTES;
+    constexpr uint32_t a_cols = F16 ? 64u : 128u;                    // tensor-memory columns of one 128-row block
     const uint32_t nct = (p.C + K1_N - 1) / K1_N;
     const uint64_t nrbp = (p.n_rows + 2 * K1_M - 1) / (2 * K1_M);
     const uint64_t my_pairs = blockIdx.x < nrbp ? (nrbp - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -417,9 +431,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
             for (uint32_t ct = 0; ct < nct; ++ct) {
                 tc::mbar_wait(&empty[stage], phase ^ 1);
                 if (k1_elect_one()) {  // the whole 64-centroid tile (all K chunks) is one linear copy of its image
-                    tc::mbar_arrive_expect_tx(&full[stage], nk * K1_BOX_BYTES);
-                    tc::bulk_load(smem + stage * K1_STAGE_BYTES, p.cent_tiles + (size_t)ct * nk * (K1_BOX_BYTES / 4),
-                                  nk * K1_BOX_BYTES, &full[stage]);
+                    tc::mbar_arrive_expect_tx(&full[stage], tile_bytes);
+                    tc::bulk_load(smem + stage * K1_STAGE_BYTES,
+                                  reinterpret_cast<const uint8_t*>(p.cent_tiles) + (size_t)ct * tile_bytes, tile_bytes,
+                                  &full[stage]);
                 }
                 __syncwarp();
                 if (++stage == K1_STAGES) {
@@ -430,7 +445,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
         }
     } else if (warp == 1) {
         // MMA issuer: converged warp, one elected lane issues.  Per tile: 2 row blocks x NK x 4 MMAs (M=128 N=64 K=8)
-        const uint32_t idesc = tc::idesc_tf32(K1_M, K1_N);
+        const uint32_t idesc = F16 ? tc::idesc_f16(K1_M, K1_N) : tc::idesc_tf32(K1_M, K1_N);
         uint32_t stage = 0, phase = 0;
         uint64_t t = 0;
         if (total_tiles && k1_elect_one()) {
@@ -459,13 +474,23 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
 #pragma unroll
                     for (uint32_t rb = 0; rb < 2; ++rb) {
                         const uint32_t d_tmem = tmem_base + K1_ACC_COL0 + (2 * rb + buf) * K1_N;
-                        const uint32_t a_tmem = tmem_base + K1_A_COL0 + rb * 128;
+                        const uint32_t a_tmem = tmem_base + K1_A_COL0 + rb * a_cols;
+                        if (F16) {
 #pragma unroll
-                        for (uint32_t kc = 0; kc < nk; ++kc) {
-                            const uint64_t db = tc::smem_desc_k_sw128(sb + kc * K1_BOX_BYTES);
+                            for (uint32_t kc = 0; kc < nk16; ++kc) {  // 64 dimensions = 32 packed columns = 4 MMAs of K 16
+                                const uint64_t db = tc::smem_desc_k_sw128(sb + kc * K1_BOX_BYTES);
 #pragma unroll
-                            for (uint32_t kk = 0; kk < K1_KC / 8; ++kk)
-                                tc::mma_tf32_ts(d_tmem, a_tmem + kc * K1_KC + 8 * kk, db + 2 * kk, idesc, (kc | kk) != 0);
+                                for (uint32_t kk = 0; kk < 4; ++kk)
+                                    tc::mma_f16_ts(d_tmem, a_tmem + kc * 32 + 8 * kk, db + 2 * kk, idesc, (kc | kk) != 0);
+                            }
+                        } else {
+#pragma unroll
+                            for (uint32_t kc = 0; kc < nk; ++kc) {
+                                const uint64_t db = tc::smem_desc_k_sw128(sb + kc * K1_BOX_BYTES);
+#pragma unroll
+                                for (uint32_t kk = 0; kk < K1_KC / 8; ++kk)
+                                    tc::mma_tf32_ts(d_tmem, a_tmem + kc * K1_KC + 8 * kk, db + 2 * kk, idesc, (kc | kk) != 0);
+                            }
                         }
                         tc::mma_commit(&tfull[2 * rb + buf]);
                     }
@@ -487,6 +512,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
         const double u = 5.9604644775390625e-08;  // 2^-24
         const double ncmax = (double)__uint_as_float(*p.ncmax_bits);
         const float INF = __int_as_float(0x7f800000);
+        const float ks = F16 ? p.key_scale : -2.0f;
+        const bool image_ok = !F16 || *p.f16_bad == 0u;
         uint64_t t = 0;
         for (uint64_t rbp = blockIdx.x; rbp < nrbp; rbp += gridDim.x) {
             const uint64_t row = (rbp * 2 + rb) * K1_M + (uint64_t)(lane_group * 32 + lane);
@@ -516,10 +543,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
                 for (int j = 0; j < 64; j += 4) {
                     const float4 n4 = *reinterpret_cast<const float4*>(nr + j);
                     uint32_t* v = j < 32 ? &va[j] : &vb[j - 32];
-                    const float k0 = __fmaf_rn(-2.0f, __uint_as_float(v[0]), n4.x);
-                    const float k1 = __fmaf_rn(-2.0f, __uint_as_float(v[1]), n4.y);
-                    const float k2 = __fmaf_rn(-2.0f, __uint_as_float(v[2]), n4.z);
-                    const float k3 = __fmaf_rn(-2.0f, __uint_as_float(v[3]), n4.w);
+                    const float k0 = __fmaf_rn(ks, __uint_as_float(v[0]), n4.x);
+                    const float k1 = __fmaf_rn(ks, __uint_as_float(v[1]), n4.y);
+                    const float k2 = __fmaf_rn(ks, __uint_as_float(v[2]), n4.z);
+                    const float k3 = __fmaf_rn(ks, __uint_as_float(v[3]), n4.w);
                     v[0] = __float_as_uint(k0), v[1] = __float_as_uint(k1), v[2] = __float_as_uint(k2),
                     v[3] = __float_as_uint(k3);
                     qm[j >> 2] = fminf(fminf(k0, k1), fminf(k2, k3));
@@ -591,9 +618,12 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
                 // both operands 2^-10 (1 + 2^-12), the accumulation allowance (n + 8) 2^-22 (same model as above)
                 const double nx = (double)__ldg(p.row_norm + row);
                 const double S = nx + ncmax;
-                const double E = (1.01 * (2.0 * p.ld + 8.0) * u + 1.001 / 1024.0 + (p.ld + 8.0) * 2.384185791015625e-07) * S;
+                // (fp16: the same 2^-11 per operand in the normal range; an element below the normal range of the
+                // scaled value is off by <= 2^-25 / scale <= 2^-38 max||x||, 2^-30 S covers every such element)
+                const double E = (1.01 * (2.0 * p.ld + 8.0) * u + 1.001 / 1024.0 + (p.ld + 8.0) * 2.384185791015625e-07 +
+                                  (F16 ? 9.313225746154785e-10 : 0.0)) * S;
                 const double rho = (p.ld + 3.0) * u;
-                const bool certified = any && ordered && ((double)k[4] + nx - E) * (1.0 - rho) > (double)bd;
+                const bool certified = image_ok && any && ordered && ((double)k[4] + nx - E) * (1.0 - rho) > (double)bd;
                 if (!certified) {
                     uint32_t at = atomicAdd(p.n_flagged, 1u);
                     p.flagged[at] = (uint32_t)row;
@@ -615,10 +645,17 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
 #pragma unroll
                     for (uint32_t c = 0; c < 8; ++c) {
                         const float4 f = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7u)) << 4));
-                        v[4 * c + 0] = round_tf32_bits(__float_as_uint(f.x));
-                        v[4 * c + 1] = round_tf32_bits(__float_as_uint(f.y));
-                        v[4 * c + 2] = round_tf32_bits(__float_as_uint(f.z));
-                        v[4 * c + 3] = round_tf32_bits(__float_as_uint(f.w));
+                        if (F16) {  // two dimensions per column, the even one in the low half
+                            const __half2 h0 = __floats2half2_rn(__fmul_rn(f.x, p.scale), __fmul_rn(f.y, p.scale));
+                            const __half2 h1 = __floats2half2_rn(__fmul_rn(f.z, p.scale), __fmul_rn(f.w, p.scale));
+                            v[2 * c + 0] = *reinterpret_cast<const uint32_t*>(&h0);
+                            v[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+                        } else {
+                            v[4 * c + 0] = round_tf32_bits(__float_as_uint(f.x));
+                            v[4 * c + 1] = round_tf32_bits(__float_as_uint(f.y));
+                            v[4 * c + 2] = round_tf32_bits(__float_as_uint(f.z));
+                            v[4 * c + 3] = round_tf32_bits(__float_as_uint(f.w));
+                        }
                     }
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&aempty[slot]);
@@ -626,7 +663,20 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
                         tc::mbar_wait(afree, (uint32_t)((i - 1) & 1));
                         tc::fence_after_thread_sync();
                     }
-                    tc::tmem_st_32(tmem_base + ((lane_group * 32u) << 16) + K1_A_COL0 + rb * 128 + kc * K1_KC, v);
+                    if (F16) {
+                        uint32_t h[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) h[e] = v[e];
+                        const uint32_t a0 = tmem_base + ((lane_group * 32u) << 16) + K1_A_COL0 + rb * a_cols + kc * 16;
+                        tc::tmem_st_16(a0, h);
+                        if ((NK & 1) && kc == nk - 1) {  // an odd number of 32-float chunks: the MMAs read 64 dimensions
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) h[e] = 0u;
+                            tc::tmem_st_16(a0 + 16, h);
+                        }
+                    } else {
+                        tc::tmem_st_32(tmem_base + ((lane_group * 32u) << 16) + K1_A_COL0 + rb * 128 + kc * K1_KC, v);
+                    }
                 }
             }
             tc::fence_before_thread_sync();

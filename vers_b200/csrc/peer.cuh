@@ -122,6 +122,10 @@ static __global__ void __launch_bounds__(256) peer_wait_copy_kernel(PeerRegion g
     if (!host_step) peer_block_consumed(g);
 }
 
+// diagnostic: globaltimer stamps of block 0 of the most recent peer_gather_merge_kernel launch of this translation unit
+// (entry, own slice published, every rank's flag seen, merged) — vers_debug_peer_times
+static __device__ unsigned long long g_peer_dbg[4];
+
 // ---- exchange + merge of the per-GPU top-k as ONE kernel: every warp stores its queries' local top-k into this
 // rank's slot on every rank (ids [nq][k] then distances [nq][k]), the last block raises the flag, then each warp waits
 // for all ranks' flags and merges world x k entries per query by (distance, id) — the same total order as
@@ -137,6 +141,8 @@ static __global__ void __launch_bounds__(PG_WARPS * 32)
     const uint64_t nk = (uint64_t)nq * k;
     const uint64_t my_slot = g.data_off + ((uint64_t)parity * g.world + g.rank) * g.slot_bytes;
     const uint32_t q0 = blockIdx.x * PG_WARPS + warp, qstride = gridDim.x * PG_WARPS;
+    const bool dbg = blockIdx.x == 0 && threadIdx.x == 0;
+    if (dbg) g_peer_dbg[0] = pg_now_ns();
 
     // 1. publish
     for (uint32_t q = q0; q < nq; q += qstride) {
@@ -151,10 +157,12 @@ static __global__ void __launch_bounds__(PG_WARPS * 32)
         }
     }
     peer_block_published(g, step);
+    if (dbg) g_peer_dbg[1] = pg_now_ns();
 
     // 2. wait for every rank's flag of this step
     if (threadIdx.x == 0) peer_wait_flags(g, step);
     __syncthreads();
+    if (dbg) g_peer_dbg[2] = pg_now_ns();
 
     // 3. merge world x k entries per query by (distance, id)
     const char* mine = g.peer_base[g.rank] + g.data_off + (uint64_t)parity * g.world * g.slot_bytes;
@@ -203,6 +211,7 @@ static __global__ void __launch_bounds__(PG_WARPS * 32)
         if (out_cnt && lane == 0) out_cnt[q] = cnt;
         __syncwarp();
     }
+    if (dbg) g_peer_dbg[3] = pg_now_ns();
     if (!host_step) peer_block_consumed(g);
 }
 

@@ -11,6 +11,7 @@
 //     [10,13) B format = 2 (TF32), bit 15/16 A/B major = 0 (K-major), [17,23) N >> 3, [24,29) M >> 4
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace vers {
@@ -121,6 +122,19 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
         : "memory");
 }
+// fp16 operands with A from tensor memory: lane = row, two K elements per 32-bit column (even K in the low half),
+// 8 columns per K = 16 step
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+        : "memory");
+}
 // arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -204,6 +218,17 @@ __device__ __forceinline__ void tmem_st_32(uint32_t taddr, const uint32_t (&r)[3
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// thread t of warp w writes 16 consecutive 32-bit columns of TMEM lane 32*(w%4)+t
+__device__ __forceinline__ void tmem_st_16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 }  // namespace tc
 
 __device__ __forceinline__ uint32_t round_tf32_bits(uint32_t u) {  // round to nearest even at bit 13
@@ -237,6 +262,42 @@ static __global__ void tile_image_tf32_kernel(const float* __restrict__ in, uint
         v.w = __uint_as_float(round_tf32_bits(__float_as_uint(v.w)));
         reinterpret_cast<float4*>(out)[i] = v;
     }
+}
+
+// The same image with fp16 elements (kind::f16 has tf32's 11-bit significand at twice the MMA rate and half the
+// operand bytes): per 64-row tile and K chunk of 64 halfs one [64 rows x 128 bytes] box in the 128-byte swizzle, values
+// fp16(x * scale) (scale = a power of two chosen by the host so that nothing overflows; `bad` counts elements that did).
+static __global__ void tile_image_f16_kernel(const float* __restrict__ in, uint64_t n, uint32_t ld, uint32_t nk16,
+                                             float scale, uint4* __restrict__ out, uint32_t* __restrict__ bad) {
+    const uint64_t n16 = ((n + 63) / 64) * nk16 * 64 * 8;  // 16-byte chunks of the image
+    uint32_t nbad = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c8 = (uint32_t)(i & 7u);         // chunk position inside the 128-byte row of the image
+        const uint32_t r = (uint32_t)((i >> 3) & 63u);  // row of the box
+        const uint64_t box = i >> 9;                    // (tile, K chunk)
+        const uint32_t kc = (uint32_t)(box % nk16);
+        const uint64_t tile = box / nk16;
+        const uint32_t src_c8 = c8 ^ (r & 7u);          // the logical chunk stored at this position
+        const uint64_t row = tile * 64 + r;
+        const uint32_t col = kc * 64 + src_c8 * 8;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (row < n && col < ld) {  // ld % 4 == 0
+            const float4 a = *reinterpret_cast<const float4*>(in + row * ld + col);
+            v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w;
+            if (col + 4 < ld) {
+                const float4 b = *reinterpret_cast<const float4*>(in + row * ld + col + 4);
+                v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+            }
+        }
+        __align__(16) __half h[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            h[e] = __float2half_rn(v[e] * scale);
+            if (!(fabsf(__half2float(h[e])) <= 65504.0f)) ++nbad;  // inf or nan
+        }
+        out[i] = *reinterpret_cast<const uint4*>(h);
+    }
+    if (nbad) atomicAdd(bad, nbad);
 }
 
 }  // namespace vers

@@ -164,6 +164,36 @@ def test_assign_tf32_first_kernel_bit_exact(vb, vo, ctx, n, dim, C, normalize, k
     km.close()
 
 
+@pytest.mark.parametrize("km_mode", [0, 3, 2])
+def test_assign_many_row_blocks_per_cta(vb, vo, ctx, km_mode):
+    """enough rows that every persistent CTA walks several row blocks (148 CTAs x 256 rows x 4), enough centroids for 20
+    tiles: the hand-over between row blocks (A operand in tensor memory, norm ring, accumulator buffers) and the
+    reconvergence of the warps after their divergent selection only show after the first block — a regression that
+    passed every small-shape test returned wrong clusters for 0.2 % of the rows from the second block on"""
+    n, dim, C = 160_000, 128, 1250
+    rows = data(vo, n, dim, n_centers=700, normalize=False)
+    pick = vo.init_rows(5, 1, C, n)[0].astype(np.int64)
+    cents = rows[pick].copy()
+    ds = vb.Dataset.upload(ctx, rows)
+    ref = vb.KMeans(ds, C)
+    ref.set_mode(1)  # exact-order engine
+    ref.set_centroids(cents)
+    ref.assign_step()
+    want = ref.assignments()
+    ref.close()
+    sample = np.arange(0, n, 37)
+    assert np.array_equal(want[sample], vo.assign(rows[sample], cents))  # the engine itself against the oracle
+    km = vb.KMeans(ds, C)
+    km.set_mode(km_mode)
+    km.set_centroids(cents)
+    for rep in range(2):
+        km.assign_step()
+        got = km.assignments()
+        assert np.array_equal(got, want), f"{int((got != want).sum())} rows differ, first {np.flatnonzero(got != want)[:5]}"
+        assert km.last_uncertified_rows <= n // 20
+    km.close()
+
+
 def test_assign_f16_kernel_scaling_and_overflow(vb, vo, ctx):
     """kind::f16 assign (mode 0, ld <= 128): rows of very different magnitudes (1e-4 .. 3e4, far outside fp16's own range: the
     kernel scales by a power of two chosen from max ||row||), and centroids set far beyond any row (their fp16 image
@@ -586,6 +616,43 @@ def test_ivf_h16_candidate_copy_falls_back_on_ties(vb, vo, ctx):
     assert np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od)) and np.array_equal(cnt, oc)
     assert list(ids[0]) == [17] + list(range(1000, 1009))
     assert st["uncertified_queries"] >= 1
+
+
+def test_ivf_host_call_graph_replay_stays_exact(vb, vo, ctx):
+    """vers_ivf_search replays its device work from a CUDA graph once a call shape repeats (call 1 eager, call 2
+    captures, calls 3+ replay): every call must return the oracle's bits for ITS queries, a changed shape or a changed
+    index (add) must start over, and both candidate modes must behave the same"""
+    n, dim, C, k = 12000, 96, 32, 10
+    rows = data(vo, n, dim, n_centers=200)
+    init = vo.init_rows(3, 1, C, n)
+    idx = vb.IVFFlatIndex.build_index(C, 1, 4, rows, init_rows=init, ctx=ctx)
+    cents, assign, _, _ = vo.ivf_build_index(rows, C, 1, 4, init)
+    off, lr = vo.ivf_lists(assign, C)
+    for mode in (4, 0):
+        idx.set_mode(mode)
+        for rep in range(6):  # different queries behind the same shape: a replay must read the new batch
+            q = data(vo, 64, dim, seed=10 + rep, n_centers=200)
+            ids, d, cnt = idx.search_batch(q, k, nprobe=8)
+            oi, od, oc = vo.ivf_search(rows, cents, off, lr, q, k, nprobe=8)
+            assert np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od)) and np.array_equal(cnt, oc), (mode, rep)
+        q = data(vo, 33, dim, seed=30, n_centers=200)  # another shape in between, then back
+        ids, d, cnt = idx.search_batch(q, 5, nprobe=4)
+        oi, od, oc = vo.ivf_search(rows, cents, off, lr, q, 5, nprobe=4)
+        assert np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od))
+    # the index changes under a warm graph: the added row must be found by the very next call of the same shape
+    q = data(vo, 64, dim, seed=11, n_centers=200)
+    for rep in range(3):
+        idx.search_batch(q, k, nprobe=8)
+    extra = (q[5] + np.float32(1e-3)).astype(np.float32)
+    new_id, cl = idx.add(extra, 0)
+    all_rows = np.vstack([rows, extra[None]])
+    all_assign = np.concatenate([assign, np.array([cl], np.uint64)])
+    off2, lr2 = vo.ivf_lists(all_assign, C)
+    for rep in range(3):
+        ids, d, cnt = idx.search_batch(q, k, nprobe=8)
+        oi, od, oc = vo.ivf_search(all_rows, cents, off2, lr2, q, k, nprobe=8)
+        assert np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od))
+    assert new_id in ids[5]
 
 
 def test_ivf_search_approximate_single_query_trait_call(vo, ivf_c1):

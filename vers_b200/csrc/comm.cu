@@ -111,7 +111,12 @@ struct vers_comm {
     size_t loc_q_cap = 0;
     unsigned merge_resident = 0;
     double last_exchange_s = 0.0;  // the row all-to-all of the most recent vers_sharded_ivf_build
+    vers::GraphCache call_graph;   // vers_sharded_ivf_search: the device work of a repeated call shape, as a CUDA graph
 };
+
+namespace vers {
+void ivf_state_stamp(const vers_ivf* ivf, uint64_t out[4]);  // ivf.cu
+}
 
 namespace vers {
 
@@ -438,6 +443,7 @@ extern "C" int32_t vers_comm_destroy(vers_comm* cm) {
     if (!cm) return VERS_OK;
     cudaSetDevice(cm->ctx->device);
     cudaStreamSynchronize(cm->ctx->stream);
+    cm->call_graph.reset();
     comm_close_peers(cm);
     cudaFree(cm->d_peer_base);
     cudaFree(cm->d_buf);
@@ -811,7 +817,19 @@ extern "C" int32_t vers_sharded_ivf_search(vers_comm* cm, vers_ivf* ivf, const f
                                         cudaMemcpyHostToDevice, ctx->stream));
         }
     }
-    VERS_TRY(sharded_search_dev(cm, ivf, d_q, nq, top_k, nprobe, d_ids, d_d, d_c));
+    {   // every rank makes the same sequence of calls, so every rank takes the same eager / capture / replay decision
+        uint64_t key[12] = {reinterpret_cast<uint64_t>(ivf), nq, top_k, nprobe, 0, 0, 0, 0,
+                            reinterpret_cast<uint64_t>(ctx->scratch), reinterpret_cast<uint64_t>(d_q),
+                            reinterpret_cast<uint64_t>(ctx->stream),
+                            ctx->scratch_bytes ^ (reinterpret_cast<uint64_t>(cm->d_probe_all) << 1) ^
+                                (reinterpret_cast<uint64_t>(cm->d_loc_ids) << 2)};
+        ivf_state_stamp(ivf, key + 4);
+        // (no lock here: sharded_search_dev takes the context mutex per stage; calls on one communicator are collective
+        // and therefore never concurrent)
+        VERS_TRY(graph_cached_run(ctx, cm->call_graph, key, [&]() {
+            return sharded_search_dev(cm, ivf, d_q, nq, top_k, nprobe, d_ids, d_d, d_c);
+        }));
+    }
     VERS_CUDA(cudaMemcpyAsync(ids, d_ids, nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
     VERS_CUDA(cudaMemcpyAsync(dists, d_d, nk * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (counts) VERS_CUDA(cudaMemcpyAsync(counts, d_c, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -98,6 +99,62 @@ int32_t make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint
 int32_t scratch_reserve(vers_ctx* ctx, size_t bytes);
 // grow-only device staging for host-pointer calls; caller holds ctx->mu
 int32_t io_reserve(vers_ctx* ctx, size_t bytes);
+
+// A host-buffer entry point that is called again and again with the same shapes (a serving loop) replays its device
+// work from a CUDA graph instead of re-launching ~25 small kernels: first call with a key runs eagerly (and sizes every
+// arena), the second captures, later ones replay.  The key holds everything the captured launches depend on (index
+// state, shapes, arena addresses, stream); any change starts over.  Capture problems of any kind fall back to eager
+// launches for good.  Caller holds ctx->mu.
+struct GraphCache {
+    uint64_t key[12] = {};
+    int state = 0;  // 0 empty, 1 key seen once, 2 graph ready, -1 disabled
+    cudaGraphExec_t exec = nullptr;
+    void reset() {
+        if (exec) cudaGraphExecDestroy(exec);
+        exec = nullptr;
+        state = 0;
+    }
+};
+
+template <class F>
+int32_t graph_cached_run(vers_ctx* ctx, GraphCache& gc, const uint64_t (&key)[12], F&& fn) {
+    static const bool off = getenv("VERS_NO_CALL_GRAPH") != nullptr;
+    if (off || ctx->timing || gc.state < 0) return fn();
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(ctx->stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        return fn();  // the caller is capturing this call itself
+    }
+    if (gc.state == 0 || memcmp(gc.key, key, sizeof(gc.key)) != 0) {
+        gc.reset();
+        memcpy(gc.key, key, sizeof(gc.key));
+        gc.state = 1;
+        return fn();
+    }
+    if (gc.state == 1) {
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            gc.state = -1;
+            return fn();
+        }
+        const uint64_t launches0 = ctx->launches;
+        const int32_t rc = fn();
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+        if (rc == VERS_OK && e == cudaSuccess && g) e = cudaGraphInstantiate(&gc.exec, g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (rc != VERS_OK || e != cudaSuccess || !gc.exec) {  // nothing ran: do it the plain way, now and from now on
+            cudaGetLastError();
+            gc.reset();
+            gc.state = -1;
+            ctx->launches = launches0;
+            return fn();
+        }
+        gc.state = 2;
+    }
+    VERS_CUDA(cudaGraphLaunch(gc.exec, ctx->stream));
+    return VERS_OK;
+}
 
 struct ScratchCarver {
     char* base;

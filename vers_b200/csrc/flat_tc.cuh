@@ -106,10 +106,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
             tc::mbar_init(&sm.empty[s], 1);
         }
         tc::mbar_init(sm.afull, 1);
-        tc::mbar_init(sm.aempty, FT_CONV_WARPS);
+        tc::mbar_init(sm.aempty, FT_CONV_WARPS * 32);  // every converter lane arrives itself
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&sm.tfull[s], 1);
-            tc::mbar_init(&sm.tempty[s], FT_EPI_WARPS);
+            tc::mbar_init(&sm.tempty[s], FT_EPI_WARPS * 32);  // every epilogue lane arrives itself
         }
         tc::mbar_init(sm.aready, FT_CONV_WARPS);
         tc::mbar_init(sm.afree, 1);
@@ -267,8 +267,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
                 tc::tmem_ld_wait_32(va);
                 tc::tmem_ld_wait_32(vb);
                 tc::fence_before_thread_sync();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&sm.tempty[buf]);
+                __syncwarp();  // also the reconvergence point of the divergent selection below: tcgen05.ld is .aligned
+                tc::mbar_arrive(&sm.tempty[buf]);  // per lane: also releases this lane's reads of the norm ring
                 if ((t & 3) == 3 && qlive) tg = fminf(tg, tau_decode(__ldcg(p.qtau + q)));
                 const float* nr = sm.nrm + (t & 3) * FT_N;
                 float qm[16];
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
                     v[4 * c + 3] = round_tf32_bits(__float_as_uint(f.w));
                 }
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(sm.aempty);
+                tc::mbar_arrive(sm.aempty);  // per lane: the staging slot's bytes are in this lane's registers
                 if (kc == 0 && i > 0) {  // the previous item's MMAs still read the A columns
                     tc::mbar_wait(sm.afree, (uint32_t)((i - 1) & 1));
                     tc::fence_after_thread_sync();

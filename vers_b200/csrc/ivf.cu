@@ -57,6 +57,7 @@ struct vers_ivf {
     float h16_scale = 1.0f;                 // power of two: no element of a row with ||row||^2 <= h16_norm2_limit overflows
     double h16_norm2_limit = 0.0;
     uint32_t* d_h16_stat = nullptr;         // [0] bits of max ||x - x~||^2 over the live rows, [1] elements that did not fit
+    vers::GraphCache call_graph;            // vers_ivf_search: the device work of a repeated call shape, as a CUDA graph
     // cache of ivf_max_chunks_per_query (host loop over the lists): valid while seg_epoch == mc_epoch
     uint64_t seg_epoch = 1, mc_epoch = 0;
     uint32_t mc_np = 0;
@@ -84,6 +85,14 @@ inline uint32_t tc_chunk_rows(const vers_ivf* ivf, uint32_t nq, uint32_t np) {
     return std::min<uint32_t>(LIST_CHUNK_ROWS, std::max<uint32_t>(TC_TAIL_CHUNK_ROWS, cr));
 }
 using ScanCfg = NarrowCfg;
+
+// everything about an index that a captured search depends on, folded into two words (graph cache keys)
+void ivf_state_stamp(const vers_ivf* ivf, uint64_t out[4]) {
+    out[0] = ivf->seg_epoch;
+    out[1] = (uint64_t)ivf->mode | ((uint64_t)ivf->h16_valid << 8) | (ivf->cap_total << 16);
+    out[2] = reinterpret_cast<uint64_t>(ivf->d_lm);
+    out[3] = reinterpret_cast<uint64_t>(ivf->d_lm16);
+}
 
 // ---------------------------------------------------------------- layout
 __global__ void gather_list_major_kernel(const float* __restrict__ rows, uint32_t ld,
@@ -1959,6 +1968,7 @@ extern "C" int32_t vers_ivf_free(vers_ivf* ivf) {
     cudaFree(ivf->d_lm_norm);
     cudaFree(ivf->d_lm16);
     cudaFree(ivf->d_h16_stat);
+    ivf->call_graph.reset();
     cudaFree(ivf->d_nxmax);
     cudaFree(ivf->d_cent_norm);
     cudaFree(ivf->d_ncmax);
@@ -2212,7 +2222,17 @@ extern "C" int32_t vers_ivf_search(vers_ivf* ivf, const float* queries, uint32_t
         VERS_CUDA(cudaMemcpy2DAsync(d_q, (size_t)ivf->ld * 4, queries, (size_t)q_stride_floats * 4,
                                     (size_t)ivf->dim * 4, nq, cudaMemcpyHostToDevice, ctx->stream));
     }
-    VERS_TRY(ivf_search_dev_locked(ivf, d_q, nq, top_k, nprobe, d_ids, d_d, d_c));
+    if (nprobe == 0) {  // reference semantics: reads a flag back mid-call, not capturable
+        VERS_TRY(ivf_search_dev_locked(ivf, d_q, nq, top_k, nprobe, d_ids, d_d, d_c));
+    } else {
+        uint64_t key[12] = {reinterpret_cast<uint64_t>(ivf), nq, top_k, nprobe, 0, 0, 0, 0,
+                            reinterpret_cast<uint64_t>(ctx->scratch), reinterpret_cast<uint64_t>(d_q),
+                            reinterpret_cast<uint64_t>(ctx->stream), ctx->scratch_bytes};
+        ivf_state_stamp(ivf, key + 4);
+        VERS_TRY(graph_cached_run(ctx, ivf->call_graph, key, [&]() {
+            return ivf_search_dev_locked(ivf, d_q, nq, top_k, nprobe, d_ids, d_d, d_c);
+        }));
+    }
     VERS_CUDA(cudaMemcpyAsync(ids, d_ids, nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
     VERS_CUDA(cudaMemcpyAsync(dists, d_d, nk * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (counts) VERS_CUDA(cudaMemcpyAsync(counts, d_c, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -324,12 +324,14 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
     const uint64_t total_items = p.item_off[p.C];
     const uint32_t nk = (p.ld + Cfg::KC_ELEMS - 1) / Cfg::KC_ELEMS;
     // consumers of a scheduled item: producer + MMA thread + epilogue warps (+ lo MMA thread + converters)
-    constexpr uint32_t SCHED_CONSUMERS = 2 + TC_EPI_WARPS + (SPLIT3 ? 1 + TC_CONV_WARPS : 0);
+    // (single-thread roles arrive once, whole-warp roles with every lane: each lane's read of the slot is released by its
+    // own arrive)
+    constexpr uint32_t SCHED_CONSUMERS = 2 + 32 * TC_EPI_WARPS + (SPLIT3 ? 1 + 32 * TC_CONV_WARPS : 0);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             tc::mbar_init(&full[s], 1);
-            tc::mbar_init(&conv[s], TC_CONV_WARPS);
+            tc::mbar_init(&conv[s], TC_CONV_WARPS * 32);  // every converter lane arrives itself
             tc::mbar_init(&empty[s], SPLIT3 ? 2 : 1);  // one commit per MMA issuer
         }
         for (int b = 0; b < 2; ++b) {
@@ -362,8 +364,8 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
     auto next_item = [&](bool leader, bool whole_warp) -> TcItem {
         tc::mbar_wait(&sfull[sslot], sphase);
         const TcItem it = sched[sslot];
-        if (whole_warp) __syncwarp();  // every lane has read the slot before the leader releases it
-        if (leader) tc::mbar_arrive(&sempty[sslot]);
+        if (whole_warp) __syncwarp();  // keeps the warp converged for the .aligned tcgen05 instructions that follow
+        if (whole_warp || leader) tc::mbar_arrive(&sempty[sslot]);
         if (++sslot == TC_SCHED) {
             sslot = 0;
             sphase ^= 1;
@@ -695,7 +697,7 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
                     tc::tmem_st_32(tmem_base + ((uint32_t)(lane_group * 32) << 16) + Cfg::ALO_COL0 + stage * TC_KC, lo);
                     tc::fence_before_thread_sync();
                     __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&conv[stage]);
+                    tc::mbar_arrive(&conv[stage]);  // per lane: this lane's reads of the stage are done
                     if (++stage == S) {
                         stage = 0;
                         phase ^= 1;

@@ -78,12 +78,12 @@ __global__ void __launch_bounds__(KA_THREADS, 1)
     if (threadIdx.x == 0) {
         for (int s = 0; s < KA_STAGES; ++s) {
             tc::mbar_init(&full[s], 1);
-            tc::mbar_init(&conv[s], KA_CONV_WARPS);
+            tc::mbar_init(&conv[s], KA_CONV_WARPS * 32);  // every converter lane arrives itself
             tc::mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
             tc::mbar_init(&tfull[b], 1);
-            tc::mbar_init(&tempty[b], KA_EPI_WARPS);
+            tc::mbar_init(&tempty[b], KA_EPI_WARPS * 32);  // every epilogue lane arrives itself
             tc::mbar_init(&nbar[b], 1);
         }
         tc::fence_barrier_init();
@@ -208,8 +208,8 @@ __global__ void __launch_bounds__(KA_THREADS, 1)
                 }
                 if (b1 < b1_in) c1 = ct * KA_N + loc;
                 tc::fence_before_thread_sync();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&tempty[buf]);
+                __syncwarp();  // also the reconvergence point of the divergent selection above: tcgen05.ld is .aligned
+                tc::mbar_arrive(&tempty[buf]);  // per lane: each lane's own reads (accumulator, norm ring) are released
                 ++tile_ctr;
             }
             if (row < p.n_rows) {
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1)
                     tc::tmem_st_32(tl + KA_ALO_COL0 + stage * KA_KC, lo);
                     tc::fence_before_thread_sync();
                     __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&conv[stage]);
+                    tc::mbar_arrive(&conv[stage]);
                     if (++stage == KA_STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -393,13 +393,13 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
         }
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&afull[s], 1);
-            tc::mbar_init(&aempty[s], K1_CONV_WARPS);
+            tc::mbar_init(&aempty[s], K1_CONV_WARPS * 32);  // every converter lane arrives itself
         }
         tc::mbar_init(aready, K1_CONV_WARPS);
         tc::mbar_init(afree, 1);
         for (int b = 0; b < 4; ++b) {
             tc::mbar_init(&tfull[b], 1);
-            tc::mbar_init(&tempty[b], K1_EPI_WARPS / 2);
+            tc::mbar_init(&tempty[b], K1_EPI_WARPS / 2 * 32);  // every epilogue lane arrives itself
             tc::mbar_init(&nbar[b], 1);
         }
         tc::fence_barrier_init();
@@ -532,8 +532,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
                 tc::tmem_ld_wait_32(vb);
                 // the accumulator is in registers: hand the buffer back before the selection work
                 tc::fence_before_thread_sync();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&tempty[2 * rb + buf]);
+                __syncwarp();  // also the reconvergence point of the divergent selection below: tcgen05.ld is .aligned
+                tc::mbar_arrive(&tempty[2 * rb + buf]);  // per lane: also releases this lane's reads of the norm ring
                 const float* nr = nrm + (t & 3) * K1_N;
                 const uint32_t c0 = ct * K1_N;
                 // phase 1 (straight-line): the 64 keys in place, the min of every quad, of every 16-column group and of
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&aempty[slot]);
+                    tc::mbar_arrive(&aempty[slot]);  // per lane: the staging slot's bytes are in this lane's registers
                     if (rb == 0 && kc == 0 && i > 0) {  // the previous pair's MMAs still read the A columns
                         tc::mbar_wait(afree, (uint32_t)((i - 1) & 1));
                         tc::fence_after_thread_sync();

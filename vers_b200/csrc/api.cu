@@ -184,6 +184,7 @@ extern "C" int32_t vers_ctx_destroy(vers_ctx* ctx) {
         for (cudaEvent_t e : ctx->ev1[i]) cudaEventDestroy(e);
     }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
     delete ctx;
     return VERS_OK;
 }

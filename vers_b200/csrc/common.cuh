@@ -61,6 +61,8 @@ struct vers_ctx {
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
     unsigned long long* scan_flags = nullptr;  // [256] inter-block carries of the chained exclusive scan
+    cudaStream_t cap_stream = nullptr;  // private stream the call graphs are captured on (the caller's stream may be
+                                        // the legacy default stream, which cannot be captured)
     std::mutex mu;
 };
 
@@ -119,6 +121,7 @@ struct GraphCache {
 template <class F>
 int32_t graph_cached_run(vers_ctx* ctx, GraphCache& gc, const uint64_t (&key)[12], F&& fn) {
     static const bool off = getenv("VERS_NO_CALL_GRAPH") != nullptr;
+    static const bool dbg = getenv("VERS_DEBUG_CALL_GRAPH") != nullptr;
     if (off || ctx->timing || gc.state < 0) return fn();
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(ctx->stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
@@ -126,24 +129,44 @@ int32_t graph_cached_run(vers_ctx* ctx, GraphCache& gc, const uint64_t (&key)[12
         return fn();  // the caller is capturing this call itself
     }
     if (gc.state == 0 || memcmp(gc.key, key, sizeof(gc.key)) != 0) {
+        if (dbg && gc.state != 0) {
+            fprintf(stderr, "[vers] call graph: key changed:");
+            for (int i = 0; i < 12; ++i)
+                if (gc.key[i] != key[i]) fprintf(stderr, " [%d] %llx -> %llx", i, (unsigned long long)gc.key[i], (unsigned long long)key[i]);
+            fprintf(stderr, "\n");
+        }
         gc.reset();
         memcpy(gc.key, key, sizeof(gc.key));
         gc.state = 1;
         return fn();
     }
     if (gc.state == 1) {
-        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        // captured on a private stream (every launch of fn goes to ctx->stream, which is swapped for the duration), replayed
+        // on the caller's
+        if (!ctx->cap_stream && cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError();
+            gc.state = -1;
+            return fn();
+        }
+        if (cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            if (dbg) fprintf(stderr, "[vers] call graph: begin capture failed: %s\n", cudaGetErrorString(cudaGetLastError()));
             cudaGetLastError();
             gc.state = -1;
             return fn();
         }
         const uint64_t launches0 = ctx->launches;
+        cudaStream_t real = ctx->stream;
+        ctx->stream = ctx->cap_stream;
         const int32_t rc = fn();
+        ctx->stream = real;
         cudaGraph_t g = nullptr;
-        cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+        cudaError_t e = cudaStreamEndCapture(ctx->cap_stream, &g);
         if (rc == VERS_OK && e == cudaSuccess && g) e = cudaGraphInstantiate(&gc.exec, g, 0);
         if (g) cudaGraphDestroy(g);
         if (rc != VERS_OK || e != cudaSuccess || !gc.exec) {  // nothing ran: do it the plain way, now and from now on
+            if (dbg)
+                fprintf(stderr, "[vers] call graph: capture failed (rc %d: %s; cuda: %s), staying eager\n", rc,
+                        vers_last_error(), cudaGetErrorString(e));
             cudaGetLastError();
             gc.reset();
             gc.state = -1;
@@ -151,6 +174,7 @@ int32_t graph_cached_run(vers_ctx* ctx, GraphCache& gc, const uint64_t (&key)[12
             return fn();
         }
         gc.state = 2;
+        if (dbg) fprintf(stderr, "[vers] call graph: captured %llu launches\n", (unsigned long long)(ctx->launches - launches0));
     }
     VERS_CUDA(cudaGraphLaunch(gc.exec, ctx->stream));
     return VERS_OK;

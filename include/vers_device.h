@@ -205,7 +205,9 @@ int32_t vers_ivf_last_search_stats(const vers_ivf* ivf, uint64_t out[8]);
 int32_t vers_ivf_set_mode(vers_ivf* ivf, int32_t mode);
 /* Index::search_approximate (ivfflat.rs:153-198) for a batch.  nprobe == 0: the reference's semantics (nearest
  * list, spill to the next list while fewer than top_k found, output = concatenated per-list prefixes).
- * nprobe >= 1 (extension, BASELINE config 4): global top_k by (distance, id) over the nprobe nearest lists. */
+ * nprobe >= 1 (extension, BASELINE config 4): global top_k by (distance, id) over the nprobe nearest lists.
+ * A call shape (nq, top_k, nprobe) that repeats on an unchanged index replays its device work from a cached CUDA graph
+ * (first call eager, second captured, later ones replayed; environment VERS_NO_CALL_GRAPH=1 disables it). */
 int32_t vers_ivf_search(vers_ivf* ivf, const float* queries, uint32_t nq, uint32_t q_stride_floats, uint32_t top_k,
                         uint32_t nprobe, uint64_t* ids, float* dists, uint32_t* counts);
 int32_t vers_ivf_search_dev(vers_ivf* ivf, const float* d_queries, uint32_t nq, uint32_t top_k, uint32_t nprobe,

@@ -191,7 +191,7 @@ extern "C" int32_t vers_ctx_destroy(vers_ctx* ctx) {
 
 extern "C" int32_t vers_ctx_set_stream(vers_ctx* ctx, void* cuda_stream) {
     if (!ctx) return fail(VERS_ERR_ARG, "ctx_set_stream: null ctx");
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     // switching INTO a capturing stream (CUDA graph capture of a search step): a synchronize would invalidate the
     // capture; the caller has drained the old stream before starting the capture
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -220,7 +220,7 @@ extern "C" int32_t vers_ctx_launch_count(vers_ctx* ctx, uint64_t* out) {
 
 extern "C" int32_t vers_ctx_enable_timing(vers_ctx* ctx, int32_t on) {
     if (!ctx) return fail(VERS_ERR_ARG, "ctx_enable_timing: null");
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     if (on && ctx->ev0[0].empty()) {
         for (int i = 0; i < KF_COUNT; ++i) {
@@ -297,7 +297,7 @@ extern "C" int32_t vers_dataset_synth(vers_ctx* ctx, uint64_t seed, uint64_t cen
     VERS_TRY(dataset_alloc(ctx, n, dim, row0, out));
     vers_dataset* ds = *out;
     if (n) {
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
         synth_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ds->d_rows, n, dim, ds->ld, seed, center_seed, kind,
                                                                  n_centers, row0);
         VERS_LAUNCH_CHECK(ctx);
@@ -310,7 +310,7 @@ extern "C" int32_t vers_dataset_normalize(vers_dataset* ds) {
     if (!ds) return fail(VERS_ERR_ARG, "dataset_normalize: null");
     if (ds->n == 0) return VERS_OK;
     vers_ctx* ctx = ds->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     normalize_kernel<<<(unsigned)ceil_div(ds->n, NORM_ROWS), NORM_ROWS, 0, ctx->stream>>>(ds->d_rows, ds->n, ds->dim,
                                                                                          ds->ld);

@@ -346,7 +346,7 @@ static int32_t sharded_search_dev(vers_comm* cm, vers_ivf* ivf, const float* d_q
     if (nql < per) VERS_CUDA(cudaMemsetAsync(cm->d_probe_local, 0xff, probe_bytes, ctx->stream));
     if (nql) VERS_TRY(vers_ivf_probe_dev(ivf, d_queries + (size_t)q0 * ld, nql, np, cm->d_probe_local));
     {   // (b) all-gather of the probe lists over peer memory
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
         const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div(probe_bytes >> 4, 256), (uint64_t)ctx->sm_count);
         peer_publish_kernel<<<grid, 256, 0, ctx->stream>>>(cm->probe_rg, reinterpret_cast<const uint4*>(cm->d_probe_local),
                                                           probe_bytes, 0);
@@ -362,7 +362,7 @@ static int32_t sharded_search_dev(vers_comm* cm, vers_ivf* ivf, const float* d_q
     VERS_TRY(vers_ivf_search_probed_dev(ivf, d_queries, nq, top_k, np, cm->d_probe_all, cm->d_loc_ids, cm->d_loc_d,
                                         cm->d_loc_cnt));
     {   // (d) exchange + merge of the per-rank top-k, one kernel
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
         const size_t smem = (size_t)PG_WARPS * top_k * 12;
         if (!cm->merge_resident) VERS_TRY(peer_resident_blocks(ctx, (size_t)PG_WARPS * VERS_MAX_TOPK * 12, &cm->merge_resident));
         const unsigned grid = std::min<unsigned>((unsigned)ceil_div(nq, PG_WARPS), cm->merge_resident);
@@ -534,7 +534,7 @@ extern "C" int32_t vers_sharded_kmeans_fit(vers_comm* cm, vers_kmeans* km, const
         VERS_CUDA(cudaMalloc(&d_init, (size_t)C * 8));
         cudaError_t e = cudaMemcpyAsync(d_init, init_rows_global, (size_t)C * 8, cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) {
-            std::lock_guard<std::mutex> lk(ctx->mu);
+            std::lock_guard<std::recursive_mutex> lk(ctx->mu);
             comm_gather_init_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(ds->d_rows, ld, ds->n, ds->id_base, d_init, C,
                                                                      km->d_cents);
             ctx->launches += 1;
@@ -656,7 +656,7 @@ extern "C" int32_t vers_sharded_ivf_build(vers_comm* cm, vers_kmeans* km, vers_i
     VERS_CUDA(cudaMalloc(&b.hist, (size_t)C * 8 * 2));
     VERS_CUDA(cudaMemsetAsync(b.hist, 0, (size_t)C * 8 * 2, s));
     if (n) {
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
         comm_hist64_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(km->d_assign, n, b.hist);
         VERS_LAUNCH_CHECK(ctx);
     }
@@ -682,7 +682,7 @@ extern "C" int32_t vers_sharded_ivf_build(vers_comm* cm, vers_kmeans* km, vers_i
     VERS_CUDA(cudaMalloc(&b.iota, n1 * 4));
     VERS_CUDA(cudaMalloc(&b.order, n1 * 4));
     if (n) {
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
         comm_dest_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(km->d_assign, b.owner, n, b.dest, b.iota);
         VERS_LAUNCH_CHECK(ctx);
         int end_bit = 1;
@@ -711,7 +711,7 @@ extern "C" int32_t vers_sharded_ivf_build(vers_comm* cm, vers_kmeans* km, vers_i
     VERS_CUDA(cudaMalloc(&b.recv_ids, nr1 * 8));
     VERS_CUDA(cudaMalloc(&b.recv_assign, nr1 * 4));
     if (n) {
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
         comm_pack_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(ds->d_rows, ld, b.order, km->d_assign, n, ds->id_base,
                                                           b.send_rows, b.send_ids, b.send_assign);
         VERS_LAUNCH_CHECK(ctx);
@@ -797,7 +797,7 @@ extern "C" int32_t vers_sharded_ivf_search(vers_comm* cm, vers_ivf* ivf, const f
     float* d_d;
     uint32_t* d_c;
     {
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
         ScratchCarver plan(nullptr);
         plan.plan<float>((size_t)nq * ld);
         plan.plan<uint64_t>(nk);
@@ -824,8 +824,9 @@ extern "C" int32_t vers_sharded_ivf_search(vers_comm* cm, vers_ivf* ivf, const f
                             ctx->scratch_bytes ^ (reinterpret_cast<uint64_t>(cm->d_probe_all) << 1) ^
                                 (reinterpret_cast<uint64_t>(cm->d_loc_ids) << 2)};
         ivf_state_stamp(ivf, key + 4);
-        // (no lock here: sharded_search_dev takes the context mutex per stage; calls on one communicator are collective
-        // and therefore never concurrent)
+        // the context mutex (recursive) is held across the whole call: while a capture swaps ctx->stream no other thread
+        // may enqueue work through this context
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
         VERS_TRY(graph_cached_run(ctx, cm->call_graph, key, [&]() {
             return sharded_search_dev(cm, ivf, d_q, nq, top_k, nprobe, d_ids, d_d, d_c);
         }));

@@ -63,7 +63,7 @@ struct vers_ctx {
     unsigned long long* scan_flags = nullptr;  // [256] inter-block carries of the chained exclusive scan
     cudaStream_t cap_stream = nullptr;  // private stream the call graphs are captured on (the caller's stream may be
                                         // the legacy default stream, which cannot be captured)
-    std::mutex mu;
+    std::recursive_mutex mu;  // recursive: a host-buffer entry point holds it across the device-pointer calls it is made of
 };
 
 struct vers_dataset {

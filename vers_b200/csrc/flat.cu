@@ -745,7 +745,7 @@ extern "C" int32_t vers_flat_search_dev(vers_dataset* ds, const float* d_queries
                                         uint32_t metric, uint64_t* d_ids, float* d_dists, uint32_t* d_counts) {
     if (!ds || (!d_queries && nq) || !d_ids || !d_dists) return fail(VERS_ERR_ARG, "flat_search_dev: null argument");
     if (metric > VERS_METRIC_COSINE) return fail(VERS_ERR_ARG, "flat_search_dev: unknown metric %u", metric);
-    std::lock_guard<std::mutex> lk(ds->ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ds->ctx->mu);
     VERS_CUDA(cudaSetDevice(ds->ctx->device));
     return flat_search_dev_locked(ds, d_queries, nq, top_k, metric, d_ids, d_dists, d_counts);
 }
@@ -792,7 +792,7 @@ extern "C" int32_t vers_flat_search(vers_dataset* ds, const float* queries, uint
     float* d_d;
     uint32_t* d_c;
     if (metric > VERS_METRIC_COSINE) return fail(VERS_ERR_ARG, "flat_search: unknown metric %u", metric);
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     {   // device staging from the context's grow-only I/O arena: no allocation on the steady-state path
         ScratchCarver plan(nullptr);
         plan.plan<float>((size_t)nq * ds->ld);
@@ -832,7 +832,7 @@ extern "C" int32_t vers_topk_merge_dev(vers_ctx* ctx, const uint64_t* d_ids_all,
     if (!ctx || !d_ids_all || !d_dists_all || !d_ids || !d_dists) return fail(VERS_ERR_ARG, "topk_merge_dev: null");
     if (top_k > VERS_MAX_TOPK) return fail(VERS_ERR_UNSUPPORTED, "top_k %u > %u", top_k, VERS_MAX_TOPK);
     if (nq == 0 || top_k == 0) return VERS_OK;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     merge_ids_kernel<<<(unsigned)ceil_div(nq, MERGE_WARPS), MERGE_WARPS * 32, (size_t)MERGE_WARPS * top_k * 12,
                        ctx->stream>>>(d_ids_all, d_dists_all, parts, part_stride_ids ? part_stride_ids : (uint64_t)nq * top_k,

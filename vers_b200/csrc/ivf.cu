@@ -638,7 +638,7 @@ static int32_t ivf_from_state(vers_kmeans* km, float cost, uint32_t attempt, ver
     VERS_CUDA(cudaMemsetAsync(ivf->d_ncmax, 0, 4, ctx->stream));
     ivf->cap_total = ds->n;
     {
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
         VERS_TRY(kmeans_build_csr(km));
         VERS_CUDA(cudaMemcpyAsync(ivf->d_cents, km->d_cents, (size_t)km->C * ds->ld * 4, cudaMemcpyDeviceToDevice,
                                   ctx->stream));
@@ -2150,7 +2150,7 @@ extern "C" int32_t vers_ivf_search_dev(vers_ivf* ivf, const float* d_queries, ui
     if (!ivf || (!d_queries && nq) || !d_ids || !d_dists) return fail(VERS_ERR_ARG, "ivf_search_dev: null argument");
     if (top_k > VERS_MAX_TOPK) return fail(VERS_ERR_UNSUPPORTED, "top_k %u > %u", top_k, VERS_MAX_TOPK);
     if (nq == 0 || top_k == 0) return VERS_OK;
-    std::lock_guard<std::mutex> lk(ivf->ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ivf->ctx->mu);
     VERS_CUDA(cudaSetDevice(ivf->ctx->device));
     return ivf_search_dev_locked(ivf, d_queries, nq, top_k, nprobe, d_ids, d_dists, d_counts);
 }
@@ -2166,7 +2166,7 @@ extern "C" int32_t vers_ivf_probe_dev(vers_ivf* ivf, const float* d_queries, uin
     if (nq == 0 || nprobe == 0) return VERS_OK;
     if (nprobe > ivf->C || nprobe > VERS_MAX_TOPK) return fail(VERS_ERR_ARG, "ivf_probe_dev: nprobe %u out of range", nprobe);
     vers_ctx* ctx = ivf->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     const RankTable ctab = centroid_table(ivf);
     const ProbePlan pplan = probe_plan(ctx, ctab, nq, nprobe);
@@ -2184,7 +2184,7 @@ extern "C" int32_t vers_ivf_search_probed_dev(vers_ivf* ivf, const float* d_quer
     if (top_k > VERS_MAX_TOPK) return fail(VERS_ERR_UNSUPPORTED, "top_k %u > %u", top_k, VERS_MAX_TOPK);
     if (nprobe == 0 || nprobe > ivf->C) return fail(VERS_ERR_ARG, "ivf_search_probed_dev: nprobe %u out of range", nprobe);
     if (nq == 0 || top_k == 0) return VERS_OK;
-    std::lock_guard<std::mutex> lk(ivf->ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ivf->ctx->mu);
     VERS_CUDA(cudaSetDevice(ivf->ctx->device));
     return ivf_search_dev_locked(ivf, d_queries, nq, top_k, nprobe, d_ids, d_dists, d_counts, d_probe_ids);
 }
@@ -2201,7 +2201,7 @@ extern "C" int32_t vers_ivf_search(vers_ivf* ivf, const float* queries, uint32_t
         return VERS_OK;
     }
     vers_ctx* ctx = ivf->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     const size_t nk = (size_t)nq * top_k;
     ScratchCarver plan(nullptr);
@@ -2281,7 +2281,7 @@ extern "C" int32_t vers_ivf_add(vers_ivf* ivf, const float* embedding, uint64_t 
     (void)vec_id;  // the reference ignores the caller's id: `let vec_id = self.assignments.len()` (ivfflat.rs:209)
     if (!ivf || !embedding) return fail(VERS_ERR_ARG, "ivf_add: null argument");
     vers_ctx* ctx = ivf->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     float* d_row = nullptr;
     VERS_TRY(upload_queries(ctx, embedding, 1, ivf->dim, ivf->dim, ivf->ld, &d_row));
@@ -2394,7 +2394,7 @@ extern "C" int32_t vers_ivf_add_batch(vers_ivf* ivf, const float* embeddings, ui
     if (n == 0) return VERS_OK;
     if (n >= 0x7fffffffull || ivf->n + n >= 0xffffffffull) return fail(VERS_ERR_UNSUPPORTED, "ivf_add_batch: too many rows");
     vers_ctx* ctx = ivf->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     float* d_rows = nullptr;

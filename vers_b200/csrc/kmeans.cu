@@ -342,7 +342,7 @@ extern "C" int32_t vers_kmeans_create(vers_dataset* ds, uint32_t num_clusters, v
         vers_kmeans_free(km);
         return fail(VERS_ERR_NOMEM, "kmeans_create: cudaMalloc failed: %s", cudaGetErrorString(e));
     }
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     VERS_CUDA(cudaMemsetAsync(km->d_cents, 0, cl * 4, ctx->stream));
     if (ds->n) {
         iota_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(km->d_iota, ds->n);
@@ -360,7 +360,7 @@ extern "C" int32_t vers_kmeans_init_from_rows(vers_kmeans* km, const uint64_t* i
     for (uint32_t j = 0; j < km->C; ++j)
         if (init_rows[j] >= ds->n) return fail(VERS_ERR_ARG, "kmeans_init_from_rows: row %llu out of range",
                                                (unsigned long long)init_rows[j]);
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     uint64_t* d_idx = nullptr;
     VERS_CUDA(cudaMalloc(&d_idx, (size_t)km->C * 8));
@@ -586,7 +586,7 @@ static int32_t kmeans_assign_tc(vers_kmeans* km) {
 extern "C" int32_t vers_kmeans_assign_step(vers_kmeans* km) {
     if (!km) return fail(VERS_ERR_ARG, "kmeans_assign_step: null");
     vers_dataset* ds = km->ds;
-    std::lock_guard<std::mutex> lk(ds->ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ds->ctx->mu);
     VERS_CUDA(cudaSetDevice(ds->ctx->device));
     km->csr_valid = false;
     if (km->mode != 1 && ds->ld >= KA_KC && ds->n >= 1 && ds->n < 0x7fffffffull) return kmeans_assign_tc(km);
@@ -613,7 +613,7 @@ extern "C" int32_t vers_kmeans_sums_step_dev(vers_kmeans* km, float* d_sums_io, 
     if (!km || !d_sums_io || !d_counts_io) return fail(VERS_ERR_ARG, "kmeans_sums_step_dev: null argument");
     vers_dataset* ds = km->ds;
     vers_ctx* ctx = ds->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     VERS_TRY(kmeans_build_csr(km));
     const uint32_t groups = ((ds->ld >> 2) + 31) / 32;
@@ -630,7 +630,7 @@ extern "C" int32_t vers_kmeans_finalize_step_dev(vers_kmeans* km, const float* d
     if (!km || !d_sums || !d_counts) return fail(VERS_ERR_ARG, "kmeans_finalize_step_dev: null argument");
     vers_dataset* ds = km->ds;
     vers_ctx* ctx = ds->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     VERS_CUDA(cudaMemsetAsync(km->d_flag, 0, 4, ctx->stream));
     finalize_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(d_sums, d_counts, km->d_cents, km->d_next, km->C,
@@ -653,7 +653,7 @@ extern "C" int32_t vers_kmeans_cost_step(vers_kmeans* km, float* cost_io) {
     vers_dataset* ds = km->ds;
     vers_ctx* ctx = ds->ctx;
     if (ds->n == 0) return VERS_OK;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     if (!km->d_rowdist) VERS_CUDA(cudaMalloc(&km->d_rowdist, ds->n * 4 + 4));
     float* d_acc = km->d_rowdist + ds->n;

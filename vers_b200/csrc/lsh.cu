@@ -63,7 +63,7 @@ extern "C" int32_t vers_lsh_hash_dev(vers_dataset* ds, const float* d_planes, ui
     if (!ds || !d_planes || !d_consts || !d_bits) return fail(VERS_ERR_ARG, "lsh_hash_dev: null argument");
     if (ds->n == 0 || num_planes == 0) return VERS_OK;
     vers_ctx* ctx = ds->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     HashParams p;
     p.A = RowSrc{ds->d_rows, nullptr, ds->ld, ds->n};

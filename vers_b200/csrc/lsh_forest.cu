@@ -760,7 +760,7 @@ extern "C" int32_t vers_lsh_build_index(vers_ctx* ctx, const float* rows, uint64
     *out = nullptr;
     if (dim == 0 || stride_floats < dim) return fail(VERS_ERR_ARG, "lsh_build_index: bad dim/stride");
     if (n >= 0xffffffffull) return fail(VERS_ERR_UNSUPPORTED, "lsh_build_index: more than 2^32-2 rows");
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     vers_lsh* L = new vers_lsh();
     L->ctx = ctx;
@@ -938,7 +938,7 @@ extern "C" int32_t vers_lsh_search(vers_lsh* L, const float* queries, uint32_t n
         return VERS_OK;
     }
     vers_ctx* ctx = L->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     VERS_TRY(sync_device_mirror(L));
     // every leaf is visited at most once per traversal, so L->n candidates per tree always suffice; start small and
@@ -1005,7 +1005,7 @@ extern "C" int32_t vers_lsh_search(vers_lsh* L, const float* queries, uint32_t n
 extern "C" int32_t vers_lsh_add(vers_lsh* L, const float* embedding, uint64_t vec_id) {
     if (!L || !embedding) return fail(VERS_ERR_ARG, "lsh_add: null argument");
     vers_ctx* ctx = L->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     // insert (lsh.rs:218-251) stores vec_id ITSELF in the leaf as a row index (quirk kept).  The reference would only
@@ -1110,7 +1110,7 @@ extern "C" int32_t vers_lsh_from_parts(vers_ctx* ctx, const float* values, uint6
     *out = nullptr;
     if (dim == 0 || stride_floats < dim) return fail(VERS_ERR_ARG, "lsh_from_parts: bad dim/stride");
     if (n >= 0xffffffffull) return fail(VERS_ERR_UNSUPPORTED, "lsh_from_parts: more than 2^32-2 rows");
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     vers_lsh* L = new vers_lsh();

@@ -169,7 +169,7 @@ extern "C" int32_t vers_pair_distances_simd_dev(vers_dataset* ds, const float* d
                                   "multiple of 4 floats and >= dim");
     if (n_pairs == 0) return VERS_OK;
     if (nq == 0) return fail(VERS_ERR_ARG, "pair_distances_simd_dev: pairs without queries");
-    std::lock_guard<std::mutex> lk(ds->ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ds->ctx->mu);
     VERS_CUDA(cudaSetDevice(ds->ctx->device));
     return pair_distances_launch(ds, d_queries, nq, q_stride_floats, d_pair_query, d_pair_row, n_pairs, metric, d_out,
                                  d_bad_count);
@@ -186,7 +186,7 @@ extern "C" int32_t vers_pair_distances_simd(vers_dataset* ds, const float* queri
     if (nq == 0) return fail(VERS_ERR_ARG, "pair_distances_simd: pairs without queries");
     vers_ctx* ctx = ds->ctx;
     VERS_CUDA(cudaSetDevice(ctx->device));
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     ScratchCarver plan(nullptr);
     plan.plan<float>((size_t)nq * ds->ld);
     plan.plan<uint64_t>(n_pairs);

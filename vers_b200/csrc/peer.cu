@@ -92,7 +92,7 @@ extern "C" int32_t vers_peer_gather_merge_dev(vers_peer* p, const uint64_t* d_lo
         return fail(VERS_ERR_ARG, "peer_gather_merge: %u x %u entries exceed the slot of %llu bytes", nq, top_k,
                     (unsigned long long)p->slot_bytes);
     vers_ctx* ctx = p->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
     // every block must be resident while it waits for the peers: the grid is bounded by the occupancy of this kernel
     // and the warps loop over the queries

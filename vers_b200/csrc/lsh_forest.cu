@@ -225,10 +225,39 @@ struct ForestDev {
     uint32_t ld, dim, slot_cap, num_trees;
 };
 
-// lane 0 walks the reference's left-to-right dot; the other lanes wait (the chain is sequential by contract)
+// The reference's left-to-right dot (lsh.rs:27-29, base.rs:91-93).  Only the ADD chain is sequential by contract: the
+// products coef[i] * q[i] are formed by the whole warp (coalesced 16-byte loads of the plane, separately rounded
+// multiplies) into shared memory `prod` [ld], then lane 0 folds them in order.  With prod == null lane 0 does everything
+// itself (one thread fetching the plane float by float: 25x slower on a plane that is not cached).
 __device__ __forceinline__ bool plane_bit(const float* __restrict__ coef, float constant, const float* qs, uint32_t dim,
-                                          int lane) {
+                                          int lane, float* prod = nullptr, uint32_t ld = 0) {
     int bit = 0;
+    if (prod) {
+        const float4* c4 = reinterpret_cast<const float4*>(coef);
+        const float4* q4 = reinterpret_cast<const float4*>(qs);
+        for (uint32_t i = lane; i < (ld >> 2); i += 32) {
+            const float4 c = __ldg(c4 + i), q = q4[i];
+            reinterpret_cast<float4*>(prod)[i] =
+                make_float4(__fmul_rn(c.x, q.x), __fmul_rn(c.y, q.y), __fmul_rn(c.z, q.z), __fmul_rn(c.w, q.w));
+        }
+        __syncwarp();
+        if (lane == 0) {
+            float s = 0.0f;
+            uint32_t i = 0;
+            for (; i + 4 <= dim; i += 4) {
+                const float4 p = *reinterpret_cast<const float4*>(prod + i);
+                s = __fadd_rn(s, p.x);
+                s = __fadd_rn(s, p.y);
+                s = __fadd_rn(s, p.z);
+                s = __fadd_rn(s, p.w);
+            }
+            for (; i < dim; ++i) s = __fadd_rn(s, prod[i]);
+            bit = __fadd_rn(s, constant) >= 0.0f;
+        }
+        bit = __shfl_sync(FULL_MASK, bit, 0);
+        __syncwarp();  // prod is rewritten at the next level
+        return bit != 0;
+    }
     if (lane == 0) {
         float s = 0.0f;
         for (uint32_t i = 0; i < dim; ++i) s = __fadd_rn(s, __fmul_rn(__ldg(coef + i), qs[i]));
@@ -251,21 +280,83 @@ __device__ __forceinline__ float exact_l2sq_row(const float* __restrict__ row, c
     return s;
 }
 
+// The same exact-order distances for (up to) 32 rows at once, lane = row: the rows are scattered over the table, so a
+// lane walking its own row through global memory pays a dependent DRAM round trip every few elements.  Here the warp
+// stages the rows chunk by chunk (64 dimensions; cp.async, 16 bytes per lane and copy, two rows per instruction, the next
+// chunk in flight while the current one is consumed) into a padded shared-memory tile that lane i then walks
+// sequentially — the summation order per row is unchanged.  stage: [2][32][FR_LDS] floats of this warp.
+template <int FR_KCH>
+struct FrCfg {
+    static constexpr int LDS = FR_KCH + 4;
+    static constexpr size_t STAGE_BYTES = (size_t)2 * 32 * LDS * 4;
+};
+template <int FR_KCH>
+__device__ __forceinline__ float staged_l2sq_32(const float* __restrict__ table, uint32_t ld, uint32_t my_row, bool live,
+                                                const float* qs, float* stage, int lane) {
+    constexpr int FR_LDS = FrCfg<FR_KCH>::LDS, LPR = FR_KCH / 4, RPI = 32 / LPR;  // lanes per row chunk, rows per copy
+    const int half = lane / LPR, sub = lane % LPR;
+    const uint32_t nch = (ld + FR_KCH - 1) / FR_KCH;
+    auto issue = [&](uint32_t c) {
+        const uint32_t col = c * FR_KCH + sub * 4;
+        float* tb = stage + (size_t)(c & 1u) * 32 * FR_LDS;
+#pragma unroll
+        for (int i = 0; i < 32 / RPI; ++i) {
+            const uint32_t r = __shfl_sync(FULL_MASK, my_row, RPI * i + half);
+            const bool ok = __shfl_sync(FULL_MASK, (int)live, RPI * i + half) != 0 && col < ld;
+            cp_async16(tb + (RPI * i + half) * FR_LDS + sub * 4, ok ? (const void*)(table + (uint64_t)r * ld + col) : (const void*)table, ok);
+        }
+        cp_async_commit();
+    };
+    float s = 0.0f;
+    issue(0);
+    for (uint32_t c = 0; c < nch; ++c) {
+        const uint32_t k0 = c * FR_KCH, kn = min((uint32_t)FR_KCH, ld - k0);
+        if (c + 1 < nch) {
+            issue(c + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        const float* tl = stage + ((size_t)(c & 1u) * 32 + lane) * FR_LDS;
+        if (live) {
+#pragma unroll 4
+            for (uint32_t i = 0; i < kn; i += 4) {
+                const float4 a = *reinterpret_cast<const float4*>(tl + i);
+                const float4 b = *reinterpret_cast<const float4*>(qs + k0 + i);
+                float t;
+                t = __fsub_rn(a.x, b.x); s = __fadd_rn(s, __fmul_rn(t, t));
+                t = __fsub_rn(a.y, b.y); s = __fadd_rn(s, __fmul_rn(t, t));
+                t = __fsub_rn(a.z, b.z); s = __fadd_rn(s, __fmul_rn(t, t));
+                t = __fsub_rn(a.w, b.w); s = __fadd_rn(s, __fmul_rn(t, t));
+            }
+        }
+        __syncwarp();
+    }
+    return s;
+}
+
 // one warp per (query, tree): tree_result (lsh.rs:163-216) with an explicit stack
-__global__ void __launch_bounds__(128)
+constexpr int FT_WPB = 2;  // warps per block: the warps are independent and bound by latency, small blocks pack the SM
+template <int KCH>
+__global__ void __launch_bounds__(FT_WPB * 32)
     forest_traverse_kernel(ForestDev f, const float* __restrict__ queries, uint32_t nq, uint32_t top_k,
                            uint32_t cand_cap, uint32_t* __restrict__ cand, uint32_t* __restrict__ cand_cnt,
                            uint32_t* overflow) {
     extern __shared__ __align__(16) unsigned char fsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t w = (uint64_t)blockIdx.x * 4 + warp;
+    const uint64_t w = (uint64_t)blockIdx.x * FT_WPB + warp;
     if (w >= (uint64_t)nq * f.num_trees) return;
     const uint32_t q = (uint32_t)(w / f.num_trees), t = (uint32_t)(w % f.num_trees);
-    // shared memory per warp: query [ld] | stack nodes [LSH_STACK] | stack n | stack stage+backup | top-n list
-    const size_t per_warp = (size_t)f.ld * 4 + LSH_STACK * 12 + (size_t)top_k * 8;
+    // shared memory per warp: row staging of the leaf scans (between leaves: the plane products) | query [ld] | stack
+    // nodes [LSH_STACK] | stack n | stack stage+backup | top-n list
+    constexpr size_t FR_STAGE_BYTES = FrCfg<KCH>::STAGE_BYTES;
+    const size_t per_warp = FR_STAGE_BYTES + (size_t)f.ld * 4 + LSH_STACK * 12 + (size_t)top_k * 8;
     unsigned char* base = fsm + warp * ((per_warp + 15) & ~size_t(15));
-    float* qs = reinterpret_cast<float*>(base);
-    uint32_t* st_node = reinterpret_cast<uint32_t*>(base + (size_t)f.ld * 4);
+    float* stage = reinterpret_cast<float*>(base);
+    float* qs = reinterpret_cast<float*>(base + FR_STAGE_BYTES);
+    float* prod = (size_t)f.ld * 4 <= FR_STAGE_BYTES ? stage : nullptr;  // very wide rows: lane 0 walks the plane alone
+    uint32_t* st_node = reinterpret_cast<uint32_t*>(base + FR_STAGE_BYTES + (size_t)f.ld * 4);
     int32_t* st_n = reinterpret_cast<int32_t*>(st_node + LSH_STACK);
     uint32_t* st_aux = reinterpret_cast<uint32_t*>(st_n + LSH_STACK);  // bit31 = waiting for backup, low bits = backup node
     float* ld_ = reinterpret_cast<float*>(st_aux + LSH_STACK);
@@ -308,8 +399,7 @@ __global__ void __launch_bounds__(128)
                 for (uint32_t i0 = 0; i0 < len; i0 += 32) {
                     uint32_t i = i0 + lane;
                     bool live = i < len;
-                    float d = 0.0f;
-                    if (live) d = exact_l2sq_row(f.values + (uint64_t)items[i] * f.ld, qs, f.ld);
+                    const float d = staged_l2sq_32<KCH>(f.values, f.ld, live ? items[i] : 0u, live, qs, stage, lane);
                     while (n > 0) {
                         bool pass = live && entry_less<uint32_t>(d, i, ld_[n - 1], lp[n - 1]);
                         unsigned m = __ballot_sync(FULL_MASK, pass);
@@ -332,7 +422,7 @@ __global__ void __launch_bounds__(128)
             continue;
         }
         if (aux == 0xffffffffu) {  // first visit: hash, descend into the main side
-            bool above = plane_bit(f.planes + (uint64_t)f.plane[g] * f.ld, f.consts[f.plane[g]], qs, f.dim, lane);
+            bool above = plane_bit(f.planes + (uint64_t)f.plane[g] * f.ld, f.consts[f.plane[g]], qs, f.dim, lane, prod, f.ld);
             uint32_t main_n = above ? f.right[g] : f.left[g];
             uint32_t back_n = above ? f.left[g] : f.right[g];
             if (sp >= LSH_STACK) {
@@ -374,6 +464,7 @@ __global__ void __launch_bounds__(128)
 }
 
 // one warp per query: union of the trees' candidates, exact distances, top-k by (distance, row index) -> ids[idx]
+template <int KCH>
 __global__ void __launch_bounds__(128)
     forest_rerank_kernel(ForestDev f, const float* __restrict__ queries, uint32_t nq, uint32_t top_k, uint32_t cand_cap,
                          const uint32_t* __restrict__ cand, const uint32_t* __restrict__ cand_cnt,
@@ -382,10 +473,12 @@ __global__ void __launch_bounds__(128)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * 4 + warp;
     if (q >= nq) return;
-    const size_t per_warp = (size_t)f.ld * 4 + (size_t)top_k * 8;
+    constexpr size_t FR_STAGE_BYTES = FrCfg<KCH>::STAGE_BYTES;
+    const size_t per_warp = FR_STAGE_BYTES + (size_t)f.ld * 4 + (size_t)top_k * 8;
     unsigned char* base = rsm3 + warp * ((per_warp + 15) & ~size_t(15));
-    float* qs = reinterpret_cast<float*>(base);
-    float* sd = reinterpret_cast<float*>(base + (size_t)f.ld * 4);
+    float* stage = reinterpret_cast<float*>(base);
+    float* qs = reinterpret_cast<float*>(base + FR_STAGE_BYTES);
+    float* sd = reinterpret_cast<float*>(base + FR_STAGE_BYTES + (size_t)f.ld * 4);
     uint32_t* sp = reinterpret_cast<uint32_t*>(sd + top_k);
     for (uint32_t i = lane; i < f.ld; i += 32) qs[i] = queries[(uint64_t)q * f.ld + i];
     for (uint32_t e = lane; e < top_k; e += 32) {
@@ -394,15 +487,26 @@ __global__ void __launch_bounds__(128)
     }
     __syncwarp();
     const int k = (int)top_k;
-    for (uint32_t t = 0; t < f.num_trees; ++t) {
-        const uint32_t cnt = cand_cnt[(uint64_t)q * f.num_trees + t];
-        const uint32_t* c = cand + ((uint64_t)q * f.num_trees + t) * cand_cap;
-        for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {
+    // the trees' candidate lists back to back: 32 candidates per round (a tree contributes ~top_k of them, so a round
+    // per tree left two thirds of the lanes idle).  Order does not matter: top-k by the total order (distance, row),
+    // duplicates dropped by row.
+    uint32_t total = 0;
+    for (uint32_t t = 0; t < f.num_trees; ++t) total += cand_cnt[(uint64_t)q * f.num_trees + t];
+    {
+        for (uint32_t i0 = 0; i0 < total; i0 += 32) {
             uint32_t i = i0 + lane;
-            bool live = i < cnt;
-            uint32_t idx = live ? c[i] : 0xffffffffu;
-            float d = 0.0f;
-            if (live) d = exact_l2sq_row(f.values + (uint64_t)idx * f.ld, qs, f.ld);
+            bool live = i < total;
+            uint32_t idx = 0xffffffffu;
+            if (live) {
+                uint32_t rest = i, t = 0;
+                for (;; ++t) {
+                    const uint32_t c = cand_cnt[(uint64_t)q * f.num_trees + t];
+                    if (rest < c) break;
+                    rest -= c;
+                }
+                idx = cand[((uint64_t)q * f.num_trees + t) * cand_cap + rest];
+            }
+            const float d = staged_l2sq_32<KCH>(f.values, f.ld, live ? idx : 0u, live, qs, stage, lane);
             while (true) {
                 bool pass = live && entry_less<uint32_t>(d, idx, sd[k - 1], sp[k - 1]);
                 unsigned m = __ballot_sync(FULL_MASK, pass);
@@ -970,11 +1074,15 @@ extern "C" int32_t vers_lsh_search(vers_lsh* L, const float* queries, uint32_t n
                                     cudaMemcpyHostToDevice, ctx->stream));
         VERS_CUDA(cudaMemsetAsync(d_over, 0, 16, ctx->stream));
         {
-            size_t per_warp = ((size_t)L->ld * 4 + LSH_STACK * 12 + (size_t)top_k * 8 + 15) & ~size_t(15);
-            size_t smem = per_warp * 4;
-            VERS_CUDA(cudaFuncSetAttribute(forest_traverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            forest_traverse_kernel<<<(unsigned)ceil_div(npt, 4), 128, smem, ctx->stream>>>(
-                f, d_q, nq, top_k, (uint32_t)cand_cap, d_cand, d_cnt, d_over);
+            // 32 dimensions per staged chunk: 8.7 KB of staging per warp keeps ~18 of these latency-bound warps on an SM
+            // (measured on C3, 1000-query batch: 64-dimension chunks 1.51 ms per batch, 32: 1.09 ms, with 2-warp blocks and
+            // the plane products sharing the staging buffer 1.01 ms; 16-dimension chunks the same)
+            size_t per_warp = (FrCfg<32>::STAGE_BYTES + (size_t)L->ld * 4 + LSH_STACK * 12 + (size_t)top_k * 8 + 15) & ~size_t(15);
+            size_t smem = per_warp * FT_WPB;
+            auto kern = forest_traverse_kernel<32>;
+            VERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)ceil_div(npt, FT_WPB), FT_WPB * 32, smem, ctx->stream>>>(f, d_q, nq, top_k, (uint32_t)cand_cap,
+                                                                                  d_cand, d_cnt, d_over);
             VERS_LAUNCH_CHECK(ctx);
         }
         uint32_t over = 0;
@@ -987,10 +1095,10 @@ extern "C" int32_t vers_lsh_search(vers_lsh* L, const float* queries, uint32_t n
             continue;
         }
         {
-            size_t per_warp = ((size_t)L->ld * 4 + (size_t)top_k * 8 + 15) & ~size_t(15);
+            size_t per_warp = (FrCfg<64>::STAGE_BYTES + (size_t)L->ld * 4 + (size_t)top_k * 8 + 15) & ~size_t(15);
             size_t smem = per_warp * 4;
-            VERS_CUDA(cudaFuncSetAttribute(forest_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            forest_rerank_kernel<<<(unsigned)ceil_div(nq, 4), 128, smem, ctx->stream>>>(
+            VERS_CUDA(cudaFuncSetAttribute(forest_rerank_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            forest_rerank_kernel<64><<<(unsigned)ceil_div(nq, 4), 128, smem, ctx->stream>>>(
                 f, d_q, nq, top_k, (uint32_t)cand_cap, d_cand, d_cnt, L->d_ids, d_ids, d_d, d_c);
             VERS_LAUNCH_CHECK(ctx);
         }

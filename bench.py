@@ -489,6 +489,28 @@ def main_ours(args):
     torch.cuda.synchronize()
     e2e_matches = bool(torch.equal(ids_dev.cpu(), h_ids))
 
+    # ---- the reference's own call shape: ONE query per call (Index::search_approximate(query, top_k), ivfflat.rs:153),
+    #      host buffers in and out.  nprobe 0 = the reference's nearest-list-plus-spill semantics (exact order everywhere),
+    #      nprobe = args.nprobe = the batch path's semantics for one query.  Latency-bound: a call streams the centroid
+    #      table and one (or nprobe) lists, 20 MB or so; reported as microseconds per call.
+    single = None
+    if ws == 1:
+        single = {}
+        one_ids = torch.empty((1, args.k), dtype=torch.int64).pin_memory()
+        one_d = torch.empty((1, args.k), dtype=torch.float32).pin_memory()
+        one_c = torch.empty((1,), dtype=torch.int32).pin_memory()
+        for name, npb in (("reference_semantics_nprobe0", 0), (f"nprobe{args.nprobe}", args.nprobe)):
+            def one(i, npb=npb):
+                _abi.check(vb.lib().vers_ivf_search(index.ivf.h, h_q.data_ptr() + (i % args.nq) * qds.ld * 4, 1, qds.ld,
+                                                    args.k, npb, one_ids.data_ptr(), one_d.data_ptr(), one_c.data_ptr()))
+            for i in range(20):
+                one(i)
+            t0 = time.perf_counter()
+            for i in range(200):
+                one(i)
+            single[name + "_us_per_call"] = (time.perf_counter() - t0) / 200 * 1e6
+        single["call"] = "vers_ivf_search(nq = 1) with host buffers, 200 different queries one after the other"
+
     spot = None
     if not args.no_spotcheck:
         try:
@@ -556,7 +578,7 @@ def main_ours(args):
                         "call": "vers_sharded_ivf_search (host buffers in and out)"},
                 "exchange": ("probe lists: peer-memory all-gather (remote stores + flags); top-k: ONE fused peer "
                              "gather+merge kernel; no NCCL call inside a step" if ws > 1 else None),
-                "peer_exchange_us": peer_us,
+                "peer_exchange_us": peer_us, "single_query": single,
                 "parity_spotcheck": spot,
                 "gpu_launches": launches, "launch_mode": "cuda_graph_replay" if graph is not None else "eager",
                 "eager_ms_per_step": eager_ms / args.steps, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,

@@ -67,6 +67,7 @@ struct FlatStreamParams {
     uint32_t k, kpad, tile_rows;
     float* part_d;         // [nq][gridDim.x][k]
     uint32_t* part_p;
+    float* dense_out;      // optional [NQ][n]: every distance is written out, nothing is selected (small-batch probe)
 };
 
 __device__ __forceinline__ bool fs_elect_one() {
@@ -210,13 +211,17 @@ __global__ void __launch_bounds__((FS_GROUPS * NH + 1) * 32, 1) flat_stream_kern
             for (int q = 0; q < NQW; ++q) {
                 float v = acc[q];
                 if (OP == OP_DOT) v = __fsub_rn(1.0f, v);  // cosine distance 1 - dot (base.rs:155)
-                fs_fold(my_d + (size_t)q * p.kpad, my_p + (size_t)q * p.kpad, p.k, v, (uint32_t)row, has_row && row < p.n, lane);
+                if (p.dense_out) {
+                    if (has_row && row < p.n) p.dense_out[(uint64_t)(half * NQW + q) * p.n + row] = v;
+                } else {
+                    fs_fold(my_d + (size_t)q * p.kpad, my_p + (size_t)q * p.kpad, p.k, v, (uint32_t)row, has_row && row < p.n, lane);
+                }
             }
         }
     }
     __syncthreads();
     // fold the groups' lists of every query into group 0's, write the CTA's partial result
-    if (warp < CONS && warp % FS_GROUPS == 0) {
+    if (!p.dense_out && warp < CONS && warp % FS_GROUPS == 0) {
         const int half = warp / FS_GROUPS;
         for (int ql = 0; ql < NQW; ++ql) {
             float* sd = list_d + ((size_t)warp * NQW + ql) * p.kpad;
@@ -294,6 +299,7 @@ int32_t flat_stream_search(vers_ctx* ctx, const float* rows, uint64_t n, uint32_
     p.tile_rows = tile_rows;
     p.part_d = sc.take<float>((size_t)NQ * grid * k);
     p.part_p = sc.take<uint32_t>((size_t)NQ * grid * k);
+    p.dense_out = nullptr;
     p.queries = d_queries;
     if (NQ != nq) {
         VERS_CUDA(cudaMemsetAsync(qpad, 0, (size_t)NQ * ld * 4, ctx->stream));
@@ -327,6 +333,55 @@ int32_t flat_stream_search(vers_ctx* ctx, const float* rows, uint64_t n, uint32_
     return launch_merge(ctx, mp);
 }
 
+// Every exact distance of nq <= 8 queries to the n rows of a table, dense_out [NQ][n] (NQ = nq rounded up to 1, 2, 4, 8;
+// rows of the padding queries are garbage), with the streaming kernel above.  qpad: [8][ld] floats of scratch.  Returns
+// VERS_ERR_UNSUPPORTED when the shape does not fit the kernel (the caller then takes the tile engine).  Caller holds
+// ctx->mu and owns the scratch.
+bool flat_stream_fits(uint32_t ld, uint32_t nq) {
+    if (nq == 0 || nq > 8) return false;
+    const uint32_t NQ = nq == 1 ? 1 : nq == 2 ? 2 : nq <= 4 ? 4 : 8;
+    const uint32_t NH = NQ >= 4 ? 4 : NQ, NQW = NQ / NH, CONS = FS_GROUPS * NH;
+    const size_t fixed = (size_t)NQ * ld * 4 + (size_t)CONS * NQW * 32 * 8 + 2 * FS_STAGES * 8 + 128;
+    return fixed + (size_t)FS_STAGES * 4 * ld * 4 <= (size_t)227 * 1024;
+}
+int32_t flat_stream_dense(vers_ctx* ctx, const float* rows, uint64_t n, uint32_t ld, const float* d_queries, uint32_t nq,
+                          float* qpad, float* dense_out, int family) {
+    if (!flat_stream_fits(ld, nq) || n == 0 || n >= 0xffffffffull || (reinterpret_cast<uintptr_t>(rows) & 15) != 0)
+        return VERS_ERR_UNSUPPORTED;
+    const uint32_t NQ = nq == 1 ? 1 : nq == 2 ? 2 : nq <= 4 ? 4 : 8;
+    const uint32_t NH = NQ >= 4 ? 4 : NQ, NQW = NQ / NH, CONS = FS_GROUPS * NH;
+    const uint32_t kpad = 32;
+    const size_t fixed = (size_t)NQ * ld * 4 + (size_t)CONS * NQW * kpad * 8 + 2 * FS_STAGES * 8 + 128;
+    const size_t budget = 227 * 1024;
+    const uint32_t tile_rows = (uint32_t)std::min<size_t>(FS_MAX_ROWS, (budget - fixed) / ((size_t)FS_STAGES * ld * 4));
+    const size_t smem = (size_t)FS_STAGES * tile_rows * ld * 4 + fixed;
+    const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div(n, tile_rows), (uint64_t)ctx->sm_count);
+    FlatStreamParams p;
+    p.rows = rows;
+    p.n = n;
+    p.ld = ld;
+    p.k = 1;
+    p.kpad = kpad;
+    p.tile_rows = tile_rows;
+    p.part_d = nullptr;
+    p.part_p = nullptr;
+    p.dense_out = dense_out;
+    p.queries = d_queries;
+    if (NQ != nq) {
+        VERS_CUDA(cudaMemsetAsync(qpad, 0, (size_t)NQ * ld * 4, ctx->stream));
+        VERS_CUDA(cudaMemcpyAsync(qpad, d_queries, (size_t)nq * ld * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        p.queries = qpad;
+    }
+    FamilyTimer ft(ctx, family);
+    switch (NQ) {
+        case 1: VERS_TRY((launch_flat_stream<1, 1>(ctx, p, VERS_METRIC_L2SQ, grid, smem))); break;
+        case 2: VERS_TRY((launch_flat_stream<1, 2>(ctx, p, VERS_METRIC_L2SQ, grid, smem))); break;
+        case 4: VERS_TRY((launch_flat_stream<1, 4>(ctx, p, VERS_METRIC_L2SQ, grid, smem))); break;
+        default: VERS_TRY((launch_flat_stream<2, 4>(ctx, p, VERS_METRIC_L2SQ, grid, smem))); break;
+    }
+    return VERS_OK;
+}
+
 constexpr int MERGE_WARPS = 4;
 
 __global__ void __launch_bounds__(MERGE_WARPS * 32) merge_topk_kernel(MergeParams p) {
@@ -353,18 +408,27 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) merge_topk_kernel(MergeParam
         end = beg + p.per_query;
     }
     const int k = (int)p.k;
+    // the next 32 entries are requested before the current ones are folded (a warp walking thousands of entries with a
+    // trip to memory per round was 0.5 ms of the one-query call); the id behind an entry is only looked up when its
+    // distance can still enter the list
+    uint32_t pp_n = 0xffffffffu;
+    float v_n = 0.f;
+    if (beg + lane < end) {
+        pp_n = p.part_p[beg + lane];
+        v_n = p.part_d[beg + lane];
+    }
     for (uint64_t e0 = beg; e0 < end; e0 += 32) {
-        uint64_t e = e0 + lane;
-        float v = 0.f;
+        const uint32_t pp = pp_n;
+        const float v = v_n;
+        pp_n = 0xffffffffu;
+        if (e0 + 32 + lane < end) {
+            pp_n = p.part_p[e0 + 32 + lane];
+            v_n = p.part_d[e0 + 32 + lane];
+        }
         uint64_t id = 0;
-        bool live = false;
-        if (e < end) {
-            uint32_t pp = p.part_p[e];
-            if (pp != 0xffffffffu) {
-                live = true;
-                v = p.part_d[e];
-                id = p.map ? p.map[pp] : p.id_base + pp;
-            }
+        bool live = pp != 0xffffffffu && !(v > sd[k - 1]);
+        if (__any_sync(FULL_MASK, live)) {
+            if (live) id = p.map ? p.map[pp] : p.id_base + pp;
         }
         while (true) {
             bool pass = live && entry_less<uint64_t>(v, id, sd[k - 1], sp[k - 1]);

@@ -61,12 +61,15 @@ struct vers_ivf {
     // cache of ivf_max_chunks_per_query (host loop over the lists): valid while seg_epoch == mc_epoch
     uint64_t seg_epoch = 1, mc_epoch = 0;
     uint32_t mc_np = 0;
-    uint64_t mc_val[2] = {0, 0};
+    uint64_t mc_val[3] = {0, 0, 0};
 };
 
 namespace vers {
 
 constexpr uint32_t LIST_CHUNK_ROWS = 4096;  // rows per work item; multiple of NarrowCfg::TA
+constexpr uint32_t LIST_CHUNK_ROWS_SMALL = 256;  // ... for batches of <= 8 queries (the reference's one-query call): a
+                                                 // 2441-row list becomes 10 items instead of one CTA's 0.4 ms walk
+constexpr uint32_t SMALL_BATCH = 8;
 // tensor-core scan: the last sixth of the lists (the work items handed out last) is cut into small items so that the
 // persistent CTAs drain together; everything before keeps whole-list items (one partial list per (query, list))
 // (measured on the bench workload: 256..2048 rows and 1/10..1/3 of the lists are all within 1 % of each other)
@@ -357,6 +360,8 @@ __global__ void __launch_bounds__(1024) group_fused_kernel(GroupParams g, uint64
 
 // ---------------------------------------------------------------- list scan (the dominant kernel)
 struct ListScanParams {
+    uint32_t chunk_rows;  // rows per work item (multiple of Cfg::TA): LIST_CHUNK_ROWS, or LIST_CHUNK_ROWS_SMALL when a
+                          // handful of queries would otherwise leave one CTA to walk a whole list
     const float* lm;
     const float* queries;
     uint32_t ld, C, k, kpad;
@@ -408,7 +413,7 @@ __global__ void __launch_bounds__(Cfg::NT, (Cfg::TILE_FLOATS * 4 > 110 * 1024) ?
         const uint32_t l = s_list;
         if (local < 0) break;
         const uint32_t len = p.seg_len[l];
-        const uint32_t nch = (len + LIST_CHUNK_ROWS - 1) / LIST_CHUNK_ROWS;
+        const uint32_t nch = (len + p.chunk_rows - 1) / p.chunk_rows;
         const uint32_t group = (uint32_t)(local / nch), chunk = (uint32_t)(local % nch);
         const uint64_t q0 = p.lq_off[l] + (uint64_t)group * Cfg::TB;
         const uint64_t m_l = p.lq_off[l + 1] - p.lq_off[l];
@@ -416,8 +421,8 @@ __global__ void __launch_bounds__(Cfg::NT, (Cfg::TILE_FLOATS * 4 > 110 * 1024) ?
         const uint64_t base_pos = p.seg_off[l];
         RowSrc A{p.lm + base_pos * p.ld, nullptr, p.ld, len};
         RowSrc B{p.queries, p.lq_query + q0, p.ld, nB};
-        const uint64_t r0 = (uint64_t)chunk * LIST_CHUNK_ROWS;
-        const uint64_t r1 = min((uint64_t)len, r0 + LIST_CHUNK_ROWS);
+        const uint64_t r0 = (uint64_t)chunk * p.chunk_rows;
+        const uint64_t r1 = min((uint64_t)len, r0 + p.chunk_rows);
         if (MODE == 0) {
             lists_init<Cfg>(list_d, list_p, p.kpad);
             for (uint64_t a0 = r0; a0 < r1; a0 += Cfg::TA) {
@@ -781,15 +786,17 @@ static uint64_t ivf_max_chunks_per_query_uncached(const vers_ivf* ivf, uint32_t 
 
 // [0]: whole-list items (LIST_CHUNK_ROWS), [1]: every list cut into TC_TAIL_CHUNK_ROWS items (upper bound of the
 // tensor-core scan's mixed chunking)
-static void ivf_max_chunks(vers_ivf* ivf, uint32_t np, uint64_t out[2]) {
+static void ivf_max_chunks(vers_ivf* ivf, uint32_t np, uint64_t out[3]) {
     if (ivf->mc_epoch != ivf->seg_epoch || ivf->mc_np != np) {
         ivf->mc_val[0] = ivf_max_chunks_per_query_uncached(ivf, np, LIST_CHUNK_ROWS);
         ivf->mc_val[1] = ivf_max_chunks_per_query_uncached(ivf, np, TC_TAIL_CHUNK_ROWS);
+        ivf->mc_val[2] = ivf_max_chunks_per_query_uncached(ivf, np, LIST_CHUNK_ROWS_SMALL);
         ivf->mc_epoch = ivf->seg_epoch;
         ivf->mc_np = np;
     }
     out[0] = ivf->mc_val[0];
     out[1] = ivf->mc_val[1];
+    out[2] = ivf->mc_val[2];
 }
 
 // ---------------------------------------------------------------- candidate pass: merge, exact rerank, certificate
@@ -1211,7 +1218,10 @@ static int32_t run_group(vers_ivf* ivf, const SearchBufs& b, uint32_t nq, uint32
     // the fused single-block kernel only for the exact redo pass, which almost always has nothing to do: ONE launch
     // that returns at once instead of seven (measured with work to do: 85 us for 32000 pairs in one block against 31 us
     // for the multi-block path, so the main grouping keeps the latter)
-    const bool fused = skip_if_zero != nullptr && ivf->C <= GROUP_FUSED_MAX_C && npairs <= GROUP_FUSED_MAX_PAIRS;
+    // ... and for a handful of queries (the reference's one-query call): a few hundred pairs, where one small launch
+    // beats seven
+    const bool fused = (skip_if_zero != nullptr || npairs <= 2048) && ivf->C <= GROUP_FUSED_MAX_C &&
+                       npairs <= GROUP_FUSED_MAX_PAIRS;
     // lq_cnt, cursor and the work counter are carved back to back: one memset (counter[1], the short flag, survives)
     if (!fused) VERS_CUDA(cudaMemsetAsync(b.lq_cnt, 0, (size_t)((char*)b.counter - (char*)b.lq_cnt) + 8, ctx->stream));
     GroupParams g;
@@ -1262,9 +1272,10 @@ static int32_t run_group(vers_ivf* ivf, const SearchBufs& b, uint32_t nq, uint32
 
 template <class Cfg, int MODE>
 static int32_t run_list_scan(vers_ivf* ivf, const SearchBufs& b, const float* d_queries, uint32_t nq, uint32_t klist,
-                             const uint32_t* skip_if_zero = nullptr) {
+                             const uint32_t* skip_if_zero = nullptr, uint32_t chunk_rows = LIST_CHUNK_ROWS) {
     vers_ctx* ctx = ivf->ctx;
     ListScanParams lp;
+    lp.chunk_rows = chunk_rows;
     lp.lm = ivf->d_lm;
     lp.queries = d_queries;
     lp.ld = ivf->ld;
@@ -1390,6 +1401,7 @@ struct RankTable {
 };
 struct ProbePlan {
     ScanPlan exact;
+    bool stream = false;  // <= 8 queries against a small table: streaming dense distances + radix select + sort
     bool tc = false;
     bool dense = false;  // tc && C small: all C keys per query are written out and selected by probe_select_kernel
     uint32_t nch = 0, chunk_rows = 0, M = 0;
@@ -1435,6 +1447,20 @@ static ProbePlan probe_plan(const vers_ctx* ctx, const RankTable& tb, uint32_t n
     pp.bytes = (pp.exact.bytes + 255) & ~size_t(255);
     pp.tc = tb.allow_tc && nq >= 32 && np <= 64 && tb.n >= 512 && tb.n >= 4ull * np && tb.ld >= TC_KC &&
             tb.n < 0x7fffffffull;
+    // the reference's one-query call (and any batch of <= 8): the tile engine leaves one CTA per 256 centroids to walk
+    // them and one warp to merge thousands of entries (0.6 ms of a 1.1 ms call); the streaming kernel writes all C exact
+    // distances in ~10 us, a radix select + a rank sort pick the np nearest in (distance, index) order
+    pp.stream = !pp.tc && nq <= SMALL_BATCH && np <= 128 && tb.n >= np && tb.n <= PROBE_DENSE_MAX_C &&
+                flat_stream_fits(tb.ld, nq);
+    if (pp.stream) {
+        ScratchCarver sc(nullptr);
+        sc.plan<float>((size_t)8 * tb.ld);
+        sc.plan<float>((size_t)8 * tb.n);
+        sc.plan<uint32_t>((size_t)nq * np);
+        sc.plan<float>((size_t)nq * np);
+        sc.plan<float>(nq);
+        pp.bytes = std::max(pp.bytes, (sc.off + 255) & ~size_t(255));
+    }
     if (pp.tc) {
         pp.M = np <= 32 ? 64 : 128;
         pp.dense = tb.n <= PROBE_DENSE_MAX_C;
@@ -1582,9 +1608,50 @@ __global__ void probe_scatter_kernel(const uint32_t* __restrict__ fail_idx, cons
 }
 
 // scratch: [0, pp.bytes) of the context arena.  out_ids / out_d: [nq][np]
+// the M selected (position, key) pairs of every query in (key, position) order -> ids and distances
+__global__ void __launch_bounds__(128) probe_sort_kernel(const uint32_t* __restrict__ cand_pos,
+                                                        const float* __restrict__ cand_key, uint32_t M, uint64_t id_base,
+                                                        uint64_t* __restrict__ out_ids, float* __restrict__ out_d,
+                                                        uint32_t* __restrict__ out_cnt) {
+    __shared__ float sk[128];
+    __shared__ uint32_t spos[128];
+    const uint32_t q = blockIdx.x, t = threadIdx.x;
+    if (t < M) {
+        sk[t] = cand_key[(uint64_t)q * M + t];
+        spos[t] = cand_pos[(uint64_t)q * M + t];
+    }
+    __syncthreads();
+    if (t < M) {
+        const float kt = sk[t];
+        const uint32_t pt = spos[t];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < M; ++j) rank += (sk[j] < kt || (sk[j] == kt && spos[j] < pt)) ? 1u : 0u;
+        out_ids[(uint64_t)q * M + rank] = id_base + pt;
+        out_d[(uint64_t)q * M + rank] = kt;
+    }
+    if (t == 0 && out_cnt) out_cnt[q] = M;
+}
+
 static int32_t probe_run(vers_ctx* ctx, const RankTable& tb, const ProbePlan& pp, const float* d_queries, uint32_t nq,
                          uint32_t np, uint64_t* out_ids, float* out_d, uint32_t* out_cnt, int family) {
     RowSrc CA{tb.rows, nullptr, tb.ld, tb.n};
+    if (pp.stream) {
+        ScratchCarver sc(ctx->scratch);
+        float* qpad = sc.take<float>((size_t)8 * tb.ld);
+        float* dense = sc.take<float>((size_t)8 * tb.n);
+        uint32_t* cpos = sc.take<uint32_t>((size_t)nq * np);
+        float* ckey = sc.take<float>((size_t)nq * np);
+        float* bound = sc.take<float>(nq);
+        const int32_t rc = flat_stream_dense(ctx, tb.rows, tb.n, tb.ld, d_queries, nq, qpad, dense, family);
+        if (rc == VERS_OK) {
+            probe_select_kernel<<<nq, 256, (size_t)tb.n * 4, ctx->stream>>>(dense, (uint32_t)tb.n, np, cpos, ckey, bound);
+            VERS_LAUNCH_CHECK(ctx);
+            probe_sort_kernel<<<nq, 128, 0, ctx->stream>>>(cpos, ckey, np, tb.id_base, out_ids, out_d, out_cnt);
+            VERS_LAUNCH_CHECK(ctx);
+            return VERS_OK;
+        }
+        if (rc != VERS_ERR_UNSUPPORTED) return rc;
+    }
     if (!pp.tc) {
         RowSrc QB{d_queries, nullptr, tb.ld, nq};
         return scan_topk_run(ctx, pp.exact, ctx->scratch, CA, QB, nq, tb.ld, np, VERS_METRIC_L2SQ, nullptr, tb.id_base,
@@ -1817,11 +1884,12 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
     const bool h16 = use_tc && ivf->mode == 4;  // 16-bit candidate copy
     if (h16) VERS_TRY(ivf_ensure_h16(ivf));
     const uint64_t npairs = (uint64_t)nq * np;
-    uint64_t mc[2];
+    uint64_t mc[3];
     ivf_max_chunks(ivf, np, mc);
-    const uint64_t max_chunks = std::max<uint64_t>((uint64_t)nq * mc[0], 1);
+    const uint32_t exact_chunk = nq <= SMALL_BATCH ? LIST_CHUNK_ROWS_SMALL : LIST_CHUNK_ROWS;  // exact-order scans
+    const uint64_t max_chunks = std::max<uint64_t>((uint64_t)nq * (nq <= SMALL_BATCH ? mc[2] : mc[0]), 1);
     size_t entries = (size_t)max_chunks * ScanCfg::NSPLIT * k;
-    if (approx) entries = std::max(entries, (size_t)max_chunks * StreamCfg::NSPLIT * M);
+    if (approx) entries = std::max(entries, (size_t)std::max<uint64_t>((uint64_t)nq * mc[0], 1) * StreamCfg::NSPLIT * M);
     if (use_tc) entries = std::max(entries, (size_t)nq * std::max<uint64_t>(mc[1], 1) * TC_PARTS * M);
 
     // the probe carves its buffers from the front of the arena, ours come after it
@@ -1878,8 +1946,8 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
         ref_plan_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, ctx->stream>>>(b.probe_ids, ivf->d_seg_len, nq, np, k,
                                                                              b.used, short_flag);
         VERS_LAUNCH_CHECK(ctx);
-        VERS_TRY(run_group(ivf, b, nq, np, b.used, nullptr, true));
-        VERS_TRY((run_list_scan<ScanCfg, 0>(ivf, b, d_queries, nq, k)));
+        VERS_TRY(run_group(ivf, b, nq, np, b.used, nullptr, true, ScanCfg::TB, exact_chunk, exact_chunk));
+        VERS_TRY((run_list_scan<ScanCfg, 0>(ivf, b, d_queries, nq, k, nullptr, exact_chunk)));
         ref_assemble_kernel<<<(unsigned)ceil_div(nq, 4), 128, (size_t)4 * k * 8, ctx->stream>>>(
             b.part_d, b.part_p, b.pair_chunk_off, b.used, ivf->d_lm_ids, nq, np, k, ScanCfg::NSPLIT, d_ids, d_d, d_cnt);
         VERS_LAUNCH_CHECK(ctx);
@@ -1928,9 +1996,9 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
     // 2b / exact mode: exact-order scan of the probed lists, merge by (distance, id)
     // (approximate path: every kernel of this pass returns at once when no query failed its certificate)
     const uint32_t* skip = approx ? reinterpret_cast<const uint32_t*>(ivf->d_stats + 4) : nullptr;
-    VERS_TRY(run_group(ivf, b, nq, np, nullptr, qmask, !approx, ScanCfg::TB, LIST_CHUNK_ROWS, LIST_CHUNK_ROWS, 0xffffffffu,
-                       nullptr, skip));
-    VERS_TRY((run_list_scan<ScanCfg, 0>(ivf, b, d_queries, nq, k, skip)));
+    VERS_TRY(run_group(ivf, b, nq, np, nullptr, qmask, !approx, ScanCfg::TB, exact_chunk, exact_chunk, 0xffffffffu, nullptr,
+                       skip));
+    VERS_TRY((run_list_scan<ScanCfg, 0>(ivf, b, d_queries, nq, k, skip, exact_chunk)));
     MergeParams mp;
     mp.part_d = b.part_d;
     mp.part_p = b.part_p;

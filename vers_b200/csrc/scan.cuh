@@ -70,6 +70,11 @@ int32_t flat_search_tc_plan_and_run(vers_ctx* ctx, const float* rows, uint64_t n
                                     uint32_t* d_cnt, bool* used_tc, int flat_path = 0, float** row_tiles_io = nullptr);
 int32_t launch_rownorm(vers_ctx* ctx, const float* rows, uint32_t ld, uint64_t n, float* norm, uint32_t* nmax_bits);
 
+// small-batch streaming scan (flat.cu): every exact l2sq distance of nq <= 8 queries to a row table, dense [NQ][n]
+bool flat_stream_fits(uint32_t ld, uint32_t nq);
+int32_t flat_stream_dense(vers_ctx* ctx, const float* rows, uint64_t n, uint32_t ld, const float* d_queries, uint32_t nq,
+                          float* qpad, float* dense_out, int family);
+
 // exclusive scan of n uint32 -> uint64 out[n+1] (single block; n up to a few million is fine)
 int32_t launch_exclusive_scan(vers_ctx* ctx, const uint32_t* d_in, uint64_t n, uint64_t* d_out,
                               const uint32_t* skip_if_zero = nullptr);

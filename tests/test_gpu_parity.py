@@ -711,6 +711,11 @@ def test_ivf_add_then_search(vb, vo, ctx):
     all_assign = np.array(all_assign, np.uint64)
     assert len(idx) == n + 300
     assert np.array_equal(idx.assignments, all_assign)
+    bad = extra[0].copy()
+    bad[3] = np.nan  # partial_cmp(..).unwrap() panics on the NaN distance (ivfflat.rs:207): nothing may change
+    with pytest.raises(vb.VersPanic):
+        idx.add(bad, 0)
+    assert len(idx) == n + 300 and np.array_equal(idx.assignments, all_assign)
     off, lr = vo.ivf_lists(all_assign, C)
     q = data(vo, 50, dim, seed=2)
     for nprobe in (0, 3):

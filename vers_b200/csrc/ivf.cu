@@ -2351,25 +2351,33 @@ extern "C" int32_t vers_ivf_add(vers_ivf* ivf, const float* embedding, uint64_t 
     vers_ctx* ctx = ivf->ctx;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     VERS_CUDA(cudaSetDevice(ctx->device));
-    float* d_row = nullptr;
-    VERS_TRY(upload_queries(ctx, embedding, 1, ivf->dim, ivf->dim, ivf->ld, &d_row));
-    uint64_t* d_best = nullptr;
-    float* d_bd = nullptr;
+    // nearest centroid, first minimum on ties (min_by, ivfflat.rs:201-207) == top-1 by (d, centroid index): the same
+    // probe as a one-query search (staging from the context's arenas: no allocation per add)
+    const RankTable ctab = centroid_table(ivf);
+    const ProbePlan pplan = probe_plan(ctx, ctab, 1, 1);
+    VERS_TRY(scratch_reserve(ctx, pplan.bytes + 256));
+    VERS_TRY(io_reserve(ctx, (size_t)ivf->ld * 4 + 512));
+    float* d_row = reinterpret_cast<float*>(ctx->io);
+    uint64_t* d_best = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(ctx->io) + (((size_t)ivf->ld * 4 + 255) & ~size_t(255)));
+    float* d_bd = reinterpret_cast<float*>(d_best + 1);
     int32_t rc = VERS_OK;
-    if (cudaMalloc(&d_best, 8) != cudaSuccess || cudaMalloc(&d_bd, 4) != cudaSuccess)
-        rc = fail(VERS_ERR_NOMEM, "ivf_add: cudaMalloc");
     uint64_t best = 0;
-    if (rc == VERS_OK) {
-        // nearest centroid, first minimum on ties (min_by, ivfflat.rs:201-207) == top-1 by (d, centroid index)
-        RowSrc CA{ivf->d_cents, nullptr, ivf->ld, ivf->C};
-        RowSrc QB{d_row, nullptr, ivf->ld, 1};
-        rc = scan_topk_dev(ctx, CA, QB, 1, ivf->ld, 1, VERS_METRIC_L2SQ, nullptr, 0, d_best, d_bd, nullptr, KF_PROBE);
+    float bd = 0.0f;
+    {
+        std::vector<float> row(ivf->ld, 0.0f);
+        memcpy(row.data(), embedding, (size_t)ivf->dim * 4);
+        cudaError_t e = cudaMemcpyAsync(d_row, row.data(), (size_t)ivf->ld * 4, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // `row` goes out of scope
+        if (e != cudaSuccess) rc = fail(VERS_ERR_CUDA, "ivf_add: %s", cudaGetErrorString(e));
     }
+    if (rc == VERS_OK) rc = probe_run(ctx, ctab, pplan, d_row, 1, 1, d_best, d_bd, nullptr, KF_PROBE);
     if (rc == VERS_OK) {
         cudaError_t e = cudaMemcpyAsync(&best, d_best, 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&bd, d_bd, 4, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = fail(VERS_ERR_CUDA, "ivf_add: %s", cudaGetErrorString(e));
     }
+    if (rc == VERS_OK && bd != bd) best = ivf->C;  // a NaN distance: the select kernel cannot order it
     if (rc == VERS_OK && best >= ivf->C)  // every distance compared false (NaN / inf - inf in the embedding)
         rc = fail(VERS_ERR_PANIC, "ivf_add: a distance is NaN (partial_cmp(..).unwrap() panics, ivfflat.rs:207)");
     if (rc == VERS_OK) {
@@ -2415,9 +2423,6 @@ extern "C" int32_t vers_ivf_add(vers_ivf* ivf, const float* embedding, uint64_t 
             }
         }
     }
-    cudaFree(d_row);
-    cudaFree(d_best);
-    cudaFree(d_bd);
     return rc;
 }
 

@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(128)
 
 // one warp per tree: the leaf a new row lands in (insert, lsh.rs:225-236)
 __global__ void forest_descend_kernel(ForestDev f, const float* __restrict__ row, uint32_t* __restrict__ leaf_node) {
-    extern __shared__ __align__(16) float dsm[];
+    extern __shared__ __align__(16) float dsm[];  // the row [ld], then the plane products [ld]
     const int lane = threadIdx.x & 31;
     const uint32_t t = blockIdx.x;
     for (uint32_t i = lane; i < f.ld; i += 32) dsm[i] = row[i];
@@ -550,7 +550,7 @@ __global__ void forest_descend_kernel(ForestDev f, const float* __restrict__ row
     uint32_t node = 0;
     while (f.kind[nb + node] == 0) {
         uint32_t g = nb + node;
-        bool above = plane_bit(f.planes + (uint64_t)f.plane[g] * f.ld, f.consts[f.plane[g]], dsm, f.dim, lane);
+        bool above = plane_bit(f.planes + (uint64_t)f.plane[g] * f.ld, f.consts[f.plane[g]], dsm, f.dim, lane, dsm + f.ld, f.ld);
         node = above ? f.right[g] : f.left[g];
     }
     if (lane == 0) leaf_node[t] = node;
@@ -1134,20 +1134,27 @@ extern "C" int32_t vers_lsh_add(vers_lsh* L, const float* embedding, uint64_t ve
     const uint64_t new_row = L->n;
     L->n += 1;
     L->ids.push_back(vec_id);
-    L->ids_dirty = true;
+    // the device mirrors follow in place (one id, one leaf length per tree): re-uploading ten megabytes of node arrays
+    // and ids after every add was most of a 1.6 ms call
+    if (!L->ids_dirty && L->d_ids && L->ids.size() <= L->ids_cap)
+        VERS_CUDA(cudaMemcpyAsync(L->d_ids + (L->ids.size() - 1), &L->ids.back(), 8, cudaMemcpyHostToDevice, s));
+    else
+        L->ids_dirty = true;
     if (L->num_trees == 0) return VERS_OK;
     VERS_TRY(sync_device_mirror(L));
     const uint32_t member = (uint32_t)vec_id;
-    uint32_t* d_leaf = nullptr;
-    VERS_CUDA(cudaMalloc(&d_leaf, (size_t)L->num_trees * 4));
+    VERS_TRY(io_reserve(ctx, (size_t)L->num_trees * 4 + 256));
+    uint32_t* d_leaf = reinterpret_cast<uint32_t*>(ctx->io);
     ForestDev f = forest_dev(L);
-    forest_descend_kernel<<<L->num_trees, 32, (size_t)L->ld * 4, s>>>(f, L->d_values + new_row * L->ld, d_leaf);
+    forest_descend_kernel<<<L->num_trees, 32, (size_t)L->ld * 8, s>>>(f, L->d_values + new_row * L->ld, d_leaf);
     ctx->launches += 1;
     std::vector<uint32_t> leaf(L->num_trees);
     cudaError_t e = cudaMemcpyAsync(leaf.data(), d_leaf, (size_t)L->num_trees * 4, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    cudaFree(d_leaf);
     if (e != cudaSuccess) return fail(VERS_ERR_CUDA, "lsh_add: %s", cudaGetErrorString(e));
+    std::vector<uint32_t> new_len(L->num_trees, 0);  // staging of the in-place leaf-length updates (alive until the sync)
+    uint64_t tree_base = 0;
+    const bool mirror_clean = !L->nodes_dirty;
     std::vector<BuildRoot> splits;
     std::vector<uint32_t> split_members;
     for (uint32_t t = 0; t < L->num_trees; ++t) {
@@ -1167,11 +1174,16 @@ extern "C" int32_t vers_lsh_add(vers_lsh* L, const float* embedding, uint64_t ve
         } else {
             VERS_CUDA(cudaMemcpyAsync(L->d_leaf_items + (uint64_t)T.slot[node] * L->slot_cap + len, &member, 4,
                                       cudaMemcpyHostToDevice, s));
-            VERS_CUDA(cudaStreamSynchronize(s));
             T.leaf_len[node] = len + 1;
-            L->nodes_dirty = true;
+            new_len[t] = len + 1;
+            if (mirror_clean)
+                VERS_CUDA(cudaMemcpyAsync(L->d_leaf_len + tree_base + node, &new_len[t], 4, cudaMemcpyHostToDevice, s));
+            else
+                L->nodes_dirty = true;
         }
+        tree_base += T.kind.size();
     }
+    VERS_CUDA(cudaStreamSynchronize(s));
     if (!splits.empty()) {
         uint32_t *d_a = nullptr, *d_b = nullptr;
         size_t tot = split_members.size();

@@ -301,7 +301,8 @@ def test_kmeans_chained_shards_reproduce_global_order(vb, vo, ctx):
 
 
 @pytest.mark.parametrize("n,dim,nq,k", [(50000, 300, 100, 10), (20000, 768, 33, 10), (70000, 128, 257, 1),
-                                        (6000, 96, 64, 37), (150000, 64, 40, 64)])
+                                        (6000, 96, 64, 37), (150000, 64, 40, 64), (30000, 300, 20, 10),
+                                        (9000, 100, 9, 16), (200000, 48, 32, 3)])
 def test_flat_search_tensor_core_path_bit_exact(vb, vo, ctx, n, dim, nq, k):
     """large batches take tensor-core candidate keys -> exact rerank -> certificate (-> exact redo): same ids and
     distance bits as search_exhaustive, and the same as the exact-order engine (mode 1)"""
@@ -313,7 +314,8 @@ def test_flat_search_tensor_core_path_bit_exact(vb, vo, ctx, n, dim, nq, k):
     oi, od, oc = vo.exhaustive(rows, q, k, 0, id_base=77)
     assert np.array_equal(cnt, oc) and np.array_equal(ids, oi) and np.array_equal(bits(d), bits(od))
     # batches of >= 96 queries over rows of <= 320 floats with k <= 16 run tc_flat_kernel (ONE tf32 MMA per K step:
-    # candidate values carry the tf32 rounding of both operands); the others the split-precision list-scan kernel
+    # candidate values carry the tf32 rounding of both operands); the others (from 9 queries on) the split-precision
+    # list-scan kernel
     single_tf32 = nq >= 96 and dim <= 320 and k <= 16 and n >= 4096
     assert st["reranked"] > 0 and st["uncertified_queries"] <= nq // 4
     assert st["max_candidate_error"] < (2e-3 if single_tf32 else 2e-5)
@@ -329,10 +331,13 @@ def test_flat_search_tensor_core_path_bit_exact(vb, vo, ctx, n, dim, nq, k):
 
 @pytest.mark.parametrize("n,dim,nq,k,normalize", [(100000, 300, 1000, 10, True), (40000, 128, 130, 16, True),
                                                   (5000, 64, 96, 5, False), (9000, 36, 200, 1, True),
-                                                  (4100, 320, 128, 10, False), (33333, 100, 257, 10, True)])
+                                                  (4100, 320, 128, 10, False), (33333, 100, 257, 10, True),
+                                                  (9000, 300, 40, 10, True), (12000, 64, 33, 5, False),
+                                                  (20000, 128, 95, 16, True)])
 def test_flat_search_query_block_kernel_bit_exact(vb, vo, ctx, n, dim, nq, k, normalize):
     """tc_flat_kernel: 128 queries resident in tensor memory, the table streamed in 64-row tiles once per query block;
-    last query block partly empty, last slice / last tile ragged, K chunks 2..10, unnormalised rows"""
+    last query block partly empty, last slice / last tile ragged, K chunks 2..10, unnormalised rows; batches below 96
+    queries take the list-scan style kernel with 32 candidates and the shared bound (same statistics)"""
     rows = data(vo, n, dim, n_centers=50, normalize=normalize)
     q = data(vo, nq, dim, seed=2, n_centers=50, normalize=normalize)
     q[3] = rows[n - 1]  # the very last row of the table is its own nearest neighbour

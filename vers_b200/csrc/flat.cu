@@ -767,7 +767,7 @@ using namespace vers;
 static int32_t flat_search_dev_locked(vers_dataset* ds, const float* d_queries, uint32_t nq, uint32_t top_k,
                                       uint32_t metric, uint64_t* d_ids, float* d_dists, uint32_t* d_counts) {
     vers_ctx* ctx = ds->ctx;
-    if (metric == VERS_METRIC_L2SQ && ds->flat_mode != 1 && nq >= 32 && top_k >= 1 && top_k <= 64) {
+    if (metric == VERS_METRIC_L2SQ && ds->flat_mode != 1 && nq >= tc_min_batch() && top_k >= 1 && top_k <= 64) {
         // large batches: tensor-core candidate keys -> exact-order rerank -> certificate -> exact redo (ivf.cu)
         if (!ds->d_norm) {
             // all or nothing; ||row||^2 padded with +inf up to a multiple of 64 rows (tc_flat_kernel reads whole tiles)

@@ -42,7 +42,7 @@ struct TcFlatParams {
     const float* row_norm;  // [round_up(n, 64)] ||x||^2 (any order), +inf past n
     float* part_d;          // [nq][nslices][32]
     uint32_t* part_p;
-    uint32_t* qtau;         // [nq] order-preserving encoding of the query's shared bound (TAU_INF at launch)
+    uint32_t* qtau;         // [nq][4] order-preserving encoding of the query's shared bound slots (TAU_INF at launch)
 };
 
 struct FtSmem {
@@ -211,8 +211,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
         const uint32_t tid = lane_group * 32 + lane;  // query of the block == TMEM lane
         const float INF = __int_as_float(0x7f800000);
         uint64_t t = 0;
-        // merges the queue of thread `who` (c entries) into its list; returns the new 32nd key (+inf while not full)
-        auto flush = [&](uint32_t who, uint32_t c) -> float {
+        // merges the queue of thread `who` (c entries) into its list; returns the new (32nd key, 8th key), +inf while
+        // the list holds fewer entries
+        auto flush = [&](uint32_t who, uint32_t c) -> float2 {
             const uint32_t tq = lane_group * 32 + who;
             __syncwarp();
             float d = (uint32_t)lane < c ? sm.qkey[lane * FT_M + tq] : INF;
@@ -237,9 +238,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
             sm.lkey[lane * FT_M + tq] = ld_;
             sm.lpos[lane * FT_M + tq] = lr_;
             __syncwarp();
-            const float last_d = __shfl_sync(FULL_MASK, ld_, 31);
-            const uint32_t last_p = __shfl_sync(FULL_MASK, lr_, 31);
-            return last_p != 0xffffffffu ? last_d : INF;
+            const float last_d = __shfl_sync(FULL_MASK, ld_, 31), d8 = __shfl_sync(FULL_MASK, ld_, TC_SLOT_RANK - 1);
+            const uint32_t last_p = __shfl_sync(FULL_MASK, lr_, 31), p8 = __shfl_sync(FULL_MASK, lr_, TC_SLOT_RANK - 1);
+            return make_float2(last_p != 0xffffffffu ? last_d : INF, p8 != 0xffffffffu ? d8 : INF);
         };
         for (uint64_t it = blockIdx.x; it < nitems; it += gridDim.x) {
             uint64_t r0, r1;
@@ -253,8 +254,11 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
                 sm.lpos[e * FT_M + tid] = 0xffffffffu;
             }
             uint32_t qcnt = 0;
-            float thr_own = INF;
-            float tg = qlive ? tau_decode(__ldcg(p.qtau + q)) : -INF;  // dead query rows never insert
+            float thr_own = INF, pub_own = INF;
+            // shared bound: 4 slots per query, slot = slice mod 4 holds the smallest 8th key of any list of those slices;
+            // 4 x 8 distinct rows lie at or below the largest slot (same argument as TcScanParams::qtau, ivf_tc.cuh)
+            uint32_t* my_slot = p.qtau + 4 * (uint64_t)q + (uint32_t)((it / p.nqb) & 3u);
+            float tg = qlive ? tau_decode(tau_shared_bits(p.qtau, q)) : -INF;  // dead query rows never insert
             for (uint64_t r = r0; r < r1; r += FT_N, ++t) {
                 const uint32_t buf = (uint32_t)(t & 1), tph = (uint32_t)((t >> 1) & 1);
                 tc::mbar_wait(&sm.nbar[t & 3], (uint32_t)((t >> 2) & 1));
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
                 tc::fence_before_thread_sync();
                 __syncwarp();  // also the reconvergence point of the divergent selection below: tcgen05.ld is .aligned
                 tc::mbar_arrive(&sm.tempty[buf]);  // per lane: also releases this lane's reads of the norm ring
-                if ((t & 3) == 3 && qlive) tg = fminf(tg, tau_decode(__ldcg(p.qtau + q)));
+                if ((t & 3) == 3 && qlive) tg = fminf(tg, tau_decode(tau_shared_bits(p.qtau, q)));
                 const float* nr = sm.nrm + (t & 3) * FT_N;
                 float qm[16];
 #pragma unroll
@@ -323,11 +327,14 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
                     unsigned fm = __ballot_sync(FULL_MASK, qcnt == FT_QCAP);
                     while (fm) {  // warp-uniform: merge every full queue
                         const uint32_t who = (uint32_t)__ffs(fm) - 1;
-                        const float tau = flush(who, FT_QCAP);
+                        const float2 f = flush(who, FT_QCAP);
                         if ((uint32_t)lane == who) {
                             qcnt = 0;
-                            thr_own = tau;
-                            if (tau < INF) atomicMin(p.qtau + q, tau_encode(tau));
+                            thr_own = f.x;
+                            if (f.y < pub_own) {
+                                atomicMin(my_slot, tau_encode(f.y));
+                                pub_own = f.y;
+                            }
                             thr = fminf(thr_own, tg);
                         }
                         fm &= fm - 1;
@@ -340,10 +347,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
                 while (fm) {
                     const uint32_t who = (uint32_t)__ffs(fm) - 1;
                     const uint32_t c = __shfl_sync(FULL_MASK, qcnt, who);
-                    const float tau = flush(who, c);
+                    const float2 f = flush(who, c);
                     if ((uint32_t)lane == who) {
                         qcnt = 0;
-                        if (tau < INF) atomicMin(p.qtau + q, tau_encode(tau));
+                        if (f.y < pub_own) atomicMin(my_slot, tau_encode(f.y));
                     }
                     fm &= fm - 1;
                 }

@@ -146,7 +146,7 @@ struct GroupParams {
     uint32_t nq, np, C;
     uint32_t tb;          // queries per work-item group (8 for the SIMT scans, 32 for the tensor-core scan)
     uint32_t chunk_rows, chunk_rows_tail, tail_list0;  // rows per work item: lists >= tail_list0 use chunk_rows_tail
-    uint32_t* qtau;       // optional [nq]: per-query shared bound of the tensor-core scan, reset here
+    uint32_t* qtau;       // optional [nq][4]: per-query shared bound (4 slots) of the tensor-core scan, reset here
     const uint32_t* skip_if_zero;  // optional: the whole pass is a no-op when this device word is 0 (no query to redo)
     uint32_t* lq_cnt;     // [C]   queries per list
     uint32_t* pair_nch;   // [nq*np] chunks of the pair's list (0 for inactive pairs / empty lists)
@@ -163,7 +163,8 @@ __global__ void group_count_kernel(GroupParams g) {
     uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
     if (pi >= g.nq * g.np) return;
     uint32_t q = pi / g.np, s = pi % g.np;
-    if (g.qtau && pi < g.nq) g.qtau[pi] = 0xff800000u;  // TAU_INF (ivf_tc.cuh): +inf in the ordered encoding
+    if (g.qtau && pi < g.nq)  // TAU_INF (ivf_tc.cuh): +inf in the ordered encoding
+        reinterpret_cast<uint4*>(g.qtau)[pi] = make_uint4(0xff800000u, 0xff800000u, 0xff800000u, 0xff800000u);
     uint32_t nch = 0;
     if ((!g.used || s < g.used[q]) && (!g.qmask || g.qmask[q] != 0)) {
         uint32_t l = (uint32_t)g.probe_ids[pi];
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(1024) group_fused_kernel(GroupParams g, uint64
     const uint32_t tid = threadIdx.x, npairs = g.nq * g.np;
     for (uint32_t l = tid; l < g.C; l += 1024) s_cnt[l] = 0;
     if (g.qtau)
-        for (uint32_t q = tid; q < g.nq; q += 1024) g.qtau[q] = 0xff800000u;  // TAU_INF (ivf_tc.cuh)
+        for (uint32_t q = tid; q < 4 * g.nq; q += 1024) g.qtau[q] = 0xff800000u;  // TAU_INF (ivf_tc.cuh)
     if (tid == 0) *work_counter = 0ull;
     __syncthreads();
     // 1. chunks of every active pair's list, queries per list (unrolled: the loads of 8 pairs are in flight together)
@@ -830,18 +831,20 @@ __device__ __forceinline__ void cm_merge_asc(float& d, uint32_t& p, int lane) { 
     }
 }
 
-// one BLOCK (4 warps) per query: each warp folds every 4th group of runs into its own top-M, then warp 0 folds the
-// other three warps' sorted results (handed over through shared memory) into the final list
-template <int R>
-__global__ void __launch_bounds__(128)
+// one BLOCK (W warps) per query: each warp folds every W-th group of runs into its own top-M, then warp 0 folds the
+// other warps' sorted results (handed over through shared memory) into the final list.  W = 4 for the inverted-list
+// scan (~100 runs per query, 1000 queries), 16 when a few queries each own thousands of runs (a table scanned in
+// hundreds of work items: the walk is a chain of dependent trips to the partial lists, so more warps, not more bytes)
+template <int R, int W>
+__global__ void __launch_bounds__(32 * W)
     cand_merge_kernel(const float* __restrict__ part_d, const uint32_t* __restrict__ part_p,
                       const uint64_t* __restrict__ pair_chunk_off, uint32_t nq, uint32_t np, uint32_t nsplit,
                       uint32_t* __restrict__ cand_pos, float* __restrict__ cand_key, float* __restrict__ cand_bound) {
     constexpr uint32_t M = 32 * R;
     constexpr int PF = 4;  // runs fetched together
-    __shared__ float xd[3][R][32];
-    __shared__ uint32_t xp[3][R][32];
-    __shared__ float xfull[3];
+    __shared__ float xd[W - 1][R][32];
+    __shared__ uint32_t xp[W - 1][R][32];
+    __shared__ float xfull[W - 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x;
     const float INF = __int_as_float(0x7f800000);
@@ -896,8 +899,8 @@ __global__ void __launch_bounds__(128)
     };
     uint64_t e0 = beg + (uint64_t)warp * 32 * PF;
     if (e0 < end) load(e0, fd, fp);
-    for (; e0 < end; e0 += 4 * 32 * PF) {
-        const uint64_t e1 = e0 + 4 * 32 * PF;
+    for (; e0 < end; e0 += W * 32 * PF) {
+        const uint64_t e1 = e0 + W * 32 * PF;
         if (e1 < end) load(e1, nd, npp);
 #pragma unroll
         for (int f = 0; f < PF; ++f) {
@@ -922,7 +925,7 @@ __global__ void __launch_bounds__(128)
     }
     __syncthreads();
     if (warp > 0) return;
-    for (int w = 0; w < 3; ++w) {
+    for (int w = 0; w < W - 1; ++w) {
         tfull = fminf(tfull, xfull[w]);
 #pragma unroll
         for (int r = 0; r < R; ++r) fold(xd[w][r][lane], xp[w][r][lane]);  // sorted runs of 32, ascending overall
@@ -943,17 +946,20 @@ __global__ void __launch_bounds__(128)
 
 static int32_t launch_cand_merge(vers_ctx* ctx, uint32_t M, const float* part_d, const uint32_t* part_p,
                                  const uint64_t* pair_chunk_off, uint32_t nq, uint32_t np, uint32_t nsplit,
-                                 uint32_t* cand_pos, float* cand_key, float* cand_bound) {
+                                 uint32_t* cand_pos, float* cand_key, float* cand_bound, uint64_t runs_per_query = 0) {
     const unsigned grid = nq;
-    if (M == 32)
-        cand_merge_kernel<1><<<grid, 128, 0, ctx->stream>>>(part_d, part_p, pair_chunk_off, nq, np, nsplit, cand_pos,
-                                                           cand_key, cand_bound);
+    if (M == 32 && runs_per_query >= 256)
+        cand_merge_kernel<1, 16><<<grid, 512, 0, ctx->stream>>>(part_d, part_p, pair_chunk_off, nq, np, nsplit, cand_pos,
+                                                               cand_key, cand_bound);
+    else if (M == 32)
+        cand_merge_kernel<1, 4><<<grid, 128, 0, ctx->stream>>>(part_d, part_p, pair_chunk_off, nq, np, nsplit, cand_pos,
+                                                              cand_key, cand_bound);
     else if (M == 64)
-        cand_merge_kernel<2><<<grid, 128, 0, ctx->stream>>>(part_d, part_p, pair_chunk_off, nq, np, nsplit, cand_pos,
-                                                           cand_key, cand_bound);
+        cand_merge_kernel<2, 4><<<grid, 128, 0, ctx->stream>>>(part_d, part_p, pair_chunk_off, nq, np, nsplit, cand_pos,
+                                                              cand_key, cand_bound);
     else if (M == 128)
-        cand_merge_kernel<4><<<grid, 128, 0, ctx->stream>>>(part_d, part_p, pair_chunk_off, nq, np, nsplit, cand_pos,
-                                                           cand_key, cand_bound);
+        cand_merge_kernel<4, 4><<<grid, 128, 0, ctx->stream>>>(part_d, part_p, pair_chunk_off, nq, np, nsplit, cand_pos,
+                                                              cand_key, cand_bound);
     else
         return fail(VERS_ERR_ARG, "cand_merge: unsupported candidate count %u", M);
     VERS_LAUNCH_CHECK(ctx);
@@ -1205,7 +1211,7 @@ struct SearchBufs {
     float* gq;     // [npairs + 32][ld] queries regrouped by list (tensor-core scan only), tf32 hi part
     float* gq_lo;  // [npairs + 32][ld] their tf32 lo part (split-precision scan)
     float* cand_key;  // [nq][M] candidate keys (observed-error statistic)
-    uint32_t* qtau;   // [nq] shared per-query bound of the tensor-core scan
+    uint32_t* qtau;   // [nq][4] shared per-query bound of the tensor-core scan
 };
 
 static int32_t run_group(vers_ivf* ivf, const SearchBufs& b, uint32_t nq, uint32_t np, const uint32_t* used,
@@ -1410,7 +1416,7 @@ struct ProbePlan {
 
 struct ProbeBufs {
     uint64_t *seg_off, *lq_off, *item_off, *pair_chunk_off;
-    uint32_t *seg_len, *lq_pair, *cand_pos, *fail, *fail_idx, *n_fail, *part_p;
+    uint32_t *seg_len, *lq_pair, *cand_pos, *fail, *fail_idx, *n_fail, *part_p, *qtau;
     unsigned long long *counter, *pstats;
     float *gq, *gq_lo, *part_d, *cand_key, *bound, *tmp_d, *dense;
     uint64_t* tmp_ids;
@@ -1439,13 +1445,14 @@ static void probe_carve(ScratchCarver& sc, const RankTable& tb, const ProbePlan&
     b.fail_idx = sc.take<uint32_t>(nq);
     b.tmp_ids = sc.take<uint64_t>((size_t)nq * np);
     b.tmp_d = sc.take<float>((size_t)nq * np);
+    b.qtau = sc.take<uint32_t>((size_t)4 * nq);
 }
 
 static ProbePlan probe_plan(const vers_ctx* ctx, const RankTable& tb, uint32_t nq, uint32_t np) {
     ProbePlan pp;
     pp.exact = scan_topk_plan(ctx, tb.n, nq, np);
     pp.bytes = (pp.exact.bytes + 255) & ~size_t(255);
-    pp.tc = tb.allow_tc && nq >= 32 && np <= 64 && tb.n >= 512 && tb.n >= 4ull * np && tb.ld >= TC_KC &&
+    pp.tc = tb.allow_tc && nq >= tc_min_batch() && np <= 64 && tb.n >= 512 && tb.n >= 4ull * np && tb.ld >= TC_KC &&
             tb.n < 0x7fffffffull;
     // the reference's one-query call (and any batch of <= 8): the tile engine leaves one CTA per 256 centroids to walk
     // them and one warp to merge thousands of entries (0.6 ms of a 1.1 ms call); the streaming kernel writes all C exact
@@ -1462,12 +1469,17 @@ static ProbePlan probe_plan(const vers_ctx* ctx, const RankTable& tb, uint32_t n
         pp.bytes = std::max(pp.bytes, (sc.off + 255) & ~size_t(255));
     }
     if (pp.tc) {
-        pp.M = np <= 32 ? 64 : 128;
         pp.dense = tb.n <= PROBE_DENSE_MAX_C;
+        // large tables: 32 candidates certify up to 16 requested entries (the inverted-list scan's rule), and 32 is what
+        // one epilogue list holds: only then can the work items of a query share one running bound.  The dense probe
+        // selects from all keys anyway and keeps 64: k-means leaves tied (zero-vector) centroids behind
+        // (ivfflat.rs:63-67), and 8 requested lists must not fail their certificate on 30 of those
+        pp.M = (!pp.dense && np <= 16) ? 32 : np <= 32 ? 64 : 128;
         const uint32_t ngroups = (nq + TC_NQ - 1) / TC_NQ;
-        // small tables (the centroids): one wave of work items; large ones (a dataset): ~8 items per SM, and a chunk
-        // must keep its row offsets in 16 bits
-        const uint32_t target = tb.n <= 65536 ? (uint32_t)ctx->sm_count : (uint32_t)ctx->sm_count * 8;
+        // small tables (the centroids): one wave of work items; large ones (a dataset): ~2 items per SM (every item
+        // costs a pipeline fill and, per query, 4 partial lists the merge has to walk: 1M x 300, 32 queries with 8 items
+        // per SM: scan 0.51 ms + merge 0.20 ms), and a chunk must keep its row offsets in 16 bits
+        const uint32_t target = tb.n <= 65536 ? (uint32_t)ctx->sm_count : (uint32_t)ctx->sm_count * 2;
         uint64_t nch = std::max<uint32_t>(1, target / ngroups);
         nch = std::min<uint64_t>(nch, (tb.n + TC_M - 1) / TC_M);
         uint64_t cr = round_up((uint32_t)((tb.n + nch - 1) / nch), (uint32_t)TC_M);
@@ -1581,7 +1593,8 @@ __global__ void __launch_bounds__(256)
 
 // work-item tables of the probe: one "list" (the centroid table) probed by every query, nch chunks
 __global__ void probe_tables_kernel(uint32_t C, uint32_t nq, uint32_t nch, uint64_t* seg_off, uint32_t* seg_len,
-                                    uint64_t* lq_off, uint64_t* item_off, uint64_t* pair_chunk_off, uint32_t* lq_pair) {
+                                    uint64_t* lq_off, uint64_t* item_off, uint64_t* pair_chunk_off, uint32_t* lq_pair,
+                                    uint32_t* qtau) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         seg_off[0] = 0;
@@ -1592,7 +1605,10 @@ __global__ void probe_tables_kernel(uint32_t C, uint32_t nq, uint32_t nch, uint6
         item_off[1] = (uint64_t)((nq + TC_NQ - 1) / TC_NQ) * nch;
     }
     if (i <= nq) pair_chunk_off[i] = (uint64_t)i * nch;
-    if (i < nq) lq_pair[i] = i;
+    if (i < nq) {
+        lq_pair[i] = i;
+        reinterpret_cast<uint4*>(qtau)[i] = make_uint4(TAU_INF, TAU_INF, TAU_INF, TAU_INF);
+    }
 }
 
 __global__ void probe_scatter_kernel(const uint32_t* __restrict__ fail_idx, const uint32_t* __restrict__ n_fail,
@@ -1664,7 +1680,7 @@ static int32_t probe_run(vers_ctx* ctx, const RankTable& tb, const ProbePlan& pp
     FamilyTimer ft(ctx, family);
     VERS_CUDA(cudaMemsetAsync(b.counter, 0, (size_t)((char*)b.n_fail - (char*)b.counter) + 4, ctx->stream));  // + pstats
     probe_tables_kernel<<<(unsigned)ceil_div(nq + 1, 256), 256, 0, ctx->stream>>>(
-        (uint32_t)tb.n, nq, pp.nch, b.seg_off, b.seg_len, b.lq_off, b.item_off, b.pair_chunk_off, b.lq_pair);
+        (uint32_t)tb.n, nq, pp.nch, b.seg_off, b.seg_len, b.lq_off, b.item_off, b.pair_chunk_off, b.lq_pair, b.qtau);
     VERS_LAUNCH_CHECK(ctx);
     gather_queries_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_queries, nullptr, b.lq_off, 1, tb.ld, b.gq,
                                                                      b.gq_lo, 1);
@@ -1685,8 +1701,11 @@ static int32_t probe_run(vers_ctx* ctx, const RankTable& tb, const ProbePlan& pp
     tp.part_d = b.part_d;
     tp.part_p = b.part_p;
     tp.counter = b.counter;
-    tp.qtau = nullptr;  // M = 64 > 32 candidates are kept: no shared bound
-    tp.lq_query = nullptr;
+    // 32 candidates: every work item of a query prunes with the query's running 32nd-best key (without it each of the
+    // ~8 items per SM restarts from +inf and the selection, not the stream, bounds the kernel: 1M x 300, 32 queries
+    // 1.32 ms -> see profiles/README.md).  More than 32 candidates are merged from 32-entry lists: no shared bound.
+    tp.qtau = (pp.M == 32 && !pp.dense) ? b.qtau : nullptr;
+    tp.lq_query = b.lq_pair;  // grouped pair i is query i
     tp.dense_out = pp.dense ? b.dense : nullptr;
     tp.dense_ld = tb.n;
     tp.key_scale = -2.0f;
@@ -1697,7 +1716,7 @@ static int32_t probe_run(vers_ctx* ctx, const RankTable& tb, const ProbePlan& pp
         VERS_LAUNCH_CHECK(ctx);
     } else {
         VERS_TRY(launch_cand_merge(ctx, pp.M, b.part_d, b.part_p, b.pair_chunk_off, nq, 1, TC_PARTS, b.cand_pos,
-                                   b.cand_key, b.bound));
+                                   b.cand_key, b.bound, (uint64_t)pp.nch * TC_PARTS));
     }
     VERS_TRY(launch_rerank(ctx, pp.M, tb.rows, nullptr, tb.id_base, tb.ld, d_queries, nq, np, b.cand_pos, b.bound,
                            tb.nmax_bits, b.cand_key, 2, out_ids, out_d, out_cnt, b.fail, tb.stats, b.fail_idx, b.n_fail));
@@ -1725,7 +1744,7 @@ struct QblockBufs {
     uint64_t *pair_chunk_off, *tmp_ids;
 };
 static void qblock_carve(ScratchCarver& sc, const QblockPlan& qp, uint32_t nq, uint32_t k, QblockBufs& b) {
-    b.qtau = sc.take<uint32_t>(nq);
+    b.qtau = sc.take<uint32_t>((size_t)4 * nq);
     b.n_fail = sc.take<uint32_t>(1);
     b.pair_chunk_off = sc.take<uint64_t>((size_t)nq + 1);
     b.part_d = sc.take<float>((size_t)nq * qp.nslices * FT_LIST);
@@ -1738,11 +1757,21 @@ static void qblock_carve(ScratchCarver& sc, const QblockPlan& qp, uint32_t nq, u
     b.tmp_ids = sc.take<uint64_t>((size_t)nq * k);
     b.tmp_d = sc.take<float>((size_t)nq * k);
 }
+// smallest batch that takes the query-block kernel (one pass of the table per 128 queries; the list-scan style kernel
+// takes one per 32: 1M x 300, 32 queries 0.42 ms, 64: 0.68 ms, 95: 0.94 ms)
+static uint32_t qblock_min_batch() {
+    static const uint32_t v = [] {
+        const char* e = getenv("VERS_QBLOCK_MIN_NQ");
+        const int x = e ? atoi(e) : 96;
+        return (uint32_t)(x < 1 ? 1 : x);
+    }();
+    return v;
+}
 static QblockPlan qblock_plan(const vers_ctx* ctx, uint64_t n, uint32_t ld, uint32_t nq, uint32_t k) {
     QblockPlan qp;
     qp.nk = (ld + FT_KC - 1) / FT_KC;
     // eligible: enough queries to fill 128-wide blocks, rows that fit tensor memory, a top-k the 32 candidates cover
-    if (nq < 96 || qp.nk > FT_MAX_KCH || ld < FT_KC || k > 16 || n < 4096 || n >= 0x7fffffffull) return qp;
+    if (nq < qblock_min_batch() || qp.nk > FT_MAX_KCH || ld < FT_KC || k > 16 || n < 4096 || n >= 0x7fffffffull) return qp;
     qp.nqb = (nq + FT_M - 1) / FT_M;
     const uint32_t want_items = (uint32_t)ctx->sm_count * 4;
     uint64_t nsl = std::max<uint64_t>(1, (want_items + qp.nqb - 1) / qp.nqb);
@@ -1768,7 +1797,7 @@ static QblockPlan qblock_plan(const vers_ctx* ctx, uint64_t n, uint32_t ld, uint
 __global__ void qblock_tables_kernel(uint32_t nq, uint32_t nslices, uint64_t* pair_chunk_off, uint32_t* qtau) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= nq) pair_chunk_off[i] = (uint64_t)i * nslices;
-    if (i < nq) qtau[i] = TAU_INF;
+    if (i < nq) reinterpret_cast<uint4*>(qtau)[i] = make_uint4(TAU_INF, TAU_INF, TAU_INF, TAU_INF);
 }
 
 static int32_t qblock_run(vers_ctx* ctx, const RankTable& tb, const QblockPlan& qp, const float* row_tiles,
@@ -1803,7 +1832,8 @@ static int32_t qblock_run(vers_ctx* ctx, const RankTable& tb, const QblockPlan& 
     const uint64_t nitems = (uint64_t)qp.nslices * qp.nqb;
     tc_flat_kernel<<<(unsigned)std::min<uint64_t>(nitems, ctx->sm_count), FT_THREADS, qp.smem, ctx->stream>>>(tm_q, p);
     VERS_LAUNCH_CHECK(ctx);
-    VERS_TRY(launch_cand_merge(ctx, 32, b.part_d, b.part_p, b.pair_chunk_off, nq, 1, 1, b.cand_pos, b.cand_key, b.bound));
+    VERS_TRY(launch_cand_merge(ctx, 32, b.part_d, b.part_p, b.pair_chunk_off, nq, 1, 1, b.cand_pos, b.cand_key, b.bound,
+                               nq <= 256 ? qp.nslices : 0));  // many queries: the blocks are the parallelism
     VERS_TRY(launch_rerank(ctx, 32, tb.rows, nullptr, tb.id_base, tb.ld, d_queries, nq, k, b.cand_pos, b.bound,
                            tb.nmax_bits, b.cand_key, 3, out_ids, out_d, out_cnt, b.fail, tb.stats, b.fail_idx, b.n_fail));
     // exact redo of the uncertified queries: the launch is sized for nq, the blocks read n_fail
@@ -1920,7 +1950,7 @@ static int32_t ivf_search_dev_locked(vers_ivf* ivf, const float* d_queries, uint
         b.gq = sc.take<float>(use_tc ? (size_t)(npairs + TC_NQ) * ivf->ld : 4);
         b.gq_lo = sc.take<float>((split3 || h16) ? (size_t)(npairs + TC_NQ) * ivf->ld : 4);
         b.cand_key = sc.take<float>((size_t)nq * M);
-        b.qtau = sc.take<uint32_t>(nq);
+        b.qtau = sc.take<uint32_t>((size_t)4 * nq);
     };
     {
         ScratchCarver plan(nullptr);

@@ -44,6 +44,8 @@ namespace vers {
 
 constexpr int TC_M = 128, TC_NQ = 32, TC_KC = 32, TC_SCHED = 4;
 constexpr int TC_PARTS = 4;       // partial lists per (pair, chunk): one per TMEM lane group
+constexpr int TC_SLOT_RANK = 32 / TC_PARTS;  // a list publishes its 8th key into its lane group's slot of the shared bound
+static_assert(TC_PARTS == 4, "the shared bound is read as one uint4 per query");
 constexpr int TC_EPI_WARP0 = 4, TC_EPI_WARPS = 8, TC_CONV_WARP0 = 12, TC_CONV_WARPS = 4;
 constexpr int TC_QPW = TC_NQ / 2;  // query columns per epilogue warp (at most)
 constexpr int TC_QCAP = 32;       // queue entries per (epilogue warp, query)
@@ -187,11 +189,15 @@ struct TcScanParams {
     float* part_d;
     uint32_t* part_p;
     unsigned long long* counter;
-    // optional (null: off): per-query running bound shared by all work items of the launch.  qtau[q] holds, in an
-    // order-preserving uint32 encoding, the smallest 32nd key any (lane group, item) list of query q has reached.
-    // A row whose key exceeds it cannot be among the query's 32 best keys (that list alone holds 32 better rows and
-    // only improves), so later items start selective instead of re-learning the threshold from +inf.  The merged
-    // top-32 and its bound do not depend on the timing of these updates.  Requires merged M == 32.
+    // optional (null: off): per-query running bound shared by all work items of the launch, [nq][TC_PARTS] in an
+    // order-preserving uint32 encoding.  Slot g of query q holds the smallest 8th key any list of TMEM lane group g
+    // (any item, any CTA) has reached: that list alone holds 8 rows at or below it, the lane groups scan disjoint rows,
+    // so 4 x 8 = 32 distinct rows lie at or below the LARGEST of the four slots — a row whose key exceeds that cannot be
+    // among the query's 32 best keys.  (One slot fed with whole lists' 32nd keys is the same argument with one list;
+    // it stays near the 32/rows-per-list quantile, 3.7 % for 864 rows, where 62 % of all 32-row slices still hold a
+    // passing row; the minimum over hundreds of lists of an 8th key is ~0.2 %.)  Later items start selective instead of
+    // re-learning the threshold from +inf.  The merged top-32 and its bound do not depend on the timing of these
+    // updates.  Requires merged M == 32.
     uint32_t* qtau;
     const uint32_t* lq_query;  // grouped pair -> query
     // optional (null: off): no selection at all, every key is written to dense_out[grouped pair][row position]
@@ -267,7 +273,8 @@ __device__ __forceinline__ void sel_cmpx(float& d, uint32_t& r, int j, bool keep
 }
 // Folds the c (<= 32) queued entries of one query into its sorted 32-entry list; returns the new 32nd key.
 //   lk/lr: the list (ascending, lane i = i-th smallest); qk/qr: the queue.  Whole warp, converged.
-__device__ __noinline__ float sel_flush(float* lk, uint16_t* lr, const float* qk, const uint16_t* qr, uint32_t c, int lane) {
+// returns (the list's 32nd key, its 8th key): +inf while the list holds fewer entries
+__device__ __noinline__ float2 sel_flush(float* lk, uint16_t* lr, const float* qk, const uint16_t* qr, uint32_t c, int lane) {
     __syncwarp();  // the queue writes of the other lanes are visible
     float d = (uint32_t)lane < c ? qk[lane] : __int_as_float(0x7f800000);
     uint32_t r = (uint32_t)lane < c ? (uint32_t)qr[lane] : 0xffffu;
@@ -293,7 +300,12 @@ __device__ __noinline__ float sel_flush(float* lk, uint16_t* lr, const float* qk
     lk[lane] = ld_;
     lr[lane] = (uint16_t)lrr;
     __syncwarp();
-    return __shfl_sync(FULL_MASK, ld_, 31);
+    return make_float2(__shfl_sync(FULL_MASK, ld_, 31), __shfl_sync(FULL_MASK, ld_, TC_SLOT_RANK - 1));
+}
+// the shared bound of query q: the largest of its TC_PARTS slots (see TcScanParams::qtau)
+__device__ __forceinline__ uint32_t tau_shared_bits(const uint32_t* qtau, uint32_t q) {
+    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(qtau) + q);
+    return max(max(v.x, v.y), max(v.z, v.w));
 }
 
 template <int PREC>
@@ -543,17 +555,30 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
                     const uint64_t row = a0 + (uint64_t)(lane_group * 32 + lane);
                     const bool rowlive = row < t.r1;
                     const float nx = rowlive ? __ldg(p.lm_norm + t.base_pos + row) : 0.0f;
-                    for (uint32_t j = 0; j < nlive; ++j) {
-                        float dot = tc::tmem_ld_1_nowait(tacc + col0 + j);
-                        float w = 0.0f, z = 0.0f;
-                        if (TWO_B) w = tc::tmem_ld_1_nowait(tacc + t.nq + col0 + j);
-                        if (SPLIT3) z = tc::tmem_ld_1_nowait(tacc + 2 * t.nq + col0 + j);
-                        tc::tmem_ld_wait3(dot, w, z);
-                        if (SPLIT3) dot = __fadd_rn(dot, __fadd_rn(w, z));
-                        if (H16) dot = __fmaf_rn(w, H16_LO_INV, dot);
-                        if (rowlive)
-                            p.dense_out[(t.q0 + col0 + j) * p.dense_ld + t.base_pos + row] =
-                                __fmaf_rn(H16 ? p.key_scale : -2.0f, dot, nx);
+                    // 8 accumulator columns of every block per load: one TMEM round trip per 8 queries (col0 + the
+                    // live count rounded up to 8 stays inside the block: both halves hold <= t.nq / 2 columns)
+                    for (uint32_t c8 = 0; c8 < nlive; c8 += 8) {
+                        uint32_t d0[8], d1[8], d2[8];
+                        tc::tmem_ld_8_nowait(tacc + col0 + c8, d0);
+                        if (TWO_B) tc::tmem_ld_8_nowait(tacc + t.nq + col0 + c8, d1);
+                        if (SPLIT3) tc::tmem_ld_8_nowait(tacc + 2 * t.nq + col0 + c8, d2);
+                        if (SPLIT3)
+                            tc::tmem_ld_wait_24(d0, d1, d2);
+                        else if (TWO_B)
+                            tc::tmem_ld_wait_16(d0, d1);
+                        else
+                            tc::tmem_ld_wait_8(d0);
+#pragma unroll
+                        for (uint32_t jj = 0; jj < 8; ++jj) {
+                            if (c8 + jj < nlive) {  // warp-uniform
+                                float dot = __uint_as_float(d0[jj]);
+                                if (SPLIT3) dot = __fadd_rn(dot, __fadd_rn(__uint_as_float(d1[jj]), __uint_as_float(d2[jj])));
+                                if (H16) dot = __fmaf_rn(__uint_as_float(d1[jj]), H16_LO_INV, dot);
+                                if (rowlive)
+                                    p.dense_out[(t.q0 + col0 + c8 + jj) * p.dense_ld + t.base_pos + row] =
+                                        __fmaf_rn(H16 ? p.key_scale : -2.0f, dot, nx);
+                            }
+                        }
                     }
                     tc::fence_before_thread_sync();
                     __syncwarp();
@@ -564,6 +589,7 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
             }
             // lane j keeps query j's threshold (its list's 32nd key, or the query's shared bound) and queue fill
             float my_tau = __int_as_float(0x7f800000);
+            float my_pub = __int_as_float(0x7f800000);  // what this list has published so far
             uint32_t my_cnt = 0, my_q = 0;
             uint64_t my_base = 0;  // where query `lane`'s partial list of this (item, lane group) goes: fetched now, so
                                    // the two dependent loads are long done when the item ends
@@ -572,7 +598,7 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
                 my_base = ((p.pair_chunk_off[pair] + t.chunk) * TC_PARTS + lane_group) * 32;
                 if (p.qtau) {
                     my_q = p.lq_query[t.q0 + col0 + lane];
-                    my_tau = tau_decode(__ldcg(p.qtau + my_q));
+                    my_tau = tau_decode(tau_shared_bits(p.qtau, my_q));
                 }
             }
             for (uint32_t j = 0; j < nlive; ++j) {
@@ -589,7 +615,7 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
                 const uint32_t buf = tile_ctr & 1, tphase = (tile_ctr >> 1) & 1;
                 uint32_t tau_bits = TAU_INF;
                 if (p.qtau && (uint32_t)lane < nlive && a0 != t.r0)  // bounds published by other CTAs meanwhile
-                    tau_bits = __ldcg(p.qtau + my_q);
+                    tau_bits = tau_shared_bits(p.qtau, my_q);
                 tc::mbar_wait(&tfull[buf], tphase);
                 tc::fence_after_thread_sync();
                 const uint32_t tacc = tmem_base + ((uint32_t)(lane_group * 32) << 16) + buf * Cfg::ACC_COLS;
@@ -608,9 +634,13 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
                         uint32_t c = __shfl_sync(FULL_MASK, my_cnt, j);
                         uint32_t n = __popc(m);
                         if (c + n > TC_QCAP) {  // make room: fold the queue into the list, which tightens tau
-                            tau = fminf(tau, sel_flush(lk + j * 32, lr + j * 32, qk + j * TC_QCAP, qr + j * TC_QCAP, c, lane));
+                            const float2 f = sel_flush(lk + j * 32, lr + j * 32, qk + j * TC_QCAP, qr + j * TC_QCAP, c, lane);
+                            tau = fminf(tau, f.x);
                             if ((uint32_t)lane == j) {
-                                if (p.qtau && tau < my_tau) atomicMin(p.qtau + my_q, tau_encode(tau));
+                                if (p.qtau && f.y < my_pub) {
+                                    atomicMin(p.qtau + 4 * my_q + lane_group, tau_encode(f.y));
+                                    my_pub = f.y;
+                                }
                                 my_tau = tau;
                             }
                             c = 0;
@@ -642,16 +672,24 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
                         }
                     }
                 } else {
-                    for (uint32_t j = 0; j < nlive; ++j) {
-                        float dot = tc::tmem_ld_1_nowait(tacc + c_hh + j);
-                        float w = 0.0f, z = 0.0f;
+                    for (uint32_t c8 = 0; c8 < nlive; c8 += 8) {
+                        uint32_t hh[8], hl[8], lh[8];
+                        tc::tmem_ld_8_nowait(tacc + c_hh + c8, hh);
                         if (SPLIT3) {
-                            w = tc::tmem_ld_1_nowait(tacc + c_hl + j);  // x_hi . q_lo
-                            z = tc::tmem_ld_1_nowait(tacc + c_lh + j);  // x_lo . q_hi
+                            tc::tmem_ld_8_nowait(tacc + c_hl + c8, hl);  // x_hi . q_lo
+                            tc::tmem_ld_8_nowait(tacc + c_lh + c8, lh);  // x_lo . q_hi
+                            tc::tmem_ld_wait_24(hh, hl, lh);
+                        } else {
+                            tc::tmem_ld_wait_8(hh);
                         }
-                        tc::tmem_ld_wait3(dot, w, z);
-                        if (SPLIT3) dot = __fadd_rn(dot, __fadd_rn(w, z));
-                        consider(j, __fmaf_rn(-2.0f, dot, nx));
+#pragma unroll
+                        for (uint32_t jj = 0; jj < 8; ++jj) {
+                            if (c8 + jj < nlive) {  // warp-uniform
+                                float dot = __uint_as_float(hh[jj]);
+                                if (SPLIT3) dot = __fadd_rn(dot, __fadd_rn(__uint_as_float(hl[jj]), __uint_as_float(lh[jj])));
+                                consider(c8 + jj, __fmaf_rn(-2.0f, dot, nx));
+                            }
+                        }
                     }
                 }
                 tc::fence_before_thread_sync();
@@ -663,8 +701,8 @@ __global__ void __launch_bounds__(TcCfg<PREC>::THREADS, 1)
             for (uint32_t j = 0; j < nlive; ++j) {
                 const uint32_t c = __shfl_sync(FULL_MASK, my_cnt, j);
                 if (c) {
-                    const float tau = sel_flush(lk + j * 32, lr + j * 32, qk + j * TC_QCAP, qr + j * TC_QCAP, c, lane);
-                    if (p.qtau && (uint32_t)lane == j && tau < my_tau) atomicMin(p.qtau + my_q, tau_encode(tau));
+                    const float2 f = sel_flush(lk + j * 32, lr + j * 32, qk + j * TC_QCAP, qr + j * TC_QCAP, c, lane);
+                    if (p.qtau && (uint32_t)lane == j && f.y < my_pub) atomicMin(p.qtau + 4 * my_q + lane_group, tau_encode(f.y));
                 }
                 const uint64_t base = __shfl_sync(FULL_MASK, my_base, j);
                 const uint32_t r = lr[j * 32 + lane];

@@ -72,6 +72,15 @@ int32_t launch_rownorm(vers_ctx* ctx, const float* rows, uint32_t ld, uint64_t n
 
 // small-batch streaming scan (flat.cu): every exact l2sq distance of nq <= 8 queries to a row table, dense [NQ][n]
 bool flat_stream_fits(uint32_t ld, uint32_t nq);
+// smallest query batch that takes the tensor-core candidate path against one table (probe / exhaustive search)
+inline uint32_t tc_min_batch() {
+    static const uint32_t v = [] {
+        const char* e = getenv("VERS_TC_MIN_NQ");
+        const int x = e ? atoi(e) : 9;
+        return (uint32_t)(x < 1 ? 1 : x);
+    }();
+    return v;
+}
 int32_t flat_stream_dense(vers_ctx* ctx, const float* rows, uint64_t n, uint32_t ld, const float* d_queries, uint32_t nq,
                           float* qpad, float* dense_out, int family);
 

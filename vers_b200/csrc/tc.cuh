@@ -177,6 +177,16 @@ __device__ __forceinline__ void tmem_ld_wait_16(uint32_t (&a)[8], uint32_t (&b)[
                  : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
                    "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7])::"memory");
 }
+__device__ __forceinline__ void tmem_ld_wait_8(uint32_t (&a)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7])::"memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_24(uint32_t (&a)[8], uint32_t (&b)[8], uint32_t (&c)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                   "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
+                   "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7])::"memory");
+}
 // 32 consecutive fp32 columns per thread, issue only — pair with tmem_ld_wait_32()
 __device__ __forceinline__ void tmem_ld_32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(

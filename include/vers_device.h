@@ -92,10 +92,11 @@ int32_t vers_flat_search(vers_dataset* ds, const float* queries, uint32_t nq, ui
 /* d_queries: device, nq rows of ld floats (ld = dataset ld, zero padded); outputs device [nq][top_k] */
 int32_t vers_flat_search_dev(vers_dataset* ds, const float* d_queries, uint32_t nq, uint32_t top_k, uint32_t metric,
                              uint64_t* d_ids, float* d_dists, uint32_t* d_counts);
-/* Batches of >= 32 queries with top_k <= 64 and the L2 metric take the two-stage path of the inverted-list scan over
- * the whole dataset: tensor-core candidate keys (TMA + tcgen05 kind::tf32, split hi/lo) -> exact-order rerank of the
- * 64/128 best -> rounding-error certificate -> exact-order redo of uncertified queries.  ids and distance bits are
- * the reference's either way.  mode 1 forces the exact-order engine (tests, timing).  Stats of the last tensor-core
+/* Up to 8 queries: one exact-order streaming pass (HBM-bound for 1-2 queries).  Batches of >= 9 queries with
+ * top_k <= 64 and the L2 metric take the two-stage path of the inverted-list scan over the whole dataset: tensor-core
+ * candidate keys (TMA + tcgen05 kind::tf32; split hi/lo with one pass of the table per 32 queries below 96 queries, one
+ * pass per 128 queries from a tile-major image above) -> exact-order rerank of the 32/64/128 best -> rounding-error
+ * certificate -> exact-order redo of uncertified queries.  ids and distance bits are the reference's either way.  mode 1 forces the exact-order engine (tests, timing).  Stats of the last tensor-core
  * search: out[4] = uncertified queries, out[5] = rows re-ranked, out[6] = bit pattern of the largest observed
  * |candidate value - exact value|; all zero when the exact-order engine ran. */
 int32_t vers_flat_set_mode(vers_dataset* ds, int32_t mode);

@@ -146,3 +146,57 @@ def test_threshold_encoding_is_order_preserving():
     assert int(enc(np.float32(np.inf))) == 0xFF800000
     for v in vals:
         assert dec(enc(v)).view(np.uint32) == np.float32(v).view(np.uint32)
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("ties", [False, True])
+def test_shared_bound_of_four_slots_never_drops_a_top32_row(seed, ties):
+    """The per-query bound shared by the work items of a candidate scan (csrc/ivf_tc.cuh TcScanParams::qtau,
+    csrc/flat_tc.cuh): 4 slots, a list publishes its 8th key (atomicMin) into the slot of its class, rows are pruned
+    against the LARGEST slot and against the own list's 32nd key.  Lists of different classes cover disjoint rows, so
+    32 distinct rows lie at or below the bound.  Model: items run in a random interleaving with stale reads of the
+    slots; whatever the timing, the union of the partial lists must contain the true 32 smallest (key, position)
+    entries, and every dropped row must have key >= the 32nd merged key (the bound cand_merge hands the certificate)."""
+    rng = np.random.default_rng(100 + seed)
+    n_items, rows_per_item, tile = 12, 512, 128
+    n = n_items * rows_per_item
+    keys = rng.standard_normal(n).astype(np.float32)
+    if ties:
+        keys = np.round(keys * 4) / np.float32(4)  # many equal keys, also at the bound
+    slots = np.full(4, INF, np.float32)
+    # list state per (item, lane group): sorted (key, pos) entries, at most 32
+    lists = {(it, g): [] for it in range(n_items) for g in range(4)}
+    published = {(it, g): INF for it in range(n_items) for g in range(4)}
+    dropped = []
+    # every item is a sequence of tiles; interleave the tiles of all items at random (CTAs progress independently)
+    cursor = [0] * n_items
+    stale = {it: INF for it in range(n_items)}  # the bound an item last read (refreshed once per tile, may be old)
+    pending = [it for it in range(n_items) for _ in range(rows_per_item // tile)]
+    rng.shuffle(pending)
+    for it in pending:
+        t0 = cursor[it]
+        cursor[it] += tile
+        if rng.random() < 0.7:  # a refresh may be skipped: stale values are larger, hence safe
+            stale[it] = min(stale[it], float(slots.max()))
+        for g in range(4):  # lane group g owns rows g*32 .. g*32+31 of the tile
+            L = lists[(it, g)]
+            for r in range(t0 + g * 32, t0 + g * 32 + 32):
+                pos = it * rows_per_item + r
+                own32 = L[31][0] if len(L) == 32 else INF
+                tau = min(stale[it], own32)
+                if keys[pos] <= tau:
+                    L.append((float(keys[pos]), pos))
+                    L.sort()
+                    if len(L) > 32:
+                        dropped.append(L.pop())  # evicted by 32 smaller entries of its own list
+                else:
+                    dropped.append((float(keys[pos]), pos))
+            if len(L) >= 8 and L[7][0] < published[(it, g)]:  # flush: publish the 8th key into slot g
+                published[(it, g)] = L[7][0]
+                slots[g] = min(slots[g], np.float32(L[7][0]))
+    merged = sorted(e for L in lists.values() for e in L)
+    truth = sorted((float(k), i) for i, k in enumerate(keys))
+    assert merged[:32] == truth[:32]
+    bound = merged[31][0]
+    assert all(k >= bound for k, _ in dropped)
+    assert float(slots.max()) >= truth[31][0]  # the bound itself never undercuts the true 32nd key
